@@ -1,0 +1,249 @@
+// card.cu -- K3 (unions / progressive prefix unions), K4 (register histogram + Ertl MLE) and the
+// K6 all-pairs shape.  All three are HBM/L2-streaming kernels over u8 register arrays.
+//
+//   dashing union -z -o OUT in...      reference lib/sketch_classes.py:368-373   -> union_max_kernel
+//   dashing card --presketched p...    reference lib/sketch_classes.py:306-321   -> hist_kernel + mle_kernel
+//   progressive unions                 reference lib/huffman_dandd.py:624-663    -> prefix_union_kernel
+//   pairwise two-leaf spiders          reference lib/huffman_dandd.py:666-695    -> prefix_union_kernel (2 steps)
+//
+// Histograms use thread-private counters in shared memory laid out [bin][thread]: a warp's 32
+// increments land in 32 different banks, so they cost two conflict-free shared accesses each
+// instead of a serialised shared-memory atomic (register values concentrate in a handful of bins,
+// the worst case for atomics).
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace dd {
+
+// -------------------------------------------------------------------------------------------------
+// K4a: histogram of u8 registers.  grid (slices, nsk)
+// -------------------------------------------------------------------------------------------------
+constexpr int kHistThreads = 128;
+constexpr int kHistSlices = 8;
+
+__device__ __forceinline__ void hist_add_word(uint32_t *s_hist, uint32_t w, int nthreads) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const uint32_t v = min((w >> (8 * b)) & 0xffu, (uint32_t)(DD_HIST_BINS - 1));
+        s_hist[v * nthreads + threadIdx.x]++;
+    }
+}
+
+// Sum the thread-private counters of every bin and add them to a global histogram row.
+template <int NT>
+__device__ __forceinline__ void hist_flush(const uint32_t *s_hist, uint32_t *g_hist) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b = warp; b < DD_HIST_BINS; b += NT / 32) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int t = lane; t < NT; t += 32) s += s_hist[b * NT + t];
+        s = __reduce_add_sync(0xffffffffu, s);
+        if (lane == 0 && s) atomicAdd(&g_hist[b], s);
+    }
+}
+
+__global__ void __launch_bounds__(kHistThreads)
+hist_kernel(const uint8_t *__restrict__ regs, int p, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t s_hist[DD_HIST_BINS * kHistThreads];
+    for (int i = threadIdx.x; i < DD_HIST_BINS * kHistThreads; i += kHistThreads) s_hist[i] = 0;
+    __syncthreads();
+    const size_t m = (size_t)1 << p;
+    const int sk = blockIdx.y;
+    if (m >= 16) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(regs + (size_t)sk * m);
+        const size_t nvec = m / 16;
+        const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
+        const size_t v0 = (size_t)blockIdx.x * per, v1 = min(nvec, v0 + per);
+        for (size_t v = v0 + threadIdx.x; v < v1; v += kHistThreads) {
+            const uint4 x = __ldg(src + v);
+            hist_add_word(s_hist, x.x, kHistThreads);
+            hist_add_word(s_hist, x.y, kHistThreads);
+            hist_add_word(s_hist, x.z, kHistThreads);
+            hist_add_word(s_hist, x.w, kHistThreads);
+        }
+    } else if (blockIdx.x == 0) {
+        for (size_t i = threadIdx.x; i < m; i += kHistThreads) {
+            const uint32_t v = min((uint32_t)regs[(size_t)sk * m + i], (uint32_t)(DD_HIST_BINS - 1));
+            s_hist[v * kHistThreads + threadIdx.x]++;
+        }
+    }
+    __syncthreads();
+    hist_flush<kHistThreads>(s_hist, hist + (size_t)sk * DD_HIST_BINS);
+}
+
+// -------------------------------------------------------------------------------------------------
+// K4b: Ertl MLE, one thread per sketch (f64, a few hundred flops each)
+// -------------------------------------------------------------------------------------------------
+__global__ void mle_kernel(const uint32_t *__restrict__ hist, int nsk, int p, double *__restrict__ cards) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsk) return;
+    uint32_t c[DD_HIST_BINS + 2];
+#pragma unroll
+    for (int j = 0; j < DD_HIST_BINS; ++j) c[j] = hist[(size_t)i * DD_HIST_BINS + j];
+    c[DD_HIST_BINS] = c[DD_HIST_BINS + 1] = 0;
+    cards[i] = ertl_mle(c, p);
+}
+
+// -------------------------------------------------------------------------------------------------
+// K3a: n-ary union, element-wise max over a device array of pointers
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+union_max_kernel(const uint8_t *const *__restrict__ in, int n_in, size_t len, uint8_t *__restrict__ out) {
+    const size_t nvec = len / 16;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+        uint4 acc = make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < n_in; ++j) {
+            const uint4 x = __ldg(reinterpret_cast<const uint4 *>(in[j]) + v);
+            acc.x = __vmaxu4(acc.x, x.x);
+            acc.y = __vmaxu4(acc.y, x.y);
+            acc.z = __vmaxu4(acc.z, x.z);
+            acc.w = __vmaxu4(acc.w, x.w);
+        }
+        reinterpret_cast<uint4 *>(out)[v] = acc;
+    }
+    // tail (len not a multiple of 16)
+    for (size_t i = nvec * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len;
+         i += (size_t)gridDim.x * blockDim.x) {
+        uint8_t a = 0;
+        for (int j = 0; j < n_in; ++j) a = max(a, in[j][i]);
+        out[i] = a;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K3b: progressive prefix unions with fused histograms.  grid (slices, nk, n_ord).
+// Each thread keeps the running max of 64 registers (4 x uint4) in registers while the ordering's
+// genomes stream past; after every step the CTA histograms its 16 KiB slice of the running union.
+// -------------------------------------------------------------------------------------------------
+constexpr int kPfxThreads = 256;
+constexpr int kPfxVec = 4;                                 // uint4 per thread
+constexpr int kPfxSliceBytes = kPfxThreads * kPfxVec * 16; // 16 KiB
+
+__global__ void __launch_bounds__(kPfxThreads)
+prefix_union_kernel(const uint8_t *__restrict__ regs, const int32_t *__restrict__ order, int n_steps, int n_genomes,
+                    int nk, int p, int final_only, uint32_t *__restrict__ hist, uint8_t *__restrict__ unions) {
+    // u8 thread-private counters would overflow only past 255 registers per thread per step; a
+    // thread sees 64, so one byte per (bin, thread) is enough: 16 KiB of shared memory.
+    __shared__ __align__(16) uint8_t s_hist[DD_HIST_BINS * kPfxThreads];
+    // byte slot of this thread inside a bin row: lane -> its own 32-bit word (= its own bank), the
+    // four bytes of a word belong to four different warps, so a warp's increments never conflict
+    const uint32_t my_slot = ((threadIdx.x & 31u) << 2) | ((threadIdx.x >> 5) & 3u) | ((threadIdx.x >> 7) << 7);
+    const size_t m = (size_t)1 << p;
+    const int k = blockIdx.y, o = blockIdx.z;
+    const size_t slice0 = (size_t)blockIdx.x * kPfxSliceBytes;
+    uint4 run[kPfxVec];
+#pragma unroll
+    for (int q = 0; q < kPfxVec; ++q) run[q] = make_uint4(0, 0, 0, 0);
+
+    for (int step = 0; step < n_steps; ++step) {
+        const int g = order[(size_t)o * n_steps + step];
+        if (g >= 0 && g < n_genomes) {
+            const uint8_t *src = regs + ((size_t)g * nk + k) * m + slice0;
+#pragma unroll
+            for (int q = 0; q < kPfxVec; ++q) {
+                const size_t off = ((size_t)q * kPfxThreads + threadIdx.x) * 16;
+                if (slice0 + off < m) {
+                    const uint4 x = __ldg(reinterpret_cast<const uint4 *>(src + off));
+                    run[q].x = __vmaxu4(run[q].x, x.x);
+                    run[q].y = __vmaxu4(run[q].y, x.y);
+                    run[q].z = __vmaxu4(run[q].z, x.z);
+                    run[q].w = __vmaxu4(run[q].w, x.w);
+                }
+            }
+        }
+        if (final_only && step != n_steps - 1) continue;
+        const size_t row = final_only ? (size_t)o * nk + k : ((size_t)o * n_steps + step) * nk + k;
+        // histogram of the running union
+        for (int i = threadIdx.x; i < DD_HIST_BINS * kPfxThreads / 16; i += kPfxThreads)
+            reinterpret_cast<uint4 *>(s_hist)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kPfxVec; ++q) {
+            const size_t off = ((size_t)q * kPfxThreads + threadIdx.x) * 16;
+            if (slice0 + off < m) {
+                const uint32_t w[4] = {run[q].x, run[q].y, run[q].z, run[q].w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const uint32_t v = min((w[c] >> (8 * b)) & 0xffu, (uint32_t)(DD_HIST_BINS - 1));
+                        s_hist[v * kPfxThreads + my_slot]++;
+                    }
+                if (unions) *reinterpret_cast<uint4 *>(unions + row * m + slice0 + off) = run[q];
+            }
+        }
+        __syncthreads();
+        // bin totals: each warp sums 8 bins; a lane adds the 8 byte counters of one 64-bit word
+        {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            for (int b = warp; b < DD_HIST_BINS; b += kPfxThreads / 32) {
+                const uint2 x = reinterpret_cast<const uint2 *>(s_hist + b * kPfxThreads)[lane];
+                // horizontal byte sums: (x & 0x00ff00ff) + ((x >> 8) & 0x00ff00ff) keeps 16-bit lanes
+                uint32_t s = (x.x & 0x00ff00ffu) + ((x.x >> 8) & 0x00ff00ffu) + (x.y & 0x00ff00ffu) +
+                             ((x.y >> 8) & 0x00ff00ffu);
+                s = (s & 0xffffu) + (s >> 16);
+                s = __reduce_add_sync(0xffffffffu, s);
+                if (lane == 0 && s) atomicAdd(&hist[row * DD_HIST_BINS + b], s);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+cudaError_t card_hist(const uint8_t *d_regs, int nsk, int p, uint32_t *d_hist, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, (size_t)nsk * DD_HIST_BINS * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    if (nsk == 0) return cudaSuccess;
+    const size_t m = (size_t)1 << p;
+    int slices = (int)((m / 16 + kHistThreads * 8 - 1) / (kHistThreads * 8));  // >= 8 uint4 per thread
+    if (slices < 1) slices = 1;
+    if (slices > kHistSlices) slices = kHistSlices;
+    for (int s0 = 0; s0 < nsk; s0 += 65535) {  // gridDim.y limit
+        const int cnt = nsk - s0 < 65535 ? nsk - s0 : 65535;
+        hist_kernel<<<dim3(slices, cnt), kHistThreads, 0, stream>>>(d_regs + (size_t)s0 * m, p,
+                                                                    d_hist + (size_t)s0 * DD_HIST_BINS);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t mle_from_hist(const uint32_t *d_hist, int nsk, int p, double *d_cards, cudaStream_t stream) {
+    if (nsk == 0) return cudaSuccess;
+    mle_kernel<<<(nsk + 63) / 64, 64, 0, stream>>>(d_hist, nsk, p, d_cards);
+    return cudaGetLastError();
+}
+
+cudaError_t union_max(const uint8_t *const *d_in, int n_in, size_t len, uint8_t *d_out, cudaStream_t stream) {
+    if (len == 0) return cudaSuccess;
+    size_t blocks = (len / 16 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    union_max_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_in, n_in, len, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t prefix_union_hist(const uint8_t *d_regs, const int32_t *d_order, int n_ord, int n_steps, int n_genomes,
+                              int nk, int p, int final_only, uint32_t *d_hist, uint8_t *d_unions,
+                              cudaStream_t stream) {
+    const int out_steps = final_only ? 1 : n_steps;
+    const size_t rows = (size_t)n_ord * out_steps * nk;
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, rows * DD_HIST_BINS * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    if (rows == 0) return cudaSuccess;
+    const size_t m = (size_t)1 << p;
+    const unsigned slices = (unsigned)((m + kPfxSliceBytes - 1) / kPfxSliceBytes);
+    for (int o0 = 0; o0 < n_ord; o0 += 65535) {  // gridDim.z limit
+        const int cnt = n_ord - o0 < 65535 ? n_ord - o0 : 65535;
+        const size_t roff = (size_t)o0 * out_steps * nk;
+        prefix_union_kernel<<<dim3(slices, nk, cnt), kPfxThreads, 0, stream>>>(
+            d_regs, d_order + (size_t)o0 * n_steps, n_steps, n_genomes, nk, p, final_only,
+            d_hist + roff * DD_HIST_BINS, d_unions ? d_unions + roff * m : nullptr);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace dd

@@ -1,0 +1,292 @@
+"""Engine: the batched GPU operations behind the drop-in sketch objects.
+
+PyTorch is used only to own device memory and streams; every operation is one or a few calls
+into the C ABI (include/dandd_b200.h) on torch's current stream, so `torch.cuda.Event` timing
+and stream semantics work as usual.  One Engine per process / per GPU."""
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DD_EXACT_BITMAP_MAXK, DD_HIST_BINS, DandDError, check
+
+
+def kmask_of(ks: Iterable[int]) -> int:
+    m = 0
+    for k in ks:
+        k = int(k)
+        if not 1 <= k <= 32:
+            raise ValueError(f"k={k} outside 1..32 (HLL estimation supports k<=32; reference README.md:82)")
+        m |= 1 << (k - 1)
+    if m == 0:
+        raise ValueError("no k values given")
+    return m
+
+
+def ks_of(kmask: int) -> List[int]:
+    return [k for k in range(1, 33) if (kmask >> (k - 1)) & 1]
+
+
+@dataclass
+class PackedSeq:
+    """A FASTA packed into the 2-bit symbol stream (layout: include/dandd_b200.h, K1)."""
+    codes: torch.Tensor       # uint8 storage holding the u32 code words
+    invalid: torch.Tensor     # uint8 storage holding the u32 break-bit words
+    state: torch.Tensor       # 32 bytes: dd_pack_state
+    cap_symbols: int
+    text_bytes: int
+    _nsym: Optional[int] = None
+
+    @property
+    def nsym(self) -> int:
+        """Number of symbols (reads the device state: synchronises)."""
+        if self._nsym is None:
+            st = self.state.cpu().numpy().view(np.uint64)
+            if int(st[3]) & 1:
+                raise DandDError("packed stream overflowed its capacity")
+            self._nsym = int(st[0])
+        return self._nsym
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise DandDError("no CUDA device visible to torch; dandd_b200 has no CPU fallback")
+        check(self.lib.dd_init(int(device)), "dd_init")
+        self.device = torch.device("cuda", int(device))
+        torch.cuda.set_device(self.device)
+        sm, maj, mnr, l2, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t(), C.c_size_t()
+        check(self.lib.dd_device_info(int(device), C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(l2), C.byref(mem)))
+        self.sm_count, self.cc, self.l2_bytes, self.total_mem = sm.value, (maj.value, mnr.value), l2.value, mem.value
+        self._ws = {}
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _buf(self, nbytes: int, tag: str) -> torch.Tensor:
+        """Grow-only scratch tensors keyed by role (uint8)."""
+        t = self._ws.get(tag)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._ws[tag] = t
+        return t
+
+    def _dev_u8(self, data) -> torch.Tensor:
+        if isinstance(data, torch.Tensor):
+            return data.to(self.device, dtype=torch.uint8).contiguous().view(-1)
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        arr = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        if arr.size == 0:
+            return torch.empty(0, dtype=torch.uint8, device=self.device)
+        return torch.from_numpy(arr.copy() if not arr.flags.writeable else arr).to(self.device, non_blocking=False)
+
+    # ---- K1 ---------------------------------------------------------------------------------
+    @staticmethod
+    def skip_preamble(text) -> int:
+        """Offset of the first '>' (kseq ignores everything before it); len if none."""
+        if isinstance(text, torch.Tensor):
+            hit = (text == 62).nonzero()
+            return int(hit[0]) if hit.numel() else int(text.numel())
+        arr = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.asarray(text)
+        hit = np.flatnonzero(arr == 62)
+        return int(hit[0]) if hit.size else int(arr.size)
+
+    def pack(self, text, chunk_bytes: Optional[int] = None) -> PackedSeq:
+        """FASTA text (bytes / numpy / torch uint8) -> PackedSeq.  `chunk_bytes` packs in several
+        chunks through the carried state (used by the tests to exercise streaming)."""
+        d_text = self._dev_u8(text)
+        off = self.skip_preamble(d_text) if d_text.numel() else 0
+        n = int(d_text.numel()) - off
+        if off % 16 and n > 0:
+            d_text = d_text[off:].clone()   # keep the 128-bit loads aligned
+        elif off:
+            d_text = d_text[off:]
+        cb, ib = self.lib.dd_pack_codes_bytes(max(n, 1)), self.lib.dd_pack_invalid_bytes(max(n, 1))
+        codes = torch.empty(cb, dtype=torch.uint8, device=self.device)
+        invalid = torch.empty(ib, dtype=torch.uint8, device=self.device)
+        state = torch.empty(32, dtype=torch.uint8, device=self.device)
+        st = self.stream
+        check(self.lib.dd_pack_reset(codes.data_ptr(), cb, invalid.data_ptr(), ib, state.data_ptr(), st), "dd_pack_reset")
+        chunk = int(chunk_bytes) if chunk_bytes else max(n, 1)
+        wsb = self.lib.dd_pack_workspace_bytes(min(chunk, max(n, 1)))
+        ws = self._buf(wsb, "pack")
+        pos = 0
+        while pos < n:
+            ln = min(chunk, n - pos)
+            part = d_text[pos:pos + ln]
+            if part.data_ptr() % 16:
+                part = part.clone()
+            check(self.lib.dd_pack_fasta(part.data_ptr(), ln, codes.data_ptr(), invalid.data_ptr(), max(n, 1),
+                                         state.data_ptr(), ws.data_ptr(), ws.numel(), st), "dd_pack_fasta")
+            pos += ln
+        return PackedSeq(codes, invalid, state, max(n, 1), n)
+
+    # ---- K2 (+K4 for the leaf cardinalities) ------------------------------------------------------
+    def sketch(self, seq: PackedSeq, ks: Sequence[int], p: int = 20, canon: bool = True,
+               out: Optional[torch.Tensor] = None, ranges=None, floor_every: Optional[int] = None):
+        """All-k HLL sketch of one packed sequence.  Returns (regs [nk, 2^p] uint8, cards [nk] f64),
+        both on the device.  `ranges` (list of (begin, end) symbol ranges) forces chunked updates."""
+        kmask = kmask_of(ks)
+        nk = bin(kmask).count("1")
+        m = 1 << p
+        wsb = self.lib.dd_sketch_workspace_bytes(nk, p)
+        ws = self._buf(wsb, "sketch")
+        st = self.stream
+        regs = out if out is not None else torch.empty((nk, m), dtype=torch.uint8, device=self.device)
+        assert regs.is_contiguous() and regs.numel() == nk * m
+        hist = torch.empty((nk, DD_HIST_BINS), dtype=torch.int32, device=self.device)
+        cards = torch.empty(nk, dtype=torch.float64, device=self.device)
+        check(self.lib.dd_sketch_begin(ws.data_ptr(), ws.numel(), nk, p, st), "dd_sketch_begin")
+        if ranges is None and floor_every:
+            n = seq.nsym                      # needs the symbol count on the host: one sync
+            ranges = [(b, min(n, b + floor_every)) for b in range(0, n, floor_every)]
+        if ranges is None:
+            # whole stream in one launch; the symbol count stays on the device (no host sync)
+            self._update_from_state(seq, kmask, p, canon, ws, st)
+        else:
+            seen = 0
+            for (b, e) in ranges:
+                check(self.lib.dd_sketch_update_range(seq.codes.data_ptr(), seq.invalid.data_ptr(), int(b), int(e), kmask,
+                                                      p, int(canon), ws.data_ptr(), ws.numel(), st), "dd_sketch_update_range")
+                seen += e - b
+                if floor_every and seen >= (16 << p):
+                    check(self.lib.dd_sketch_refresh_floor(ws.data_ptr(), ws.numel(), kmask, p, st), "dd_sketch_refresh_floor")
+        check(self.lib.dd_sketch_end(ws.data_ptr(), ws.numel(), nk, p, regs.data_ptr(), hist.data_ptr(), cards.data_ptr(), st),
+              "dd_sketch_end")
+        return regs, cards
+
+    def _update_from_state(self, seq, kmask, p, canon, ws, st):
+        # the pack state says [prev_nsym, nsym); for a whole-stream sketch rewind prev_nsym to 0
+        state = seq.state.clone()
+        state.view(torch.int64)[1] = 0
+        check(self.lib.dd_sketch_update(seq.codes.data_ptr(), seq.invalid.data_ptr(), state.data_ptr(), seq.text_bytes,
+                                        kmask, p, int(canon), ws.data_ptr(), ws.numel(), st), "dd_sketch_update")
+        self._keep = state  # keep alive until the stream has consumed it
+
+    def sketch_fasta_host(self, text: bytes, ks: Sequence[int], p: int = 20, canon: bool = True,
+                          want_regs: bool = True, pinned_regs: Optional[torch.Tensor] = None):
+        """The host-buffer C-ABI path: FASTA bytes in host memory -> (regs numpy [nk, 2^p] or None,
+        cards numpy [nk]).  H2D, pack, sketch, estimate, D2H all inside the one call."""
+        kmask = kmask_of(ks)
+        nk = bin(kmask).count("1")
+        m = 1 << p
+        if isinstance(text, torch.Tensor):
+            h_ptr, n = text.data_ptr(), text.numel()
+        else:
+            arr = np.frombuffer(text, dtype=np.uint8)
+            h_ptr, n = arr.ctypes.data, arr.size
+        wsb = self.lib.dd_sketch_fasta_host_workspace_bytes(n, nk, p)
+        ws = self._buf(wsb, "host")
+        cards = np.empty(nk, dtype=np.float64)
+        regs = None
+        r_ptr = None
+        if want_regs:
+            if pinned_regs is not None:
+                regs, r_ptr = pinned_regs, pinned_regs.data_ptr()
+            else:
+                regs = np.empty((nk, m), dtype=np.uint8)
+                r_ptr = regs.ctypes.data
+        check(self.lib.dd_sketch_fasta_host(h_ptr, n, kmask, p, int(canon), r_ptr, cards.ctypes.data, None, ws.data_ptr(),
+                                            ws.numel(), self.stream), "dd_sketch_fasta_host")
+        return regs, cards
+
+    # ---- K4 ---------------------------------------------------------------------------------
+    def cards(self, regs: torch.Tensor, p: int) -> torch.Tensor:
+        """Ertl-MLE cardinality of each sketch in regs [..., 2^p] (uint8, device)."""
+        m = 1 << p
+        flat = regs.contiguous().view(-1, m)
+        nsk = flat.shape[0]
+        hist = torch.empty((nsk, DD_HIST_BINS), dtype=torch.int32, device=self.device)
+        out = torch.empty(nsk, dtype=torch.float64, device=self.device)
+        check(self.lib.dd_card_ertl_mle(flat.data_ptr(), nsk, p, out.data_ptr(), hist.data_ptr(), self.stream), "dd_card_ertl_mle")
+        return out.view(regs.shape[:-1])
+
+    # ---- K3 ---------------------------------------------------------------------------------
+    def union(self, sketches: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Register-wise max of equally sized uint8 device tensors (`dashing union`)."""
+        n = sketches[0].numel()
+        keep = [s.contiguous() for s in sketches]
+        ptrs = torch.tensor([s.data_ptr() for s in keep], dtype=torch.int64).to(self.device)
+        out = torch.empty_like(keep[0])
+        check(self.lib.dd_union_max(ptrs.data_ptr(), len(keep), n, out.data_ptr(), self.stream), "dd_union_max")
+        self._keep = (keep, ptrs)
+        return out
+
+    def prefix_union_cards(self, regs: torch.Tensor, orders, p: int, final_only: bool = False,
+                           materialize: bool = False):
+        """regs [n_genomes, nk, 2^p]; orders [n_ord, n_steps] genome indices (-1 = skip).
+        Returns cards [n_ord, n_steps or 1, nk] f64 (and the unions if materialize)."""
+        n_g, nk, m = regs.shape
+        assert m == 1 << p and regs.is_contiguous()
+        order = torch.as_tensor(np.asarray(orders, dtype=np.int32)).to(self.device).contiguous()
+        n_ord, n_steps = order.shape
+        osteps = 1 if final_only else n_steps
+        hist = torch.empty((n_ord, osteps, nk, DD_HIST_BINS), dtype=torch.int32, device=self.device)
+        cards = torch.empty((n_ord, osteps, nk), dtype=torch.float64, device=self.device)
+        unions = torch.empty((n_ord, osteps, nk, m), dtype=torch.uint8, device=self.device) if materialize else None
+        check(self.lib.dd_prefix_union_card(regs.data_ptr(), order.data_ptr(), n_ord, n_steps, n_g, nk, p, int(final_only),
+                                            cards.data_ptr(), hist.data_ptr(), unions.data_ptr() if materialize else None,
+                                            self.stream), "dd_prefix_union_card")
+        self._keep = order
+        return (cards, unions) if materialize else cards
+
+    def pairwise_cards(self, regs: torch.Tensor, pairs, p: int) -> torch.Tensor:
+        """card(A u B) for every listed pair and every k: [n_pairs, nk] f64."""
+        n_g, nk, m = regs.shape
+        pr = torch.as_tensor(np.asarray(pairs, dtype=np.int32).reshape(-1, 2)).to(self.device).contiguous()
+        n_pairs = pr.shape[0]
+        hist = torch.empty((n_pairs, nk, DD_HIST_BINS), dtype=torch.int32, device=self.device)
+        cards = torch.empty((n_pairs, nk), dtype=torch.float64, device=self.device)
+        check(self.lib.dd_pairwise_union_card(regs.data_ptr(), n_g, nk, p, pr.data_ptr(), n_pairs, cards.data_ptr(),
+                                              hist.data_ptr(), self.stream), "dd_pairwise_union_card")
+        self._keep = pr
+        return cards
+
+    # ---- K5 ---------------------------------------------------------------------------------
+    def exact_counts(self, seqs: Sequence[PackedSeq], k: int, canon: bool = True, capacity: Optional[int] = None) -> List[int]:
+        """Insert the sequences one after another into one k-mer set and return the number of
+        distinct (canonical) k-mers after each: [|S1|, |S1 u S2|, ...] (exact, KMC semantics)."""
+        nsyms = [s.nsym for s in seqs]
+        if capacity is None:
+            capacity = 1024
+            while capacity < 2 * max(1, sum(nsyms)):
+                capacity *= 2
+        wsb = self.lib.dd_exact_workspace_bytes(k, capacity)
+        ws = self._buf(wsb, "exact")
+        st = self.stream
+        counts = torch.zeros(len(seqs), dtype=torch.int64, device=self.device)
+        check(self.lib.dd_exact_begin(ws.data_ptr(), ws.numel(), k, capacity, st), "dd_exact_begin")
+        for i, (s, n) in enumerate(zip(seqs, nsyms)):
+            check(self.lib.dd_exact_insert(s.codes.data_ptr(), s.invalid.data_ptr(), 0, n, k, int(canon), ws.data_ptr(),
+                                           ws.numel(), capacity, st), "dd_exact_insert")
+            check(self.lib.dd_exact_count(ws.data_ptr(), ws.numel(), k, capacity, counts[i:].data_ptr(), st), "dd_exact_count")
+        out = counts.cpu().numpy().astype(np.uint64)
+        if (out == np.uint64(0xFFFFFFFFFFFFFFFF)).any():
+            raise DandDError("exact k-mer table overflowed; pass a larger capacity")
+        return [int(v) for v in out]
+
+
+_default_engine = None
+
+
+def get_engine() -> Engine:
+    """Process-wide engine on LOCAL_RANK's GPU (torchrun) or device 0."""
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_engine
+
+
+def set_engine(engine) -> None:
+    """Install a different engine object (another device; tests install an oracle-backed double
+    here to exercise the host logic on machines without a GPU)."""
+    global _default_engine
+    _default_engine = engine

@@ -1,0 +1,190 @@
+/*
+ * dandd_b200.h -- C ABI of the B200-native DandD sketch-and-count hot path.
+ *
+ * The reference (jessicabonnie/dandd) has NO FFI: its seam to the arithmetic is a set of shell
+ * command strings built by SketchObj subclasses and run through subprocess.  Each entry point
+ * below replaces one of those command lines; the citation gives the reference site (paths are
+ * relative to the reference repository root).  INTEGRATION.md shows the ctypes stubs a reference
+ * maintainer would add at those sites.
+ *
+ * Conventions
+ *   - Every function returns DD_OK (0) or a negative DD_ERR_* code; dd_last_error() returns a
+ *     thread-local message for the last failure.  There is no CPU fallback: on a machine without
+ *     an sm_100 device dd_init() fails and nothing else may be called.
+ *   - The caller owns every buffer.  Pointers named d_* are DEVICE pointers (e.g. torch tensors'
+ *     data_ptr()), pointers named h_* are HOST pointers.  The library allocates nothing that
+ *     outlives a call; scratch space is passed in as (d_ws, ws_bytes) sized by the matching
+ *     *_workspace_bytes() query.
+ *   - All device work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default
+ *     stream) and is asynchronous unless the name ends in _host.
+ *   - k values travel as a bit mask: bit (k-1) set <=> k-mer length k is requested, 1 <= k <= 32
+ *     (`maxk<=32 for estimation`, README.md:82; lib/huffman_dandd.py:109-110).  "slot" j of a
+ *     [nk][...] output is the j-th set bit of the mask in increasing k.
+ *   - A sketch is 2^p one-byte HyperLogLog registers (p = --registers, default 20,
+ *     lib/dandd_cmd.py:187), bit-identical to what `dashing sketch -S p` builds.
+ */
+#ifndef DANDD_B200_H
+#define DANDD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DD_ABI_VERSION 1
+
+#define DD_OK 0
+#define DD_ERR_ARG (-1)       /* bad argument (null pointer, k/p out of range, ...) */
+#define DD_ERR_CUDA (-2)      /* a CUDA runtime call or kernel launch failed        */
+#define DD_ERR_WORKSPACE (-3) /* workspace smaller than *_workspace_bytes() says    */
+#define DD_ERR_DEVICE (-4)    /* no usable sm_100 device                            */
+
+#define DD_HIST_BINS 64 /* register-value histogram: bin j = #registers == j (j <= 64-p+1 < 64) */
+
+typedef void *dd_stream;
+
+#if defined(__GNUC__)
+#define DD_API __attribute__((visibility("default")))
+#else
+#define DD_API
+#endif
+
+DD_API const char *dd_last_error(void);
+DD_API int dd_abi_version(void);
+/* Select `device` for the calling thread and verify it is compute capability 10.x. */
+DD_API int dd_init(int device);
+DD_API int dd_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes, size_t *total_mem);
+
+/* ===========================================================================================
+ * K1  FASTA text -> packed symbol stream.
+ * Replaces the FASTA parsing half of `dashing sketch ... <fasta>` (lib/sketch_classes.py:351-366)
+ * and of `kmc ... -fm <fasta>` (lib/sketch_classes.py:434-449).
+ *
+ * Stream layout (device memory, caller-owned, zero-filled by dd_pack_reset):
+ *   codes   : uint32 words, 16 symbols per word, symbol s in word s/16 at bits [31-2(s%16) : 30-2(s%16)]
+ *             (first symbol most significant), A/a=0 C/c=1 G/g=2 T/t=3;
+ *   invalid : uint32 words, 32 symbols per word, symbol s in word s/32 at bit 31-(s%32); a set bit
+ *             means "k-mer windows restart here" (any byte other than ACGTacgt, and one synthetic
+ *             symbol per '>' header line so that k-mers never span records);
+ *   state   : dd_pack_state, carried from chunk to chunk so a FASTA can be streamed.
+ * Text rules: a line whose first byte is '>' is a header; '\n' and '\r' are not
+ * sequence; text before the first '>' of a file must be skipped by the caller (dd_*_host do it).
+ * =========================================================================================== */
+typedef struct dd_pack_state {
+    uint64_t nsym;      /* symbols in the stream so far                                   */
+    uint64_t prev_nsym; /* value of nsym before the most recent dd_pack_fasta call        */
+    uint32_t in_header; /* 1 if the text consumed so far ends inside a header line        */
+    uint32_t last_byte; /* last text byte consumed ('\n' initially: start of a line)      */
+    uint64_t reserved;
+} dd_pack_state;
+
+DD_API size_t dd_pack_codes_bytes(size_t max_text_bytes);
+DD_API size_t dd_pack_invalid_bytes(size_t max_text_bytes);
+DD_API size_t dd_pack_workspace_bytes(size_t chunk_bytes);
+DD_API int dd_pack_reset(uint32_t *d_codes, size_t codes_bytes, uint32_t *d_invalid, size_t invalid_bytes,
+                  dd_pack_state *d_state, dd_stream stream);
+/* Append the symbols of text chunk [d_text, d_text+n_bytes) to the stream.  d_text should be
+ * 16-byte aligned for full speed.  cap_symbols = capacity of codes/invalid in symbols. */
+DD_API int dd_pack_fasta(const uint8_t *d_text, size_t n_bytes, uint32_t *d_codes, uint32_t *d_invalid,
+                  size_t cap_symbols, dd_pack_state *d_state, void *d_ws, size_t ws_bytes, dd_stream stream);
+
+/* ===========================================================================================
+ * K2  fused all-k canonical-k-mer HyperLogLog sketch.
+ * Replaces the whole fan-out
+ *     parallel -j 95% ' dashing sketch [--no-canon] -k{} -S p --prefix DIR fasta ' ::: k1 k2 ...
+ * (lib/huffman_dandd.py:217 building lib/sketch_classes.py:351-366): one pass over the packed
+ * stream updates the registers of every requested k.
+ *   begin  : zero the accumulators held in the workspace;
+ *   update : sketch stream symbols [state.prev_nsym, state.nsym) (k-mers ENDING in that range, so
+ *            chunked packing + update is exact), or an explicit [sym_begin, sym_end) range;
+ *   end    : write the final u8 registers [nk][2^p], and optionally the register histograms and
+ *            Ertl-MLE cardinalities (what `dashing card` would print for each of the nk sketches).
+ * canon = 1 hashes min(kmer, reverse complement) (default), 0 = --no-canon
+ * (lib/sketch_classes.py:20-29).
+ * =========================================================================================== */
+DD_API size_t dd_sketch_workspace_bytes(int nk, int p);
+DD_API int dd_sketch_begin(void *d_ws, size_t ws_bytes, int nk, int p, dd_stream stream);
+DD_API int dd_sketch_update(const uint32_t *d_codes, const uint32_t *d_invalid, const dd_pack_state *d_state,
+                     size_t max_new_symbols, uint32_t kmask, int p, int canon, void *d_ws, size_t ws_bytes,
+                     dd_stream stream);
+DD_API int dd_sketch_update_range(const uint32_t *d_codes, const uint32_t *d_invalid, uint64_t sym_begin, uint64_t sym_end,
+                           uint32_t kmask, int p, int canon, void *d_ws, size_t ws_bytes, dd_stream stream);
+/* Recompute the per-k lower bound min(register) used to skip no-op updates (long genomes). */
+DD_API int dd_sketch_refresh_floor(void *d_ws, size_t ws_bytes, uint32_t kmask, int p, dd_stream stream);
+DD_API int dd_sketch_end(void *d_ws, size_t ws_bytes, int nk, int p, uint8_t *d_regs, uint32_t *d_hist /*[nk][64] or NULL*/,
+                  double *d_cards /*[nk] or NULL*/, dd_stream stream);
+
+/* ===========================================================================================
+ * K4  cardinality: register histogram + Ertl maximum-likelihood estimate.
+ * Replaces `dashing card --presketched <paths...>` (lib/sketch_classes.py:306-321); d_cards[i] is
+ * the number the reference would store in cardkey[path_i].  d_hist ([nsk][64] uint32) receives the
+ * histograms and doubles as scratch; it must be provided.
+ * =========================================================================================== */
+DD_API int dd_card_ertl_mle(const uint8_t *d_regs, int nsk, int p, double *d_cards, uint32_t *d_hist, dd_stream stream);
+/* Estimator alone, from histograms (host-callable building block; also used by K3/K6). */
+DD_API int dd_mle_from_hist(const uint32_t *d_hist, int nsk, int p, double *d_cards, dd_stream stream);
+
+/* ===========================================================================================
+ * K3  unions.
+ * dd_union_max replaces `dashing union -z -o OUT in1 .. inN` (lib/sketch_classes.py:368-373):
+ * d_in is a DEVICE array of n_in device pointers, each to `len` bytes; d_out = element-wise max.
+ *
+ * dd_prefix_union_card replaces the progressive-union loop (lib/huffman_dandd.py:624-663): for
+ * every ordering o and step i it forms the union of genomes order[o][0..i] and its cardinality
+ * for each of the nk sketches per genome -- as a running max, n reads instead of the reference's
+ * n(n+1)/2.  Entries of d_order < 0 are skipped (ragged orderings).
+ *   d_regs   [n_genomes][nk][2^p] u8         d_order [n_ord][n_steps] int32
+ *   d_cards  [n_ord][n_steps][nk] f64        d_hist  [n_ord][n_steps][nk][64] u32 (scratch+output)
+ *   d_unions NULL, or [n_ord][n_steps][nk][2^p] u8 to materialise every prefix union
+ *   final_only != 0: only the union of each whole ordering is estimated/materialised -- the n-ary
+ *   union of a tree node (lib/huffman_dandd.py:412-438); the step dimension of the outputs then
+ *   has extent 1: d_cards [n_ord][nk], d_hist [n_ord][nk][64], d_unions [n_ord][nk][2^p].
+ * =========================================================================================== */
+DD_API int dd_union_max(const uint8_t *const *d_in, int n_in, size_t len, uint8_t *d_out, dd_stream stream);
+DD_API int dd_prefix_union_card(const uint8_t *d_regs, const int32_t *d_order, int n_ord, int n_steps, int n_genomes,
+                         int nk, int p, int final_only, double *d_cards, uint32_t *d_hist, uint8_t *d_unions,
+                         dd_stream stream);
+
+/* ===========================================================================================
+ * K6  all-pairs union cardinalities (the shape of lib/huffman_dandd.py:666-695 and
+ * helpers/allpairs.py:360-370): for each listed pair (a,b) and each of the nk sketches,
+ * card(max(regs[a], regs[b])).
+ *   d_pairs [n_pairs][2] int32      d_cards [n_pairs][nk] f64     d_hist [n_pairs][nk][64] u32
+ * =========================================================================================== */
+DD_API int dd_pairwise_union_card(const uint8_t *d_regs, int n_genomes, int nk, int p, const int32_t *d_pairs,
+                           int64_t n_pairs, double *d_cards, uint32_t *d_hist, dd_stream stream);
+
+/* ===========================================================================================
+ * K5  --exact: number of distinct (canonical) k-mers, KMC semantics.
+ * Replaces `kmc -ci1 -cs2 -kK [-b] -fm ...` + `kmc_tools info` (lib/sketch_classes.py:389-399,
+ * 434-449) and, by inserting several streams into one set, `kmc_tools complex` unions (:451-465).
+ * The set lives in the workspace: a 4^k-bit presence bitmap when k <= DD_EXACT_BITMAP_MAXK, else
+ * an open-addressing table of 64-bit keys with `capacity` slots (power of two, must exceed the
+ * number of distinct k-mers; dd_exact_count reports overflow as DD_ERR_WORKSPACE).
+ * =========================================================================================== */
+#define DD_EXACT_BITMAP_MAXK 16
+DD_API size_t dd_exact_workspace_bytes(int k, uint64_t capacity);
+DD_API int dd_exact_begin(void *d_ws, size_t ws_bytes, int k, uint64_t capacity, dd_stream stream);
+DD_API int dd_exact_insert(const uint32_t *d_codes, const uint32_t *d_invalid, uint64_t sym_begin, uint64_t sym_end, int k,
+                    int canon, void *d_ws, size_t ws_bytes, uint64_t capacity, dd_stream stream);
+/* Distinct k-mers inserted since dd_exact_begin -> *d_count (device u64); cumulative, so calling
+ * it after each genome gives the progressive exact unions. */
+DD_API int dd_exact_count(void *d_ws, size_t ws_bytes, int k, uint64_t capacity, uint64_t *d_count, dd_stream stream);
+
+/* ===========================================================================================
+ * Host-buffer convenience path (what bench.py's e2e number times): one FASTA held in host memory
+ * -> H2D copy -> K1 -> K2 -> K4 -> D2H of cardinalities (and registers if h_regs != NULL);
+ * synchronises the stream before returning.  Equivalent to the reference running
+ * `dashing sketch` + `dashing card` for every k of the mask on that file.
+ * =========================================================================================== */
+DD_API size_t dd_sketch_fasta_host_workspace_bytes(size_t n_bytes, int nk, int p);
+DD_API int dd_sketch_fasta_host(const uint8_t *h_text, size_t n_bytes, uint32_t kmask, int p, int canon,
+                         uint8_t *h_regs /*[nk][2^p] or NULL*/, double *h_cards /*[nk]*/, uint8_t *d_regs_or_null,
+                         void *d_ws, size_t ws_bytes, dd_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DANDD_B200_H */

@@ -1,0 +1,73 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports exactly the symbols
+include/dandd_b200.h declares, refuses to run without a device (no CPU fallback), and the
+product package never reaches into oracle/.  No compute call is made here."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from dandd_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "dandd_b200.h")).read()
+    return sorted(set(re.findall(r"DD_API\s+[\w\s\*]+?\b(dd_\w+)\s*\(", txt)))
+
+
+def test_header_and_binding_agree(lib):
+    from dandd_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 26
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "dandd_b200", "libdandd_b200.so")], text=True)
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert set(header_symbols()) <= exported
+    assert all(s.startswith("dd_") for s in exported), exported  # nothing else leaks out
+
+
+def test_abi_version_and_size_queries(lib):
+    assert lib.dd_abi_version() == 1
+    assert lib.dd_pack_codes_bytes(1 << 20) >= (1 << 20) // 4
+    assert lib.dd_pack_invalid_bytes(1 << 20) >= (1 << 20) // 8
+    assert lib.dd_sketch_workspace_bytes(23, 20) >= 23 * 4 * (1 << 20)
+    assert lib.dd_exact_workspace_bytes(12, 0) >= (4 ** 12) // 8
+    assert lib.dd_exact_workspace_bytes(20, 1 << 20) >= 8 << 20
+
+
+def test_no_cpu_fallback_without_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    assert lib.dd_init(0) < 0
+    assert b"no CPU fallback" in lib.dd_last_error()
+    from dandd_b200.engine import Engine
+    from dandd_b200._lib import DandDError
+    with pytest.raises(DandDError):
+        Engine(0)
+
+
+def test_argument_errors_are_reported(lib):
+    assert lib.dd_sketch_begin(None, 0, 3, 20, None) == -1
+    assert b"dd_sketch_begin" in lib.dd_last_error()
+    assert lib.dd_exact_begin(None, 0, 40, 0, None) == -1
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dandd_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")) or f == "dandd":
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)
+                assert "liboracle" not in src and "pyoracle" not in src, os.path.join(dirpath, f)

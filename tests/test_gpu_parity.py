@@ -1,0 +1,252 @@
+"""Parity of the CUDA path with the oracle, through the C ABI, on a real B200 (-m gpu).
+
+Bar (north-star): HLL registers and exact counts bit-identical; cardinalities within 1e-6
+relative (we hold 1e-9); sizes the oracle finishes in seconds, plus size-independent properties
+at the full config-2 genome size."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+from tests.util import adversarial_fasta, decode_packed, mutate, random_bases, to_fasta
+
+pytestmark = pytest.mark.gpu
+CARD_RTOL = 1e-9   # target is 1e-6 (BASELINE.json north_star); same f64 algorithm => far tighter
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from dandd_b200 import build
+    build.build()
+    from dandd_b200.engine import Engine
+    return Engine(0)
+
+
+def packed_to_numpy(seq):
+    n = seq.nsym
+    return decode_packed(seq.codes.cpu().numpy().view(np.uint32), seq.invalid.cpu().numpy().view(np.uint32), n)
+
+
+# ---------------------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("variant", ["plain", "crlf", "no_final_newline", "one_long_line", "preamble", "big"])
+@pytest.mark.parametrize("chunk", [None, 4096 + 16, 100000])
+def test_pack_bit_exact(eng, variant, chunk):
+    rng = np.random.default_rng(hash(variant) % 1000)
+    txt = adversarial_fasta(rng, n=70000)
+    if variant == "crlf":
+        txt = txt.replace(b"\n", b"\r\n")
+    elif variant == "no_final_newline":
+        txt = txt.rstrip(b"\n")
+    elif variant == "one_long_line":
+        txt = to_fasta([(b"x", random_bases(rng, 300001))], width=10 ** 9)
+    elif variant == "preamble":
+        txt = b"; comment line\nACGT\n" + txt
+    elif variant == "big":
+        txt = to_fasta([(b"c%d" % i, mutate(rng, random_bases(rng, 400000))) for i in range(5)], width=80)
+    want = orc.fasta_symbols(txt)
+    seq = eng.pack(txt, chunk_bytes=chunk)
+    assert seq.nsym == want.size
+    assert np.array_equal(packed_to_numpy(seq), want)
+
+
+def test_pack_empty_and_headers_only(eng):
+    for txt in (b"", b"no records at all\n", b">only a header", b">h1\n>h2\n\n>h3\n"):
+        want = orc.fasta_symbols(txt)
+        seq = eng.pack(txt)
+        assert seq.nsym == want.size
+        assert np.array_equal(packed_to_numpy(seq), want)
+
+
+# ---------------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("p", [8, 12, 20])
+@pytest.mark.parametrize("canon", [True, False])
+def test_sketch_all_k_bit_exact(eng, p, canon):
+    rng = np.random.default_rng(p)
+    txt = adversarial_fasta(rng, n=50000)
+    sym = orc.fasta_symbols(txt)
+    ks = list(range(1, 33))
+    regs, cards = eng.sketch(eng.pack(txt), ks, p=p, canon=canon)
+    regs, cards = regs.cpu().numpy(), cards.cpu().numpy()
+    for i, k in enumerate(ks):
+        want = orc.hll_sketch(sym, k, p, canon)
+        assert np.array_equal(regs[i], want), (k, p, canon)
+        assert cards[i] == pytest.approx(orc.card(want, p), rel=CARD_RTOL)
+
+
+def test_sketch_k_subsets_and_slots(eng):
+    rng = np.random.default_rng(3)
+    txt = to_fasta([(b"g", random_bases(rng, 30000))])
+    sym = orc.fasta_symbols(txt)
+    seq = eng.pack(txt)
+    for ks in ([14], [10, 32], [2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31], list(range(10, 33))):
+        regs, _ = eng.sketch(seq, ks, p=10)
+        regs = regs.cpu().numpy()
+        for i, k in enumerate(sorted(ks)):
+            assert np.array_equal(regs[i], orc.hll_sketch(sym, k, 10)), (ks, k)
+
+
+def test_sketch_chunked_ranges_and_floor_filter_exact(eng):
+    """Streaming updates over unaligned ranges, with the min-register floor refreshed between
+    chunks (n/m = 800, so the floor is well above zero), change nothing."""
+    rng = np.random.default_rng(4)
+    txt = to_fasta([(b"a", random_bases(rng, 120000)), (b"b", random_bases(rng, 85000))], width=70)
+    sym = orc.fasta_symbols(txt)
+    seq = eng.pack(txt)
+    ks = [4, 9, 16, 17, 25, 32]
+    n = seq.nsym
+    cuts = [0, 7, 16, 1000, 33333, 33334, 150001, n]
+    a, _ = eng.sketch(seq, ks, p=8, ranges=list(zip(cuts[:-1], cuts[1:])))
+    b, cb = eng.sketch(seq, ks, p=8, floor_every=20000)
+    for i, k in enumerate(ks):
+        want = orc.hll_sketch(sym, k, 8)
+        assert np.array_equal(a[i].cpu().numpy(), want), k
+        assert np.array_equal(b[i].cpu().numpy(), want), k
+        assert float(cb[i]) == pytest.approx(orc.card(want, 8), rel=CARD_RTOL)
+
+
+def test_sketch_degenerate_inputs(eng):
+    for txt in (b"", b">h\n", b">h\nACG\n", b">h\nNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNN\n"):
+        regs, cards = eng.sketch(eng.pack(txt), [4, 20], p=8)
+        assert int(regs.sum()) == 0 and float(cards.abs().sum()) == 0.0
+    # poly-T >= 32 is a valid k-mer run (SURVEY.md A.6 default) and canonicalises to poly-A
+    txt = b">t\n" + b"T" * 40 + b"\n"
+    regs, _ = eng.sketch(eng.pack(txt), [32], p=8)
+    assert np.array_equal(regs[0].cpu().numpy(), orc.hll_sketch(orc.fasta_symbols(txt), 32, 8))
+    assert int((regs[0] > 0).sum()) == 1
+
+
+def test_host_buffer_path_matches_oracle(eng):
+    rng = np.random.default_rng(5)
+    txt = b"leading junk\n" + adversarial_fasta(rng, n=40000)
+    sym = orc.fasta_symbols(txt)
+    ks = [7, 16, 21, 32]
+    regs, cards = eng.sketch_fasta_host(txt, ks, p=12)
+    for i, k in enumerate(ks):
+        want = orc.hll_sketch(sym, k, 12)
+        assert np.array_equal(regs[i], want)
+        assert cards[i] == pytest.approx(orc.card(want, 12), rel=CARD_RTOL)
+
+
+def test_host_buffer_path_multi_chunk_with_floor(eng):
+    """> 32 MiB of text: exercises the double-buffered copy stream, chunked packing through the
+    carried state and the floor refresh of the host path."""
+    rng = np.random.default_rng(6)
+    txt = to_fasta([(b"chr%d" % i, random_bases(rng, 9_000_000)) for i in range(4)], width=80)
+    assert len(txt) > (32 << 20)
+    sym = orc.fasta_symbols(txt)
+    ks = [12, 31]
+    regs, cards = eng.sketch_fasta_host(txt, ks, p=12)
+    for i, k in enumerate(ks):
+        want = orc.hll_sketch(sym, k, 12)
+        assert np.array_equal(regs[i], want)
+        assert cards[i] == pytest.approx(orc.card(want, 12), rel=CARD_RTOL)
+
+
+def test_full_size_genome_properties(eng):
+    """Config-2 size (5 Mbp, p=20): bit-exact against the oracle for three k, plus properties
+    that need no oracle: idempotence (sketching twice == once) and union == sketch of both."""
+    rng = np.random.default_rng(2)
+    anc = random_bases(rng, 5_000_000)
+    ta = to_fasta([(b"anc", anc)], width=80)
+    tb = to_fasta([(b"mut", mutate(rng, anc))], width=80)
+    ks = list(range(10, 33))
+    sa, sb = eng.pack(ta), eng.pack(tb)
+    ra, ca = eng.sketch(sa, ks, p=20)
+    rb, _ = eng.sketch(sb, ks, p=20)
+    syma = orc.fasta_symbols(ta)
+    for k in (10, 21, 32):
+        want = orc.hll_sketch(syma, k, 20)
+        assert np.array_equal(ra[k - 10].cpu().numpy(), want), k
+        assert float(ca[k - 10]) == pytest.approx(orc.card(want, 20), rel=CARD_RTOL)
+    ra2, _ = eng.sketch(sa, ks, p=20)
+    assert bool((ra2 == ra).all())
+    both = eng.pack(ta + tb)
+    rab, _ = eng.sketch(both, ks, p=20)
+    assert bool((rab == eng.union([ra, rb])).all())
+
+
+# ------------------------------------------------------------------------------------------ K3/K4/K6
+def make_sketches(eng, rng, n_genomes, ks, p, length=20000):
+    anc = random_bases(rng, length)
+    regs, syms = [], []
+    for g in range(n_genomes):
+        txt = to_fasta([(b"g%d" % g, mutate(rng, anc, sub=0.05))])
+        syms.append(orc.fasta_symbols(txt))
+        regs.append(eng.sketch(eng.pack(txt), ks, p=p)[0])
+    import torch
+    return torch.stack(regs).contiguous(), syms
+
+
+def test_cards_and_union(eng):
+    import torch
+    rng = np.random.default_rng(7)
+    ks, p = [8, 14, 27], 12
+    regs, _ = make_sketches(eng, rng, 5, ks, p)
+    cards = eng.cards(regs, p).cpu().numpy()
+    h = regs.cpu().numpy()
+    for g in range(5):
+        for i in range(len(ks)):
+            assert cards[g, i] == pytest.approx(orc.card(h[g, i], p), rel=CARD_RTOL)
+    u = eng.union([regs[g] for g in range(5)]).cpu().numpy()
+    assert np.array_equal(u, h.max(axis=0))
+    # empty and saturated sketches
+    z = torch.zeros((1, 1 << p), dtype=torch.uint8, device=regs.device)
+    assert float(eng.cards(z, p)) == 0.0
+    s = torch.full((1, 1 << p), 64 - p + 1, dtype=torch.uint8, device=regs.device)
+    assert np.isinf(float(eng.cards(s, p)))
+
+
+@pytest.mark.parametrize("p", [8, 14, 16])
+def test_prefix_union_cards(eng, p):
+    rng = np.random.default_rng(8 + p)
+    ks = [10, 15, 20, 31]
+    n = 6
+    regs, _ = make_sketches(eng, rng, n, ks, p)
+    orders = [list(range(n)), [5, 3, 1, 0, 2, 4], [2, 2, 2, 1, 1, 0], [4, -1, 0, -1, 3, 1]]
+    cards, unions = eng.prefix_union_cards(regs, orders, p, materialize=True)
+    cards, unions, h = cards.cpu().numpy(), unions.cpu().numpy(), regs.cpu().numpy()
+    for o, order in enumerate(orders):
+        run = np.zeros_like(h[0])
+        for s, g in enumerate(order):
+            if g >= 0:
+                run = np.maximum(run, h[g])
+            assert np.array_equal(unions[o, s], run)
+            for i in range(len(ks)):
+                assert cards[o, s, i] == pytest.approx(orc.card(run[i], p), rel=CARD_RTOL)
+    fin = eng.prefix_union_cards(regs, orders, p, final_only=True).cpu().numpy()
+    assert fin.shape == (len(orders), 1, len(ks))
+    assert np.allclose(fin[:, 0], cards[:, -1], rtol=0, atol=0)
+
+
+def test_pairwise_union_cards(eng):
+    rng = np.random.default_rng(9)
+    ks, p, n = [12, 21], 12, 7
+    regs, _ = make_sketches(eng, rng, n, ks, p)
+    pairs = [(a, b) for a in range(n) for b in range(a, n)]
+    got = eng.pairwise_cards(regs, pairs, p).cpu().numpy()
+    h = regs.cpu().numpy()
+    for j, (a, b) in enumerate(pairs):
+        for i in range(len(ks)):
+            assert got[j, i] == pytest.approx(orc.card(np.maximum(h[a, i], h[b, i]), p), rel=CARD_RTOL)
+
+
+# ---------------------------------------------------------------------------------------------- K5
+@pytest.mark.parametrize("k", [1, 4, 11, 16, 17, 24, 32])
+@pytest.mark.parametrize("canon", [True, False])
+def test_exact_counts_progressive(eng, k, canon):
+    rng = np.random.default_rng(10 + k)
+    anc = random_bases(rng, 30000)
+    txts = [adversarial_fasta(rng, n=20000)] + [to_fasta([(b"m%d" % i, mutate(rng, anc, sub=0.02))]) for i in range(3)]
+    txts.append(b">polyT\n" + b"T" * 100 + b"\n")
+    seqs = [eng.pack(t) for t in txts]
+    syms = [orc.fasta_symbols(t) for t in txts]
+    got = eng.exact_counts(seqs, k, canon)
+    want = [orc.exact_count(syms[:i + 1], k, canon) for i in range(len(syms))]
+    assert got == want
+
+
+def test_exact_table_overflow_is_loud(eng):
+    from dandd_b200._lib import DandDError
+    rng = np.random.default_rng(11)
+    seq = eng.pack(to_fasta([(b"x", random_bases(rng, 50000))]))
+    with pytest.raises(DandDError):
+        eng.exact_counts([seq], 25, capacity=1024)

@@ -1,0 +1,113 @@
+"""The shipped host+device arithmetic (dandd_b200/csrc/common.cuh) executed on the CPU through
+tests/host_emul.cpp and checked against the oracle: packer classification + transition-function
+algebra, window extraction, canonical k-mers, Wang hash, register rule, Ertl MLE.  These are the
+bit-deciding pieces of the CUDA kernels; the -m gpu tests check the kernels themselves."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+from tests.util import adversarial_fasta, decode_packed, random_bases, to_fasta
+
+U8P, U32P = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+
+
+def emul_pack(L, text: bytes, chunk=None):
+    """Pack `text` (already starting at its first '>') in one or several chunks."""
+    n = len(text)
+    codes = np.zeros(n // 16 + 4, dtype=np.uint32)
+    invalid = np.zeros(n // 32 + 4, dtype=np.uint32)
+    last, hdr = C.c_uint32(ord("\n")), C.c_uint32(0)
+    buf = np.frombuffer(text, dtype=np.uint8)
+    nsym, off = 0, 0
+    chunk = chunk or max(n, 1)
+    while off < n:
+        part = np.ascontiguousarray(buf[off:off + chunk])
+        got = L.emul_pack(part.ctypes.data_as(U8P), part.size, codes.ctypes.data_as(U32P), invalid.ctypes.data_as(U32P),
+                          nsym, C.byref(last), C.byref(hdr))
+        assert got != 2 ** 64 - 1, "transition-function algebra disagrees with the sequential walk"
+        nsym += got
+        off += chunk
+    return codes, invalid, nsym
+
+
+def emul_sketch(L, codes, invalid, nsym, k, p, canon=True, ranges=None):
+    regs = np.zeros(1 << p, dtype=np.uint8)
+    for b, e in (ranges or [(0, nsym)]):
+        L.emul_sketch(codes.ctypes.data_as(U32P), invalid.ctypes.data_as(U32P), b, e, k, p, int(canon),
+                      regs.ctypes.data_as(U8P))
+    return regs
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+@pytest.mark.parametrize("chunk", [None, 16, 48, 1000, 4096])
+def test_pack_matches_oracle_symbols(host_emul, seed, chunk):
+    rng = np.random.default_rng(seed)
+    txt = adversarial_fasta(rng, n=3000 + 517 * seed)
+    if seed == 1:
+        txt = txt.replace(b"\n", b"\r\n")         # CRLF
+    if seed == 2:
+        txt = txt.rstrip(b"\n")                   # no trailing newline
+    if seed == 3:
+        txt = to_fasta([(b"one-line", random_bases(rng, 5000))], width=100000)  # single long line
+    want = orc.fasta_symbols(txt)
+    codes, invalid, nsym = emul_pack(host_emul, txt, chunk)
+    assert nsym == want.size
+    assert np.array_equal(decode_packed(codes, invalid, nsym), want)
+
+
+def test_pack_header_spanning_chunks(host_emul):
+    txt = b">" + b"x" * 100 + b"\nACGT\n>" + b"y" * 37 + b">>>\nGGGG\n>z"
+    want = orc.fasta_symbols(txt)
+    for chunk in (16, 32, 64, 7 * 16):
+        codes, invalid, nsym = emul_pack(host_emul, txt, chunk)
+        assert np.array_equal(decode_packed(codes, invalid, nsym), want), chunk
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 8, 15, 16, 17, 23, 31, 32])
+@pytest.mark.parametrize("canon", [True, False])
+def test_sketch_arithmetic_matches_oracle(host_emul, k, canon):
+    rng = np.random.default_rng(100 + k)
+    txt = adversarial_fasta(rng, n=5000)
+    sym = orc.fasta_symbols(txt)
+    codes, invalid, nsym = emul_pack(host_emul, txt)
+    for p in (8, 12):
+        want = orc.hll_sketch(sym, k, p, canon)
+        got = emul_sketch(host_emul, codes, invalid, nsym, k, p, canon)
+        assert np.array_equal(got, want), (k, p, canon)
+    # chunked updates over arbitrary (unaligned) symbol ranges are exact
+    cuts = [0, 5, 16, 37, 1000, 1001, 4097, nsym]
+    got = emul_sketch(host_emul, codes, invalid, nsym, k, 12, canon, ranges=list(zip(cuts[:-1], cuts[1:])))
+    assert np.array_equal(got, orc.hll_sketch(sym, k, 12, canon))
+
+
+def test_hash_rank_index_formulations(host_emul):
+    rng = np.random.default_rng(5)
+    xs = rng.integers(0, 1 << 63, 2000, dtype=np.uint64).tolist() + [0, 1, (1 << 64) - 1, 1 << 43, (1 << 44) - 1, 1 << 44]
+    for x in xs:
+        assert host_emul.emul_wang(x) == orc.wang(x)
+        for p in (4, 10, 20, 26):
+            q = 64 - p
+            rest = x & ((1 << q) - 1)
+            rank = q - rest.bit_length() + 1
+            assert host_emul.emul_rank(x, p) == rank
+            assert host_emul.emul_rank_split(x, p) == rank
+            assert host_emul.emul_index(x, p) == x >> q
+            assert host_emul.emul_index_split(x, p) == x >> q
+
+
+def test_device_mle_matches_oracle(host_emul):
+    rng = np.random.default_rng(9)
+    for p, n in [(8, 10), (8, 3000), (12, 100), (12, 50000), (16, 10 ** 6), (20, 5 * 10 ** 6)]:
+        h = rng.integers(0, 1 << 63, n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, n, dtype=np.uint64)
+        q = 64 - p
+        idx = (h >> np.uint64(q)).astype(np.int64)
+        rest = (h & np.uint64((1 << q) - 1))
+        lz = q - np.floor(np.log2(np.maximum(rest.astype(np.float64), 1.0))).astype(np.int64)  # approximate, fine here
+        regs = np.zeros(1 << p, dtype=np.uint8)
+        np.maximum.at(regs, idx, np.clip(lz, 1, q + 1).astype(np.uint8))
+        c = orc.hist(regs, p)
+        hist64 = np.ascontiguousarray(c[:64])
+        got = host_emul.emul_mle(hist64.ctypes.data_as(U32P), p)
+        assert got == pytest.approx(orc.ertl_mle(c, p), rel=1e-12)

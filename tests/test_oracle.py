@@ -1,0 +1,132 @@
+"""The oracle against known answers and against its independent numpy twin.
+
+There are no reference goldens to pin to (the reference has no tests and its
+arithmetic lives in absent third-party binaries), so the pins are: hand-computable vectors, the
+survey's check values, agreement of two independently written restatements, a high-precision
+solve of Ertl's ML equation, and the committed fixtures under tests/golden/."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+from oracle import ref_numpy as ref
+from tests.util import adversarial_fasta, mutate, random_bases, to_fasta
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_wang_known_answers():
+    # SURVEY.md A.4 check values
+    assert orc.wang(0) == 0x77CFA1EEF01BCA90
+    assert orc.wang(1) == 0x5BCA7C69B794F8CE
+    xs = np.array([0, 1, 2, 0xFFFFFFFFFFFFFFFF, 0x0123456789ABCDEF], dtype=np.uint64)
+    assert [orc.wang(int(x)) for x in xs] == [int(v) for v in ref.wang_np(xs)]
+
+
+def test_revcomp_and_canonical_by_hand():
+    # ACGT (00 01 10 11 = 0x1B) is its own reverse complement; AAAA <-> TTTT
+    assert orc.revcomp(0x1B, 4) == 0x1B
+    assert orc.revcomp(0x00, 4) == 0xFF
+    sym = np.array([0, 1, 2, 3, 3, 3], dtype=np.uint8)  # ACGTTT
+    # 3-mers: ACG(6)->min(6,CGT=27)=6, CGT->6, GTT(47)->min(47,AAC=1)=1, TTT(63)->AAA=0
+    assert orc.kmers(sym, 3).tolist() == [6, 6, 1, 0]
+    assert orc.kmers(sym, 3, canon=False).tolist() == [6, 27, 47, 63]
+
+
+def test_register_rule_by_hand():
+    # one k-mer -> one register: index = top p bits, rank = 1 + leading zeros of the rest
+    sym = np.array([0, 0, 0, 0], dtype=np.uint8)
+    h = orc.wang(0)
+    p = 8
+    regs = orc.hll_sketch(sym, 4, p)
+    idx = h >> (64 - p)
+    rest = h & ((1 << (64 - p)) - 1)
+    rank = (64 - p) - rest.bit_length() + 1
+    assert regs[idx] == rank and int(regs.sum()) == rank
+
+
+def test_fasta_symbol_rules():
+    s = orc.fasta_symbols(b"junk before\n>h1 x\nACGT\nacgt\r\nNN\n\n>h2\nTT>A\n>h3")
+    #            break A C G T a c g t  N  N  break T T > A break
+    assert s.tolist() == [4, 0, 1, 2, 3, 0, 1, 2, 3, 4, 4, 4, 3, 3, 4, 0, 4]
+    assert orc.fasta_symbols(b"no header here\nACGT\n").size == 0
+    assert orc.fasta_symbols(b"").size == 0
+    # k-mers never span records or invalid characters; short records contribute nothing
+    s = orc.fasta_symbols(b">a\nACG\n>b\nTTT\n")
+    assert orc.kmers(s, 3, canon=False).tolist() == [6, 63]
+    assert orc.kmers(s, 4).size == 0
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_c_oracle_equals_numpy_twin(seed):
+    rng = np.random.default_rng(seed)
+    txt = adversarial_fasta(rng)
+    s1, s2 = orc.fasta_symbols(txt), ref.fasta_symbols_py(txt)
+    assert np.array_equal(s1, s2)
+    for k in (1, 2, 7, 15, 16, 17, 24, 31, 32):
+        for canon in (True, False):
+            assert np.array_equal(orc.kmers(s1, k, canon), ref.kmers_np(s2, k, canon)), (k, canon)
+        for p in (8, 12):
+            assert np.array_equal(orc.hll_sketch(s1, k, p), ref.hll_sketch_np(s2, k, p)), (k, p)
+        assert orc.exact_count([s1], k) == ref.exact_count_np([s2], k)
+
+
+def test_union_is_sketch_of_concatenation():
+    rng = np.random.default_rng(7)
+    a = orc.fasta_symbols(to_fasta([(b"a", random_bases(rng, 5000))]))
+    b = orc.fasta_symbols(to_fasta([(b"b", random_bases(rng, 4000))]))
+    for k in (11, 21):
+        ra, rb = orc.hll_sketch(a, k, 10), orc.hll_sketch(b, k, 10)
+        both = orc.hll_sketch(b, k, 10, regs=orc.hll_sketch(a, k, 10))
+        assert np.array_equal(orc.union_max([ra, rb]), both)
+        assert orc.exact_count([a, b], k) == len(set(orc.kmers(a, k).tolist()) | set(orc.kmers(b, k).tolist()))
+
+
+@pytest.mark.parametrize("p,n", [(8, 50), (10, 5000), (12, 3000), (12, 200000), (14, 1_000_000)])
+def test_ertl_mle_matches_exact_root_and_truth(p, n):
+    rng = np.random.default_rng(p * 1000 + n % 997)
+    h = rng.integers(0, 1 << 63, n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, n, dtype=np.uint64)
+    q = 64 - p
+    idx = (h >> np.uint64(q)).astype(np.int64)
+    rest = h & np.uint64((1 << q) - 1)
+    bl = np.array([int(v).bit_length() for v in rest.tolist()])
+    regs = np.zeros(1 << p, dtype=np.uint8)
+    np.maximum.at(regs, idx, (q - bl + 1).astype(np.uint8))
+    c = orc.hist(regs, p)
+    est = orc.ertl_mle(c, p)
+    assert est == pytest.approx(ref.ertl_mle_py(c, p), rel=1e-12)
+    assert est == pytest.approx(ref.ertl_ml_root_mp(c, p), rel=1e-6)      # the north-star tolerance
+    assert est == pytest.approx(n, rel=6 * 1.04 / math.sqrt(1 << p))     # and it estimates n
+
+
+def test_mle_edge_histograms():
+    p, q = 10, 54
+    m = 1 << p
+    c = np.zeros(66, dtype=np.uint32); c[0] = m
+    assert orc.ertl_mle(c, p) == 0.0
+    c = np.zeros(66, dtype=np.uint32); c[q + 1] = m
+    assert math.isinf(orc.ertl_mle(c, p))
+    c = np.zeros(66, dtype=np.uint32); c[0] = m - 1; c[1] = 1
+    assert orc.ertl_mle(c, p) == pytest.approx(1.0, rel=1e-3)
+
+
+def test_golden_fixtures():
+    """tests/golden/oracle_vectors.json was produced by tests/golden/make_oracle_vectors.py from the
+    numpy twin; the C oracle must reproduce it bit for bit (registers via their byte sums and
+    histograms, cardinalities to 1e-12)."""
+    with open(os.path.join(GOLD, "oracle_vectors.json")) as f:
+        gold = json.load(f)
+    for case in gold["cases"]:
+        rng = np.random.default_rng(case["seed"])
+        txt = adversarial_fasta(rng, n=case["n"])
+        sym = orc.fasta_symbols(txt)
+        assert int(sym.size) == case["nsym"] and int((sym == 4).sum()) == case["nbreak"]
+        for row in case["rows"]:
+            regs = orc.hll_sketch(sym, row["k"], case["p"], canon=row["canon"])
+            assert orc.hist(regs, case["p"])[:len(row["hist"])].tolist() == row["hist"]
+            assert int(np.dot(regs.astype(np.int64), np.arange(regs.size) % 251)) == row["checksum"]
+            assert orc.card(regs, case["p"]) == pytest.approx(row["card"], rel=1e-12)
+            assert orc.exact_count([sym], row["k"], canon=row["canon"]) == row["exact"]
