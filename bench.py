@@ -176,6 +176,8 @@ def run_ours(args):
     from dandd_b200.engine import Engine, kmask_of
     from dandd_b200._lib import check
     eng = Engine(local)
+    if os.environ.get("DD_K_PER_PASS"):
+        check(eng.lib.dd_set_option(b"sketch_k_per_pass", int(os.environ["DD_K_PER_PASS"])), "dd_set_option")
     dev = eng.device
     nk, m = len(KS), 1 << P
 

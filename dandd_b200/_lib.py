@@ -29,6 +29,7 @@ SIGNATURES = {
     "dd_last_error": (C.c_char_p, []),
     "dd_abi_version": (_i, []),
     "dd_init": (_i, [_i]),
+    "dd_set_option": (_i, [C.c_char_p, C.c_long]),
     "dd_device_info": (_i, [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),
     "dd_pack_codes_bytes": (_sz, [_sz]),
     "dd_pack_invalid_bytes": (_sz, [_sz]),

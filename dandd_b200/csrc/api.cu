@@ -31,7 +31,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 
 cudaStream_t S(dd_stream s) { return static_cast<cudaStream_t>(s); }
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-bool bad_p(int p) { return p < 4 || p > 26; }
+bool bad_p(int p) { return p < 5 || p > 26; }
 int popc(uint32_t x) { return __builtin_popcount(x); }
 
 }  // namespace
@@ -66,6 +66,16 @@ int dd_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size
     if (l2_bytes) *l2_bytes = (size_t)prop.l2CacheSize;
     if (total_mem) *total_mem = prop.totalGlobalMem;
     return DD_OK;
+}
+
+int dd_set_option(const char *name, long value) {
+    if (!name) return fail(DD_ERR_ARG, "dd_set_option: null name");
+    if (!strcmp(name, "sketch_k_per_pass")) {
+        if (value < 0 || value > 32) return fail(DD_ERR_ARG, "dd_set_option: sketch_k_per_pass must be 0..32");
+        dd::g_k_per_pass = (int)value;
+        return DD_OK;
+    }
+    return fail(DD_ERR_ARG, "dd_set_option: unknown option '%s'", name);
 }
 
 // ---- K1 ------------------------------------------------------------------------------------------
@@ -104,7 +114,7 @@ int dd_sketch_begin(void *d_ws, size_t ws_bytes, int nk, int p, dd_stream stream
 static int sketch_check(const void *c, const void *i, uint32_t kmask, int p, void *ws, size_t ws_bytes, const char *fn) {
     if (!c || !i || !ws) return fail(DD_ERR_ARG, "%s: null pointer", fn);
     if (kmask == 0) return fail(DD_ERR_ARG, "%s: empty k mask", fn);
-    if (bad_p(p)) return fail(DD_ERR_ARG, "%s: p=%d outside [4,26]", fn, p);
+    if (bad_p(p)) return fail(DD_ERR_ARG, "%s: p=%d outside [5,26]", fn, p);
     if (ws_bytes < dd::sketch_workspace_bytes(popc(kmask), p)) return fail(DD_ERR_WORKSPACE, "%s: workspace too small", fn);
     return DD_OK;
 }

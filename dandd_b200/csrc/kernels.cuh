@@ -16,7 +16,8 @@ cudaError_t pack_reset(uint32_t *d_codes, size_t codes_bytes, uint32_t *d_invali
 cudaError_t pack_fasta(const uint8_t *d_text, size_t n, uint32_t *d_codes, uint32_t *d_invalid, size_t cap_symbols,
                        dd_pack_state *d_state, void *d_ws, cudaStream_t stream);
 
-// ---- K2 (sketch.cu).  Workspace = [SketchWsHeader | u32 accumulators [nk][2^p]]
+// ---- K2 (sketch.cu).  Workspace = [SketchWsHeader | u16 accumulators [nk][2^p]]
+extern int g_k_per_pass;
 struct SketchWsHeader {
     uint8_t floor[32];  // floor[k-1] <= min(register of k): updates with rank <= floor are no-ops
     uint32_t use_floor;

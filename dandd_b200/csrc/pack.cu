@@ -173,7 +173,7 @@ pack_write_kernel(const uint8_t *__restrict__ text, size_t n, const PackTileOut 
     const uint32_t entry_last = hdr->entry_last_byte;
     uint32_t row_state = (uint32_t)tile_out[tile].state;
     uint64_t g_row = st->prev_nsym + seg_base[tile / hdr->seg_len] + tile_out[tile].local_off;
-    const size_t cap_words16 = cap_symbols >> 4, cap_words32 = cap_symbols >> 5;
+    const size_t cap_words16 = (cap_symbols + 15) >> 4, cap_words32 = (cap_symbols + 31) >> 5;
 
 #pragma unroll 1
     for (int r = 0; r < kPackRows; ++r) {

@@ -14,10 +14,14 @@
 // symbol loop is not, which keeps the body (~1.1k instructions for 31 k) inside the instruction
 // cache.
 //
-// Registers are accumulated as one u32 per register with RED.MAX (there is no byte-wide atomic
-// max); dd_sketch_end narrows them to u8.  The accumulators of one genome (nk x 4 MiB at p=20)
-// are L2-resident on B200, so the scattered updates never reach HBM.  Bound: INT32 issue and the
-// L2 scattered-update rate -- not HBM (see DESIGN.md for the roofline bookkeeping).
+// There is no byte-wide atomic max, and one u32 per register (nk x 4 MiB per genome at p=20) does
+// not stay L2-resident: ncu showed 51 % of the RED sectors missing and 2.4 GB of DRAM write-back
+// per 5 Mbp genome (profiles/r01).  Registers are therefore accumulated two to a 32-bit word with
+// REDG.E.MAX.F16x2 (`red.global.max.noftz.v2.f16`): a rank r <= 45 is stored as the f16 *subnormal*
+// whose bit pattern is r, positive f16 values order like their bit patterns, .noftz keeps
+// subnormals, and the other half of the operand is +0.0, the identity of max over ranks -- so each
+// half is an independent, exact integer max.  dd_sketch_end narrows the u16 halves to u8.
+// Bound: INT32 issue and the L2 reduction rate -- not HBM.
 #include <cuda_runtime.h>
 
 #include <utility>
@@ -34,9 +38,10 @@ struct SketchArgs {
     const uint32_t *invalid;
     const dd_pack_state *state;  // if non-null the symbol range is [state->prev_nsym, state->nsym)
     uint64_t sym_begin, sym_end;
-    uint32_t kmask;
+    uint32_t kmask;               // every k of the sketch (defines the accumulator slots)
+    uint32_t kmask_run;           // the k values this launch updates (subset of kmask)
     int p;
-    uint32_t *acc;                // [nk][2^p]
+    uint32_t *acc;                // [nk][2^p / 2] words, two u16 registers per word
     const SketchWsHeader *hdr;
 };
 
@@ -64,35 +69,46 @@ __device__ __forceinline__ uint64_t mad64x32(uint64_t x, uint32_t c, uint64_t ad
     return r;
 }
 
-// One (symbol, k) update.  Branch-free apart from the warp-uniform "is this k requested" test:
+// Max-update of one u16 register packed two to a word (see the header comment).
+__device__ __forceinline__ void red_max_u16(uint32_t *word, uint32_t half, uint32_t rank) {
+    const uint32_t val = rank << (16u * half);  // the untouched half carries +0.0
+    asm volatile("{ .reg .b16 l, h; mov.b32 {l, h}, %1; red.global.max.noftz.v2.f16 [%0], {l, h}; }" ::"l"(word), "r"(val)
+                 : "memory");
+}
+
+// One (symbol, k) update.  Branch-free apart from the warp-uniform "is this k requested" tests:
 // an invalid window only predicates the RED off, so neighbouring k bodies can be interleaved.
 template <int K, bool kCanon>
-__device__ __forceinline__ void update_one_k(const Window &win, int run, uint32_t kmask, int p, uint32_t *acc,
-                                             uint32_t &off_k, const uint32_t (&floor4)[8]) {
+__device__ __forceinline__ void update_one_k(const Window &win, int run, uint32_t kmask, uint32_t kmask_run, int p,
+                                             uint32_t *acc, uint32_t &off_k, const uint32_t (&floor4)[8]) {
     if (!((kmask >> (K - 1)) & 1u)) return;  // warp-uniform
-    const uint64_t v = kmer_value<K>(win, kCanon);
-    // dd::wang64 (common.cuh) with the multiplications pinned to the FMA pipe
-    uint64_t h = mad64x32(v, 0x1FFFFFu, 0xFFFFFFFFFFFFFFFFull);
-    h ^= h >> 24;
-    h = mul64x32(h, 265u);
-    h ^= h >> 14;
-    h = mul64x32(h, 21u);
-    h ^= h >> 28;
-    h = mul64x32(h, 0x80000001u);
-    const uint32_t hi = (uint32_t)(h >> 32), lo = (uint32_t)h;
-    // rank = 1 + leading zeros of the low (64-p) bits, capped at 64-p+1
-    const uint32_t rem_hi = hi & (0xffffffffu >> p);
-    const uint32_t rank = (rem_hi ? (uint32_t)__clz((int)rem_hi) : 32u + (uint32_t)__clz((int)lo)) + 1u - (uint32_t)p;
-    const uint32_t floor_k = (floor4[(K - 1) >> 2] >> (8 * ((K - 1) & 3))) & 0xffu;
-    if (run >= K && rank > floor_k) atomicMax(acc + (off_k + (hi >> (32 - p))), rank);
-    off_k += 1u << p;
+    if ((kmask_run >> (K - 1)) & 1u) {       // warp-uniform
+        const uint64_t v = kmer_value<K>(win, kCanon);
+        // dd::wang64 (common.cuh) with the multiplications pinned to the FMA pipe
+        uint64_t h = mad64x32(v, 0x1FFFFFu, 0xFFFFFFFFFFFFFFFFull);
+        h ^= h >> 24;
+        h = mul64x32(h, 265u);
+        h ^= h >> 14;
+        h = mul64x32(h, 21u);
+        h ^= h >> 28;
+        h = mul64x32(h, 0x80000001u);
+        const uint32_t hi = (uint32_t)(h >> 32), lo = (uint32_t)h;
+        // rank = 1 + leading zeros of the low (64-p) bits, capped at 64-p+1
+        const uint32_t rem_hi = hi & (0xffffffffu >> p);
+        const uint32_t rank = (rem_hi ? (uint32_t)__clz((int)rem_hi) : 32u + (uint32_t)__clz((int)lo)) + 1u - (uint32_t)p;
+        const uint32_t floor_k = (floor4[(K - 1) >> 2] >> (8 * ((K - 1) & 3))) & 0xffu;
+        const uint32_t idx = hi >> (32 - p);
+        if (run >= K && rank > floor_k) red_max_u16(acc + (off_k + (idx >> 1)), idx & 1u, rank);
+    }
+    off_k += 1u << (p - 1);
 }
 
 template <bool kCanon, int... Ks>
 __device__ __forceinline__ void update_all_k(std::integer_sequence<int, Ks...>, const Window &win, int run,
-                                             uint32_t kmask, int p, uint32_t *acc, const uint32_t (&floor4)[8]) {
+                                             uint32_t kmask, uint32_t kmask_run, int p, uint32_t *acc,
+                                             const uint32_t (&floor4)[8]) {
     uint32_t off_k = 0;
-    (update_one_k<Ks + 1, kCanon>(win, run, kmask, p, acc, off_k, floor4), ...);
+    (update_one_k<Ks + 1, kCanon>(win, run, kmask, kmask_run, p, acc, off_k, floor4), ...);
 }
 
 template <bool kCanon>
@@ -133,20 +149,21 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_allk_kernel(SketchArgs 
         const Window win = window_at(w0, w1, w2, r0, r1, r2, j);
         const int run = all_valid ? 32 : valid_run(invalid_window(i0, i1, sm_base + (uint32_t)j));
         if (run == 0) continue;
-        update_all_k<kCanon>(std::make_integer_sequence<int, 32>{}, win, run, a.kmask, a.p, a.acc, floor4);
+        update_all_k<kCanon>(std::make_integer_sequence<int, 32>{}, win, run, a.kmask, a.kmask_run, a.p, a.acc, floor4);
     }
 }
 
 // ---- per-slot min(register): the "floor" filter ---------------------------------------------------
 __global__ void __launch_bounds__(256) floor_min_kernel(const uint32_t *__restrict__ acc, int p, SketchWsHeader *hdr,
                                                         uint32_t *scratch /*[nk]*/) {
-    // grid (slices, nk); scratch pre-set to 0xff
-    const size_t m = (size_t)1 << p;
-    const uint32_t *t = acc + (size_t)blockIdx.y * m;
-    uint32_t mn = 0xffu;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m / 4; i += (size_t)gridDim.x * blockDim.x) {
+    // grid (slices, nk); scratch pre-set to 0xff.  acc rows are 2^p u16 registers = 2^(p-1) words.
+    const size_t nwords = (size_t)1 << (p - 1);
+    const uint32_t *t = acc + (size_t)blockIdx.y * nwords;
+    uint32_t mn = 0xffffu;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords / 4; i += (size_t)gridDim.x * blockDim.x) {
         const uint4 v = reinterpret_cast<const uint4 *>(t)[i];
-        mn = min(mn, min(min(v.x, v.y), min(v.z, v.w)));
+        const uint32_t w = __vminu2(__vminu2(v.x, v.y), __vminu2(v.z, v.w));
+        mn = min(mn, min(w & 0xffffu, w >> 16));
     }
     mn = __reduce_min_sync(0xffffffffu, mn);
     if ((threadIdx.x & 31) == 0) atomicMin(&scratch[blockIdx.y], mn);
@@ -172,23 +189,26 @@ finalize_kernel(const uint32_t *__restrict__ acc, int p, uint8_t *__restrict__ r
     __shared__ uint32_t s_hist[DD_HIST_BINS * kFinThreads];
     const size_t m = (size_t)1 << p;
     const int table = blockIdx.y;
-    const uint4 *src = reinterpret_cast<const uint4 *>(acc + (size_t)table * m);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(regs + (size_t)table * m);
+    // 8 u16 accumulators (one uint4) -> 8 u8 registers (one uint2)
+    const uint4 *src = reinterpret_cast<const uint4 *>(acc + (size_t)table * (m / 2));
+    uint2 *dst = reinterpret_cast<uint2 *>(regs + (size_t)table * m);
     if (hist)
         for (int i = threadIdx.x; i < DD_HIST_BINS * kFinThreads; i += kFinThreads) s_hist[i] = 0;
     __syncthreads();
-    const size_t nquads = m / 4;
-    const size_t per = (nquads + gridDim.x - 1) / gridDim.x;
-    const size_t q0 = (size_t)blockIdx.x * per, q1 = min(nquads, q0 + per);
+    const size_t noct = m / 8;
+    const size_t per = (noct + gridDim.x - 1) / gridDim.x;
+    const size_t q0 = (size_t)blockIdx.x * per, q1 = min(noct, q0 + per);
     for (size_t q = q0 + threadIdx.x; q < q1; q += kFinThreads) {
         const uint4 v = __ldcs(src + q);
-        const uint32_t b0 = min(v.x, 255u), b1 = min(v.y, 255u), b2 = min(v.z, 255u), b3 = min(v.w, 255u);
-        dst[q] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        // bytes 0 and 2 of each word are the low bytes of its two u16 registers (ranks < 256)
+        const uint2 out = make_uint2(__byte_perm(v.x, v.y, 0x6420), __byte_perm(v.z, v.w, 0x6420));
+        dst[q] = out;
         if (hist) {
-            s_hist[min(b0, 63u) * kFinThreads + threadIdx.x]++;
-            s_hist[min(b1, 63u) * kFinThreads + threadIdx.x]++;
-            s_hist[min(b2, 63u) * kFinThreads + threadIdx.x]++;
-            s_hist[min(b3, 63u) * kFinThreads + threadIdx.x]++;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                s_hist[min((out.x >> (8 * b)) & 0xffu, 63u) * kFinThreads + threadIdx.x]++;
+                s_hist[min((out.y >> (8 * b)) & 0xffu, 63u) * kFinThreads + threadIdx.x]++;
+            }
         }
     }
     if (!hist) return;
@@ -204,8 +224,10 @@ finalize_kernel(const uint32_t *__restrict__ acc, int p, uint8_t *__restrict__ r
 }
 
 // ---- host side ----------------------------------------------------------------------------------
+int g_k_per_pass = 0;  // tuning knob, see dd_set_option("sketch_k_per_pass", n)
+
 size_t sketch_workspace_bytes(int nk, int p) {
-    return sizeof(SketchWsHeader) + 256 + (size_t)nk * sizeof(uint32_t) * ((size_t)1 << p);
+    return sizeof(SketchWsHeader) + 256 + (size_t)nk * sizeof(uint16_t) * ((size_t)1 << p);
 }
 static SketchWsHeader *ws_hdr(void *ws) { return static_cast<SketchWsHeader *>(ws); }
 static uint32_t *ws_scratch(void *ws) { return reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ws) + sizeof(SketchWsHeader)); }
@@ -225,6 +247,7 @@ cudaError_t sketch_update(const uint32_t *d_codes, const uint32_t *d_invalid, co
     a.sym_begin = sym_begin;
     a.sym_end = sym_end;
     a.kmask = kmask;
+    a.kmask_run = kmask;
     a.p = p;
     a.acc = ws_acc(d_ws);
     a.hdr = ws_hdr(d_ws);
@@ -233,8 +256,21 @@ cudaError_t sketch_update(const uint32_t *d_codes, const uint32_t *d_invalid, co
     // +2 words: the range may start and end in the middle of a word
     const size_t nwords = (nsym + 15) / 16 + 2;
     const unsigned grid = (unsigned)((nwords + kSketchThreads - 1) / kSketchThreads);
-    if (canon) sketch_allk_kernel<true><<<grid, kSketchThreads, 0, stream>>>(a);
-    else sketch_allk_kernel<false><<<grid, kSketchThreads, 0, stream>>>(a);
+    // Optionally split the k set over several launches so that the accumulators touched by one
+    // launch (2^(p+1) bytes per k) stay L2-resident; 0 = all k in one launch.
+    const int per_pass = g_k_per_pass > 0 ? g_k_per_pass : 32;
+    uint32_t todo = kmask;
+    while (todo) {
+        uint32_t run = 0;
+        for (int c = 0; c < per_pass && todo; ++c) {
+            const uint32_t low = todo & (0u - todo);
+            run |= low;
+            todo ^= low;
+        }
+        a.kmask_run = run;
+        if (canon) sketch_allk_kernel<true><<<grid, kSketchThreads, 0, stream>>>(a);
+        else sketch_allk_kernel<false><<<grid, kSketchThreads, 0, stream>>>(a);
+    }
     return cudaGetLastError();
 }
 

@@ -55,6 +55,10 @@ DD_API const char *dd_last_error(void);
 DD_API int dd_abi_version(void);
 /* Select `device` for the calling thread and verify it is compute capability 10.x. */
 DD_API int dd_init(int device);
+/* Tuning knobs (never change results).  "sketch_k_per_pass" = n: K2 updates at most n k values per
+ * kernel launch (0 = all in one), trading re-reads of the packed stream for L2 residency of the
+ * accumulators. */
+DD_API int dd_set_option(const char *name, long value);
 DD_API int dd_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes, size_t *total_mem);
 
 /* ===========================================================================================

@@ -40,7 +40,7 @@ def test_abi_version_and_size_queries(lib):
     assert lib.dd_abi_version() == 1
     assert lib.dd_pack_codes_bytes(1 << 20) >= (1 << 20) // 4
     assert lib.dd_pack_invalid_bytes(1 << 20) >= (1 << 20) // 8
-    assert lib.dd_sketch_workspace_bytes(23, 20) >= 23 * 4 * (1 << 20)
+    assert lib.dd_sketch_workspace_bytes(23, 20) >= 23 * 2 * (1 << 20)
     assert lib.dd_exact_workspace_bytes(12, 0) >= (4 ** 12) // 8
     assert lib.dd_exact_workspace_bytes(20, 1 << 20) >= 8 << 20
 
