@@ -46,6 +46,7 @@ SIGNATURES = {
     "dd_mle_from_hist": (_i, [_vp, _i, _i, _vp, _vp]),
     "dd_union_max": (_i, [_vp, _i, _sz, _vp, _vp]),
     "dd_prefix_union_card": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dd_union_sets_card": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dd_pairwise_union_card": (_i, [_vp, _i, _i, _i, _vp, _i64, _vp, _vp, _vp]),
     "dd_exact_workspace_bytes": (_sz, [_i, _u64]),
     "dd_exact_begin": (_i, [_vp, _sz, _i, _u64, _vp]),

@@ -191,6 +191,19 @@ int dd_prefix_union_card(const uint8_t *d_regs, const int32_t *d_order, int n_or
     return DD_OK;
 }
 
+int dd_union_sets_card(const uint8_t *const *d_members, int n_sets, int n_steps, int p, int final_only, double *d_cards,
+                       uint32_t *d_hist, uint8_t *d_unions, dd_stream stream) {
+    if (n_sets == 0 || n_steps == 0) return DD_OK;
+    if (!d_members || !d_cards || !d_hist || n_sets < 0 || n_steps < 0 || bad_p(p))
+        return fail(DD_ERR_ARG, "dd_union_sets_card: bad argument");
+    const size_t rows = (size_t)n_sets * (final_only ? 1 : n_steps);
+    if (rows > 0x7fffffff) return fail(DD_ERR_ARG, "dd_union_sets_card: too many (set, step) rows");
+    DD_CUDA(dd::union_sets_hist(d_members, n_sets, n_steps, p, final_only, d_hist, d_unions, S(stream)),
+            "dd_union_sets_card(hist)");
+    DD_CUDA(dd::mle_from_hist(d_hist, (int)rows, p, d_cards, S(stream)), "dd_union_sets_card(mle)");
+    return DD_OK;
+}
+
 int dd_pairwise_union_card(const uint8_t *d_regs, int n_genomes, int nk, int p, const int32_t *d_pairs, int64_t n_pairs,
                            double *d_cards, uint32_t *d_hist, dd_stream stream) {
     if (n_pairs == 0) return DD_OK;

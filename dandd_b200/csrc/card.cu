@@ -121,9 +121,13 @@ constexpr int kPfxThreads = 256;
 constexpr int kPfxVec = 4;                                 // uint4 per thread
 constexpr int kPfxSliceBytes = kPfxThreads * kPfxVec * 16; // 16 KiB
 
+// kPtrTable = false: members are genome indices into regs[n_genomes][nk][2^p], grid (slices, nk, n_ord)
+// kPtrTable = true : members are device pointers to 2^p-byte sketches,      grid (slices, n_sets, 1)
+template <bool kPtrTable>
 __global__ void __launch_bounds__(kPfxThreads)
-prefix_union_kernel(const uint8_t *__restrict__ regs, const int32_t *__restrict__ order, int n_steps, int n_genomes,
-                    int nk, int p, int final_only, uint32_t *__restrict__ hist, uint8_t *__restrict__ unions) {
+prefix_union_kernel(const uint8_t *__restrict__ regs, const int32_t *__restrict__ order,
+                    const uint8_t *const *__restrict__ members, int n_steps, int n_genomes, int nk, int p,
+                    int final_only, uint32_t *__restrict__ hist, uint8_t *__restrict__ unions) {
     // u8 thread-private counters would overflow only past 255 registers per thread per step; a
     // thread sees 64, so one byte per (bin, thread) is enough: 16 KiB of shared memory.
     __shared__ __align__(16) uint8_t s_hist[DD_HIST_BINS * kPfxThreads];
@@ -138,9 +142,15 @@ prefix_union_kernel(const uint8_t *__restrict__ regs, const int32_t *__restrict_
     for (int q = 0; q < kPfxVec; ++q) run[q] = make_uint4(0, 0, 0, 0);
 
     for (int step = 0; step < n_steps; ++step) {
-        const int g = order[(size_t)o * n_steps + step];
-        if (g >= 0 && g < n_genomes) {
-            const uint8_t *src = regs + ((size_t)g * nk + k) * m + slice0;
+        const uint8_t *src = nullptr;
+        if (kPtrTable) {
+            src = members[(size_t)k * n_steps + step];
+        } else {
+            const int g = order[(size_t)o * n_steps + step];
+            if (g >= 0 && g < n_genomes) src = regs + ((size_t)g * nk + k) * m;
+        }
+        if (src) {
+            src += slice0;
 #pragma unroll
             for (int q = 0; q < kPfxVec; ++q) {
                 const size_t off = ((size_t)q * kPfxThreads + threadIdx.x) * 16;
@@ -154,7 +164,8 @@ prefix_union_kernel(const uint8_t *__restrict__ regs, const int32_t *__restrict_
             }
         }
         if (final_only && step != n_steps - 1) continue;
-        const size_t row = final_only ? (size_t)o * nk + k : ((size_t)o * n_steps + step) * nk + k;
+        const size_t row = kPtrTable ? (final_only ? (size_t)k : (size_t)k * n_steps + step)
+                                     : (final_only ? (size_t)o * nk + k : ((size_t)o * n_steps + step) * nk + k);
         // histogram of the running union
         for (int i = threadIdx.x; i < DD_HIST_BINS * kPfxThreads / 16; i += kPfxThreads)
             reinterpret_cast<uint4 *>(s_hist)[i] = make_uint4(0, 0, 0, 0);
@@ -239,8 +250,30 @@ cudaError_t prefix_union_hist(const uint8_t *d_regs, const int32_t *d_order, int
     for (int o0 = 0; o0 < n_ord; o0 += 65535) {  // gridDim.z limit
         const int cnt = n_ord - o0 < 65535 ? n_ord - o0 : 65535;
         const size_t roff = (size_t)o0 * out_steps * nk;
-        prefix_union_kernel<<<dim3(slices, nk, cnt), kPfxThreads, 0, stream>>>(
-            d_regs, d_order + (size_t)o0 * n_steps, n_steps, n_genomes, nk, p, final_only,
+        prefix_union_kernel<false><<<dim3(slices, nk, cnt), kPfxThreads, 0, stream>>>(
+            d_regs, d_order + (size_t)o0 * n_steps, nullptr, n_steps, n_genomes, nk, p, final_only,
+            d_hist + roff * DD_HIST_BINS, d_unions ? d_unions + roff * m : nullptr);
+    }
+    return cudaGetLastError();
+}
+
+// Pointer-table form: set s is the list members[s][0..n_steps) of device sketches (NULL = skip).
+// With nk := n_sets and one "ordering" the row arithmetic of the kernel gives row = s (final_only)
+// or s * n_steps + step.
+cudaError_t union_sets_hist(const uint8_t *const *d_members, int n_sets, int n_steps, int p, int final_only,
+                            uint32_t *d_hist, uint8_t *d_unions, cudaStream_t stream) {
+    const int out_steps = final_only ? 1 : n_steps;
+    const size_t rows = (size_t)n_sets * out_steps;
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, rows * DD_HIST_BINS * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    if (rows == 0) return cudaSuccess;
+    const size_t m = (size_t)1 << p;
+    const unsigned slices = (unsigned)((m + kPfxSliceBytes - 1) / kPfxSliceBytes);
+    for (int s0 = 0; s0 < n_sets; s0 += 65535) {  // gridDim.y limit
+        const int cnt = n_sets - s0 < 65535 ? n_sets - s0 : 65535;
+        const size_t roff = (size_t)s0 * out_steps;
+        prefix_union_kernel<true><<<dim3(slices, cnt, 1), kPfxThreads, 0, stream>>>(
+            nullptr, nullptr, d_members + (size_t)s0 * n_steps, n_steps, 0, cnt, p, final_only,
             d_hist + roff * DD_HIST_BINS, d_unions ? d_unions + roff * m : nullptr);
     }
     return cudaGetLastError();

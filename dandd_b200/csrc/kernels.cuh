@@ -42,6 +42,9 @@ cudaError_t prefix_union_hist(const uint8_t *d_regs, const int32_t *d_order, int
                               int nk, int p, int final_only, uint32_t *d_hist, uint8_t *d_unions,
                               cudaStream_t stream);
 
+cudaError_t union_sets_hist(const uint8_t *const *d_members, int n_sets, int n_steps, int p, int final_only,
+                            uint32_t *d_hist, uint8_t *d_unions, cudaStream_t stream);
+
 // ---- K5 (exact.cu).  Workspace = [ExactWsHeader | bitmap or key table]
 struct ExactWsHeader {
     unsigned long long count;     // distinct keys inserted (hash-set mode; bitmap mode counts on demand)

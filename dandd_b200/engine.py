@@ -238,6 +238,23 @@ class Engine:
         self._keep = order
         return (cards, unions) if materialize else cards
 
+    def union_sets(self, member_ptrs, p: int, final_only: bool = True, materialize: bool = False):
+        """member_ptrs: int64 [n_sets, n_steps] device addresses of 2^p-byte sketches (0 = skip).
+        Returns cards [n_sets, n_steps or 1] f64 (and unions [n_sets, n_steps or 1, 2^p] if asked).
+        The caller keeps the member tensors alive until the stream has run."""
+        ptrs = torch.as_tensor(np.ascontiguousarray(member_ptrs, dtype=np.int64)).to(self.device)
+        n_sets, n_steps = ptrs.shape
+        osteps = 1 if final_only else n_steps
+        m = 1 << p
+        hist = torch.empty((n_sets, osteps, DD_HIST_BINS), dtype=torch.int32, device=self.device)
+        cards = torch.empty((n_sets, osteps), dtype=torch.float64, device=self.device)
+        unions = torch.empty((n_sets, osteps, m), dtype=torch.uint8, device=self.device) if materialize else None
+        check(self.lib.dd_union_sets_card(ptrs.data_ptr(), n_sets, n_steps, p, int(final_only), cards.data_ptr(),
+                                          hist.data_ptr(), unions.data_ptr() if materialize else None, self.stream),
+              "dd_union_sets_card")
+        self._keep = ptrs
+        return (cards, unions) if materialize else cards
+
     def pairwise_cards(self, regs: torch.Tensor, pairs, p: int) -> torch.Tensor:
         """card(A u B) for every listed pair and every k: [n_pairs, nk] f64."""
         n_g, nk, m = regs.shape

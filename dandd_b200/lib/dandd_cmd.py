@@ -1,0 +1,191 @@
+"""Command-line front end: `dandd tree | progressive | kij` (reference lib/dandd_cmd.py).
+
+Same sub-commands, flags, defaults and output file names as the reference, so existing scripts
+and pickles keep working; the `info` sub-parser exists without a handler there (reference
+:235-246) and is omitted here.  One addition: `--device N` selects the GPU (default: LOCAL_RANK
+or 0).  Flag tables below cite the reference lines they mirror.
+"""
+import argparse
+import os
+import pickle
+import sys
+
+import huffman_dandd
+from huffman_dandd import write_listdict_to_csv
+
+VERSION = "%(prog)s 1.0.0 (dandd_b200)"
+
+
+def insert_pre_ext(filename, string):
+    stem, dot, ext = filename.rpartition(".")
+    return f"{stem}.{string}.{ext}" if dot else f"{string}.{filename}"
+
+
+# (flags, keyword arguments) tables -------------------------------------------------------------------
+UNIVERSAL = [  # reference :23-30
+    (("--version",), dict(action="version", version=VERSION)),
+    (("--verbose", "-v"), dict(action="store_true", default=False, help="Print some trees and report steps of actions.")),
+    (("--debug",), dict(action="store_true", default=False, dest="debug", help="Show the commands this run stands in for.")),
+    (("--lowmem",), dict(action="store_true", default=False, dest="lowmem",
+                         help="Trust stored cardinalities of multi-fasta sketches whose files are gone. Not with --safe.")),
+    (("--safe",), dict(action="store_true", default=False, dest="safety",
+                       help="Re-verify every sketch name hash against the sum of its component fasta hashes.")),
+    (("--fast",), dict(action="store_true", default=False, dest="fast", help="Don't save so much stuff for second usage.")),
+    (("--device",), dict(type=int, default=None, dest="device", metavar="GPU", help="CUDA device to use (default LOCAL_RANK or 0).")),
+]
+KSWEEP = [  # reference :145-150
+    (("--ksweep",), dict(dest="ksweep", default=None, action="store_true",
+                         help="sweep k for every combination; without --mink/--maxk the range is 2..32")),
+    (("--mink",), dict(dest="mink", metavar="MINIMUM-K", required=False, default=2, type=int, help="smallest k of the sweep")),
+    (("--maxk",), dict(dest="maxk", metavar="MAXIMUM-K", required=False, default=32, type=int, help="largest k of the sweep")),
+]
+TREE = [  # reference :166-200
+    (("-s", "--tag"), dict(dest="tag", metavar="PREFIX TAG", type=str, required=False, default="dandd",
+                           help="tag used to label output files")),
+    (("-x", "--exact"), dict(dest="exact", default=False, action="store_true", required=False,
+                             help="count k-mers exactly (KMC semantics) instead of estimating")),
+    (("-d", "--datadir"), dict(dest="genomedir", default=None, type=str, metavar="FASTADIR",
+                               help="directory of fasta files; all are used unless --fastas is given")),
+    (("-o", "--out"), dict(dest="outdir", default=os.getcwd(), type=str, metavar="OUTPUT DIR", help="output directory")),
+    (("-c", "--sketchdir"), dict(dest="sketchdir", default=None, type=str, metavar="SKETCHDIR",
+                                 help="sketch database directory (default <out>/sketchdb)")),
+    (("-k", "--kstart"), dict(dest="kstart", default=12, type=int, metavar="KSTART", help="k at which the search for delta starts")),
+    (("-f", "--fastas"), dict(dest="flist_loc", metavar="FILEPATH", type=str, default=None,
+                              help="file listing the fasta paths to use, one per line")),
+    (("-l", "--label"), dict(dest="label", metavar="SUFFIX TAG", default="", required=False, help="extra label in output names")),
+    (("-n", "--nchildren"), dict(dest="nchildren", metavar="INTEGER", type=int, default=None,
+                                 help="children per tree node (default: all leaves under one root)")),
+    (("-r", "--registers"), dict(dest="registers", metavar="INTEGER", default=20, help="log2 of the number of HLL registers")),
+    (("-e", "--nthreads"), dict(dest="nthreads", metavar="INTEGER", type=int, default=0,
+                                help="kept for compatibility (KMC thread count in the reference); unused on the GPU")),
+    (("-C", "--no-canon"), dict(action="store_false", default=True, dest="canonicalize", help="use non-canonical k-mers")),
+]
+PROGRESSIVE = [  # reference :211-228
+    (("-d", "--dtree"), dict(dest="delta_tree", metavar="DELTA TREE", required=True, help="pickle produced by the tree command")),
+    (("-s", "--tag"), dict(dest="tag", metavar="species/experiment-tag-string", type=str, required=False, help="output tag")),
+    (("-r", "--orderings"), dict(dest="ordering_file", metavar="ORDERING PICKLE", type=str, default=None,
+                                 help="pickle of orderings, if not the default one named after the tag")),
+    (("-f", "--fastas"), dict(dest="flist_loc", default=None, type=str, metavar="FILEPATH", help="subset (and order) of fastas")),
+    (("-n", "--norderings"), dict(dest="norderings", default=0, type=int, metavar="NUM", help="number of random orderings")),
+    (("-o", "--outdir"), dict(dest="outdir", default=os.getcwd(), type=str, metavar="OUTPUT DIR", help="output directory")),
+    (("-l", "--label"), dict(dest="label", metavar="SUFFIX TAG", default="", required=False, help="extra label in output names")),
+    (("--step",), dict(dest="step", default=1, type=int, metavar="INTEGER", help="fastas added per progression step")),
+]
+KIJ = [  # reference :260-272
+    (("-d", "--dtree"), dict(dest="delta_tree", metavar="DELTA TREE", required=True, help="pickle produced by the tree command")),
+    (("-s", "--tag"), dict(dest="tag", metavar="PREFIX TAG", type=str, required=False, help="output tag")),
+    (("-f", "--fastas"), dict(dest="flist_loc", default=None, type=str, metavar="FILEPATH", help="subset of fastas to compare")),
+    (("-o", "--outdir"), dict(dest="outdir", default=os.getcwd(), type=str, metavar="OUTPUT DIR", help="output directory")),
+    (("-l", "--label"), dict(dest="label", metavar="SUFFIX TAG", default="", required=False, help="extra label in output names")),
+    (("--afproject",), dict(dest="afproject", default=False, action="store_true", help="also write the AFproject tuple pickle")),
+    (("--jaccard",), dict(dest="jaccard", default=False, action="store_true", help="also report per-k Jaccard")),
+]
+
+
+def _add(parser, table):
+    for flags, kwargs in table:
+        parser.add_argument(*flags, **kwargs)
+    return parser
+
+
+def add_universal_cmds(subparser: argparse.ArgumentParser):
+    return _add(subparser, UNIVERSAL)
+
+
+def _select_device(args):
+    if getattr(args, "device", None) is not None:
+        os.environ["LOCAL_RANK"] = str(args.device)
+
+
+def _load_tree(path):
+    with open(path, "rb") as fh:
+        return pickle.load(fh)
+
+
+def _read_list(path):
+    with open(path) as fh:
+        return [line.strip() for line in fh]
+
+
+def tree_command(args):
+    """reference :43-62"""
+    if not (args.genomedir or args.flist_loc):
+        print("ERROR: You must provide either a datadirectory or a fasta file list!")
+        sys.exit(1)
+    _select_device(args)
+    if not args.sketchdir:
+        args.sketchdir = os.path.join(args.outdir, "sketchdb")
+    os.makedirs(args.sketchdir, exist_ok=True)
+    os.makedirs(args.outdir, exist_ok=True)
+    tool = "dashing"
+    if args.exact:
+        tool, args.registers = "kmc", 20
+    if args.ksweep:
+        args.ksweep = (int(args.mink), int(args.maxk))
+    dtree = huffman_dandd.create_delta_tree(
+        tag=args.tag, genomedir=args.genomedir, sketchdir=args.sketchdir, kstart=args.kstart, nchildren=args.nchildren,
+        registers=args.registers, flist_loc=args.flist_loc, canonicalize=args.canonicalize, tool=tool, debug=args.debug,
+        nthreads=int(args.nthreads), safety=args.safety, fast=args.fast, verbose=args.verbose, ksweep=args.ksweep,
+        lowmem=args.lowmem)
+    dtree.save(fileprefix=dtree.make_prefix(outdir=args.outdir, tag=args.tag, label=args.label), fast=args.fast)
+
+
+def progressive_command(args):
+    """reference :65-87"""
+    _select_device(args)
+    dtree = _load_tree(args.delta_tree)
+    args.tag = args.tag or dtree.speciesinfo.tag
+    args.outfile = dtree.make_prefix(tag=args.tag, label=f"progu{args.norderings}", outdir=args.outdir)
+    dtree.experiment.update(debug=args.debug, safety=args.safety, fast=args.fast, verbose=args.verbose, lowmem=args.lowmem,
+                            baseset=set(), ksweep=(int(args.mink), int(args.maxk)) if args.ksweep else None)
+    dtree.speciesinfo.update(tool=dtree.experiment["tool"])
+    results, summary = dtree.progressive_wrapper(flist_loc=args.flist_loc, count=args.norderings,
+                                                 ordering_file=args.ordering_file, step=args.step)
+    write_listdict_to_csv(outfile=args.outfile + ".csv", listdict=results)
+    write_listdict_to_csv(outfile=args.outfile + "summary.csv", listdict=summary)
+    dtree.save(fileprefix=args.outfile)
+
+
+def kij_command(args):
+    """reference :107-132"""
+    _select_device(args)
+    dtree = _load_tree(args.delta_tree)
+    dtree.speciesinfo.update(tool=dtree.experiment["tool"])
+    args.tag = args.tag or dtree.speciesinfo.tag
+    args.outfile = dtree.make_prefix(tag=args.tag, label=args.label, outdir=args.outdir)
+    fastas = _read_list(args.flist_loc) if args.flist_loc else []
+    if args.ksweep:
+        dtree.experiment["ksweep"] = (int(args.mink), int(args.maxk))
+    dtree.ksweep(mink=int(args.mink), maxk=int(args.maxk))
+    kij_results, j_results = dtree.pairwise_spiders(sublist=fastas, mink=args.mink, maxk=args.maxk, jaccard=args.jaccard)
+    write_listdict_to_csv(outfile=args.outfile + ".kij.csv", listdict=kij_results)
+    if args.jaccard:
+        write_listdict_to_csv(outfile=args.outfile + ".j.csv", listdict=j_results)
+    dtree.speciesinfo.save_cardkey(dtree.experiment["tool"])
+    dtree.speciesinfo.save_references(fast=False)
+    if args.afproject:
+        with open(args.outfile + "_AFtuples.pickle", "wb") as fh:
+            pickle.dump(obj=dtree.prepare_AFproject(kij_results, j_results), file=fh)
+
+
+def parse_arguments():
+    """Top-level parser + the list of sub-command names (reference :138-288)."""
+    universal = add_universal_cmds(argparse.ArgumentParser(add_help=False))
+    ksweep = _add(argparse.ArgumentParser(add_help=False), KSWEEP)
+    parser = argparse.ArgumentParser(prog="DandD", description="program to explore delta values for a set of fasta files",
+                                     parents=[universal])
+    subparsers = parser.add_subparsers(title="subcommands", description="valid subcommands", help="additional help")
+    subparsers.required = True
+    specs = [
+        ("tree", TREE, tree_command,
+         "Calculate deltas for input fastas and full union. Create DandD tree object for further downstream analysis."),
+        ("progressive", PROGRESSIVE, progressive_command,
+         "Measure delta as each fasta is added to the set, over one given or several random orderings."),
+        ("kij", KIJ, kij_command, "K Independent Jaccard (and optionally per-k Jaccard) for every pair of inputs."),
+    ]
+    commands = []
+    for name, table, handler, text in specs:
+        sub = _add(subparsers.add_parser(name, help=text, parents=[universal, ksweep]), table)
+        sub.set_defaults(func=handler)
+        commands.append(name)
+    return parser, commands

@@ -1,0 +1,220 @@
+"""SketchStore: what the drop-in sketch objects (dandd_b200/lib/sketch_classes.py) call instead of
+shelling out to dashing / kmc / kmc_tools / GNU parallel.
+
+The reference's only state between commands is the sketchdb directory (files + cardinality
+pickle).  The store keeps that contract -- every sketch it produces is written to the path DandD
+expects -- and adds an HBM-resident cache of registers and packed sequences so that unions,
+progressive prefix unions and pairwise unions never re-read a file or re-sketch a FASTA:
+
+    dashing sketch (x nk via parallel)  -> leaf_sketches()      one fused all-k pass on the GPU
+    dashing union  (x nk via parallel)  -> union_sketches()     one batched max+histogram+MLE launch
+    dashing card                        -> card_of_file()
+    kmc + kmc_tools info / complex      -> exact_count()        GPU k-mer set (bitmap / hash set)
+
+One store per process; it talks to one Engine (one GPU).  There is no CPU path here.
+"""
+import gzip
+import os
+from collections import OrderedDict
+from typing import Dict, List, Sequence
+
+import numpy as np
+import torch
+
+from . import hllfile
+from .engine import Engine, get_engine
+
+ALL_HLL_KS = tuple(range(1, 33))
+
+
+def read_fasta_bytes(path: str) -> bytes:
+    """Whole FASTA as bytes; .gz is inflated on the host (dashing/kmc read .gz transparently)."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    if raw[:2] == b"\x1f\x8b":
+        raw = gzip.decompress(raw)
+    return raw
+
+
+class GpuSketchStore:
+    def __init__(self, engine: Engine = None, prefetch_all_k: bool = True, cache_bytes: int = 64 << 30,
+                 hll_compresslevel: int = None, union_files: str = None):
+        self.engine = engine or get_engine()
+        self.prefetch_all_k = prefetch_all_k
+        self.cache_bytes = cache_bytes
+        self.hll_compresslevel = int(os.environ.get("DANDD_B200_HLL_GZIP", "0")) if hll_compresslevel is None else hll_compresslevel
+        # 'full': union sketches are written out like `dashing union -o` does; 'stub': a header-only
+        # marker file (registers stay in HBM / are recomputed from the leaves on demand)
+        self.union_files = union_files or os.environ.get("DANDD_B200_UNION_FILES", "full")
+        self._regs: "OrderedDict[str, torch.Tensor]" = OrderedDict()   # sketch path -> [2^p] u8 (device)
+        self._leaf_all: Dict[tuple, dict] = {}                         # (fasta, p, canon) -> {"regs","cards","ks"}
+        self._packed: Dict[str, object] = {}                           # fasta -> PackedSeq
+        self._bytes = 0
+        self.stats = {"leaf_passes": 0, "union_launches": 0, "files_written": 0, "files_read": 0, "exact_calls": 0}
+
+    # ------------------------------------------------------------------ cache plumbing
+    def _remember(self, path: str, regs: torch.Tensor) -> None:
+        old = self._regs.pop(path, None)
+        if old is not None:
+            self._bytes -= old.numel()
+        self._regs[path] = regs
+        self._bytes += regs.numel()
+        while self._bytes > self.cache_bytes and len(self._regs) > 1:
+            _, ev = self._regs.popitem(last=False)
+            self._bytes -= ev.numel()
+
+    def registers(self, path: str) -> torch.Tensor:
+        """Device registers of the sketch stored at `path` (HBM cache, else read the file)."""
+        t = self._regs.get(path)
+        if t is None:
+            regs, _p, _ = hllfile.read_hll(path)
+            self.stats["files_read"] += 1
+            t = torch.from_numpy(regs).to(self.engine.device)
+            self._remember(path, t)
+        else:
+            self._regs.move_to_end(path)
+        return t
+
+    def forget(self, path: str) -> None:
+        t = self._regs.pop(path, None)
+        if t is not None:
+            self._bytes -= t.numel()
+
+    def _write(self, path: str, regs: torch.Tensor, p: int, card: float, leaf: bool) -> None:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        if leaf or self.union_files == "full":
+            hllfile.write_hll(path, regs.cpu().numpy(), p, card, self.hll_compresslevel)
+        else:
+            with open(path, "wb") as f:                       # non-empty marker: header only
+                f.write(hllfile.HEADER.pack(1, 0, hllfile.ERTL_MLE, hllfile.ERTL_JOINT_MLE, p, float(card)))
+        self.stats["files_written"] += 1
+
+    # ------------------------------------------------------------------ dashing sketch
+    def packed(self, fasta: str):
+        seq = self._packed.get(fasta)
+        if seq is None:
+            seq = self.engine.pack(read_fasta_bytes(fasta))
+            self._packed[fasta] = seq
+        return seq
+
+    def leaf_sketches(self, fasta: str, ks: Sequence[int], p: int, canon: bool, out_paths: Dict[int, str]) -> Dict[int, float]:
+        """Sketch `fasta` for every k in `ks` (one fused pass), write each sketch to out_paths[k]
+        and return {k: cardinality}.  With prefetch_all_k the pass covers k = 1..32 once and later
+        requests for other k of the same FASTA are served from HBM."""
+        key = (fasta, int(p), bool(canon))
+        ent = self._leaf_all.get(key)
+        need = [int(k) for k in ks]
+        if ent is None or any(k not in ent["ks"] for k in need):
+            run_ks = list(ALL_HLL_KS) if self.prefetch_all_k else sorted(set(need) | set(ent["ks"] if ent else ()))
+            seq = self.engine.pack(read_fasta_bytes(fasta))
+            regs, cards = self.engine.sketch(seq, run_ks, p=p, canon=canon)
+            ent = {"regs": regs, "cards": cards.cpu().numpy(), "ks": {k: i for i, k in enumerate(run_ks)}}
+            self._leaf_all[key] = ent
+            self.stats["leaf_passes"] += 1
+        out = {}
+        for k in need:
+            i = ent["ks"][k]
+            card = float(ent["cards"][i])
+            self._remember(out_paths[k], ent["regs"][i])
+            self._write(out_paths[k], ent["regs"][i], p, card, leaf=True)
+            out[k] = card
+        return out
+
+    # ------------------------------------------------------------------ dashing union (+ card)
+    def union_sketches(self, members_by_k: Dict[int, List[str]], p: int, out_paths: Dict[int, str]) -> Dict[int, float]:
+        """For every k: union of the sketches stored at members_by_k[k]; written to out_paths[k];
+        returns {k: cardinality}.  One launch for all k."""
+        ks = sorted(members_by_k)
+        if not ks:
+            return {}
+        width = max(len(members_by_k[k]) for k in ks)
+        tensors = [[self.registers(pth) for pth in members_by_k[k]] for k in ks]
+        ptrs = np.zeros((len(ks), width), dtype=np.int64)
+        for i, row in enumerate(tensors):
+            for j, t in enumerate(row):
+                ptrs[i, j] = t.data_ptr()
+        cards, unions = self.engine.union_sets(ptrs, p, final_only=True, materialize=True)
+        self.stats["union_launches"] += 1
+        cards = cards.cpu().numpy().reshape(len(ks))
+        out = {}
+        for i, k in enumerate(ks):
+            regs = unions[i, 0]
+            self._remember(out_paths[k], regs)
+            self._write(out_paths[k], regs, p, float(cards[i]), leaf=False)
+            out[k] = float(cards[i])
+        return out
+
+    def prefix_unions(self, leaf_paths_by_k: Dict[int, List[str]], orderings: Sequence[Sequence[int]], p: int,
+                      out_paths: Dict[tuple, str] = None, chunk_bytes: int = 4 << 30) -> np.ndarray:
+        """Cardinalities of every prefix union: [n_orderings, n_steps, nk] for the k values (sorted)
+        of leaf_paths_by_k, each listing the leaf sketches in genome-index order.  A running max per
+        (ordering, k): n sketch reads instead of the n(n+1)/2 of re-unioning every prefix.
+        out_paths maps (ordering index, step index, k) -> file path for the prefix unions that must
+        also exist as sketch files; those are materialised (chunk_bytes of HBM at a time) and
+        written once per distinct path."""
+        ks = sorted(leaf_paths_by_k)
+        orderings = np.asarray(orderings, dtype=np.int64)
+        n_ord, n_steps = orderings.shape
+        m = 1 << p
+        base = np.array([[self.registers(pth).data_ptr() for pth in leaf_paths_by_k[k]] for k in ks], dtype=np.int64)  # [nk, n]
+        ptrs = np.zeros((n_ord, len(ks), n_steps), dtype=np.int64)
+        for i in range(len(ks)):
+            ptrs[:, i, :] = np.where(orderings >= 0, base[i][np.clip(orderings, 0, None)], 0)
+        out = np.empty((n_ord, n_steps, len(ks)), dtype=np.float64)
+        want_files = bool(out_paths)
+        per_ord = len(ks) * n_steps * m
+        step_ords = max(1, chunk_bytes // per_ord) if want_files else n_ord
+        written = set()
+        for o0 in range(0, n_ord, step_ords):
+            o1 = min(n_ord, o0 + step_ords)
+            block = ptrs[o0:o1].reshape((o1 - o0) * len(ks), n_steps)
+            if want_files:
+                cards, unions = self.engine.union_sets(block, p, final_only=False, materialize=True)
+                unions = unions.view(o1 - o0, len(ks), n_steps, m)
+            else:
+                cards = self.engine.union_sets(block, p, final_only=False)
+            self.stats["union_launches"] += 1
+            cards = cards.cpu().numpy().reshape(o1 - o0, len(ks), n_steps)
+            out[o0:o1] = cards.transpose(0, 2, 1)
+            if want_files:
+                for o in range(o0, o1):
+                    for st in range(n_steps):
+                        for i, k in enumerate(ks):
+                            path = out_paths.get((o, st, k))
+                            if path and path not in written:
+                                written.add(path)
+                                self._write(path, unions[o - o0, i, st], p, float(cards[o - o0, i, st]), leaf=False)
+        return out
+
+    # ------------------------------------------------------------------ dashing card
+    def card_of_file(self, path: str, p: int = None) -> float:
+        regs = self.registers(path)
+        pp = int(regs.numel()).bit_length() - 1
+        return float(self.engine.cards(regs.view(1, -1), pp)[0])
+
+    # ------------------------------------------------------------------ kmc / kmc_tools
+    def exact_count(self, fastas: Sequence[str], k: int, canon: bool) -> int:
+        """Number of distinct (canonical) k-mers in the union of the FASTAs (KMC semantics)."""
+        self.stats["exact_calls"] += 1
+        return self.engine.exact_counts([self.packed(f) for f in fastas], int(k), canon)[-1]
+
+    def exact_prefix_counts(self, fastas: Sequence[str], k: int, canon: bool) -> List[int]:
+        self.stats["exact_calls"] += 1
+        return self.engine.exact_counts([self.packed(f) for f in fastas], int(k), canon)
+
+
+_store = None
+
+
+def get_store():
+    global _store
+    if _store is None:
+        _store = GpuSketchStore()
+    return _store
+
+
+def set_store(store) -> None:
+    """Install another store (a different device; the test-suite installs an oracle-backed double
+    here to exercise the host logic on machines without a GPU)."""
+    global _store
+    _store = store

@@ -146,6 +146,15 @@ DD_API int dd_mle_from_hist(const uint32_t *d_hist, int nsk, int p, double *d_ca
  *   union of a tree node (lib/huffman_dandd.py:412-438); the step dimension of the outputs then
  *   has extent 1: d_cards [n_ord][nk], d_hist [n_ord][nk][64], d_unions [n_ord][nk][2^p].
  * =========================================================================================== */
+/* dd_union_sets_card: the same running-max + histogram + MLE over arbitrary sketches given by
+ * address.  d_members is a DEVICE array [n_sets][n_steps] of device pointers to 2^p-byte sketches
+ * (NULL entries are skipped).  Set s, step i covers members[s][0..i].  This is the form the
+ * drop-in sketch objects use: one launch evaluates the union of a tree node for every k
+ * (n_sets = nk, final_only = 1), or every prefix of every ordering for every k.
+ *   d_cards [n_sets][n_steps or 1] f64   d_hist [n_sets][n_steps or 1][64] u32
+ *   d_unions NULL or [n_sets][n_steps or 1][2^p] u8 */
+DD_API int dd_union_sets_card(const uint8_t *const *d_members, int n_sets, int n_steps, int p, int final_only,
+                              double *d_cards, uint32_t *d_hist, uint8_t *d_unions, dd_stream stream);
 DD_API int dd_union_max(const uint8_t *const *d_in, int n_in, size_t len, uint8_t *d_out, dd_stream stream);
 DD_API int dd_prefix_union_card(const uint8_t *d_regs, const int32_t *d_order, int n_ord, int n_steps, int n_genomes,
                          int nk, int p, int final_only, double *d_cards, uint32_t *d_hist, uint8_t *d_unions,

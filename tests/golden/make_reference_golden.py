@@ -1,0 +1,173 @@
+"""Runs the UNMODIFIED reference Python (/root/reference/lib/dandd) on small synthetic datasets
+with oracle-backed stand-ins for dashing / kmc / kmc_tools / parallel first on PATH
+(oracle/shims, SURVEY.md Appendix C technique) and records what it produced -- deltas, argmax k,
+cardinalities, sketchdb layout, progressive and KIJ tables -- as tests/golden/reference_runs.json.
+
+These fixtures pin the HOST LOGIC of the drop-in layer (dandd_b200/lib/*) to the reference's own
+behaviour: the tests re-create the same inputs and require the same outputs.  They cannot pin the
+arithmetic to real Dashing/KMC (absent here; parity unpinned, see oracle/dandd_oracle.c).
+
+The reference can only be imported in the build container (/root/reference is not on the GPU
+box), hence committed fixtures.  Run from the repository root:
+    python tests/golden/make_reference_golden.py
+"""
+import csv
+import json
+import os
+import pickle
+import shutil
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle  # noqa: E402
+from tests.util import make_dataset  # noqa: E402
+
+REF = "/root/reference/lib"
+
+# --exact is broken as shipped (KMCSketchObj.sketch_check <-> check_cardinality recurse forever,
+# SURVEY.md App. B).  The golden for exact mode is produced with that ONE method replaced at run
+# time by the existence test it was meant to be; the reference files are not modified.
+EXACT_WRAPPER = r'''
+import os, sys
+sys.path.insert(0, %(ref)r)
+import sketch_classes
+def sketch_check(self, path=None):
+    path = path or self.sfp.full
+    return all(os.path.exists(path + e) and os.stat(path + e).st_size != 0 for e in (".kmc_pre", ".kmc_suf"))
+sketch_classes.KMCSketchObj.sketch_check = sketch_check
+from dandd_cmd import parse_arguments
+parser, _ = parse_arguments()
+args = parser.parse_args(sys.argv[1:])
+args.func(args)
+'''
+
+
+def run_ref(bindir, argv, exact=False, cwd=None):
+    env = dict(os.environ, PATH=bindir + os.pathsep + os.environ["PATH"], PYTHONPATH=REF, PYTHONHASHSEED="0",
+               ORC_PARALLEL_JOBS="4")
+    if exact:
+        wrapper = os.path.join(bindir, "exact_wrapper.py")
+        with open(wrapper, "w") as fh:
+            fh.write(EXACT_WRAPPER % {"ref": REF})
+        cmd = [sys.executable, wrapper] + argv
+    else:
+        cmd = [sys.executable, os.path.join(REF, "dandd")] + argv
+    subprocess.run(cmd, check=True, env=env, cwd=cwd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+
+
+def read_csv(path):
+    with open(path, newline="") as fh:
+        return list(csv.DictReader(fh))
+
+
+def rel(path, base):
+    return os.path.relpath(path, base) if path and os.path.isabs(path) else path
+
+
+def norm_fastas(text, sep):
+    return sep.join(os.path.basename(f.strip(" '[]")) for f in text.split(sep))
+
+
+def collect_tree(outdir, prefix, sketchdir, tool):
+    rows = []
+    for r in read_csv(os.path.join(outdir, prefix + "_deltas.csv")):
+        rows.append({"title": r["title"], "ngen": int(r["ngen"]), "k": int(r["k"]), "delta": float(r["delta"]),
+                     "card": float(r["card"]), "sketchloc": rel(r["sketchloc"], sketchdir),
+                     "fastas": norm_fastas(r["fastas"], "|")})
+    files = sorted(os.path.relpath(os.path.join(d, f), sketchdir) for d, _, fs in os.walk(sketchdir) for f in fs
+                   if not f.endswith((".pickle", ".bkp")))
+    cardkey = {}
+    for name in os.listdir(sketchdir):
+        if name.endswith(f"_{tool}_cardinalities.pickle"):
+            with open(os.path.join(sketchdir, name), "rb") as fh:
+                cardkey.update({rel(k, sketchdir): float(v) for k, v in pickle.load(fh).items()})
+    with open(os.path.join(sketchdir, "dandd_fastahex.pickle"), "rb") as fh:
+        fastahex = pickle.load(fh)
+    with open(os.path.join(sketchdir, "dandd_sketchinfo.pickle"), "rb") as fh:
+        sketchinfo = sorted(pickle.load(fh).keys())
+    with open(os.path.join(outdir, prefix + "_dtree.pickle"), "rb") as fh:
+        pass  # unpickling needs the reference modules; existence is enough here
+    return {"deltas": rows, "files": files, "cardkey": cardkey, "fastahex": fastahex, "sketchinfo": sketchinfo}
+
+
+def main():
+    work = tempfile.mkdtemp(prefix="dandd_golden_")
+    bindir = pyoracle.install_shims(os.path.join(work, "bin"))
+    gold = {"generator": "tests/golden/make_reference_golden.py", "runs": {}}
+    try:
+        data5 = os.path.join(work, "data5")
+        make_dataset(data5, 5, 20000, seed=21)
+        data7 = os.path.join(work, "data7")
+        make_dataset(data7, 7, 12000, seed=22, prefix="h")
+
+        # A: hill-climb spider, -k 14
+        outA = os.path.join(work, "outA")
+        run_ref(bindir, ["tree", "-d", data5, "-s", "runA", "-k", "14", "-o", outA])
+        gold["runs"]["A_tree_hillclimb"] = collect_tree(outA, "runA_5_dashing", os.path.join(outA, "sketchdb"), "dashing")
+
+        # B: k sweep 10..16, then progressive (identity ordering and 3 fixed orderings)
+        outB = os.path.join(work, "outB")
+        run_ref(bindir, ["tree", "-d", data5, "-s", "runB", "-k", "14", "-o", outB, "--ksweep", "--mink", "10", "--maxk", "16"])
+        gold["runs"]["B_tree_ksweep"] = collect_tree(outB, "runB_5_dashing", os.path.join(outB, "sketchdb"), "dashing")
+        dtreeB = os.path.join(outB, "runB_5_dashing_dtree.pickle")
+        run_ref(bindir, ["progressive", "-d", dtreeB, "-n", "1", "-o", outB, "--ksweep", "--mink", "10", "--maxk", "16"])
+        prog = read_csv(os.path.join(outB, "runB_progu1_5_dashing.csv"))
+        summ = read_csv(os.path.join(outB, "runB_progu1_5_dashing" + "summary.csv"))
+        gold["runs"]["B_progressive_identity"] = {
+            "rows": [{"ngen": int(r["ngen"]), "kval": int(r["kval"]), "delta": r["delta"], "ordering": int(r["ordering"]),
+                      "fastas": norm_fastas(r["fastas"], ",")} for r in prog],
+            "summary": [{"ngen": int(r["ngen"]), "kval": int(r["kval"]), "card": float(r["card"]),
+                         "delta_pos": float(r["delta_pos"]), "title": r["title"], "ordering": int(r["ordering"])} for r in summ]}
+        orderings = {(0, 1, 2, 3, 4), (4, 2, 0, 1, 3), (3, 4, 1, 0, 2)}
+        ofile = os.path.join(work, "orderings.pickle")
+        with open(ofile, "wb") as fh:
+            pickle.dump(orderings, fh)
+        run_ref(bindir, ["progressive", "-d", dtreeB, "-r", ofile, "-s", "runBo", "-o", outB, "--ksweep", "--mink", "10",
+                         "--maxk", "16"])
+        summ = read_csv(os.path.join(outB, "runBo_progu0_5_dashing" + "summary.csv"))
+        # ordering numbers follow list(set) order, which is process-specific: key rows by member set instead
+        gold["runs"]["B_progressive_orderings"] = {
+            "orderings": sorted(orderings),
+            "cells": sorted({(r["title"], int(r["kval"]), float(r["card"])) for r in summ})}
+
+        # F: progressive with the hill-climb (no k sweep), identity ordering, on A's tree
+        dtreeA = os.path.join(outA, "runA_5_dashing_dtree.pickle")
+        run_ref(bindir, ["progressive", "-d", dtreeA, "-n", "1", "-o", outA])
+        prog = read_csv(os.path.join(outA, "runA_progu1_5_dashing.csv"))
+        gold["runs"]["F_progressive_hillclimb"] = {
+            "rows": [{"ngen": int(r["ngen"]), "kval": int(r["kval"]), "delta": float(r["delta"]),
+                      "fastas": norm_fastas(r["fastas"], ",")} for r in prog]}
+
+        # C: KIJ + per-k Jaccard on A's tree
+        run_ref(bindir, ["kij", "-d", dtreeA, "-o", outA, "--jaccard", "--mink", "12", "--maxk", "14"])
+        kij = read_csv(os.path.join(outA, "runA_5_dashing.kij.csv"))
+        jac = read_csv(os.path.join(outA, "runA_5_dashing.j.csv"))
+        gold["runs"]["C_kij"] = {
+            "kij": [{"Atitle": r["Atitle"], "Btitle": r["Btitle"], "Ak": int(r["Ak"]), "Bk": int(r["Bk"]), "ABk": int(r["ABk"]),
+                     "Adelta": float(r["Adelta"]), "Bdelta": float(r["Bdelta"]), "ABdelta": float(r["ABdelta"]),
+                     "KIJ": float(r["KIJ"])} for r in kij],
+            "jaccard": [{"Atitle": r["Atitle"], "Btitle": r["Btitle"], "kval": int(r["kval"]), "Acard": float(r["Acard"]),
+                         "Bcard": float(r["Bcard"]), "ABcard": float(r["ABcard"]), "jaccard": float(r["jaccard"])} for r in jac]}
+
+        # D: --nchildren 3 over 7 FASTAs (the lopsided tree of SURVEY.md App. C.14)
+        outD = os.path.join(work, "outD")
+        run_ref(bindir, ["tree", "-d", data7, "-s", "runD", "-k", "13", "-o", outD, "-n", "3"])
+        gold["runs"]["D_tree_nchildren3"] = collect_tree(outD, "runD_7_dashing", os.path.join(outD, "sketchdb"), "dashing")
+
+        # E: --exact (one reference method patched at run time, see EXACT_WRAPPER)
+        outE = os.path.join(work, "outE")
+        run_ref(bindir, ["tree", "-d", data5, "-s", "runE", "-k", "14", "-o", outE, "--exact"], exact=True)
+        gold["runs"]["E_tree_exact"] = collect_tree(outE, "runE_5_kmc", os.path.join(outE, "sketchdb"), "kmc")
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_runs.json")
+    with open(out, "w") as fh:
+        json.dump(gold, fh, indent=1, sort_keys=True)
+    print("wrote", out, {k: len(v.get("deltas", v.get("rows", v.get("kij", v.get("cells", []))))) for k, v in gold["runs"].items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,129 @@
+"""The end-to-end drop-in scenarios, shared by the CPU run (oracle-backed store double,
+tests/test_host_logic.py) and the GPU run (real store, tests/test_host_gpu.py).  Each scenario
+replays on the same deterministic inputs what tests/golden/make_reference_golden.py ran through the
+unmodified reference, and requires the same outputs."""
+import os
+import pickle
+
+import pytest
+
+from tests.host_harness import (assert_tree_matches, close, collect_tree, gold_runs, norm_fastas, read_csv, run_dandd)
+from tests.util import make_dataset
+
+
+def scenario_tree_hillclimb(tmp):
+    data = make_dataset(os.path.join(tmp, "data5"), 5, 20000, seed=21)
+    out = os.path.join(tmp, "outA")
+    run_dandd(["tree", "-d", os.path.dirname(data[0]), "-s", "runA", "-k", "14", "-o", out])
+    ours = collect_tree(out, "runA_5_dashing", os.path.join(out, "sketchdb"), "dashing")
+    assert_tree_matches(ours, gold_runs()["A_tree_hillclimb"])
+    return out
+
+
+def scenario_rerun_is_fully_cached(tmp, store):
+    """A second identical run must not sketch, union or estimate anything."""
+    out = scenario_tree_hillclimb(tmp)
+    before = dict(store.stats)
+    run_dandd(["tree", "-d", os.path.join(tmp, "data5"), "-s", "runA", "-k", "14", "-o", out])
+    after = store.stats
+    assert after["leaf_passes"] == before["leaf_passes"] and after["union_launches"] == before["union_launches"]
+    assert after["files_written"] == before["files_written"]
+
+
+def scenario_ksweep_and_progressive(tmp):
+    data = make_dataset(os.path.join(tmp, "data5"), 5, 20000, seed=21)
+    out = os.path.join(tmp, "outB")
+    sweep = ["--ksweep", "--mink", "10", "--maxk", "16"]
+    run_dandd(["tree", "-d", os.path.dirname(data[0]), "-s", "runB", "-k", "14", "-o", out] + sweep)
+    gold = gold_runs()
+    assert_tree_matches(collect_tree(out, "runB_5_dashing", os.path.join(out, "sketchdb"), "dashing"), gold["B_tree_ksweep"])
+    dtree = os.path.join(out, "runB_5_dashing_dtree.pickle")
+
+    run_dandd(["progressive", "-d", dtree, "-n", "1", "-o", out] + sweep)
+    rows = read_csv(os.path.join(out, "runB_progu1_5_dashing.csv"))
+    want = gold["B_progressive_identity"]
+    assert [(int(r["ngen"]), int(r["kval"]), r["delta"], int(r["ordering"]), norm_fastas(r["fastas"], ",")) for r in rows] == \
+           [(r["ngen"], r["kval"], r["delta"], r["ordering"], r["fastas"]) for r in want["rows"]]
+    summ = read_csv(os.path.join(out, "runB_progu1_5_dashingsummary.csv"))
+    assert len(summ) == len(want["summary"])
+    for a, b in zip(summ, want["summary"]):
+        assert (int(a["ngen"]), int(a["kval"]), a["title"], int(a["ordering"])) == (b["ngen"], b["kval"], b["title"], b["ordering"])
+        assert close(float(a["card"]), b["card"]) and close(float(a["delta_pos"]), b["delta_pos"])
+
+    want = gold["B_progressive_orderings"]
+    ofile = os.path.join(tmp, "orderings.pickle")
+    with open(ofile, "wb") as fh:
+        pickle.dump({tuple(o) for o in want["orderings"]}, fh)
+    run_dandd(["progressive", "-d", dtree, "-r", ofile, "-s", "runBo", "-o", out] + sweep)
+    summ = read_csv(os.path.join(out, "runBo_progu0_5_dashingsummary.csv"))
+    cells = sorted({(r["title"], int(r["kval"]), float(r["card"])) for r in summ})
+    assert [(t, k) for t, k, _ in cells] == [(t, k) for t, k, _ in want["cells"]]
+    for (_, _, a), (_, _, b) in zip(cells, want["cells"]):
+        assert close(a, b)
+
+
+def scenario_progressive_hillclimb_and_kij(tmp):
+    out = scenario_tree_hillclimb(tmp)
+    gold = gold_runs()
+    dtree = os.path.join(out, "runA_5_dashing_dtree.pickle")
+    run_dandd(["progressive", "-d", dtree, "-n", "1", "-o", out])
+    rows = read_csv(os.path.join(out, "runA_progu1_5_dashing.csv"))
+    want = gold["F_progressive_hillclimb"]["rows"]
+    assert [(int(r["ngen"]), int(r["kval"]), norm_fastas(r["fastas"], ",")) for r in rows] == \
+           [(r["ngen"], r["kval"], r["fastas"]) for r in want]
+    for a, b in zip(rows, want):
+        assert close(float(a["delta"]), b["delta"])
+
+    run_dandd(["kij", "-d", dtree, "-o", out, "--jaccard", "--mink", "12", "--maxk", "14"])
+    kij = read_csv(os.path.join(out, "runA_5_dashing.kij.csv"))
+    want = gold["C_kij"]
+    assert len(kij) == len(want["kij"]) == 10
+    for a, b in zip(kij, want["kij"]):
+        assert (a["Atitle"], a["Btitle"], int(a["Ak"]), int(a["Bk"]), int(a["ABk"])) == \
+               (b["Atitle"], b["Btitle"], b["Ak"], b["Bk"], b["ABk"])
+        for f in ("Adelta", "Bdelta", "ABdelta"):
+            assert close(float(a[f]), b[f])
+        assert float(a["KIJ"]) == pytest.approx(b["KIJ"], rel=1e-7)
+    jac = read_csv(os.path.join(out, "runA_5_dashing.j.csv"))
+    assert len(jac) == len(want["jaccard"])
+    for a, b in zip(jac, want["jaccard"]):
+        assert (a["Atitle"], a["Btitle"], int(a["kval"])) == (b["Atitle"], b["Btitle"], b["kval"])
+        for f in ("Acard", "Bcard", "ABcard"):
+            assert close(float(a[f]), b[f])
+        assert float(a["jaccard"]) == pytest.approx(b["jaccard"], rel=1e-6, abs=1e-9)
+
+
+def scenario_tree_nchildren(tmp):
+    data = make_dataset(os.path.join(tmp, "data7"), 7, 12000, seed=22, prefix="h")
+    out = os.path.join(tmp, "outD")
+    run_dandd(["tree", "-d", os.path.dirname(data[0]), "-s", "runD", "-k", "13", "-o", out, "-n", "3"])
+    assert_tree_matches(collect_tree(out, "runD_7_dashing", os.path.join(out, "sketchdb"), "dashing"),
+                        gold_runs()["D_tree_nchildren3"])
+
+
+def scenario_tree_exact(tmp):
+    data = make_dataset(os.path.join(tmp, "data5"), 5, 20000, seed=21)
+    out = os.path.join(tmp, "outE")
+    run_dandd(["tree", "-d", os.path.dirname(data[0]), "-s", "runE", "-k", "14", "-o", out, "--exact"])
+    assert_tree_matches(collect_tree(out, "runE_5_kmc", os.path.join(out, "sketchdb"), "kmc"),
+                        gold_runs()["E_tree_exact"], exact=True)
+
+
+def scenario_pickle_roundtrip(tmp):
+    """The dtree pickle names classes by the reference's top-level module names."""
+    out = scenario_tree_hillclimb(tmp)
+    raw = open(os.path.join(out, "runA_5_dashing_dtree.pickle"), "rb").read()
+    for name in (b"huffman_dandd", b"DeltaSpider", b"sketch_classes", b"DashSketchObj", b"SketchFilePath",
+                 b"species_specifics", b"SpeciesSpecifics"):
+        assert name in raw
+    assert b"dandd_b200" not in raw
+    tree = pickle.loads(raw)
+    assert sorted(vars(tree)) == sorted(["_dt", "delta", "experiment", "fastas", "kstart", "maxk", "mink", "ngen", "root",
+                                         "speciesinfo"])
+    node = tree.root
+    assert sorted(vars(node)) == sorted(["bestk", "card", "children", "delta", "experiment", "fastas", "ksketches", "maxk",
+                                         "mink", "ngen", "node_title", "progeny", "speciesinfo"])
+    assert len(node.ksketches) >= 100 and node.ksketches[0].kval == 0
+    obj = node.ksketches[node.bestk]
+    assert sorted(vars(obj)) == sorted(["kval", "sketch", "cmd", "sfp", "delta_pos", "card", "speciesinfo", "experiment",
+                                        "_presketches"])

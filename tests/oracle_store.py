@@ -1,0 +1,92 @@
+"""OracleStore: a CPU double of dandd_b200.store.GpuSketchStore for the `-m "not gpu"` tests.
+
+TEST INFRASTRUCTURE.  It lets the host logic (naming, caching, hill-climb, tree shapes, CSV and
+pickle outputs) be exercised in a container without a GPU by answering the store's questions from
+the CPU oracle.  The product never imports this module; on the GPU box the same tests run against
+the real store (tests/test_host_gpu.py)."""
+import gzip
+import os
+
+import numpy as np
+
+from dandd_b200 import hllfile
+from oracle import pyoracle as orc
+
+
+def _read_fasta(path):
+    raw = open(path, "rb").read()
+    return gzip.decompress(raw) if raw[:2] == b"\x1f\x8b" else raw
+
+
+class OracleStore:
+    def __init__(self, union_files="full"):
+        self.union_files = union_files
+        self._regs = {}
+        self._syms = {}
+        self.stats = {"leaf_passes": 0, "union_launches": 0, "files_written": 0, "files_read": 0, "exact_calls": 0}
+
+    def symbols(self, fasta):
+        if fasta not in self._syms:
+            self._syms[fasta] = orc.fasta_symbols(_read_fasta(fasta))
+        return self._syms[fasta]
+
+    def registers(self, path):
+        if path not in self._regs:
+            self._regs[path] = hllfile.read_hll(path)[0]
+            self.stats["files_read"] += 1
+        return self._regs[path]
+
+    def forget(self, path):
+        self._regs.pop(path, None)
+
+    def _write(self, path, regs, p, card):
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        hllfile.write_hll(path, regs, p, card)
+        self._regs[path] = regs
+        self.stats["files_written"] += 1
+
+    def leaf_sketches(self, fasta, ks, p, canon, out_paths):
+        self.stats["leaf_passes"] += 1
+        out = {}
+        for k in ks:
+            regs = orc.hll_sketch(self.symbols(fasta), int(k), p, canon)
+            out[k] = orc.card(regs, p)
+            self._write(out_paths[k], regs, p, out[k])
+        return out
+
+    def union_sketches(self, members_by_k, p, out_paths):
+        self.stats["union_launches"] += 1
+        out = {}
+        for k, members in members_by_k.items():
+            regs = orc.union_max([self.registers(m) for m in members])
+            out[k] = orc.card(regs, p)
+            self._write(out_paths[k], regs, p, out[k])
+        return out
+
+    def prefix_unions(self, leaf_paths_by_k, orderings, p, out_paths=None, chunk_bytes=0):
+        self.stats["union_launches"] += 1
+        ks = sorted(leaf_paths_by_k)
+        orderings = np.asarray(orderings)
+        out = np.zeros((orderings.shape[0], orderings.shape[1], len(ks)))
+        for o, order in enumerate(orderings):
+            for i, k in enumerate(ks):
+                run = np.zeros(1 << p, dtype=np.uint8)
+                for st, g in enumerate(order):
+                    if g >= 0:
+                        run = np.maximum(run, self.registers(leaf_paths_by_k[k][g]))
+                    out[o, st, i] = orc.card(run, p)
+                    path = (out_paths or {}).get((o, st, k))
+                    if path and not os.path.exists(path):
+                        self._write(path, run.copy(), p, out[o, st, i])
+        return out
+
+    def card_of_file(self, path, p=None):
+        regs = self.registers(path)
+        return orc.card(regs, int(regs.size).bit_length() - 1)
+
+    def exact_count(self, fastas, k, canon):
+        self.stats["exact_calls"] += 1
+        return orc.exact_count([self.symbols(f) for f in fastas], int(k), canon)
+
+    def exact_prefix_counts(self, fastas, k, canon):
+        return [orc.exact_count([self.symbols(f) for f in fastas[:i + 1]], int(k), canon) for i in range(len(fastas))]

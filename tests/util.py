@@ -83,3 +83,24 @@ def kmask_of(ks):
     for k in ks:
         m |= 1 << (k - 1)
     return m
+
+
+def make_dataset(directory, n_genomes, length, seed, sub=0.03, indel=0.002, prefix="g"):
+    """n mutated copies of one random ancestor, written as <prefix><i>.fasta (multi-record, odd line
+    width).  Deterministic: the golden generator and the tests call this with the same arguments."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    anc = random_bases(rng, length)
+    paths = []
+    for g in range(n_genomes):
+        r = np.random.default_rng(seed * 100 + g)
+        seq = mutate(r, anc, sub=sub, indel=indel)
+        cut = int(seq.size * (0.4 + 0.05 * g))
+        seq[cut // 2:cut // 2 + 3] = ord("N")
+        recs = [(b"%s%d_a len=%d" % (prefix.encode(), g, cut), seq[:cut]), (b"%s%d_b" % (prefix.encode(), g), seq[cut:])]
+        path = os.path.join(directory, f"{prefix}{g}.fasta")
+        with open(path, "wb") as fh:
+            fh.write(to_fasta(recs, width=70))
+        paths.append(path)
+    return paths
