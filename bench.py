@@ -155,8 +155,8 @@ def workload_config(n_gpus):
                         "p=20, leaf sketches + cardinalities + progressive unions over 30 orderings",
             "genomes_per_gpu": N_GENOMES, "genome_bp": GENOME_BP, "k_min": KS[0], "k_max": KS[-1], "registers_log2": P,
             "orderings": N_ORDERINGS, "parallelism": f"genomes sharded over {n_gpus} GPU(s)",
-            "l2_policy": "inputs + register arrays per step (60 MB text + 1.1 GB accumulators + 276 MiB registers) "
-                         "exceed the 126 MB L2, no explicit flush"}
+            "l2_policy": "per-step working set (60 MB text + 276 MiB registers + 46 MiB accumulators re-zeroed per "
+                         "genome) exceeds the 126 MB L2; no explicit flush"}
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -170,8 +170,9 @@ def run_ours(args):
     if rank == 0:
         build.build()
     torch.cuda.set_device(local)
+    from dandd_b200 import dist as dd_dist
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dd_dist.init("nccl")
         dist.barrier()
     from dandd_b200.engine import Engine, kmask_of
     from dandd_b200._lib import check
@@ -198,7 +199,7 @@ def run_ours(args):
         (N>1) all-reduce MAX of the rank's full union + its cardinalities."""
         leaf_cards = []
         for g, dt in enumerate(d_texts):
-            seq = eng.pack(dt)
+            seq = eng.pack(dt, start=0)
             if time_k2:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 eng._k2_events = (e0, e1)
@@ -207,19 +208,29 @@ def run_ours(args):
                 k2_events.append(eng._k2_events)
                 eng._k2_events = None
             leaf_cards.append(c)
+        return leaf_cards, progressive_and_union()
+
+    def progressive_and_union():
+        """K3/K4 over the rank's genomes; at N>1 the one exchange step of the path: the union sketch
+        of the whole job = MAX all-reduce of the rank unions, then its cardinalities."""
         prog = eng.prefix_union_cards(regs, orders, P)
         full = None
         if world > 1:
-            full = eng.union([regs[g] for g in range(N_GENOMES)])
-            dist.all_reduce(full, op=dist.ReduceOp.MAX)
+            full = dd_dist.union_over_ranks(eng.union([regs[g] for g in range(N_GENOMES)]))
             full = eng.cards(full, P)
-        return leaf_cards, prog, full
+        return prog, full
 
     def step_e2e():
+        """The same step through the host-buffer C ABI: FASTA in pinned host memory -> H2D ->
+        K1 -> K2 -> K4, registers stay in HBM, every cardinality comes back to the host."""
         out = []
-        for h in pinned:
-            _, cards = eng.sketch_fasta_host(h, KS, p=P, want_regs=False)
+        for g, h in enumerate(pinned):
+            _, cards = eng.sketch_fasta_host(h, KS, p=P, want_regs=False, out_dev=regs[g])
             out.append(cards)
+        prog, full = progressive_and_union()
+        out.append(prog.cpu())
+        if full is not None:
+            out.append(full.cpu())
         return out
 
     def sync():
@@ -300,8 +311,10 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": "Gbp/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(sum(len(t) for t, _ in texts)), "d2h_bytes_per_step": N_GENOMES * nk * 8,
-                "note": "dd_sketch_fasta_host per genome from pinned memory; cardinalities copied back, registers stay in HBM"},
+                "h2d_bytes_per_step": int(sum(len(t) for t, _ in texts)) + int(orders.nbytes),
+                "d2h_bytes_per_step": N_GENOMES * nk * 8 + N_ORDERINGS * N_GENOMES * nk * 8 + (nk * 8 if world > 1 else 0),
+                "note": "dd_sketch_fasta_host per genome from pinned memory + progressive unions; every cardinality "
+                        "is copied back to the host, registers stay in HBM"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "roofline": {"kernel": "sketch_allk_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,

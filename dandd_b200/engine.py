@@ -99,11 +99,16 @@ class Engine:
         hit = np.flatnonzero(arr == 62)
         return int(hit[0]) if hit.size else int(arr.size)
 
-    def pack(self, text, chunk_bytes: Optional[int] = None) -> PackedSeq:
+    def pack(self, text, chunk_bytes: Optional[int] = None, start: Optional[int] = None) -> PackedSeq:
         """FASTA text (bytes / numpy / torch uint8) -> PackedSeq.  `chunk_bytes` packs in several
-        chunks through the carried state (used by the tests to exercise streaming)."""
+        chunks through the carried state (used by the tests to exercise streaming).  `start` = offset
+        of the first '>' if the caller knows it (device-resident text is otherwise scanned for it)."""
+        if start is None and not isinstance(text, torch.Tensor):
+            start = self.skip_preamble(text)          # on the host, before the upload
         d_text = self._dev_u8(text)
-        off = self.skip_preamble(d_text) if d_text.numel() else 0
+        if start is None:
+            start = self.skip_preamble(d_text) if d_text.numel() else 0
+        off = min(int(start), int(d_text.numel()))
         n = int(d_text.numel()) - off
         if off % 16 and n > 0:
             d_text = d_text[off:].clone()   # keep the 128-bit loads aligned
@@ -172,9 +177,11 @@ class Engine:
         self._keep = state  # keep alive until the stream has consumed it
 
     def sketch_fasta_host(self, text: bytes, ks: Sequence[int], p: int = 20, canon: bool = True,
-                          want_regs: bool = True, pinned_regs: Optional[torch.Tensor] = None):
+                          want_regs: bool = True, pinned_regs: Optional[torch.Tensor] = None,
+                          out_dev: Optional[torch.Tensor] = None):
         """The host-buffer C-ABI path: FASTA bytes in host memory -> (regs numpy [nk, 2^p] or None,
-        cards numpy [nk]).  H2D, pack, sketch, estimate, D2H all inside the one call."""
+        cards numpy [nk]).  H2D, pack, sketch, estimate, D2H all inside the one call.  `out_dev`
+        (uint8 [nk, 2^p] on the device) additionally keeps the registers resident in HBM."""
         kmask = kmask_of(ks)
         nk = bin(kmask).count("1")
         m = 1 << p
@@ -194,7 +201,11 @@ class Engine:
             else:
                 regs = np.empty((nk, m), dtype=np.uint8)
                 r_ptr = regs.ctypes.data
-        check(self.lib.dd_sketch_fasta_host(h_ptr, n, kmask, p, int(canon), r_ptr, cards.ctypes.data, None, ws.data_ptr(),
+        d_ptr = None
+        if out_dev is not None:
+            assert out_dev.is_contiguous() and out_dev.numel() == nk * m and out_dev.dtype == torch.uint8
+            d_ptr = out_dev.data_ptr()
+        check(self.lib.dd_sketch_fasta_host(h_ptr, n, kmask, p, int(canon), r_ptr, cards.ctypes.data, d_ptr, ws.data_ptr(),
                                             ws.numel(), self.stream), "dd_sketch_fasta_host")
         return regs, cards
 

@@ -1,0 +1,74 @@
+"""The N>1 path on CPU: world_size 2, gloo.  Sharding is deterministic and balanced, the MAX
+all-reduce / all-gather of register arrays reproduces the single-process union bit for bit, and
+splitting the progressive orderings across ranks loses nothing."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dandd_b200 import dist as dd_dist
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    r, w = dd_dist.init("gloo")
+    assert (r, w) == (rank, world)
+    rng = np.random.default_rng(0)                     # same data on every rank; each keeps its shard
+    n, nk, m = 5, 3, 1 << 10
+    allregs = torch.from_numpy(rng.integers(0, 40, (n, nk, m), dtype=np.uint8))
+    sizes = [50, 10, 40, 30, 20]
+    owners = dd_dist.shard_by_size(sizes, world)
+    assert sorted(sum(owners, [])) == list(range(n))
+    local = allregs[owners[rank]].clone()
+    # union over ranks == union over all genomes
+    mine = local.max(dim=0).values.clone() if local.shape[0] else torch.zeros((nk, m), dtype=torch.uint8)
+    full = dd_dist.union_over_ranks(mine)
+    assert torch.equal(full, allregs.max(dim=0).values)
+    # gather restores global genome order
+    got = dd_dist.gather_registers(local, owners)
+    assert torch.equal(got, allregs)
+    cards = dd_dist.gather_cards(local.double().mean(dim=2), owners)
+    assert torch.allclose(cards, allregs.double().mean(dim=2))
+    # orderings split across ranks cover everything exactly once
+    mine = list(dd_dist.split_work(7))
+    bucket = [None] * world
+    dist.all_gather_object(bucket, mine)
+    assert sorted(sum(bucket, [])) == list(range(7))
+    cnt = dd_dist.sum_counts(torch.tensor([rank + 1], dtype=torch.int64))
+    assert int(cnt) == world * (world + 1) // 2
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(tmpdir, f"ok{rank}"), "w").close()
+
+
+def test_two_rank_gloo(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_shard_by_size_balance():
+    sizes = [3100, 3000, 2900, 50, 40, 30, 20, 10]
+    owners = dd_dist.shard_by_size(sizes, 4)
+    loads = [sum(sizes[i] for i in o) for o in owners]
+    assert max(loads) <= 3100 and sorted(sum(owners, [])) == list(range(8))
+    assert dd_dist.shard_by_size(sizes, 4) == owners        # deterministic
+    assert dd_dist.shard_by_size([5, 5, 5], 1) == [[0, 1, 2]]
+
+
+def test_single_process_is_identity():
+    t = torch.arange(12, dtype=torch.uint8).reshape(2, 2, 3)
+    assert dd_dist.world() == (0, 1)
+    assert torch.equal(dd_dist.union_over_ranks(t.clone()), t)
+    assert torch.equal(dd_dist.gather_registers(t, [[0, 1]]), t)
+    assert list(dd_dist.split_work(5)) == [0, 1, 2, 3, 4]
