@@ -21,7 +21,6 @@ because neither Dashing nor GNU parallel exists here (see oracle/dandd_oracle.c 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -82,32 +81,49 @@ def make_orderings(n, count, seed):
 
 # ------------------------------------------------------------------------------------- clock sampler
 class ClockSampler(threading.Thread):
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region through in-process NVML
+    (nvidia_ml_py).  Spawning nvidia-smi instead stalls kernel launches for tens of milliseconds on
+    these boxes -- it inflated a 15 ms step to 47 ms -- so the handle is opened before warm-up and
+    each sample is two cheap NVML queries."""
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, period=0.01):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.samples, self.stop_flag, self.period = [], False, period
+        self.active = False
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
 
     def run(self):
+        if self.h is None:
+            return
+        nv = self.nv
         while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.05)
+            if self.active:
+                try:
+                    self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                         int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+                except Exception:  # noqa: BLE001
+                    pass
+            time.sleep(self.period)
 
     def summary(self):
-        if not self.samples:
+        if self.h is None or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+        nv = self.nv
+        sm = sorted(s[0] for s in self.samples)
+        bits = 0
+        for _, r in self.samples:
+            bits |= r
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": [n for n, b in names.items() if bits & b],
                 "samples": len(sm)}
 
 
@@ -192,22 +208,22 @@ def run_ours(args):
         pinned.append(h)
     orders = make_orderings(N_GENOMES, N_ORDERINGS, seed=2)
     regs = torch.empty((N_GENOMES, nk, m), dtype=torch.uint8, device=dev)
+    leaf_hist = torch.empty((N_GENOMES, nk, 64), dtype=torch.int32, device=dev)
     k2_events = []
 
     def step_resident(time_k2=False):
         """pack + all-k sketch + leaf cards for every genome, progressive prefix-union cards,
         (N>1) all-reduce MAX of the rank's full union + its cardinalities."""
-        leaf_cards = []
         for g, dt in enumerate(d_texts):
             seq = eng.pack(dt, start=0)
             if time_k2:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 eng._k2_events = (e0, e1)
-            _, c = eng.sketch(seq, KS, p=P, out=regs[g])
+            eng.sketch(seq, KS, p=P, out=regs[g], hist_out=leaf_hist[g])
             if time_k2:
                 k2_events.append(eng._k2_events)
                 eng._k2_events = None
-            leaf_cards.append(c)
+        leaf_cards = eng.mle(leaf_hist, P)          # one estimator launch for all 12 x 23 leaf sketches
         return leaf_cards, progressive_and_union()
 
     def progressive_and_union():
@@ -264,15 +280,18 @@ def run_ours(args):
             ev[1].record()
     eng._update_from_state = hooked
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler.active = True
     ms_step, res = timed(lambda: step_resident(time_k2=True), args.steps)
+    sampler.active = False
     k2_ms = [a.elapsed_time(b) for a, b in k2_events]
     for _ in range(max(args.warmup, 3)):
         step_e2e()
+    sampler.active = True
     ms_e2e, _ = timed(step_e2e, args.steps)
     sampler.stop_flag = True
 
@@ -305,7 +324,7 @@ def run_ours(args):
     cpu_dt, cpu_bases = cpu_sketch_sample(texts[:1], KS, P, threads)
     cpu_value = cpu_bases / cpu_dt / 1e9
 
-    launches_per_step = N_GENOMES * (1 + 3 + 1 + 1 + 1) + 2 + (3 if world > 1 else 0)
+    launches_per_step = N_GENOMES * (1 + 3 + 1 + 1) + 1 + 2 + (3 if world > 1 else 0)
     line = {
         "metric": "Gbp/s sketched (all k)", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

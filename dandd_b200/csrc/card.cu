@@ -13,64 +13,46 @@
 #include <cuda_runtime.h>
 
 #include "common.cuh"
+#include "hist.cuh"
 #include "kernels.cuh"
 
 namespace dd {
 
 // -------------------------------------------------------------------------------------------------
-// K4a: histogram of u8 registers.  grid (slices, nsk)
+// K4a: histogram of u8 registers.  grid (slices, nsk); a thread counts at most 240 registers
+// between flushes.
 // -------------------------------------------------------------------------------------------------
-constexpr int kHistThreads = 128;
-constexpr int kHistSlices = 8;
+constexpr int kHistVecPerFlush = 15;  // 15 x 16 registers = 240 <= 255
 
-__device__ __forceinline__ void hist_add_word(uint32_t *s_hist, uint32_t w, int nthreads) {
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        const uint32_t v = min((w >> (8 * b)) & 0xffu, (uint32_t)(DD_HIST_BINS - 1));
-        s_hist[v * nthreads + threadIdx.x]++;
-    }
-}
-
-// Sum the thread-private counters of every bin and add them to a global histogram row.
-template <int NT>
-__device__ __forceinline__ void hist_flush(const uint32_t *s_hist, uint32_t *g_hist) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int b = warp; b < DD_HIST_BINS; b += NT / 32) {
-        uint32_t s = 0;
-#pragma unroll
-        for (int t = lane; t < NT; t += 32) s += s_hist[b * NT + t];
-        s = __reduce_add_sync(0xffffffffu, s);
-        if (lane == 0 && s) atomicAdd(&g_hist[b], s);
-    }
-}
-
-__global__ void __launch_bounds__(kHistThreads)
+__global__ void __launch_bounds__(kPhThreads)
 hist_kernel(const uint8_t *__restrict__ regs, int p, uint32_t *__restrict__ hist) {
-    __shared__ uint32_t s_hist[DD_HIST_BINS * kHistThreads];
-    for (int i = threadIdx.x; i < DD_HIST_BINS * kHistThreads; i += kHistThreads) s_hist[i] = 0;
-    __syncthreads();
+    __shared__ __align__(16) uint8_t s_hist[kPhBytes];
+    const uint32_t slot = ph_slot();
     const size_t m = (size_t)1 << p;
     const int sk = blockIdx.y;
-    if (m >= 16) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(regs + (size_t)sk * m);
-        const size_t nvec = m / 16;
-        const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
-        const size_t v0 = (size_t)blockIdx.x * per, v1 = min(nvec, v0 + per);
-        for (size_t v = v0 + threadIdx.x; v < v1; v += kHistThreads) {
-            const uint4 x = __ldg(src + v);
-            hist_add_word(s_hist, x.x, kHistThreads);
-            hist_add_word(s_hist, x.y, kHistThreads);
-            hist_add_word(s_hist, x.z, kHistThreads);
-            hist_add_word(s_hist, x.w, kHistThreads);
+    uint32_t *g_hist = hist + (size_t)sk * DD_HIST_BINS;
+    const uint4 *src = reinterpret_cast<const uint4 *>(regs + (size_t)sk * m);
+    const size_t nvec = m / 16;
+    const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
+    const size_t v0 = (size_t)blockIdx.x * per, v1 = min(nvec, v0 + per);
+    for (size_t base = v0; base < v1; base += (size_t)kPhThreads * kHistVecPerFlush) {
+        ph_zero(s_hist);
+        __syncthreads();
+#pragma unroll 5
+        for (int i = 0; i < kHistVecPerFlush; ++i) {
+            const size_t v = base + (size_t)i * kPhThreads + threadIdx.x;
+            if (v < v1) {
+                const uint4 x = __ldg(src + v);
+                ph_add_word(s_hist, slot, x.x);
+                ph_add_word(s_hist, slot, x.y);
+                ph_add_word(s_hist, slot, x.z);
+                ph_add_word(s_hist, slot, x.w);
+            }
         }
-    } else if (blockIdx.x == 0) {
-        for (size_t i = threadIdx.x; i < m; i += kHistThreads) {
-            const uint32_t v = min((uint32_t)regs[(size_t)sk * m + i], (uint32_t)(DD_HIST_BINS - 1));
-            s_hist[v * kHistThreads + threadIdx.x]++;
-        }
+        __syncthreads();
+        ph_flush(s_hist, g_hist);
+        __syncthreads();
     }
-    __syncthreads();
-    hist_flush<kHistThreads>(s_hist, hist + (size_t)sk * DD_HIST_BINS);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -113,13 +95,17 @@ union_max_kernel(const uint8_t *const *__restrict__ in, int n_in, size_t len, ui
 }
 
 // -------------------------------------------------------------------------------------------------
-// K3b: progressive prefix unions with fused histograms.  grid (slices, nk, n_ord).
-// Each thread keeps the running max of 64 registers (4 x uint4) in registers while the ordering's
-// genomes stream past; after every step the CTA histograms its 16 KiB slice of the running union.
+// K3b: progressive prefix unions with fused histograms.
+// Each thread keeps the running max of 128 registers (8 x uint4) in registers while the members of
+// a set stream past; after every step the CTA histograms its 32 KiB slice of the running union with
+// thread-private byte counters and adds the bin totals to the global row of that (set, step).
+// (An incremental variant that only moved the counters of changed registers was measured 1.6x
+// SLOWER: under SIMT a byte position is processed as soon as one lane of the warp changed, so
+// nothing is skipped and every change costs two read-modify-writes -- profiles/r01_notes.md.)
 // -------------------------------------------------------------------------------------------------
-constexpr int kPfxThreads = 256;
-constexpr int kPfxVec = 4;                                 // uint4 per thread
-constexpr int kPfxSliceBytes = kPfxThreads * kPfxVec * 16; // 16 KiB
+constexpr int kPfxThreads = kPhThreads;
+constexpr int kPfxVec = 8;                                 // uint4 per thread (128 registers <= 255)
+constexpr int kPfxSliceBytes = kPfxThreads * kPfxVec * 16; // 32 KiB
 
 // kPtrTable = false: members are genome indices into regs[n_genomes][nk][2^p], grid (slices, nk, n_ord)
 // kPtrTable = true : members are device pointers to 2^p-byte sketches,      grid (slices, n_sets, 1)
@@ -128,12 +114,8 @@ __global__ void __launch_bounds__(kPfxThreads)
 prefix_union_kernel(const uint8_t *__restrict__ regs, const int32_t *__restrict__ order,
                     const uint8_t *const *__restrict__ members, int n_steps, int n_genomes, int nk, int p,
                     int final_only, uint32_t *__restrict__ hist, uint8_t *__restrict__ unions) {
-    // u8 thread-private counters would overflow only past 255 registers per thread per step; a
-    // thread sees 64, so one byte per (bin, thread) is enough: 16 KiB of shared memory.
-    __shared__ __align__(16) uint8_t s_hist[DD_HIST_BINS * kPfxThreads];
-    // byte slot of this thread inside a bin row: lane -> its own 32-bit word (= its own bank), the
-    // four bytes of a word belong to four different warps, so a warp's increments never conflict
-    const uint32_t my_slot = ((threadIdx.x & 31u) << 2) | ((threadIdx.x >> 5) & 3u) | ((threadIdx.x >> 7) << 7);
+    __shared__ __align__(16) uint8_t s_hist[kPhBytes];
+    const uint32_t slot = ph_slot();
     const size_t m = (size_t)1 << p;
     const int k = blockIdx.y, o = blockIdx.z;
     const size_t slice0 = (size_t)blockIdx.x * kPfxSliceBytes;
@@ -166,39 +148,21 @@ prefix_union_kernel(const uint8_t *__restrict__ regs, const int32_t *__restrict_
         if (final_only && step != n_steps - 1) continue;
         const size_t row = kPtrTable ? (final_only ? (size_t)k : (size_t)k * n_steps + step)
                                      : (final_only ? (size_t)o * nk + k : ((size_t)o * n_steps + step) * nk + k);
-        // histogram of the running union
-        for (int i = threadIdx.x; i < DD_HIST_BINS * kPfxThreads / 16; i += kPfxThreads)
-            reinterpret_cast<uint4 *>(s_hist)[i] = make_uint4(0, 0, 0, 0);
+        ph_zero(s_hist);
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < kPfxVec; ++q) {
             const size_t off = ((size_t)q * kPfxThreads + threadIdx.x) * 16;
             if (slice0 + off < m) {
-                const uint32_t w[4] = {run[q].x, run[q].y, run[q].z, run[q].w};
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const uint32_t v = min((w[c] >> (8 * b)) & 0xffu, (uint32_t)(DD_HIST_BINS - 1));
-                        s_hist[v * kPfxThreads + my_slot]++;
-                    }
+                ph_add_word(s_hist, slot, run[q].x);
+                ph_add_word(s_hist, slot, run[q].y);
+                ph_add_word(s_hist, slot, run[q].z);
+                ph_add_word(s_hist, slot, run[q].w);
                 if (unions) *reinterpret_cast<uint4 *>(unions + row * m + slice0 + off) = run[q];
             }
         }
         __syncthreads();
-        // bin totals: each warp sums 8 bins; a lane adds the 8 byte counters of one 64-bit word
-        {
-            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-            for (int b = warp; b < DD_HIST_BINS; b += kPfxThreads / 32) {
-                const uint2 x = reinterpret_cast<const uint2 *>(s_hist + b * kPfxThreads)[lane];
-                // horizontal byte sums: (x & 0x00ff00ff) + ((x >> 8) & 0x00ff00ff) keeps 16-bit lanes
-                uint32_t s = (x.x & 0x00ff00ffu) + ((x.x >> 8) & 0x00ff00ffu) + (x.y & 0x00ff00ffu) +
-                             ((x.y >> 8) & 0x00ff00ffu);
-                s = (s & 0xffffu) + (s >> 16);
-                s = __reduce_add_sync(0xffffffffu, s);
-                if (lane == 0 && s) atomicAdd(&hist[row * DD_HIST_BINS + b], s);
-            }
-        }
+        ph_flush(s_hist, hist + row * DD_HIST_BINS);
         __syncthreads();
     }
 }
@@ -211,12 +175,12 @@ cudaError_t card_hist(const uint8_t *d_regs, int nsk, int p, uint32_t *d_hist, c
     if (e != cudaSuccess) return e;
     if (nsk == 0) return cudaSuccess;
     const size_t m = (size_t)1 << p;
-    int slices = (int)((m / 16 + kHistThreads * 8 - 1) / (kHistThreads * 8));  // >= 8 uint4 per thread
+    // one flush round (256 threads x 240 registers = 60 KiB) per CTA where the sketch is big enough
+    int slices = (int)((m + (size_t)kPhThreads * kHistVecPerFlush * 16 - 1) / ((size_t)kPhThreads * kHistVecPerFlush * 16));
     if (slices < 1) slices = 1;
-    if (slices > kHistSlices) slices = kHistSlices;
     for (int s0 = 0; s0 < nsk; s0 += 65535) {  // gridDim.y limit
         const int cnt = nsk - s0 < 65535 ? nsk - s0 : 65535;
-        hist_kernel<<<dim3(slices, cnt), kHistThreads, 0, stream>>>(d_regs + (size_t)s0 * m, p,
+        hist_kernel<<<dim3(slices, cnt), kPhThreads, 0, stream>>>(d_regs + (size_t)s0 * m, p,
                                                                     d_hist + (size_t)s0 * DD_HIST_BINS);
     }
     return cudaGetLastError();

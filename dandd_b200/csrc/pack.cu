@@ -18,9 +18,9 @@
 namespace dd {
 
 constexpr int kPackThreads = 256;
-constexpr int kPackRows = 4;
+constexpr int kPackRows = 1;  // 4 KiB tiles: ~1200 CTAs for a 5 MB genome keep every SM busy
 constexpr int kRowBytes = kPackThreads * 16;      // 4096
-constexpr int kTileBytes = kRowBytes * kPackRows; // 16384
+constexpr int kTileBytes = kRowBytes * kPackRows;
 constexpr int kScanThreads = 1024;
 
 struct PackWsHeader {
@@ -116,7 +116,7 @@ pack_scan_kernel(const uint8_t *__restrict__ text, size_t n, const uint64_t *__r
                  PackTileOut *__restrict__ tile_out, uint64_t *__restrict__ seg_base, PackWsHeader *__restrict__ hdr,
                  dd_pack_state *__restrict__ st, size_t cap_symbols) {
     __shared__ uint64_t s_warp[32];
-    __shared__ uint64_t s_sum[kScanThreads];
+    __shared__ uint64_t s_sum[1];
     const size_t seg_len = (ntiles + kScanThreads - 1) / kScanThreads;
     const size_t t0 = (size_t)threadIdx.x * seg_len;
     const size_t t1 = t0 + seg_len < ntiles ? t0 + seg_len : ntiles;
@@ -139,15 +139,30 @@ pack_scan_kernel(const uint8_t *__restrict__ text, size_t n, const uint64_t *__r
         local += xfer_cnt(g, state);
         state = xfer_end(g, state);
     }
-    s_sum[threadIdx.x] = local;
+    // exclusive scan of the per-thread symbol counts (warp shuffles + one pass over warp totals)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        uint64_t incl = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        __syncthreads();  // s_warp was last read inside block_scan_xfer
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint64_t before = 0, total = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) {
+            const uint64_t t = s_warp[w];
+            if (w < warp) before += t;
+            total += t;
+        }
+        seg_base[threadIdx.x] = before + incl - local;
+        s_sum[0] = total;  // every thread writes the same value
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint64_t run = 0;
-        for (int i = 0; i < kScanThreads; ++i) {
-            const uint64_t v = s_sum[i];
-            seg_base[i] = run;
-            run += v;
-        }
+        const uint64_t run = s_sum[0];
         hdr->entry_last_byte = st->last_byte;
         hdr->seg_len = (uint32_t)seg_len;
         const uint64_t before = st->nsym;

@@ -22,11 +22,20 @@
 // subnormals, and the other half of the operand is +0.0, the identity of max over ranks -- so each
 // half is an independent, exact integer max.  dd_sketch_end narrows the u16 halves to u8.
 // Bound: INT32 issue and the L2 reduction rate -- not HBM.
+//
+// Small k.  For k <= 9 there are at most 4^k distinct k-mers, so every update of such a k lands on
+// a handful of addresses and same-address L2 reductions serialise (measured at 1 Gbp: k=2 alone
+// 190 ms, k=3 87 ms, against 5.5 ms for k >= 8).  The kernel is therefore persistent (a few CTAs per
+// SM, grid-stride over 4096-symbol tiles) and each CTA keeps a presence bitmap of the canonical
+// k-mers it has already sent, for every k <= 9 (43.7 KB of shared memory): a k-mer whose bit is
+// set is dropped before hashing -- exact, because the same k-mer always produces the same
+// (register, rank) -- so a CTA issues at most 4^k reductions per small k over its whole life.
 #include <cuda_runtime.h>
 
 #include <utility>
 
 #include "common.cuh"
+#include "hist.cuh"
 #include "kernels.cuh"
 
 namespace dd {
@@ -43,7 +52,19 @@ struct SketchArgs {
     int p;
     uint32_t *acc;                // [nk][2^p / 2] words, two u16 registers per word
     const SketchWsHeader *hdr;
+    uint32_t ntiles;              // upper bound on the 256-word tiles of the symbol range
 };
+
+// Presence bitmaps for k = 1..kBitmapMaxK: 4^k bits each (at least one word).
+constexpr int kBitmapMaxK = 9;
+__host__ __device__ constexpr uint32_t bitmap_words(int k) { return (1u << (2 * k)) >= 32u ? (1u << (2 * k)) / 32u : 1u; }
+__host__ __device__ constexpr uint32_t bitmap_offset(int k) {  // words before the bitmap of k
+    uint32_t o = 0;
+    for (int j = 1; j < k; ++j) o += bitmap_words(j);
+    return o;
+}
+constexpr uint32_t kBitmapWords = bitmap_offset(kBitmapMaxK + 1);  // 10924 words = 43.7 KB
+constexpr uint32_t kSmallKMask = (1u << kBitmapMaxK) - 1u;
 
 // 64-bit x times 32-bit constant: IMAD.WIDE.U32 + IMAD, both on the FMA pipe (PTX spelled out so
 // that ptxas does not split the high-word multiply-add).
@@ -80,10 +101,23 @@ __device__ __forceinline__ void red_max_u16(uint32_t *word, uint32_t half, uint3
 // an invalid window only predicates the RED off, so neighbouring k bodies can be interleaved.
 template <int K, bool kCanon>
 __device__ __forceinline__ void update_one_k(const Window &win, int run, uint32_t kmask, uint32_t kmask_run, int p,
-                                             uint32_t *acc, uint32_t &off_k, const uint32_t (&floor4)[8]) {
+                                             uint32_t *acc, uint32_t &off_k, const uint32_t (&floor4)[8],
+                                             uint32_t *s_seen) {
     if (!((kmask >> (K - 1)) & 1u)) return;  // warp-uniform
     if ((kmask_run >> (K - 1)) & 1u) {       // warp-uniform
         const uint64_t v = kmer_value<K>(win, kCanon);
+        if (K <= kBitmapMaxK) {
+            // already sent by this CTA?  (a racing duplicate only repeats an idempotent update)
+            uint32_t *word = s_seen + bitmap_offset(K) + ((uint32_t)v >> 5);
+            const uint32_t bit = 1u << ((uint32_t)v & 31u);
+            const bool fresh = run >= K && !(*word & bit);
+            if (fresh) atomicOr(word, bit);
+            if (!fresh) run = 0;             // nothing to do for this lane
+            if (__all_sync(__activemask(), !fresh)) {
+                off_k += 1u << (p - 1);
+                return;
+            }
+        }
         // dd::wang64 (common.cuh) with the multiplications pinned to the FMA pipe
         uint64_t h = mad64x32(v, 0x1FFFFFu, 0xFFFFFFFFFFFFFFFFull);
         h ^= h >> 24;
@@ -106,13 +140,19 @@ __device__ __forceinline__ void update_one_k(const Window &win, int run, uint32_
 template <bool kCanon, int... Ks>
 __device__ __forceinline__ void update_all_k(std::integer_sequence<int, Ks...>, const Window &win, int run,
                                              uint32_t kmask, uint32_t kmask_run, int p, uint32_t *acc,
-                                             const uint32_t (&floor4)[8]) {
+                                             const uint32_t (&floor4)[8], uint32_t *s_seen) {
     uint32_t off_k = 0;
-    (update_one_k<Ks + 1, kCanon>(win, run, kmask, kmask_run, p, acc, off_k, floor4), ...);
+    (update_one_k<Ks + 1, kCanon>(win, run, kmask, kmask_run, p, acc, off_k, floor4, s_seen), ...);
 }
 
 template <bool kCanon>
 __global__ void __launch_bounds__(kSketchThreads) sketch_allk_kernel(SketchArgs a) {
+    extern __shared__ uint32_t s_seen[];  // presence bitmaps, only allocated when a k <= 9 is requested
+    const bool small_k = (a.kmask_run & kSmallKMask) != 0u;
+    if (small_k) {
+        for (uint32_t i = threadIdx.x; i < kBitmapWords; i += kSketchThreads) s_seen[i] = 0u;
+        __syncthreads();
+    }
     // per-k floors (indexed by k-1), four to a register
     uint32_t floor4[8];
     {
@@ -121,35 +161,40 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_allk_kernel(SketchArgs 
         floor4[0] = f0.x; floor4[1] = f0.y; floor4[2] = f0.z; floor4[3] = f0.w;
         floor4[4] = f1.x; floor4[5] = f1.y; floor4[6] = f1.z; floor4[7] = f1.w;
     }
-
     uint64_t sym_begin = a.sym_begin, sym_end = a.sym_end;
     if (a.state) {
         sym_begin = a.state->prev_nsym;
         sym_end = a.state->nsym;
     }
-    const uint64_t w = (sym_begin >> 4) + (uint64_t)blockIdx.x * kSketchThreads + threadIdx.x;
-    const uint64_t s0 = w << 4;
-    if (s0 >= sym_end) return;
-
-    const uint32_t w0 = __ldg(a.codes + w);
-    const uint32_t w1 = w >= 1 ? __ldg(a.codes + w - 1) : 0u;
-    const uint32_t w2 = w >= 2 ? __ldg(a.codes + w - 2) : 0u;
-    const uint64_t iw = w >> 1;
-    const uint32_t i0 = __ldg(a.invalid + iw);
-    const uint32_t i1 = iw >= 1 ? __ldg(a.invalid + iw - 1) : 0xffffffffu;  // before the stream: breaks
-    const uint32_t r0 = revcomp_word(w0), r1 = revcomp_word(w1), r2 = revcomp_word(w2);
-    const bool all_valid = (i0 | i1) == 0u;
-
-    const int j_lo = sym_begin > s0 ? (int)(sym_begin - s0) : 0;
-    const int j_hi = sym_end - s0 < 16 ? (int)(sym_end - s0) : 16;
-    const uint32_t sm_base = (uint32_t)(s0 & 31);
 
 #pragma unroll 1
-    for (int j = j_lo; j < j_hi; ++j) {
-        const Window win = window_at(w0, w1, w2, r0, r1, r2, j);
-        const int run = all_valid ? 32 : valid_run(invalid_window(i0, i1, sm_base + (uint32_t)j));
-        if (run == 0) continue;
-        update_all_k<kCanon>(std::make_integer_sequence<int, 32>{}, win, run, a.kmask, a.kmask_run, a.p, a.acc, floor4);
+    for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const uint64_t w = (sym_begin >> 4) + (uint64_t)tile * kSketchThreads + threadIdx.x;
+        const uint64_t s0 = w << 4;
+        if ((uint64_t)((sym_begin >> 4) + (uint64_t)tile * kSketchThreads) << 4 >= sym_end) break;  // CTA-uniform
+        if (s0 >= sym_end) continue;
+
+        const uint32_t w0 = __ldg(a.codes + w);
+        const uint32_t w1 = w >= 1 ? __ldg(a.codes + w - 1) : 0u;
+        const uint32_t w2 = w >= 2 ? __ldg(a.codes + w - 2) : 0u;
+        const uint64_t iw = w >> 1;
+        const uint32_t i0 = __ldg(a.invalid + iw);
+        const uint32_t i1 = iw >= 1 ? __ldg(a.invalid + iw - 1) : 0xffffffffu;  // before the stream: breaks
+        const uint32_t r0 = revcomp_word(w0), r1 = revcomp_word(w1), r2 = revcomp_word(w2);
+        const bool all_valid = (i0 | i1) == 0u;
+
+        const int j_lo = sym_begin > s0 ? (int)(sym_begin - s0) : 0;
+        const int j_hi = sym_end - s0 < 16 ? (int)(sym_end - s0) : 16;
+        const uint32_t sm_base = (uint32_t)(s0 & 31);
+
+#pragma unroll 1
+        for (int j = j_lo; j < j_hi; ++j) {
+            const Window win = window_at(w0, w1, w2, r0, r1, r2, j);
+            const int run = all_valid ? 32 : valid_run(invalid_window(i0, i1, sm_base + (uint32_t)j));
+            if (run == 0) continue;
+            update_all_k<kCanon>(std::make_integer_sequence<int, 32>{}, win, run, a.kmask, a.kmask_run, a.p, a.acc,
+                                 floor4, s_seen);
+        }
     }
 }
 
@@ -179,52 +224,59 @@ __global__ void floor_publish_kernel(SketchWsHeader *hdr, const uint32_t *scratc
     if (i == 0) hdr->use_floor = 1;
 }
 
-// ---- finalisation: u32 accumulators -> u8 registers (+ histogram) -------------------------------
-constexpr int kFinThreads = 128;
-constexpr int kFinSlices = 8;  // CTAs per table
+// ---- finalisation: u16 accumulators -> u8 registers (+ histogram) -------------------------------
+constexpr int kFinOctPerThread = 30;                                   // 30 x 8 = 240 registers <= 255 per flush
+constexpr int kFinChunk = kPhThreads * kFinOctPerThread * 8;           // registers per CTA
 
-__global__ void __launch_bounds__(kFinThreads)
+__global__ void __launch_bounds__(kPhThreads)
 finalize_kernel(const uint32_t *__restrict__ acc, int p, uint8_t *__restrict__ regs, uint32_t *__restrict__ hist) {
-    // thread-private histograms, [bin][thread] so that a warp's 32 increments hit 32 banks
-    __shared__ uint32_t s_hist[DD_HIST_BINS * kFinThreads];
+    __shared__ __align__(16) uint8_t s_hist[kPhBytes];
+    const uint32_t slot = ph_slot();
     const size_t m = (size_t)1 << p;
     const int table = blockIdx.y;
     // 8 u16 accumulators (one uint4) -> 8 u8 registers (one uint2)
     const uint4 *src = reinterpret_cast<const uint4 *>(acc + (size_t)table * (m / 2));
     uint2 *dst = reinterpret_cast<uint2 *>(regs + (size_t)table * m);
-    if (hist)
-        for (int i = threadIdx.x; i < DD_HIST_BINS * kFinThreads; i += kFinThreads) s_hist[i] = 0;
+    if (hist) ph_zero(s_hist);
     __syncthreads();
     const size_t noct = m / 8;
-    const size_t per = (noct + gridDim.x - 1) / gridDim.x;
-    const size_t q0 = (size_t)blockIdx.x * per, q1 = min(noct, q0 + per);
-    for (size_t q = q0 + threadIdx.x; q < q1; q += kFinThreads) {
-        const uint4 v = __ldcs(src + q);
-        // bytes 0 and 2 of each word are the low bytes of its two u16 registers (ranks < 256)
-        const uint2 out = make_uint2(__byte_perm(v.x, v.y, 0x6420), __byte_perm(v.z, v.w, 0x6420));
-        dst[q] = out;
-        if (hist) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                s_hist[min((out.x >> (8 * b)) & 0xffu, 63u) * kFinThreads + threadIdx.x]++;
-                s_hist[min((out.y >> (8 * b)) & 0xffu, 63u) * kFinThreads + threadIdx.x]++;
+    const size_t q0 = (size_t)blockIdx.x * (kFinChunk / 8);
+#pragma unroll 5
+    for (int i = 0; i < kFinOctPerThread; ++i) {
+        const size_t q = q0 + (size_t)i * kPhThreads + threadIdx.x;
+        if (q < noct) {
+            const uint4 v = __ldcs(src + q);
+            // bytes 0 and 2 of each word are the low bytes of its two u16 registers (ranks < 256)
+            const uint2 out = make_uint2(__byte_perm(v.x, v.y, 0x6420), __byte_perm(v.z, v.w, 0x6420));
+            dst[q] = out;
+            if (hist) {
+                ph_add_word(s_hist, slot, out.x);
+                ph_add_word(s_hist, slot, out.y);
             }
         }
     }
     if (!hist) return;
     __syncthreads();
-    // bin totals: warp w sums bins w, w+4, ...
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int b = warp; b < DD_HIST_BINS; b += kFinThreads / 32) {
-        uint32_t s = 0;
-        for (int t = lane; t < kFinThreads; t += 32) s += s_hist[b * kFinThreads + t];
-        s = __reduce_add_sync(0xffffffffu, s);
-        if (lane == 0 && s) atomicAdd(&hist[(size_t)table * DD_HIST_BINS + b], s);
-    }
+    ph_flush(s_hist, hist + (size_t)table * DD_HIST_BINS);
 }
 
 // ---- host side ----------------------------------------------------------------------------------
 int g_k_per_pass = 0;  // tuning knob, see dd_set_option("sketch_k_per_pass", n)
+
+// SM count x resident CTAs per SM for the persistent (small-k) launch, cached per variant.
+static unsigned persistent_grid(bool canon, size_t smem) {
+    static unsigned cached[2] = {0, 0};
+    unsigned &g = cached[canon ? 1 : 0];
+    if (g == 0) {
+        int dev = 0, sms = 148, per_sm = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (canon) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_allk_kernel<true>, kSketchThreads, smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_allk_kernel<false>, kSketchThreads, smem);
+        g = (unsigned)(sms * (per_sm > 0 ? per_sm : 1));
+    }
+    return g;
+}
 
 size_t sketch_workspace_bytes(int nk, int p) {
     return sizeof(SketchWsHeader) + 256 + (size_t)nk * sizeof(uint16_t) * ((size_t)1 << p);
@@ -255,7 +307,9 @@ cudaError_t sketch_update(const uint32_t *d_codes, const uint32_t *d_invalid, co
     if (nsym == 0) return cudaSuccess;
     // +2 words: the range may start and end in the middle of a word
     const size_t nwords = (nsym + 15) / 16 + 2;
-    const unsigned grid = (unsigned)((nwords + kSketchThreads - 1) / kSketchThreads);
+    const size_t ntiles = (nwords + kSketchThreads - 1) / kSketchThreads;
+    if (ntiles > 0xffffffffull) return cudaErrorInvalidValue;
+    a.ntiles = (uint32_t)ntiles;
     // Optionally split the k set over several launches so that the accumulators touched by one
     // launch (2^(p+1) bytes per k) stay L2-resident; 0 = all k in one launch.
     const int per_pass = g_k_per_pass > 0 ? g_k_per_pass : 32;
@@ -268,8 +322,17 @@ cudaError_t sketch_update(const uint32_t *d_codes, const uint32_t *d_invalid, co
             todo ^= low;
         }
         a.kmask_run = run;
-        if (canon) sketch_allk_kernel<true><<<grid, kSketchThreads, 0, stream>>>(a);
-        else sketch_allk_kernel<false><<<grid, kSketchThreads, 0, stream>>>(a);
+        // Small k present: persistent CTAs (they must live long for their bitmaps to pay off) with
+        // the bitmaps in dynamic shared memory; otherwise one CTA per tile and no shared memory.
+        const bool small_k = (run & kSmallKMask) != 0u;
+        const size_t smem = small_k ? kBitmapWords * sizeof(uint32_t) : 0;
+        unsigned grid = (unsigned)ntiles;
+        if (small_k) {
+            const unsigned resident = persistent_grid(canon != 0, smem);
+            if (grid > resident) grid = resident;
+        }
+        if (canon) sketch_allk_kernel<true><<<grid, kSketchThreads, smem, stream>>>(a);
+        else sketch_allk_kernel<false><<<grid, kSketchThreads, smem, stream>>>(a);
     }
     return cudaGetLastError();
 }
@@ -288,7 +351,8 @@ cudaError_t sketch_end(void *d_ws, int nk, int p, uint8_t *d_regs, uint32_t *d_h
     cudaError_t e;
     if (d_hist && (e = cudaMemsetAsync(d_hist, 0, (size_t)nk * DD_HIST_BINS * sizeof(uint32_t), stream)) != cudaSuccess)
         return e;
-    finalize_kernel<<<dim3(kFinSlices, nk), kFinThreads, 0, stream>>>(ws_acc(d_ws), p, d_regs, d_hist);
+    const unsigned slices = (unsigned)((((size_t)1 << p) + kFinChunk - 1) / kFinChunk);
+    finalize_kernel<<<dim3(slices, nk), kPhThreads, 0, stream>>>(ws_acc(d_ws), p, d_regs, d_hist);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (d_hist && d_cards) return mle_from_hist(d_hist, nk, p, d_cards, stream);
     return cudaSuccess;

@@ -136,9 +136,12 @@ class Engine:
 
     # ---- K2 (+K4 for the leaf cardinalities) ------------------------------------------------------
     def sketch(self, seq: PackedSeq, ks: Sequence[int], p: int = 20, canon: bool = True,
-               out: Optional[torch.Tensor] = None, ranges=None, floor_every: Optional[int] = None):
+               out: Optional[torch.Tensor] = None, ranges=None, floor_every: Optional[int] = None,
+               hist_out: Optional[torch.Tensor] = None):
         """All-k HLL sketch of one packed sequence.  Returns (regs [nk, 2^p] uint8, cards [nk] f64),
-        both on the device.  `ranges` (list of (begin, end) symbol ranges) forces chunked updates."""
+        both on the device.  `ranges` (list of (begin, end) symbol ranges) forces chunked updates.
+        With `hist_out` ([nk, 64] int32) the register histograms go there and the estimator is left to
+        a later batched mle() call (cards is then None): one MLE launch per batch, not per genome."""
         kmask = kmask_of(ks)
         nk = bin(kmask).count("1")
         m = 1 << p
@@ -147,8 +150,10 @@ class Engine:
         st = self.stream
         regs = out if out is not None else torch.empty((nk, m), dtype=torch.uint8, device=self.device)
         assert regs.is_contiguous() and regs.numel() == nk * m
-        hist = torch.empty((nk, DD_HIST_BINS), dtype=torch.int32, device=self.device)
-        cards = torch.empty(nk, dtype=torch.float64, device=self.device)
+        defer = hist_out is not None
+        hist = hist_out if defer else torch.empty((nk, DD_HIST_BINS), dtype=torch.int32, device=self.device)
+        assert hist.is_contiguous() and hist.numel() == nk * DD_HIST_BINS
+        cards = None if defer else torch.empty(nk, dtype=torch.float64, device=self.device)
         check(self.lib.dd_sketch_begin(ws.data_ptr(), ws.numel(), nk, p, st), "dd_sketch_begin")
         if ranges is None and floor_every:
             n = seq.nsym                      # needs the symbol count on the host: one sync
@@ -164,9 +169,16 @@ class Engine:
                 seen += e - b
                 if floor_every and seen >= (16 << p):
                     check(self.lib.dd_sketch_refresh_floor(ws.data_ptr(), ws.numel(), kmask, p, st), "dd_sketch_refresh_floor")
-        check(self.lib.dd_sketch_end(ws.data_ptr(), ws.numel(), nk, p, regs.data_ptr(), hist.data_ptr(), cards.data_ptr(), st),
-              "dd_sketch_end")
+        check(self.lib.dd_sketch_end(ws.data_ptr(), ws.numel(), nk, p, regs.data_ptr(), hist.data_ptr(),
+                                     None if defer else cards.data_ptr(), st), "dd_sketch_end")
         return regs, cards
+
+    def mle(self, hist: torch.Tensor, p: int) -> torch.Tensor:
+        """Ertl-MLE cardinalities from register histograms [..., 64] (int32, device)."""
+        flat = hist.contiguous().view(-1, DD_HIST_BINS)
+        out = torch.empty(flat.shape[0], dtype=torch.float64, device=self.device)
+        check(self.lib.dd_mle_from_hist(flat.data_ptr(), flat.shape[0], p, out.data_ptr(), self.stream), "dd_mle_from_hist")
+        return out.view(hist.shape[:-1])
 
     def _update_from_state(self, seq, kmask, p, canon, ws, st):
         # the pack state says [prev_nsym, nsym); for a whole-stream sketch rewind prev_nsym to 0

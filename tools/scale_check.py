@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Human-scale check of the sketch path (config 3 shape): chromosome-like records,
+1 % N runs, 50 % soft-masked (lower-case) bases, k = 2..32 (31 k), p = 20, generated on the GPU.
+
+For each size: pack time, all-k sketch time with and without the min-register floor filter, Gbp/s,
+and the invariants that need no oracle (floor on/off give identical registers; sketching the
+concatenation equals the max of the parts).  At <= 200 Mbp one k is also checked bit-exact against
+the CPU oracle.  Usage: python tools/scale_check.py [--sizes 100e6,1e9,3.1e9]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def synth_fasta(n_bases: int, n_records: int, seed: int, device) -> torch.Tensor:
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lens = torch.full((n_records,), n_bases // n_records, dtype=torch.int64)
+    lens[-1] += n_bases - int(lens.sum())
+    pieces = []
+    for r, ln in enumerate(lens.tolist()):
+        ln80 = (ln // 80) * 80
+        c = torch.randint(0, 4, (ln80,), dtype=torch.uint8, device=device, generator=g)
+        b = 65 + 2 * (c == 1).to(torch.uint8) + 6 * (c == 2).to(torch.uint8) + 19 * (c == 3).to(torch.uint8)
+        del c
+        low = torch.randint(0, 2, (ln80,), dtype=torch.uint8, device=device, generator=g)
+        b |= low * 32
+        del low
+        nruns = max(1, ln80 // 100000)               # ~1 % of the bases in N runs of 1000
+        starts = torch.randint(0, max(1, ln80 - 1000), (nruns,), device=device, generator=g)
+        idx = (starts[:, None] + torch.arange(1000, device=device)[None, :]).reshape(-1)
+        b[idx] = 78
+        body = torch.cat([b.view(-1, 80), torch.full((ln80 // 80, 1), 10, dtype=torch.uint8, device=device)], dim=1).reshape(-1)
+        head = torch.tensor(list(f">chr{r + 1} synthetic length={ln80}\n".encode()), dtype=torch.uint8, device=device)
+        pieces += [head, body]
+    return torch.cat(pieces)
+
+
+def timed(fn):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return out, e0.elapsed_time(e1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", default="100e6,1e9")
+    ap.add_argument("--chunk", type=float, default=64e6)
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--per-k", action="store_true", help="also time every k on its own (floor filter on)")
+    args = ap.parse_args()
+    from dandd_b200 import build
+    build.build()
+    from dandd_b200.engine import Engine
+    eng = Engine(0)
+    ks, p = list(range(2, 33)), 20
+    report = []
+    for size in [int(float(s)) for s in args.sizes.split(",")]:
+        text = synth_fasta(size, 24, seed=3, device=eng.device)
+        seq = eng.pack(text, start=0)                                   # first call pays the allocations
+        del seq
+        seq, t_pack = timed(lambda: eng.pack(text, start=0))
+        nsym = seq.nsym
+        eng.sketch(seq, [21], p=p)                                       # warm-up
+        (r_floor, c_floor), t_floor = timed(lambda: eng.sketch(seq, ks, p=p, floor_every=int(args.chunk)))
+        row = {"bases": size, "text_bytes": int(text.numel()), "symbols": nsym, "pack_ms": t_pack,
+               "sketch_floor_ms": t_floor, "gbp_s_floor": size / t_floor / 1e6, "chunk": int(args.chunk),
+               "pack_gb_s": text.numel() / t_pack / 1e6}
+        if size <= 1.2e9:
+            (r_plain, _), t_plain = timed(lambda: eng.sketch(seq, ks, p=p))
+            row.update(sketch_plain_ms=t_plain, gbp_s_plain=size / t_plain / 1e6,
+                       floor_equals_plain=bool((r_plain == r_floor).all()))
+            del r_plain
+        if size <= 2e8:
+            from oracle import pyoracle as orc
+            sym = orc.fasta_symbols(text.cpu().numpy().tobytes())
+            t0 = time.perf_counter()
+            want = orc.hll_sketch(sym, 21, p)
+            row.update(oracle_k21_s=time.perf_counter() - t0, oracle_k21_equal=bool(np.array_equal(r_floor[19].cpu().numpy(), want)),
+                       nsym_equal=bool(sym.size == nsym))
+        if args.per_k:
+            row["per_k_ms"] = {}
+            for k in ks:
+                _, t = timed(lambda: eng.sketch(seq, [k], p=p, floor_every=int(args.chunk)))
+                row["per_k_ms"][k] = round(t, 2)
+        cards = c_floor.cpu().numpy()
+        deltas = cards / np.array(ks)
+        row.update(argmax_k=int(ks[int(np.argmax(deltas))]), delta=float(deltas.max()))
+        report.append(row)
+        print(json.dumps(row), flush=True)
+        del text, seq, r_floor
+        torch.cuda.empty_cache()
+    if args.out:
+        with open(args.out, "w") as fh:
+            json.dump(report, fh, indent=1)
+
+
+if __name__ == "__main__":
+    main()
