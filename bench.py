@@ -249,6 +249,31 @@ def run_ours(args):
             out.append(full.cpu())
         return out
 
+    def breakdown():
+        """DD_BENCH_BREAKDOWN=1: per-rank wall/GPU time of each phase of one step (diagnostics)."""
+        def phase(fn):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return out, round(e0.elapsed_time(e1), 3), round((time.perf_counter() - t0) * 1e3, 3)
+
+        def sketch_all():
+            for g, dt in enumerate(d_texts):
+                eng.sketch(eng.pack(dt, start=0), KS, p=P, out=regs[g], hist_out=leaf_hist[g])
+        rep = {"rank": rank}
+        _, rep["sketch_gpu_ms"], rep["sketch_wall_ms"] = phase(sketch_all)
+        _, rep["mle_gpu_ms"], rep["mle_wall_ms"] = phase(lambda: eng.mle(leaf_hist, P))
+        _, rep["prefix_gpu_ms"], rep["prefix_wall_ms"] = phase(lambda: eng.prefix_union_cards(regs, orders, P))
+        if world > 1:
+            full, rep["union_gpu_ms"], rep["union_wall_ms"] = phase(lambda: eng.union([regs[g] for g in range(N_GENOMES)]))
+            _, rep["allreduce_gpu_ms"], rep["allreduce_wall_ms"] = phase(lambda: dd_dist.union_over_ranks(full))
+            _, rep["cards_gpu_ms"], rep["cards_wall_ms"] = phase(lambda: eng.cards(full, P))
+        print("BREAKDOWN " + json.dumps(rep), file=sys.stderr, flush=True)
+
     def sync():
         torch.cuda.synchronize()
         if world > 1:
@@ -285,6 +310,16 @@ def run_ours(args):
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    if world > 1:
+        # NCCL builds channels lazily over its first calls; keep that out of the timed region
+        warm = torch.zeros((nk, m), dtype=torch.uint8, device=dev)
+        for _ in range(8):
+            dd_dist.union_over_ranks(warm)
+        for _ in range(2):
+            step_resident()
+    if os.environ.get("DD_BENCH_BREAKDOWN"):
+        breakdown()
+        breakdown()
     sampler.active = True
     ms_step, res = timed(lambda: step_resident(time_k2=True), args.steps)
     sampler.active = False

@@ -4,7 +4,9 @@
 // lib/sketch_classes.py:351-366, 434-449).  HBM-streaming kernel: every text byte is read with
 // 128-bit loads (twice: a counting pass and a writing pass; the chunk is L2-resident for the second
 // when the host streams in <= 64 MiB chunks), output is 0.375 B/symbol, staged through shared
-// memory so that the global stores are whole, coalesced words.
+// memory so that the global stores are whole, coalesced words.  A thread owns 64 contiguous text
+// bytes (four 128-bit loads in flight at once) and a CTA a 16 KiB tile, so there is one block scan
+// per 16 KiB of text.
 //
 // The only sequential dependence in FASTA text is "am I inside a header line?".  Each 16-byte
 // chunk is summarised as a transition function over that one bit (dd::chunk_xfer) and the
@@ -18,9 +20,9 @@
 namespace dd {
 
 constexpr int kPackThreads = 256;
-constexpr int kPackRows = 1;  // 4 KiB tiles: ~1200 CTAs for a 5 MB genome keep every SM busy
-constexpr int kRowBytes = kPackThreads * 16;      // 4096
-constexpr int kTileBytes = kRowBytes * kPackRows;
+constexpr int kSpanChunks = 4;                         // 16-byte chunks per thread, contiguous in the text
+constexpr int kSpanBytes = 16 * kSpanChunks;           // 64
+constexpr int kTileBytes = kPackThreads * kSpanBytes;  // 16 KiB per CTA, one block scan per tile
 constexpr int kScanThreads = 1024;
 
 struct PackWsHeader {
@@ -80,9 +82,34 @@ __device__ __forceinline__ uint64_t block_scan_xfer(uint64_t f, uint64_t *s_warp
     return xfer_compose(pre, excl);
 }
 
-__device__ __forceinline__ bool chunk_at_line_start(const uint8_t *__restrict__ text, size_t off, uint32_t entry_last) {
-    const uint32_t prev = off == 0 ? entry_last : (uint32_t)text[off - 1];
-    return prev == '\n';
+// A thread's 64-byte span: the masks of its four chunks, whether each chunk starts a line, and
+// the span's transition function.  All four 128-bit loads are issued before any is used.
+struct Span {
+    ChunkMasks m[kSpanChunks];
+    uint32_t ls;  // bit c: chunk c starts at a line start
+    uint64_t f;
+};
+
+__device__ __forceinline__ Span load_span(const uint8_t *__restrict__ text, size_t off, size_t n, bool aligned,
+                                          uint32_t entry_last) {
+    Span sp;
+    sp.f = kXferIdentity;
+    sp.ls = 0;
+    uint4 v[kSpanChunks];
+#pragma unroll
+    for (int c = 0; c < kSpanChunks; ++c)
+        v[c] = (off + 16 * c < n) ? load_text16(text, off + 16 * c, n, aligned)
+                                  : make_uint4(0x0d0d0d0du, 0x0d0d0d0du, 0x0d0d0d0du, 0x0d0d0d0du);
+    uint32_t prev = off == 0 ? entry_last : (off <= n ? (uint32_t)text[off - 1] : (uint32_t)kPadByte);
+#pragma unroll
+    for (int c = 0; c < kSpanChunks; ++c) {
+        sp.m[c] = classify16(v[c].x, v[c].y, v[c].z, v[c].w);
+        const bool ls = prev == '\n';
+        sp.ls |= (ls ? 1u : 0u) << c;
+        sp.f = xfer_compose(sp.f, chunk_xfer(sp.m[c], ls));
+        prev = v[c].w >> 24;
+    }
+    return sp;
 }
 
 // ---- pass A: one transition function per tile -------------------------------------------------
@@ -90,23 +117,12 @@ __global__ void __launch_bounds__(kPackThreads)
 pack_count_kernel(const uint8_t *__restrict__ text, size_t n, const dd_pack_state *__restrict__ st,
                   uint64_t *__restrict__ tile_xfer) {
     __shared__ uint64_t s_warp[32];
-    const size_t base = (size_t)blockIdx.x * kTileBytes;
+    const size_t off = (size_t)blockIdx.x * kTileBytes + (size_t)threadIdx.x * kSpanBytes;
     const bool aligned = (reinterpret_cast<uintptr_t>(text) & 15) == 0;
-    const uint32_t entry_last = st->last_byte;
-    uint64_t tile = kXferIdentity;
-#pragma unroll 1
-    for (int r = 0; r < kPackRows; ++r) {
-        const size_t off = base + (size_t)r * kRowBytes + (size_t)threadIdx.x * 16;
-        uint64_t f = kXferIdentity;
-        if (off < n) {
-            const uint4 v = load_text16(text, off, n, aligned);
-            const ChunkMasks m = classify16(v.x, v.y, v.z, v.w);
-            f = chunk_xfer(m, chunk_at_line_start(text, off, entry_last));
-        }
-        uint64_t row;
-        block_scan_xfer(f, s_warp, &row);
-        tile = xfer_compose(tile, row);
-    }
+    uint64_t f = kXferIdentity;
+    if (off < n) f = load_span(text, off, n, aligned, st->last_byte).f;
+    uint64_t tile;
+    block_scan_xfer(f, s_warp, &tile);
     if (threadIdx.x == 0) tile_xfer[blockIdx.x] = tile;
 }
 
@@ -181,82 +197,71 @@ pack_write_kernel(const uint8_t *__restrict__ text, size_t n, const PackTileOut 
                   const dd_pack_state *__restrict__ st, uint32_t *__restrict__ codes, uint32_t *__restrict__ invalid,
                   size_t cap_symbols) {
     __shared__ uint64_t s_warp[32];
-    __shared__ __align__(16) uint8_t s_stage[kRowBytes + 64];
+    __shared__ __align__(16) uint8_t s_stage[kTileBytes + 64];
     const size_t tile = blockIdx.x;
-    const size_t base = tile * kTileBytes;
+    const size_t off = tile * kTileBytes + (size_t)threadIdx.x * kSpanBytes;
     const bool aligned = (reinterpret_cast<uintptr_t>(text) & 15) == 0;
-    const uint32_t entry_last = hdr->entry_last_byte;
-    uint32_t row_state = (uint32_t)tile_out[tile].state;
-    uint64_t g_row = st->prev_nsym + seg_base[tile / hdr->seg_len] + tile_out[tile].local_off;
+    const uint32_t tile_state = (uint32_t)tile_out[tile].state;
+    const uint64_t g_tile = st->prev_nsym + seg_base[tile / hdr->seg_len] + tile_out[tile].local_off;
     const size_t cap_words16 = (cap_symbols + 15) >> 4, cap_words32 = (cap_symbols + 31) >> 5;
 
-#pragma unroll 1
-    for (int r = 0; r < kPackRows; ++r) {
-        const size_t off = base + (size_t)r * kRowBytes + (size_t)threadIdx.x * 16;
-        ChunkMasks m = {0, 0, 0, 0, 0};
-        bool ls = false;
-        uint64_t f = kXferIdentity;
-        if (off < n) {
-            const uint4 v = load_text16(text, off, n, aligned);
-            m = classify16(v.x, v.y, v.z, v.w);
-            ls = chunk_at_line_start(text, off, entry_last);
-            f = chunk_xfer(m, ls);
-        }
-        uint64_t row;
-        const uint64_t pre = block_scan_xfer(f, s_warp, &row);
-        const uint32_t my_state = xfer_end(pre, row_state);
-        const uint32_t my_off = xfer_cnt(pre, row_state);
-        const uint32_t row_cnt = xfer_cnt(row, row_state);
-        const uint32_t lead = (uint32_t)(g_row & 31);
+    // symbols are staged as bytes (bits 1:0 code, bit 2 break) at their position in the output
+    // stream relative to the 32-symbol boundary below g_tile, so that pack-out writes whole words
+    for (int i = threadIdx.x; i < (kTileBytes + 64) / 16; i += kPackThreads)
+        reinterpret_cast<uint4 *>(s_stage)[i] = make_uint4(0, 0, 0, 0);
 
-        // zero the staging row (block_scan_xfer ended with a barrier-free read phase; the
-        // barrier below orders the previous row's pack-out reads before these writes)
-        __syncthreads();
-        for (int i = threadIdx.x; i < (kRowBytes + 64) / 16; i += kPackThreads)
-            reinterpret_cast<uint4 *>(s_stage)[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-        if (off < n) {
-            const ChunkSyms cs = chunk_symbols(m, ls, my_state != 0);
-            uint32_t rem = cs.sym, o = lead + my_off;
+    Span sp;
+    sp.f = kXferIdentity;
+    if (off < n) sp = load_span(text, off, n, aligned, hdr->entry_last_byte);
+    uint64_t all;
+    const uint64_t pre = block_scan_xfer(sp.f, s_warp, &all);  // its barriers also order the zeroing above
+    const uint32_t tile_cnt = xfer_cnt(all, tile_state);
+    const uint32_t lead = (uint32_t)(g_tile & 31);
+    if (off < n) {
+        uint32_t state = xfer_end(pre, tile_state);
+        uint32_t o = lead + xfer_cnt(pre, tile_state);
+#pragma unroll
+        for (int c = 0; c < kSpanChunks; ++c) {
+            const ChunkSyms cs = chunk_symbols(sp.m[c], (sp.ls >> c) & 1u, state != 0);
+            uint32_t rem = cs.sym;
             while (rem) {
                 const int i = __ffs((int)rem) - 1;
                 rem &= rem - 1;
-                s_stage[o++] = (uint8_t)(((m.codes >> (2 * i)) & 3u) | (((cs.brk >> i) & 1u) << 2));
+                s_stage[o++] = (uint8_t)(((sp.m[c].codes >> (2 * i)) & 3u) | (((cs.brk >> i) & 1u) << 2));
             }
+            state = cs.end_hdr;
         }
-        __syncthreads();
-        // pack-out: one 32-symbol group per thread
-        const uint32_t span = lead + row_cnt;  // staged extent
-        const uint32_t ngroups = (span + 31) >> 5;
-        const uint64_t g_base = g_row - lead;  // multiple of 32
-        for (uint32_t g = threadIdx.x; g < ngroups; g += kPackThreads) {
-            const uint4 a = reinterpret_cast<const uint4 *>(s_stage)[2 * g];
-            const uint4 b = reinterpret_cast<const uint4 *>(s_stage)[2 * g + 1];
-            const uint32_t c0 = (pack_codes4(a.x) << 24) | (pack_codes4(a.y) << 16) | (pack_codes4(a.z) << 8) | pack_codes4(a.w);
-            const uint32_t c1 = (pack_codes4(b.x) << 24) | (pack_codes4(b.y) << 16) | (pack_codes4(b.z) << 8) | pack_codes4(b.w);
-            const uint32_t iv = (pack_breaks4(a.x) << 28) | (pack_breaks4(a.y) << 24) | (pack_breaks4(a.z) << 20) |
-                                (pack_breaks4(a.w) << 16) | (pack_breaks4(b.x) << 12) | (pack_breaks4(b.y) << 8) |
-                                (pack_breaks4(b.z) << 4) | pack_breaks4(b.w);
-            const uint32_t s0 = 32 * g;
-            const uint64_t w32 = (g_base >> 5) + g;
-            const uint64_t w16 = w32 * 2;
-            // a word wholly produced by this row is stored; a word shared with a neighbouring row,
-            // tile or chunk is OR-ed (buffers are zero-filled by dd_pack_reset)
-            if (w16 < cap_words16) {
-                if (s0 >= lead && s0 + 16 <= span) codes[w16] = c0;
-                else if (c0) atomicOr(&codes[w16], c0);
-            }
-            if (w16 + 1 < cap_words16) {
-                if (s0 + 16 >= lead && s0 + 32 <= span) codes[w16 + 1] = c1;
-                else if (c1) atomicOr(&codes[w16 + 1], c1);
-            }
-            if (w32 < cap_words32) {
-                if (s0 >= lead && s0 + 32 <= span) invalid[w32] = iv;
-                else if (iv) atomicOr(&invalid[w32], iv);
-            }
+    }
+    __syncthreads();
+    // pack-out: one 32-symbol group per thread and iteration
+    const uint32_t span = lead + tile_cnt;  // staged extent
+    const uint32_t ngroups = (span + 31) >> 5;
+    const uint64_t g_base = g_tile - lead;  // multiple of 32
+    for (uint32_t g = threadIdx.x; g < ngroups; g += kPackThreads) {
+        const uint4 a = reinterpret_cast<const uint4 *>(s_stage)[2 * g];
+        const uint4 b = reinterpret_cast<const uint4 *>(s_stage)[2 * g + 1];
+        const uint32_t c0 = (pack_codes4(a.x) << 24) | (pack_codes4(a.y) << 16) | (pack_codes4(a.z) << 8) | pack_codes4(a.w);
+        const uint32_t c1 = (pack_codes4(b.x) << 24) | (pack_codes4(b.y) << 16) | (pack_codes4(b.z) << 8) | pack_codes4(b.w);
+        const uint32_t iv = (pack_breaks4(a.x) << 28) | (pack_breaks4(a.y) << 24) | (pack_breaks4(a.z) << 20) |
+                            (pack_breaks4(a.w) << 16) | (pack_breaks4(b.x) << 12) | (pack_breaks4(b.y) << 8) |
+                            (pack_breaks4(b.z) << 4) | pack_breaks4(b.w);
+        const uint32_t s0 = 32 * g;
+        const uint64_t w32 = (g_base >> 5) + g;
+        const uint64_t w16 = w32 * 2;
+        // a word wholly produced by this tile is stored; a word shared with a neighbouring tile or
+        // chunk is OR-ed (the buffers are zero-filled by dd_pack_reset)
+        if (w16 < cap_words16) {
+            if (s0 >= lead && s0 + 16 <= span) codes[w16] = c0;
+            else if (c0) atomicOr(&codes[w16], c0);
         }
-        row_state = xfer_end(row, row_state);
-        g_row += row_cnt;
+        if (w16 + 1 < cap_words16) {
+            if (s0 + 16 >= lead && s0 + 32 <= span) codes[w16 + 1] = c1;
+            else if (c1) atomicOr(&codes[w16 + 1], c1);
+        }
+        if (w32 < cap_words32) {
+            if (s0 >= lead && s0 + 32 <= span) invalid[w32] = iv;
+            else if (iv) atomicOr(&invalid[w32], iv);
+        }
     }
 }
 
