@@ -90,30 +90,38 @@ __device__ __forceinline__ uint64_t mad64x32(uint64_t x, uint32_t c, uint64_t ad
     return r;
 }
 
-// Max-update of one u16 register packed two to a word (see the header comment).
-__device__ __forceinline__ void red_max_u16(uint32_t *word, uint32_t half, uint32_t rank) {
-    const uint32_t val = rank << (16u * half);  // the untouched half carries +0.0
-    asm volatile("{ .reg .b16 l, h; mov.b32 {l, h}, %1; red.global.max.noftz.v2.f16 [%0], {l, h}; }" ::"l"(word), "r"(val)
-                 : "memory");
+// Canonical (or forward) k-mer ending at the current symbol.  For K <= 16 the whole k-mer lives in
+// one 32-bit register: mask, shift and min are single instructions.
+template <int K, bool kCanon>
+__device__ __forceinline__ uint64_t kmer_of(const Window &win) {
+    if constexpr (K <= 16) {
+        const uint32_t f = (uint32_t)win.fwd & (K == 16 ? 0xffffffffu : ((1u << (2 * (K & 15))) - 1u));
+        if (!kCanon) return f;
+        const uint32_t r = (uint32_t)(win.rc >> 32) >> (32 - 2 * K);
+        return min(f, r);
+    } else {
+        return kmer_value<K>(win, kCanon);
+    }
 }
 
-// One (symbol, k) update.  Branch-free apart from the warp-uniform "is this k requested" tests:
-// an invalid window only predicates the RED off, so neighbouring k bodies can be interleaved.
+// One (symbol, k) update.  `live` says whether this lane has a valid k-mer of this length; the
+// warp stays converged (dead lanes are only predicated off the shared-memory and global updates),
+// so the small-k early exit is a plain full-warp vote.
 template <int K, bool kCanon>
 __device__ __forceinline__ void update_one_k(const Window &win, int run, uint32_t kmask, uint32_t kmask_run, int p,
                                              uint32_t *acc, uint32_t &off_k, const uint32_t (&floor4)[8],
                                              uint32_t *s_seen) {
     if (!((kmask >> (K - 1)) & 1u)) return;  // warp-uniform
     if ((kmask_run >> (K - 1)) & 1u) {       // warp-uniform
-        const uint64_t v = kmer_value<K>(win, kCanon);
+        const uint64_t v = kmer_of<K, kCanon>(win);
+        bool live = run >= K;
         if (K <= kBitmapMaxK) {
             // already sent by this CTA?  (a racing duplicate only repeats an idempotent update)
             uint32_t *word = s_seen + bitmap_offset(K) + ((uint32_t)v >> 5);
             const uint32_t bit = 1u << ((uint32_t)v & 31u);
-            const bool fresh = run >= K && !(*word & bit);
-            if (fresh) atomicOr(word, bit);
-            if (!fresh) run = 0;             // nothing to do for this lane
-            if (__all_sync(__activemask(), !fresh)) {
+            live = live && !(*word & bit);
+            if (live) atomicOr(word, bit);
+            if (!__any_sync(0xffffffffu, live)) {
                 off_k += 1u << (p - 1);
                 return;
             }
@@ -131,8 +139,13 @@ __device__ __forceinline__ void update_one_k(const Window &win, int run, uint32_
         const uint32_t rem_hi = hi & (0xffffffffu >> p);
         const uint32_t rank = (rem_hi ? (uint32_t)__clz((int)rem_hi) : 32u + (uint32_t)__clz((int)lo)) + 1u - (uint32_t)p;
         const uint32_t floor_k = (floor4[(K - 1) >> 2] >> (8 * ((K - 1) & 3))) & 0xffu;
-        const uint32_t idx = hi >> (32 - p);
-        if (run >= K && rank > floor_k) red_max_u16(acc + (off_k + (idx >> 1)), idx & 1u, rank);
+        if (live && rank > floor_k) {
+            // register idx = hi >> (32-p) lives in word idx>>1, half idx&1
+            const uint32_t val = rank << ((hi >> (28 - p)) & 16u);
+            uint32_t *word = acc + (off_k + (hi >> (33 - p)));
+            asm volatile("{ .reg .b16 l, h; mov.b32 {l, h}, %1; red.global.max.noftz.v2.f16 [%0], {l, h}; }" ::"l"(word), "r"(val)
+                         : "memory");
+        }
     }
     off_k += 1u << (p - 1);
 }
@@ -172,26 +185,27 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_allk_kernel(SketchArgs 
         const uint64_t w = (sym_begin >> 4) + (uint64_t)tile * kSketchThreads + threadIdx.x;
         const uint64_t s0 = w << 4;
         if ((uint64_t)((sym_begin >> 4) + (uint64_t)tile * kSketchThreads) << 4 >= sym_end) break;  // CTA-uniform
-        if (s0 >= sym_end) continue;
+        const bool in_range = s0 < sym_end;   // lanes past the end stay in the loop, predicated off
 
-        const uint32_t w0 = __ldg(a.codes + w);
-        const uint32_t w1 = w >= 1 ? __ldg(a.codes + w - 1) : 0u;
-        const uint32_t w2 = w >= 2 ? __ldg(a.codes + w - 2) : 0u;
+        const uint32_t w0 = in_range ? __ldg(a.codes + w) : 0u;
+        const uint32_t w1 = in_range && w >= 1 ? __ldg(a.codes + w - 1) : 0u;
+        const uint32_t w2 = in_range && w >= 2 ? __ldg(a.codes + w - 2) : 0u;
         const uint64_t iw = w >> 1;
-        const uint32_t i0 = __ldg(a.invalid + iw);
-        const uint32_t i1 = iw >= 1 ? __ldg(a.invalid + iw - 1) : 0xffffffffu;  // before the stream: breaks
+        const uint32_t i0 = in_range ? __ldg(a.invalid + iw) : 0xffffffffu;
+        const uint32_t i1 = in_range && iw >= 1 ? __ldg(a.invalid + iw - 1) : 0xffffffffu;  // before the stream: breaks
         const uint32_t r0 = revcomp_word(w0), r1 = revcomp_word(w1), r2 = revcomp_word(w2);
         const bool all_valid = (i0 | i1) == 0u;
 
         const int j_lo = sym_begin > s0 ? (int)(sym_begin - s0) : 0;
-        const int j_hi = sym_end - s0 < 16 ? (int)(sym_end - s0) : 16;
+        const int j_hi = !in_range ? 0 : (sym_end - s0 < 16 ? (int)(sym_end - s0) : 16);
         const uint32_t sm_base = (uint32_t)(s0 & 31);
 
 #pragma unroll 1
-        for (int j = j_lo; j < j_hi; ++j) {
+        for (int j = 0; j < 16; ++j) {
             const Window win = window_at(w0, w1, w2, r0, r1, r2, j);
-            const int run = all_valid ? 32 : valid_run(invalid_window(i0, i1, sm_base + (uint32_t)j));
-            if (run == 0) continue;
+            int run = all_valid ? 32 : valid_run(invalid_window(i0, i1, sm_base + (uint32_t)j));
+            if (j < j_lo || j >= j_hi) run = 0;
+            if (!__any_sync(0xffffffffu, run != 0)) continue;  // warp-uniform
             update_all_k<kCanon>(std::make_integer_sequence<int, 32>{}, win, run, a.kmask, a.kmask_run, a.p, a.acc,
                                  floor4, s_seen);
         }
