@@ -54,6 +54,7 @@ SIGNATURES = {
     "dd_exact_count": (_i, [_vp, _sz, _i, _u64, _vp, _vp]),
     "dd_sketch_fasta_host_workspace_bytes": (_sz, [_sz, _i, _i]),
     "dd_sketch_fasta_host": (_i, [_vp, _sz, _u32, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dd_sketch_fasta_host_async": (_i, [_vp, _sz, _u32, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -290,8 +290,9 @@ size_t dd_sketch_fasta_host_workspace_bytes(size_t n_bytes, int nk, int p) {
     return carve(nullptr, n_bytes, nk, p).total + 256;
 }
 
-int dd_sketch_fasta_host(const uint8_t *h_text, size_t n_bytes, uint32_t kmask, int p, int canon, uint8_t *h_regs,
-                         double *h_cards, uint8_t *d_regs_or_null, void *d_ws, size_t ws_bytes, dd_stream stream) {
+static int sketch_fasta_host_impl(const uint8_t *h_text, size_t n_bytes, uint32_t kmask, int p, int canon, uint8_t *h_regs,
+                                  double *h_cards, uint8_t *d_regs_or_null, void *d_ws, size_t ws_bytes, dd_stream stream,
+                                  bool synchronize) {
     const int nk = popc(kmask);
     if (!h_text || !h_cards || !d_ws || nk == 0 || bad_p(p)) return fail(DD_ERR_ARG, "dd_sketch_fasta_host: bad argument");
     if (ws_bytes < dd_sketch_fasta_host_workspace_bytes(n_bytes, nk, p))
@@ -364,8 +365,20 @@ int dd_sketch_fasta_host(const uint8_t *h_text, size_t n_bytes, uint32_t kmask, 
     DD_CUDA(dd::sketch_end(w.sketch_ws, nk, p, d_regs, w.hist, w.cards, st), "sketch_end");
     DD_CUDA(cudaMemcpyAsync(h_cards, w.cards, (size_t)nk * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H cards");
     if (h_regs) DD_CUDA(cudaMemcpyAsync(h_regs, d_regs, (size_t)nk << p, cudaMemcpyDeviceToHost, st), "D2H regs");
-    DD_CUDA(cudaStreamSynchronize(st), "synchronize");
+    if (synchronize) DD_CUDA(cudaStreamSynchronize(st), "synchronize");
     return DD_OK;
+}
+
+int dd_sketch_fasta_host(const uint8_t *h_text, size_t n_bytes, uint32_t kmask, int p, int canon, uint8_t *h_regs,
+                         double *h_cards, uint8_t *d_regs_or_null, void *d_ws, size_t ws_bytes, dd_stream stream) {
+    return sketch_fasta_host_impl(h_text, n_bytes, kmask, p, canon, h_regs, h_cards, d_regs_or_null, d_ws, ws_bytes, stream,
+                                  true);
+}
+
+int dd_sketch_fasta_host_async(const uint8_t *h_text, size_t n_bytes, uint32_t kmask, int p, int canon, uint8_t *h_regs,
+                               double *h_cards, uint8_t *d_regs_or_null, void *d_ws, size_t ws_bytes, dd_stream stream) {
+    return sketch_fasta_host_impl(h_text, n_bytes, kmask, p, canon, h_regs, h_cards, d_regs_or_null, d_ws, ws_bytes, stream,
+                                  false);
 }
 
 }  // extern "C"

@@ -99,7 +99,7 @@ class Engine:
         hit = np.flatnonzero(arr == 62)
         return int(hit[0]) if hit.size else int(arr.size)
 
-    def pack(self, text, chunk_bytes: Optional[int] = None, start: Optional[int] = None) -> PackedSeq:
+    def pack(self, text, chunk_bytes: Optional[int] = None, start: Optional[int] = None, ws_tag: str = "pack") -> PackedSeq:
         """FASTA text (bytes / numpy / torch uint8) -> PackedSeq.  `chunk_bytes` packs in several
         chunks through the carried state (used by the tests to exercise streaming).  `start` = offset
         of the first '>' if the caller knows it (device-resident text is otherwise scanned for it)."""
@@ -122,7 +122,7 @@ class Engine:
         check(self.lib.dd_pack_reset(codes.data_ptr(), cb, invalid.data_ptr(), ib, state.data_ptr(), st), "dd_pack_reset")
         chunk = int(chunk_bytes) if chunk_bytes else max(n, 1)
         wsb = self.lib.dd_pack_workspace_bytes(min(chunk, max(n, 1)))
-        ws = self._buf(wsb, "pack")
+        ws = self._buf(wsb, ws_tag)   # one scratch buffer per stream in flight
         pos = 0
         while pos < n:
             ln = min(chunk, n - pos)
@@ -137,7 +137,7 @@ class Engine:
     # ---- K2 (+K4 for the leaf cardinalities) ------------------------------------------------------
     def sketch(self, seq: PackedSeq, ks: Sequence[int], p: int = 20, canon: bool = True,
                out: Optional[torch.Tensor] = None, ranges=None, floor_every: Optional[int] = None,
-               hist_out: Optional[torch.Tensor] = None):
+               hist_out: Optional[torch.Tensor] = None, ws_tag: str = "sketch"):
         """All-k HLL sketch of one packed sequence.  Returns (regs [nk, 2^p] uint8, cards [nk] f64),
         both on the device.  `ranges` (list of (begin, end) symbol ranges) forces chunked updates.
         With `hist_out` ([nk, 64] int32) the register histograms go there and the estimator is left to
@@ -146,7 +146,7 @@ class Engine:
         nk = bin(kmask).count("1")
         m = 1 << p
         wsb = self.lib.dd_sketch_workspace_bytes(nk, p)
-        ws = self._buf(wsb, "sketch")
+        ws = self._buf(wsb, ws_tag)
         st = self.stream
         regs = out if out is not None else torch.empty((nk, m), dtype=torch.uint8, device=self.device)
         assert regs.is_contiguous() and regs.numel() == nk * m
@@ -190,10 +190,14 @@ class Engine:
 
     def sketch_fasta_host(self, text: bytes, ks: Sequence[int], p: int = 20, canon: bool = True,
                           want_regs: bool = True, pinned_regs: Optional[torch.Tensor] = None,
-                          out_dev: Optional[torch.Tensor] = None):
+                          out_dev: Optional[torch.Tensor] = None, cards_out: Optional[torch.Tensor] = None,
+                          ws_tag: str = "host", sync: bool = True):
         """The host-buffer C-ABI path: FASTA bytes in host memory -> (regs numpy [nk, 2^p] or None,
         cards numpy [nk]).  H2D, pack, sketch, estimate, D2H all inside the one call.  `out_dev`
-        (uint8 [nk, 2^p] on the device) additionally keeps the registers resident in HBM."""
+        (uint8 [nk, 2^p] on the device) additionally keeps the registers resident in HBM.
+        sync=False enqueues on the current stream and returns (dd_sketch_fasta_host_async): give every
+        stream in flight its own `ws_tag` and a pinned `cards_out` (float64 [nk]), and synchronise
+        the stream before reading the results."""
         kmask = kmask_of(ks)
         nk = bin(kmask).count("1")
         m = 1 << p
@@ -203,8 +207,13 @@ class Engine:
             arr = np.frombuffer(text, dtype=np.uint8)
             h_ptr, n = arr.ctypes.data, arr.size
         wsb = self.lib.dd_sketch_fasta_host_workspace_bytes(n, nk, p)
-        ws = self._buf(wsb, "host")
-        cards = np.empty(nk, dtype=np.float64)
+        ws = self._buf(wsb, ws_tag)
+        if cards_out is not None:
+            assert cards_out.dtype == torch.float64 and cards_out.numel() == nk and cards_out.is_contiguous()
+            cards, c_ptr = cards_out, cards_out.data_ptr()
+        else:
+            cards = np.empty(nk, dtype=np.float64)
+            c_ptr = cards.ctypes.data
         regs = None
         r_ptr = None
         if want_regs:
@@ -217,8 +226,9 @@ class Engine:
         if out_dev is not None:
             assert out_dev.is_contiguous() and out_dev.numel() == nk * m and out_dev.dtype == torch.uint8
             d_ptr = out_dev.data_ptr()
-        check(self.lib.dd_sketch_fasta_host(h_ptr, n, kmask, p, int(canon), r_ptr, cards.ctypes.data, d_ptr, ws.data_ptr(),
-                                            ws.numel(), self.stream), "dd_sketch_fasta_host")
+        fn = self.lib.dd_sketch_fasta_host if sync else self.lib.dd_sketch_fasta_host_async
+        check(fn(h_ptr, n, kmask, p, int(canon), r_ptr, c_ptr, d_ptr, ws.data_ptr(), ws.numel(), self.stream),
+              "dd_sketch_fasta_host")
         return regs, cards
 
     # ---- K4 ---------------------------------------------------------------------------------

@@ -28,6 +28,7 @@ from typing import Dict, List, Set, Tuple
 from sketch_classes import DashSketchObj, KMCSketchObj, SketchFilePath, SketchObj  # noqa: F401
 from species_specifics import SpeciesSpecifics
 
+from dandd_b200 import ingest
 from dandd_b200.store import get_store
 
 HLL_MAX_K = 32      # "maxk<=32 for estimation" (reference README.md:82, lib/huffman_dandd.py:109-110)
@@ -665,6 +666,7 @@ def create_delta_tree(tag: str, genomedir: str, sketchdir: str, kstart: int, nch
         raise ValueError("You must provide either an existing directory of fastas or a file listing the paths of the "
                          f"desired fastas. The directory you provided was {speciesinfo.inputdir}.")
     fastas.sort()
+    ingest.prefetch(fastas)   # read / gunzip / blake2b in the background while the GPU works
     if nchildren:
         dtree = DeltaTree(fasta_files=fastas, speciesinfo=speciesinfo, nchildren=nchildren, experiment=experiment)
     else:

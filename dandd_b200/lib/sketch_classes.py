@@ -13,27 +13,20 @@ recorded in `.cmd` (it appears in DandD's CSV output and documents what was repl
     KMCSketchObj              reference :377-465  (exact, `kmc`, `kmc_tools info|complex`)
 """
 import glob
-import hashlib
 import os
 
 from species_specifics import SpeciesSpecifics
 
+from dandd_b200 import ingest
 from dandd_b200.store import get_store
 
 DASHINGLOC = "dashing"   # kept for API compatibility; only ever used inside the recorded .cmd text
 
 
 def blake2b(fname):
-    """Hex digest that names a FASTA (reference :12-18).  1 MiB reads instead of 4 KiB ones: same
-    digest, far fewer syscalls on multi-gigabyte inputs."""
-    digest = hashlib.blake2b()
-    with open(fname, "rb") as fh:
-        while True:
-            block = fh.read(1 << 20)
-            if not block:
-                break
-            digest.update(block)
-    return digest.hexdigest()
+    """Hex digest of the file bytes that names a FASTA (reference :12-18).  Computed by the ingest
+    pool while earlier files are being sketched (dandd_b200/ingest.py); same digest."""
+    return ingest.digest(fname)
 
 
 def canon_command(canon: bool, tool="dashing"):

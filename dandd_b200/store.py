@@ -13,7 +13,6 @@ progressive prefix unions and pairwise unions never re-read a file or re-sketch 
 
 One store per process; it talks to one Engine (one GPU).  There is no CPU path here.
 """
-import gzip
 import os
 from collections import OrderedDict
 from typing import Dict, List, Sequence
@@ -21,19 +20,16 @@ from typing import Dict, List, Sequence
 import numpy as np
 import torch
 
-from . import hllfile
+from . import hllfile, ingest
 from .engine import Engine, get_engine
 
 ALL_HLL_KS = tuple(range(1, 33))
 
 
 def read_fasta_bytes(path: str) -> bytes:
-    """Whole FASTA as bytes; .gz is inflated on the host (dashing/kmc read .gz transparently)."""
-    with open(path, "rb") as f:
-        raw = f.read()
-    if raw[:2] == b"\x1f\x8b":
-        raw = gzip.decompress(raw)
-    return raw
+    """Whole FASTA as bytes; .gz is inflated on the host (dashing/kmc read .gz transparently).
+    Served from the background ingest pool when the file was prefetched."""
+    return ingest.fasta_bytes(path)
 
 
 class GpuSketchStore:

@@ -197,6 +197,14 @@ DD_API int dd_sketch_fasta_host(const uint8_t *h_text, size_t n_bytes, uint32_t 
                          uint8_t *h_regs /*[nk][2^p] or NULL*/, double *h_cards /*[nk]*/, uint8_t *d_regs_or_null,
                          void *d_ws, size_t ws_bytes, dd_stream stream);
 
+/* Same, but returns as soon as the work is enqueued: h_text must stay valid, and h_cards / h_regs
+ * must not be read, until `stream` has been synchronised by the caller (pinned host memory makes
+ * the copies truly asynchronous).  Lets a caller keep several FASTAs in flight on different streams
+ * (one workspace per stream) so that H2D copies overlap the kernels of the previous file. */
+DD_API int dd_sketch_fasta_host_async(const uint8_t *h_text, size_t n_bytes, uint32_t kmask, int p, int canon,
+                                      uint8_t *h_regs, double *h_cards, uint8_t *d_regs_or_null, void *d_ws,
+                                      size_t ws_bytes, dd_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

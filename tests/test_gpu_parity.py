@@ -250,3 +250,28 @@ def test_exact_table_overflow_is_loud(eng):
     seq = eng.pack(to_fasta([(b"x", random_bases(rng, 50000))]))
     with pytest.raises(DandDError):
         eng.exact_counts([seq], 25, capacity=1024)
+
+
+def test_small_k_persistent_bitmaps_bit_exact(eng):
+    """k <= 9 goes through the persistent kernel with per-CTA presence bitmaps; 6.5 Mbp gives every
+    CTA several tiles, low-complexity stretches give heavily repeated k-mers, and the chunked
+    variant re-enters the kernel with fresh bitmaps mid-genome."""
+    rng = np.random.default_rng(12)
+    a = random_bases(rng, 6_500_000)
+    a[1_000_000:1_200_000] = ord("A")                       # homopolymer
+    a[2_000_000:2_300_000] = np.tile(np.frombuffer(b"ACGTTGCA", dtype=np.uint8), 37500)   # tandem repeat
+    a[3_000_000:3_000_050] = ord("N")
+    txt = to_fasta([(b"lowcomplex", a)], width=80)
+    sym = orc.fasta_symbols(txt)
+    seq = eng.pack(txt)
+    ks = list(range(1, 14)) + [21, 32]
+    regs, cards = eng.sketch(seq, ks, p=14)
+    chunked, _ = eng.sketch(seq, ks, p=14, floor_every=1_000_003)
+    for i, k in enumerate(ks):
+        want = orc.hll_sketch(sym, k, 14)
+        assert np.array_equal(regs[i].cpu().numpy(), want), k
+        assert np.array_equal(chunked[i].cpu().numpy(), want), k
+        assert float(cards[i]) == pytest.approx(orc.card(want, 14), rel=CARD_RTOL)
+    nc, _ = eng.sketch(seq, [3, 7, 9], p=14, canon=False)
+    for i, k in enumerate([3, 7, 9]):
+        assert np.array_equal(nc[i].cpu().numpy(), orc.hll_sketch(sym, k, 14, canon=False)), k
