@@ -181,7 +181,7 @@ int dd_prefix_union_card(const uint8_t *d_regs, const int32_t *d_order, int n_or
                          int p, int final_only, double *d_cards, uint32_t *d_hist, uint8_t *d_unions, dd_stream stream) {
     if (n_ord == 0 || n_steps == 0) return DD_OK;
     if (!d_regs || !d_order || !d_cards || !d_hist || n_ord < 0 || n_steps < 0 || n_genomes < 1 || nk < 1 || nk > 65535 ||
-        bad_p(p))
+        bad_p(p) || (((size_t)1 << p) + 32767) / 32768 > 65535)
         return fail(DD_ERR_ARG, "dd_prefix_union_card: bad argument");
     DD_CUDA(dd::prefix_union_hist(d_regs, d_order, n_ord, n_steps, n_genomes, nk, p, final_only, d_hist, d_unions, S(stream)),
             "dd_prefix_union_card(hist)");

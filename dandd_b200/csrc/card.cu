@@ -107,8 +107,12 @@ constexpr int kPfxThreads = kPhThreads;
 constexpr int kPfxVec = 8;                                 // uint4 per thread (128 registers <= 255)
 constexpr int kPfxSliceBytes = kPfxThreads * kPfxVec * 16; // 32 KiB
 
-// kPtrTable = false: members are genome indices into regs[n_genomes][nk][2^p], grid (slices, nk, n_ord)
-// kPtrTable = true : members are device pointers to 2^p-byte sketches,      grid (slices, n_sets, 1)
+// kPtrTable = false: members are genome indices into regs[n_genomes][nk][2^p], grid (n_ord, slices, nk)
+// kPtrTable = true : members are device pointers to 2^p-byte sketches,      grid (n_sets, slices, 1)
+// The ordering / set index is the FASTEST grid dimension on purpose: the CTAs that are resident
+// together then work on the same register slice of the same genomes under different orderings, so
+// all but the first read of a slice hit in L2 (ncu, before: L2 hit rate 2 %, 8.3 GB from DRAM per
+// launch for 30 orderings of 12 genomes; the data itself is only 276 MiB).
 template <bool kPtrTable>
 __global__ void __launch_bounds__(kPfxThreads)
 prefix_union_kernel(const uint8_t *__restrict__ regs, const int32_t *__restrict__ order,
@@ -117,8 +121,9 @@ prefix_union_kernel(const uint8_t *__restrict__ regs, const int32_t *__restrict_
     __shared__ __align__(16) uint8_t s_hist[kPhBytes];
     const uint32_t slot = ph_slot();
     const size_t m = (size_t)1 << p;
-    const int k = blockIdx.y, o = blockIdx.z;
-    const size_t slice0 = (size_t)blockIdx.x * kPfxSliceBytes;
+    const int o = kPtrTable ? 0 : (int)blockIdx.x;
+    const int k = kPtrTable ? (int)blockIdx.x : (int)blockIdx.z;   // pointer mode: k is the set index
+    const size_t slice0 = (size_t)blockIdx.y * kPfxSliceBytes;
     uint4 run[kPfxVec];
 #pragma unroll
     for (int q = 0; q < kPfxVec; ++q) run[q] = make_uint4(0, 0, 0, 0);
@@ -211,13 +216,8 @@ cudaError_t prefix_union_hist(const uint8_t *d_regs, const int32_t *d_order, int
     if (rows == 0) return cudaSuccess;
     const size_t m = (size_t)1 << p;
     const unsigned slices = (unsigned)((m + kPfxSliceBytes - 1) / kPfxSliceBytes);
-    for (int o0 = 0; o0 < n_ord; o0 += 65535) {  // gridDim.z limit
-        const int cnt = n_ord - o0 < 65535 ? n_ord - o0 : 65535;
-        const size_t roff = (size_t)o0 * out_steps * nk;
-        prefix_union_kernel<false><<<dim3(slices, nk, cnt), kPfxThreads, 0, stream>>>(
-            d_regs, d_order + (size_t)o0 * n_steps, nullptr, n_steps, n_genomes, nk, p, final_only,
-            d_hist + roff * DD_HIST_BINS, d_unions ? d_unions + roff * m : nullptr);
-    }
+    prefix_union_kernel<false><<<dim3((unsigned)n_ord, slices, (unsigned)nk), kPfxThreads, 0, stream>>>(
+        d_regs, d_order, nullptr, n_steps, n_genomes, nk, p, final_only, d_hist, d_unions);
     return cudaGetLastError();
 }
 
@@ -233,13 +233,8 @@ cudaError_t union_sets_hist(const uint8_t *const *d_members, int n_sets, int n_s
     if (rows == 0) return cudaSuccess;
     const size_t m = (size_t)1 << p;
     const unsigned slices = (unsigned)((m + kPfxSliceBytes - 1) / kPfxSliceBytes);
-    for (int s0 = 0; s0 < n_sets; s0 += 65535) {  // gridDim.y limit
-        const int cnt = n_sets - s0 < 65535 ? n_sets - s0 : 65535;
-        const size_t roff = (size_t)s0 * out_steps;
-        prefix_union_kernel<true><<<dim3(slices, cnt, 1), kPfxThreads, 0, stream>>>(
-            nullptr, nullptr, d_members + (size_t)s0 * n_steps, n_steps, 0, cnt, p, final_only,
-            d_hist + roff * DD_HIST_BINS, d_unions ? d_unions + roff * m : nullptr);
-    }
+    prefix_union_kernel<true><<<dim3((unsigned)n_sets, slices, 1), kPfxThreads, 0, stream>>>(
+        nullptr, nullptr, d_members, n_steps, 0, n_sets, p, final_only, d_hist, d_unions);
     return cudaGetLastError();
 }
 

@@ -153,6 +153,8 @@ class GpuSketchStore:
         n_ord, n_steps = orderings.shape
         m = 1 << p
         base = np.array([[self.registers(pth).data_ptr() for pth in leaf_paths_by_k[k]] for k in ks], dtype=np.int64)  # [nk, n]
+        # rows are laid out [ordering-chunk][k][ordering] at launch time: sets that read the same
+        # sketches (same k, different ordering) are adjacent, which is what keeps them in L2
         ptrs = np.zeros((n_ord, len(ks), n_steps), dtype=np.int64)
         for i in range(len(ks)):
             ptrs[:, i, :] = np.where(orderings >= 0, base[i][np.clip(orderings, 0, None)], 0)
@@ -163,14 +165,14 @@ class GpuSketchStore:
         written = set()
         for o0 in range(0, n_ord, step_ords):
             o1 = min(n_ord, o0 + step_ords)
-            block = ptrs[o0:o1].reshape((o1 - o0) * len(ks), n_steps)
+            block = np.ascontiguousarray(ptrs[o0:o1].transpose(1, 0, 2)).reshape(len(ks) * (o1 - o0), n_steps)  # [k][o]
             if want_files:
                 cards, unions = self.engine.union_sets(block, p, final_only=False, materialize=True)
-                unions = unions.view(o1 - o0, len(ks), n_steps, m)
+                unions = unions.view(len(ks), o1 - o0, n_steps, m).transpose(0, 1)   # -> [o][k][step][m]
             else:
                 cards = self.engine.union_sets(block, p, final_only=False)
             self.stats["union_launches"] += 1
-            cards = cards.cpu().numpy().reshape(o1 - o0, len(ks), n_steps)
+            cards = cards.cpu().numpy().reshape(len(ks), o1 - o0, n_steps).transpose(1, 0, 2)   # [o][k][step]
             out[o0:o1] = cards.transpose(0, 2, 1)
             if want_files:
                 for o in range(o0, o1):
