@@ -75,6 +75,10 @@ int dd_set_option(const char *name, long value) {
         dd::g_k_per_pass = (int)value;
         return DD_OK;
     }
+    if (!strcmp(name, "prefix_planes")) {
+        dd::g_prefix_planes = value != 0;
+        return DD_OK;
+    }
     return fail(DD_ERR_ARG, "dd_set_option: unknown option '%s'", name);
 }
 
@@ -183,8 +187,12 @@ int dd_prefix_union_card(const uint8_t *d_regs, const int32_t *d_order, int n_or
     if (!d_regs || !d_order || !d_cards || !d_hist || n_ord < 0 || n_steps < 0 || n_genomes < 1 || nk < 1 || nk > 65535 ||
         bad_p(p) || (((size_t)1 << p) + 32767) / 32768 > 65535)
         return fail(DD_ERR_ARG, "dd_prefix_union_card: bad argument");
-    DD_CUDA(dd::prefix_union_hist(d_regs, d_order, n_ord, n_steps, n_genomes, nk, p, final_only, d_hist, d_unions, S(stream)),
-            "dd_prefix_union_card(hist)");
+    if (!d_unions && dd::g_prefix_planes && dd::planes_supported(p))
+        DD_CUDA(dd::prefix_union_hist_planes(d_regs, d_order, n_ord, n_steps, n_genomes, nk, p, final_only, d_hist, S(stream)),
+                "dd_prefix_union_card(planes)");
+    else
+        DD_CUDA(dd::prefix_union_hist(d_regs, d_order, n_ord, n_steps, n_genomes, nk, p, final_only, d_hist, d_unions, S(stream)),
+                "dd_prefix_union_card(hist)");
     const size_t rows = (size_t)n_ord * (final_only ? 1 : n_steps) * nk;
     if (rows > 0x7fffffff) return fail(DD_ERR_ARG, "dd_prefix_union_card: too many (ordering, step, k) rows");
     DD_CUDA(dd::mle_from_hist(d_hist, (int)rows, p, d_cards, S(stream)), "dd_prefix_union_card(mle)");

@@ -175,6 +175,8 @@ prefix_union_kernel(const uint8_t *__restrict__ regs, const int32_t *__restrict_
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
+int g_prefix_planes = 1;
+
 cudaError_t card_hist(const uint8_t *d_regs, int nsk, int p, uint32_t *d_hist, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(d_hist, 0, (size_t)nsk * DD_HIST_BINS * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;

@@ -42,6 +42,11 @@ cudaError_t prefix_union_hist(const uint8_t *d_regs, const int32_t *d_order, int
                               int nk, int p, int final_only, uint32_t *d_hist, uint8_t *d_unions,
                               cudaStream_t stream);
 
+// planes.cu: the same contract as prefix_union_hist (without materialised unions) on bit-sliced sketches
+bool planes_supported(int p);
+cudaError_t prefix_union_hist_planes(const uint8_t *d_regs, const int32_t *d_order, int n_ord, int n_steps, int n_genomes,
+                                     int nk, int p, int final_only, uint32_t *d_hist, cudaStream_t stream);
+extern int g_prefix_planes;  // tuning knob: 1 = use the bit-plane kernel where it applies (default)
 cudaError_t union_sets_hist(const uint8_t *const *d_members, int n_sets, int n_steps, int p, int final_only,
                             uint32_t *d_hist, uint8_t *d_unions, cudaStream_t stream);
 

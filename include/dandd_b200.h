@@ -57,7 +57,8 @@ DD_API int dd_abi_version(void);
 DD_API int dd_init(int device);
 /* Tuning knobs (never change results).  "sketch_k_per_pass" = n: K2 updates at most n k values per
  * kernel launch (0 = all in one), trading re-reads of the packed stream for L2 residency of the
- * accumulators. */
+ * accumulators.  "prefix_planes" = 0/1: dd_prefix_union_card uses the bit-sliced kernel (default 1)
+ * or the byte kernel. */
 DD_API int dd_set_option(const char *name, long value);
 DD_API int dd_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes, size_t *total_mem);
 

@@ -275,3 +275,32 @@ def test_small_k_persistent_bitmaps_bit_exact(eng):
     nc, _ = eng.sketch(seq, [3, 7, 9], p=14, canon=False)
     for i, k in enumerate([3, 7, 9]):
         assert np.array_equal(nc[i].cpu().numpy(), orc.hll_sketch(sym, k, 14, canon=False)), k
+
+
+@pytest.mark.parametrize("p", [12, 15, 20])
+def test_bit_plane_prefix_kernel_equals_byte_kernel(eng, p):
+    """dd_prefix_union_card has two kernels (byte histograms / bit-sliced planes); on sketches whose
+    values span every bucket -- empty registers, the usual 1..15 bulk, sparse and dense 16..31,
+    32..47 and the 64-p+1 cap -- both must give the same histograms, hence identical cards."""
+    import torch
+    from dandd_b200._lib import check
+    rng = np.random.default_rng(20 + p)
+    n, nk, m = 5, 3, 1 << p
+    cap = 64 - p + 1
+    regs = np.minimum(rng.geometric(0.5, size=(n, nk, m)) + rng.integers(0, 3, size=(n, nk, 1)), cap).astype(np.uint8)
+    regs[0, 0, ::7] = 0
+    regs[1, :, : m // 3] = np.minimum(rng.integers(14, 40, size=(nk, m // 3)), cap)      # dense high buckets
+    regs[2, 1, 5] = cap
+    regs[3, 2, :] = 0                                                                   # an empty sketch
+    d = torch.from_numpy(regs).to(eng.device)
+    orders = [[0, 1, 2, 3, 4], [3, 3, 2, 0, -1], [4, 1, -1, -1, 0]]
+    check(eng.lib.dd_set_option(b"prefix_planes", 0))
+    a = eng.prefix_union_cards(d, orders, p).cpu().numpy()
+    af = eng.prefix_union_cards(d, orders, p, final_only=True).cpu().numpy()
+    check(eng.lib.dd_set_option(b"prefix_planes", 1))
+    b = eng.prefix_union_cards(d, orders, p).cpu().numpy()
+    bf = eng.prefix_union_cards(d, orders, p, final_only=True).cpu().numpy()
+    assert np.array_equal(a, b) and np.array_equal(af, bf)
+    run = np.maximum(regs[0], regs[1])
+    for i in range(nk):
+        assert b[0, 1, i] == pytest.approx(orc.card(run[i], p), rel=CARD_RTOL)
