@@ -5,8 +5,11 @@
 // 128-bit loads (twice: a counting pass and a writing pass; the chunk is L2-resident for the second
 // when the host streams in <= 64 MiB chunks), output is 0.375 B/symbol, staged through shared
 // memory so that the global stores are whole, coalesced words.  A thread owns 64 contiguous text
-// bytes (four 128-bit loads in flight at once) and a CTA a 16 KiB tile, so there is one block scan
-// per 16 KiB of text.
+// bytes and a CTA a 16 KiB tile, so there is one block scan per 16 KiB of text.  Both text passes
+// are persistent kernels (SM count x resident CTAs) that stage their tiles in shared memory with
+// the bulk-copy engine (`cp.async.bulk.shared::cluster.global` + mbarrier complete_tx, SASS
+// UBLKCP.S.G), double-buffered: tile i+1 streams in while tile i is classified, scanned and packed.
+// Text that is not 16-byte aligned falls back to per-thread 128-bit / byte loads (same results).
 //
 // The only sequential dependence in FASTA text is "am I inside a header line?".  Each 16-byte
 // chunk is summarised as a transition function over that one bit (dd::chunk_xfer) and the
@@ -112,18 +115,130 @@ __device__ __forceinline__ Span load_span(const uint8_t *__restrict__ text, size
     return sp;
 }
 
+// ---- bulk-copy (TMA) staging of text tiles -----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// one thread: expect `bytes` on the barrier and start the copy global -> shared (bytes % 16 == 0)
+__device__ __forceinline__ void tma_load_tile(uint8_t *dst, const uint8_t *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    if (bytes)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                     "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                     : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+}
+
+// Tile pipeline shared by both passes: a CTA walks tiles blockIdx.x, +gridDim.x, ...; buffer i&1
+// holds tile i.  stage_issue() is called by thread 0 only, stage_wait() by everyone; the caller's
+// end-of-iteration __syncthreads() is what makes a buffer reusable two iterations later.
+struct TilePipe {
+    uint8_t *buf[2];
+    uint64_t *bar;  // [2]
+    const uint8_t *text;
+    size_t n;
+    bool tma;       // text is 16-byte aligned
+
+    __device__ __forceinline__ uint32_t tile_bytes(size_t tile) const {
+        const size_t base = tile * kTileBytes;
+        return (uint32_t)(n - base < (size_t)kTileBytes ? n - base : (size_t)kTileBytes);
+    }
+    __device__ __forceinline__ void issue(size_t tile, int it) const {
+        if (tma) tma_load_tile(buf[it & 1], text + tile * kTileBytes, tile_bytes(tile) & ~15u, &bar[it & 1]);
+    }
+    // after this returns every thread may read bytes [0, roundup64(tile_bytes)) of buf[it&1]
+    __device__ __forceinline__ const uint8_t *wait(size_t tile, int it) const {
+        uint8_t *b = buf[it & 1];
+        const uint32_t nb = tile_bytes(tile);
+        const uint8_t *src = text + tile * kTileBytes;
+        if (tma) {
+            mbar_wait(&bar[it & 1], (uint32_t)(it >> 1) & 1u);
+            if (nb < (uint32_t)kTileBytes) {  // last tile: the < 16 trailing bytes, then inert padding
+                const uint32_t i = (nb & ~15u) + threadIdx.x;
+                if (i < ((nb + kSpanBytes - 1) & ~(uint32_t)(kSpanBytes - 1))) b[i] = i < nb ? src[i] : kPadByte;
+                __syncthreads();
+            }
+        } else {  // unaligned text: cooperative byte-safe copy
+            const uint32_t lim = (nb + kSpanBytes - 1) & ~(uint32_t)(kSpanBytes - 1);
+            for (uint32_t i = threadIdx.x; i < lim; i += kPackThreads) b[i] = i < nb ? src[i] : kPadByte;
+            __syncthreads();
+        }
+        return b;
+    }
+};
+
+// A thread's span read from the staged tile (shared memory).
+__device__ __forceinline__ Span load_span_smem(const uint8_t *tile, uint32_t off_in_tile, uint32_t prev_byte) {
+    Span sp;
+    sp.f = kXferIdentity;
+    sp.ls = 0;
+    uint4 v[kSpanChunks];
+#pragma unroll
+    for (int c = 0; c < kSpanChunks; ++c) v[c] = *reinterpret_cast<const uint4 *>(tile + off_in_tile + 16 * c);
+    uint32_t prev = prev_byte;
+#pragma unroll
+    for (int c = 0; c < kSpanChunks; ++c) {
+        sp.m[c] = classify16(v[c].x, v[c].y, v[c].z, v[c].w);
+        const bool ls = prev == '\n';
+        sp.ls |= (ls ? 1u : 0u) << c;
+        sp.f = xfer_compose(sp.f, chunk_xfer(sp.m[c], ls));
+        prev = v[c].w >> 24;
+    }
+    return sp;
+}
+
+// byte before a thread's span: previous span's last byte (same tile), else the text before the tile
+__device__ __forceinline__ uint32_t span_prev_byte(const uint8_t *tile, uint32_t off_in_tile, const uint8_t *text,
+                                                   size_t tile_base, uint32_t entry_last) {
+    if (off_in_tile) return tile[off_in_tile - 1];
+    return tile_base ? (uint32_t)text[tile_base - 1] : entry_last;
+}
+
 // ---- pass A: one transition function per tile -------------------------------------------------
 __global__ void __launch_bounds__(kPackThreads)
-pack_count_kernel(const uint8_t *__restrict__ text, size_t n, const dd_pack_state *__restrict__ st,
+pack_count_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, const dd_pack_state *__restrict__ st,
                   uint64_t *__restrict__ tile_xfer) {
+    extern __shared__ __align__(128) uint8_t s_dyn[];
     __shared__ uint64_t s_warp[32];
-    const size_t off = (size_t)blockIdx.x * kTileBytes + (size_t)threadIdx.x * kSpanBytes;
-    const bool aligned = (reinterpret_cast<uintptr_t>(text) & 15) == 0;
-    uint64_t f = kXferIdentity;
-    if (off < n) f = load_span(text, off, n, aligned, st->last_byte).f;
-    uint64_t tile;
-    block_scan_xfer(f, s_warp, &tile);
-    if (threadIdx.x == 0) tile_xfer[blockIdx.x] = tile;
+    __shared__ __align__(8) uint64_t s_bar[2];
+    TilePipe pipe;
+    pipe.buf[0] = s_dyn;
+    pipe.buf[1] = s_dyn + kTileBytes;
+    pipe.bar = s_bar;
+    pipe.text = text;
+    pipe.n = n;
+    pipe.tma = (reinterpret_cast<uintptr_t>(text) & 15) == 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0]);
+        mbar_init(&s_bar[1]);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const uint32_t entry_last = st->last_byte;
+    if (threadIdx.x == 0 && blockIdx.x < ntiles) pipe.issue(blockIdx.x, 0);
+    int it = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const size_t next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < ntiles) pipe.issue(next, it + 1);
+        const uint8_t *b = pipe.wait(tile, it);
+        const uint32_t off = threadIdx.x * kSpanBytes;
+        uint64_t f = kXferIdentity;
+        if (off < pipe.tile_bytes(tile))
+            f = load_span_smem(b, off, span_prev_byte(b, off, text, tile * kTileBytes, entry_last)).f;
+        uint64_t total;
+        block_scan_xfer(f, s_warp, &total);
+        if (threadIdx.x == 0) tile_xfer[tile] = total;
+        __syncthreads();  // buffer it&1 and s_warp are free again
+    }
 }
 
 // ---- pass B: scan tile functions, assign output offsets, advance the stream state --------------
@@ -191,77 +306,104 @@ pack_scan_kernel(const uint8_t *__restrict__ text, size_t n, const uint64_t *__r
 }
 
 // ---- pass C: emit symbols ---------------------------------------------------------------------
+constexpr size_t kWriteSmem = 2 * kTileBytes + (kTileBytes + 64);  // two text buffers + symbol staging
+
 __global__ void __launch_bounds__(kPackThreads)
-pack_write_kernel(const uint8_t *__restrict__ text, size_t n, const PackTileOut *__restrict__ tile_out,
+pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, const PackTileOut *__restrict__ tile_out,
                   const uint64_t *__restrict__ seg_base, const PackWsHeader *__restrict__ hdr,
                   const dd_pack_state *__restrict__ st, uint32_t *__restrict__ codes, uint32_t *__restrict__ invalid,
                   size_t cap_symbols) {
+    extern __shared__ __align__(128) uint8_t s_dyn[];
     __shared__ uint64_t s_warp[32];
-    __shared__ __align__(16) uint8_t s_stage[kTileBytes + 64];
-    const size_t tile = blockIdx.x;
-    const size_t off = tile * kTileBytes + (size_t)threadIdx.x * kSpanBytes;
-    const bool aligned = (reinterpret_cast<uintptr_t>(text) & 15) == 0;
-    const uint32_t tile_state = (uint32_t)tile_out[tile].state;
-    const uint64_t g_tile = st->prev_nsym + seg_base[tile / hdr->seg_len] + tile_out[tile].local_off;
-    const size_t cap_words16 = (cap_symbols + 15) >> 4, cap_words32 = (cap_symbols + 31) >> 5;
-
-    // symbols are staged as bytes (bits 1:0 code, bit 2 break) at their position in the output
-    // stream relative to the 32-symbol boundary below g_tile, so that pack-out writes whole words
-    for (int i = threadIdx.x; i < (kTileBytes + 64) / 16; i += kPackThreads)
-        reinterpret_cast<uint4 *>(s_stage)[i] = make_uint4(0, 0, 0, 0);
-
-    Span sp;
-    sp.f = kXferIdentity;
-    if (off < n) sp = load_span(text, off, n, aligned, hdr->entry_last_byte);
-    uint64_t all;
-    const uint64_t pre = block_scan_xfer(sp.f, s_warp, &all);  // its barriers also order the zeroing above
-    const uint32_t tile_cnt = xfer_cnt(all, tile_state);
-    const uint32_t lead = (uint32_t)(g_tile & 31);
-    if (off < n) {
-        uint32_t state = xfer_end(pre, tile_state);
-        uint32_t o = lead + xfer_cnt(pre, tile_state);
-#pragma unroll
-        for (int c = 0; c < kSpanChunks; ++c) {
-            const ChunkSyms cs = chunk_symbols(sp.m[c], (sp.ls >> c) & 1u, state != 0);
-            uint32_t rem = cs.sym;
-            while (rem) {
-                const int i = __ffs((int)rem) - 1;
-                rem &= rem - 1;
-                s_stage[o++] = (uint8_t)(((sp.m[c].codes >> (2 * i)) & 3u) | (((cs.brk >> i) & 1u) << 2));
-            }
-            state = cs.end_hdr;
-        }
+    __shared__ __align__(8) uint64_t s_bar[2];
+    uint8_t *s_stage = s_dyn + 2 * kTileBytes;
+    TilePipe pipe;
+    pipe.buf[0] = s_dyn;
+    pipe.buf[1] = s_dyn + kTileBytes;
+    pipe.bar = s_bar;
+    pipe.text = text;
+    pipe.n = n;
+    pipe.tma = (reinterpret_cast<uintptr_t>(text) & 15) == 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0]);
+        mbar_init(&s_bar[1]);
+        mbar_fence_init();
     }
     __syncthreads();
-    // pack-out: one 32-symbol group per thread and iteration
-    const uint32_t span = lead + tile_cnt;  // staged extent
-    const uint32_t ngroups = (span + 31) >> 5;
-    const uint64_t g_base = g_tile - lead;  // multiple of 32
-    for (uint32_t g = threadIdx.x; g < ngroups; g += kPackThreads) {
-        const uint4 a = reinterpret_cast<const uint4 *>(s_stage)[2 * g];
-        const uint4 b = reinterpret_cast<const uint4 *>(s_stage)[2 * g + 1];
-        const uint32_t c0 = (pack_codes4(a.x) << 24) | (pack_codes4(a.y) << 16) | (pack_codes4(a.z) << 8) | pack_codes4(a.w);
-        const uint32_t c1 = (pack_codes4(b.x) << 24) | (pack_codes4(b.y) << 16) | (pack_codes4(b.z) << 8) | pack_codes4(b.w);
-        const uint32_t iv = (pack_breaks4(a.x) << 28) | (pack_breaks4(a.y) << 24) | (pack_breaks4(a.z) << 20) |
-                            (pack_breaks4(a.w) << 16) | (pack_breaks4(b.x) << 12) | (pack_breaks4(b.y) << 8) |
-                            (pack_breaks4(b.z) << 4) | pack_breaks4(b.w);
-        const uint32_t s0 = 32 * g;
-        const uint64_t w32 = (g_base >> 5) + g;
-        const uint64_t w16 = w32 * 2;
-        // a word wholly produced by this tile is stored; a word shared with a neighbouring tile or
-        // chunk is OR-ed (the buffers are zero-filled by dd_pack_reset)
-        if (w16 < cap_words16) {
-            if (s0 >= lead && s0 + 16 <= span) codes[w16] = c0;
-            else if (c0) atomicOr(&codes[w16], c0);
+    const uint32_t entry_last = hdr->entry_last_byte;
+    const uint32_t seg_len = hdr->seg_len;
+    const uint64_t stream_base = st->prev_nsym;
+    const size_t cap_words16 = (cap_symbols + 15) >> 4, cap_words32 = (cap_symbols + 31) >> 5;
+    if (threadIdx.x == 0 && blockIdx.x < ntiles) pipe.issue(blockIdx.x, 0);
+    int it = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const size_t next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < ntiles) pipe.issue(next, it + 1);
+        const uint32_t tile_state = (uint32_t)tile_out[tile].state;
+        const uint64_t g_tile = stream_base + seg_base[tile / seg_len] + tile_out[tile].local_off;
+
+        // symbols are staged as bytes (bits 1:0 code, bit 2 break) at their position in the output
+        // stream relative to the 32-symbol boundary below g_tile, so that pack-out writes whole words
+        for (int i = threadIdx.x; i < (kTileBytes + 64) / 16; i += kPackThreads)
+            reinterpret_cast<uint4 *>(s_stage)[i] = make_uint4(0, 0, 0, 0);
+
+        const uint8_t *b = pipe.wait(tile, it);
+        const uint32_t off = threadIdx.x * kSpanBytes;
+        const bool active = off < pipe.tile_bytes(tile);
+        Span sp;
+        sp.f = kXferIdentity;
+        if (active) sp = load_span_smem(b, off, span_prev_byte(b, off, text, tile * kTileBytes, entry_last));
+        uint64_t all;
+        const uint64_t pre = block_scan_xfer(sp.f, s_warp, &all);  // its barriers also order the zeroing above
+        const uint32_t tile_cnt = xfer_cnt(all, tile_state);
+        const uint32_t lead = (uint32_t)(g_tile & 31);
+        if (active) {
+            uint32_t state = xfer_end(pre, tile_state);
+            uint32_t o = lead + xfer_cnt(pre, tile_state);
+#pragma unroll
+            for (int c = 0; c < kSpanChunks; ++c) {
+                const ChunkSyms cs = chunk_symbols(sp.m[c], (sp.ls >> c) & 1u, state != 0);
+                uint32_t rem = cs.sym;
+                while (rem) {
+                    const int i = __ffs((int)rem) - 1;
+                    rem &= rem - 1;
+                    s_stage[o++] = (uint8_t)(((sp.m[c].codes >> (2 * i)) & 3u) | (((cs.brk >> i) & 1u) << 2));
+                }
+                state = cs.end_hdr;
+            }
         }
-        if (w16 + 1 < cap_words16) {
-            if (s0 + 16 >= lead && s0 + 32 <= span) codes[w16 + 1] = c1;
-            else if (c1) atomicOr(&codes[w16 + 1], c1);
+        __syncthreads();
+        // pack-out: one 32-symbol group per thread and iteration
+        const uint32_t span = lead + tile_cnt;  // staged extent
+        const uint32_t ngroups = (span + 31) >> 5;
+        const uint64_t g_base = g_tile - lead;  // multiple of 32
+        for (uint32_t g = threadIdx.x; g < ngroups; g += kPackThreads) {
+            const uint4 a = reinterpret_cast<const uint4 *>(s_stage)[2 * g];
+            const uint4 bq = reinterpret_cast<const uint4 *>(s_stage)[2 * g + 1];
+            const uint32_t c0 = (pack_codes4(a.x) << 24) | (pack_codes4(a.y) << 16) | (pack_codes4(a.z) << 8) | pack_codes4(a.w);
+            const uint32_t c1 = (pack_codes4(bq.x) << 24) | (pack_codes4(bq.y) << 16) | (pack_codes4(bq.z) << 8) | pack_codes4(bq.w);
+            const uint32_t iv = (pack_breaks4(a.x) << 28) | (pack_breaks4(a.y) << 24) | (pack_breaks4(a.z) << 20) |
+                                (pack_breaks4(a.w) << 16) | (pack_breaks4(bq.x) << 12) | (pack_breaks4(bq.y) << 8) |
+                                (pack_breaks4(bq.z) << 4) | pack_breaks4(bq.w);
+            const uint32_t s0 = 32 * g;
+            const uint64_t w32 = (g_base >> 5) + g;
+            const uint64_t w16 = w32 * 2;
+            // a word wholly produced by this tile is stored; a word shared with a neighbouring tile or
+            // chunk is OR-ed (the buffers are zero-filled by dd_pack_reset)
+            if (w16 < cap_words16) {
+                if (s0 >= lead && s0 + 16 <= span) codes[w16] = c0;
+                else if (c0) atomicOr(&codes[w16], c0);
+            }
+            if (w16 + 1 < cap_words16) {
+                if (s0 + 16 >= lead && s0 + 32 <= span) codes[w16 + 1] = c1;
+                else if (c1) atomicOr(&codes[w16 + 1], c1);
+            }
+            if (w32 < cap_words32) {
+                if (s0 >= lead && s0 + 32 <= span) invalid[w32] = iv;
+                else if (iv) atomicOr(&invalid[w32], iv);
+            }
         }
-        if (w32 < cap_words32) {
-            if (s0 >= lead && s0 + 32 <= span) invalid[w32] = iv;
-            else if (iv) atomicOr(&invalid[w32], iv);
-        }
+        __syncthreads();  // text buffer it&1 and the staging area are free again
     }
 }
 
@@ -305,11 +447,26 @@ cudaError_t pack_fasta(const uint8_t *d_text, size_t n, uint32_t *d_codes, uint3
     p += align_up((nt + 1) * sizeof(PackTileOut), 256);
     uint64_t *seg_base = reinterpret_cast<uint64_t *>(p);
 
-    pack_count_kernel<<<(unsigned)nt, kPackThreads, 0, stream>>>(d_text, n, d_state, tile_xfer);
+    // persistent grids: SM count x resident CTAs (shared memory decides), never more CTAs than tiles
+    static int grid_count = 0, grid_write = 0;
+    if (grid_count == 0) {
+        int dev = 0, sms = 148, a = 1, c = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(pack_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kTileBytes));
+        cudaFuncSetAttribute(pack_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWriteSmem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, pack_count_kernel, kPackThreads, 2 * kTileBytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, pack_write_kernel, kPackThreads, kWriteSmem);
+        grid_count = sms * (a > 0 ? a : 1);
+        grid_write = sms * (c > 0 ? c : 1);
+    }
+    const unsigned ga = (unsigned)(nt < (size_t)grid_count ? nt : (size_t)grid_count);
+    const unsigned gc = (unsigned)(nt < (size_t)grid_write ? nt : (size_t)grid_write);
+    pack_count_kernel<<<ga, kPackThreads, 2 * kTileBytes, stream>>>(d_text, n, nt, d_state, tile_xfer);
     pack_scan_kernel<<<1, kScanThreads, 0, stream>>>(d_text, n, tile_xfer, nt, tile_out, seg_base, hdr, d_state,
                                                     cap_symbols);
-    pack_write_kernel<<<(unsigned)nt, kPackThreads, 0, stream>>>(d_text, n, tile_out, seg_base, hdr, d_state, d_codes,
-                                                                d_invalid, cap_symbols);
+    pack_write_kernel<<<gc, kPackThreads, kWriteSmem, stream>>>(d_text, n, nt, tile_out, seg_base, hdr, d_state, d_codes,
+                                                               d_invalid, cap_symbols);
     return cudaGetLastError();
 }
 

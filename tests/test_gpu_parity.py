@@ -304,3 +304,30 @@ def test_bit_plane_prefix_kernel_equals_byte_kernel(eng, p):
     run = np.maximum(regs[0], regs[1])
     for i in range(nk):
         assert b[0, 1, i] == pytest.approx(orc.card(run[i], p), rel=CARD_RTOL)
+
+
+def test_pack_unaligned_text_pointer(eng):
+    """The bulk-copy (TMA) staging needs 16-byte aligned text; any other pointer takes the
+    cooperative-copy fallback inside the same kernels and must give the same stream."""
+    import torch
+    from dandd_b200._lib import check
+    rng = np.random.default_rng(31)
+    txt = adversarial_fasta(rng, n=90000)
+    want = orc.fasta_symbols(txt)
+    n = len(txt)
+    for shift in (1, 7, 13):
+        base = torch.zeros(n + 64, dtype=torch.uint8, device=eng.device)
+        base[shift:shift + n] = torch.from_numpy(np.frombuffer(txt, dtype=np.uint8).copy()).to(eng.device)
+        assert (base.data_ptr() + shift) % 16 != 0
+        cb, ib = eng.lib.dd_pack_codes_bytes(n), eng.lib.dd_pack_invalid_bytes(n)
+        codes = torch.empty(cb, dtype=torch.uint8, device=eng.device)
+        inval = torch.empty(ib, dtype=torch.uint8, device=eng.device)
+        state = torch.empty(32, dtype=torch.uint8, device=eng.device)
+        ws = torch.empty(eng.lib.dd_pack_workspace_bytes(n), dtype=torch.uint8, device=eng.device)
+        check(eng.lib.dd_pack_reset(codes.data_ptr(), cb, inval.data_ptr(), ib, state.data_ptr(), eng.stream))
+        check(eng.lib.dd_pack_fasta(base.data_ptr() + shift, n, codes.data_ptr(), inval.data_ptr(), n, state.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), eng.stream))
+        nsym = int(state.cpu().numpy().view(np.uint64)[0])
+        assert nsym == want.size
+        got = decode_packed(codes.cpu().numpy().view(np.uint32), inval.cpu().numpy().view(np.uint32), nsym)
+        assert np.array_equal(got, want), shift
