@@ -28,22 +28,30 @@ constexpr int kPlThreads = 256;
 constexpr int kPlanes = 6;
 
 // ---- u8 registers -> bit planes -------------------------------------------------------------------
-// One thread per register; a warp's 32 registers form one group, six ballots give its six words.
+// One thread per group of 32 registers: two 128-bit loads, then a SWAR transpose -- for each of the
+// six bits, the four bytes of a word give a nibble with one mask, one multiply and one shift
+// (same gather as dd::gather_bit7), eight nibbles make the plane word.  Stores are one word per
+// plane per thread, contiguous across the warp.
+__device__ __forceinline__ uint32_t bit_nibble(uint32_t w, int b) {   // bit b of bytes 0..3 -> bits 0..3
+    return ((((w >> b) & 0x01010101u) * 0x00204081u) >> 21) & 0xFu;
+}
 __global__ void __launch_bounds__(256)
-to_planes_kernel(const uint8_t *__restrict__ regs, uint32_t *__restrict__ planes, int p, size_t total) {
+to_planes_kernel(const uint8_t *__restrict__ regs, uint32_t *__restrict__ planes, int p, size_t total_groups) {
     const size_t ngroups = (size_t)1 << (p - 5);
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t v = min((uint32_t)regs[t], 63u);
-        uint32_t mine = 0;
-        const int lane = threadIdx.x & 31;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_groups; g += (size_t)gridDim.x * blockDim.x) {
+        const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(regs) + 2 * g);
+        const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(regs) + 2 * g + 1);
+        const uint32_t w[8] = {__vminu4(lo.x, 0x3f3f3f3fu), __vminu4(lo.y, 0x3f3f3f3fu), __vminu4(lo.z, 0x3f3f3f3fu),
+                               __vminu4(lo.w, 0x3f3f3f3fu), __vminu4(hi.x, 0x3f3f3f3fu), __vminu4(hi.y, 0x3f3f3f3fu),
+                               __vminu4(hi.z, 0x3f3f3f3fu), __vminu4(hi.w, 0x3f3f3f3fu)};
+        const size_t sketch = g >> (p - 5), group = g & (ngroups - 1);
+        uint32_t *dst = planes + sketch * kPlanes * ngroups + group;
 #pragma unroll
         for (int b = 0; b < kPlanes; ++b) {
-            const uint32_t w = __ballot_sync(0xffffffffu, (v >> b) & 1u);
-            if (lane == b) mine = w;
-        }
-        if (lane < kPlanes) {
-            const size_t sketch = t >> p, group = (t & (((size_t)1 << p) - 1)) >> 5;   // m is a power of two
-            planes[(sketch * kPlanes + lane) * ngroups + group] = mine;
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) word |= bit_nibble(w[j], b) << (4 * j);
+            dst[(size_t)b * ngroups] = word;
         }
     }
 }
@@ -193,9 +201,10 @@ cudaError_t prefix_union_hist_planes(const uint8_t *d_regs, const int32_t *d_ord
         pool_tuned = true;
     }
     if ((e = cudaMallocAsync(reinterpret_cast<void **>(&planes), planes_bytes(n_genomes * nk, p), stream)) != cudaSuccess) return e;
-    size_t blocks = (total + 255) / 256;
+    const size_t total_groups = total >> 5;
+    size_t blocks = (total_groups + 255) / 256;
     if (blocks > (size_t)148 * 64) blocks = (size_t)148 * 64;
-    to_planes_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_regs, planes, p, total);
+    to_planes_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_regs, planes, p, total_groups);
     const size_t nvec = (m >> 5) >> 2;
     const unsigned slices = (unsigned)((nvec + kPlThreads - 1) / kPlThreads);
     prefix_union_planes_kernel<<<dim3((unsigned)n_ord, slices, (unsigned)nk), kPlThreads, 0, stream>>>(
