@@ -41,6 +41,9 @@
 namespace dd {
 
 constexpr int kSketchThreads = 256;
+#ifndef DD_XORSHIFT_ON_FMA
+#define DD_XORSHIFT_ON_FMA 0  // measured: no gain (3.1 Gbp 210 vs 203 ms); IMAD.WIDE is not cheaper than SHF here
+#endif
 
 struct SketchArgs {
     const uint32_t *codes;
@@ -90,6 +93,24 @@ __device__ __forceinline__ uint64_t mad64x32(uint64_t x, uint32_t c, uint64_t ad
     return r;
 }
 
+// h ^= h >> S with the two 32-bit right shifts done as widening multiplies by 2^(32-S) on the
+// FMA pipe (the high word of x * 2^(32-S) is x >> S, the low word is x << (32-S)), leaving only the
+// two XOR/OR LOP3s on the ALU pipe, which is the binding pipe of this kernel (ncu: ALU 67 %, FMA 11 %).
+template <int S>
+__device__ __forceinline__ uint64_t xorshr_fma(uint64_t h) {
+    uint32_t hl, hh, tl, th, ul, uh;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(hl), "=r"(hh) : "l"(h));
+    uint64_t t, u;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(hh), "r"(1u << (32 - S)));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(u) : "r"(hl), "r"(1u << (32 - S)));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(tl), "=r"(th) : "l"(t));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(ul), "=r"(uh) : "l"(u));
+    const uint32_t nl = hl ^ (uh | tl), nh = hh ^ th;
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(nl), "r"(nh));
+    return r;
+}
+
 // Canonical (or forward) k-mer ending at the current symbol.  For K <= 16 the whole k-mer lives in
 // one 32-bit register: mask, shift and min are single instructions.
 template <int K, bool kCanon>
@@ -128,11 +149,19 @@ __device__ __forceinline__ void update_one_k(const Window &win, int run, uint32_
         }
         // dd::wang64 (common.cuh) with the multiplications pinned to the FMA pipe
         uint64_t h = mad64x32(v, 0x1FFFFFu, 0xFFFFFFFFFFFFFFFFull);
+#if DD_XORSHIFT_ON_FMA
+        h = xorshr_fma<24>(h);
+        h = mul64x32(h, 265u);
+        h = xorshr_fma<14>(h);
+        h = mul64x32(h, 21u);
+        h = xorshr_fma<28>(h);
+#else
         h ^= h >> 24;
         h = mul64x32(h, 265u);
         h ^= h >> 14;
         h = mul64x32(h, 21u);
         h ^= h >> 28;
+#endif
         h = mul64x32(h, 0x80000001u);
         const uint32_t hi = (uint32_t)(h >> 32), lo = (uint32_t)h;
         // rank = 1 + leading zeros of the low (64-p) bits, capped at 64-p+1

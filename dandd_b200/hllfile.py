@@ -37,10 +37,35 @@ def write_hll(path: str, regs: np.ndarray, p: int, card: float = 0.0, compressle
     os.replace(tmp, path)   # a reader never sees a half-written sketch
 
 
+STUB_MAGIC = b"\nDANDD-B200-UNION-OF\n"
+
+
+class StubSketch(Exception):
+    """The file is a union marker (header + member list, no registers)."""
+
+    def __init__(self, path, p, card, members):
+        super().__init__(f"{path} is a union stub of {len(members)} sketches")
+        self.path, self.p, self.card, self.members = path, p, card, members
+
+
+def write_stub(path: str, p: int, card: float, members) -> None:
+    """DANDD_B200_UNION_FILES=stub: a non-empty marker instead of a full union sketch -- the header
+    (so `p` and the cached cardinality survive) followed by the member sketch paths, from which the
+    registers can be rebuilt on demand."""
+    tmp = f"{path}.tmp{os.getpid()}"
+    with open(tmp, "wb") as f:
+        f.write(HEADER.pack(1, 0, ERTL_MLE, ERTL_JOINT_MLE, p, float(card)))
+        f.write(STUB_MAGIC + "\n".join(members).encode())
+    os.replace(tmp, path)
+
+
 def read_hll(path: str):
-    """-> (registers uint8[2^p], p, cached estimate or None)."""
+    """-> (registers uint8[2^p], p, cached estimate or None); raises StubSketch for a union marker."""
     with open(path, "rb") as f:
         raw = f.read()
+    if raw[HEADER.size:HEADER.size + len(STUB_MAGIC)] == STUB_MAGIC:
+        known, _c, _e, _j, p, value = HEADER.unpack_from(raw)
+        raise StubSketch(path, p, value, raw[HEADER.size + len(STUB_MAGIC):].decode().split("\n"))
     if raw[:2] == b"\x1f\x8b":
         raw = zlib.decompress(raw, 16 + zlib.MAX_WBITS)
     if len(raw) < HEADER.size:

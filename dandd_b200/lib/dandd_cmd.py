@@ -113,6 +113,7 @@ def tree_command(args):
         print("ERROR: You must provide either a datadirectory or a fasta file list!")
         sys.exit(1)
     _select_device(args)
+    rank, world = _init_ranks()
     if not args.sketchdir:
         args.sketchdir = os.path.join(args.outdir, "sketchdb")
     os.makedirs(args.sketchdir, exist_ok=True)
@@ -127,7 +128,24 @@ def tree_command(args):
         registers=args.registers, flist_loc=args.flist_loc, canonicalize=args.canonicalize, tool=tool, debug=args.debug,
         nthreads=int(args.nthreads), safety=args.safety, fast=args.fast, verbose=args.verbose, ksweep=args.ksweep,
         lowmem=args.lowmem)
-    dtree.save(fileprefix=dtree.make_prefix(outdir=args.outdir, tag=args.tag, label=args.label), fast=args.fast)
+    if dtree is not None:   # rank 0 (or the only process)
+        dtree.save(fileprefix=dtree.make_prefix(outdir=args.outdir, tag=args.tag, label=args.label), fast=args.fast)
+    _finish_ranks(world)
+
+
+def _init_ranks():
+    """Under torchrun (WORLD_SIZE > 1) join the process group: nccl on GPUs, gloo otherwise."""
+    if int(os.environ.get("WORLD_SIZE", "1")) < 2:
+        return 0, 1
+    from dandd_b200 import dist as dd_dist
+    return dd_dist.init()
+
+
+def _finish_ranks(world):
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.barrier()
+        tdist.destroy_process_group()
 
 
 def progressive_command(args):

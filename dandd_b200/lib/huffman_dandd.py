@@ -647,6 +647,45 @@ class DeltaSpider(DeltaTree):
         raise NotImplementedError("initialization of spider by tree not yet implemented")
 
 
+def presketch_leaves_sharded(fastas, speciesinfo, experiment, kstart, halfwidth=6) -> int:
+    """One process per GPU (torchrun): every rank sketches its share of the FASTAs (largest first,
+    balanced by size) into the SHARED sketch database, ranks exchange the cardinalities they
+    computed, and rank 0 then builds the tree from files that already exist -- so the only work
+    left after this call is the unions.  Returns this process's rank.  HLL merge is exact, so the results are
+    identical to a single-GPU run.  k range: the sweep if one was asked for, else a
+    window around kstart (anything the hill-climb visits outside it is sketched on demand)."""
+    from dandd_b200 import dist as dd_dist
+    rank, world = dd_dist.world()
+    if world < 2:
+        return 0
+    if experiment["tool"] != "dashing":
+        return rank           # exact mode: rank 0 does everything (k-mer sets are not mergeable files)
+    import torch.distributed as tdist
+    lo, hi = experiment["ksweep"] if experiment["ksweep"] is not None else (kstart - halfwidth, kstart + halfwidth)
+    lo, hi = max(1, int(lo)), min(HLL_MAX_K, int(hi))
+    owners = dd_dist.shard_by_size([os.path.getsize(f) for f in fastas], world)
+    mine = [fastas[i] for i in owners[rank]]
+    ingest.prefetch(mine)
+    found = {}
+    scratch = dict(experiment, baseset=set())   # pre-sketching must not leak names into the tree's own bookkeeping
+    for path in mine:
+        leaf = DeltaTreeNode(node_title=path, children=[], speciesinfo=speciesinfo, experiment=scratch, progeny=[])
+        leaf.ksweep_update_node(mink=lo, maxk=hi)
+        template = leaf.ksketches[0].sfp.full if leaf.ksketches[0] is not None else None
+        for k in range(lo, hi + 1):
+            if template:
+                key = template.replace("{}", str(k))
+                if key in speciesinfo.cardkey:
+                    found[key] = speciesinfo.cardkey[key]
+    bucket = [None] * world
+    tdist.all_gather_object(bucket, (found, {k: v for k, v in speciesinfo.fastahex.items()}))
+    for cards, hexes in bucket:
+        speciesinfo.cardkey.update(cards)
+        for key, value in hexes.items():
+            speciesinfo.fastahex.setdefault(key, value)
+    return rank
+
+
 def create_delta_tree(tag: str, genomedir: str, sketchdir: str, kstart: int, nchildren=None, registers=0, flist_loc=None,
                       canonicalize=True, tool="dashing", debug=False, nthreads=0, safety=False, fast=False, verbose=False,
                       ksweep=None, lowmem=False):
@@ -666,6 +705,8 @@ def create_delta_tree(tag: str, genomedir: str, sketchdir: str, kstart: int, nch
         raise ValueError("You must provide either an existing directory of fastas or a file listing the paths of the "
                          f"desired fastas. The directory you provided was {speciesinfo.inputdir}.")
     fastas.sort()
+    if presketch_leaves_sharded(fastas, speciesinfo, experiment, kstart) > 0:
+        return None           # ranks > 0 only contribute leaf sketches; rank 0 builds and saves the tree
     ingest.prefetch(fastas)   # read / gunzip / blake2b in the background while the GPU works
     if nchildren:
         dtree = DeltaTree(fasta_files=fastas, speciesinfo=speciesinfo, nchildren=nchildren, experiment=experiment)

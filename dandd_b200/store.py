@@ -63,9 +63,12 @@ class GpuSketchStore:
         """Device registers of the sketch stored at `path` (HBM cache, else read the file)."""
         t = self._regs.get(path)
         if t is None:
-            regs, _p, _ = hllfile.read_hll(path)
+            try:
+                regs, _p, _ = hllfile.read_hll(path)
+                t = torch.from_numpy(regs).to(self.engine.device)
+            except hllfile.StubSketch as stub:       # union marker: rebuild from its members
+                t = self.engine.union([self.registers(m) for m in stub.members])
             self.stats["files_read"] += 1
-            t = torch.from_numpy(regs).to(self.engine.device)
             self._remember(path, t)
         else:
             self._regs.move_to_end(path)
@@ -76,13 +79,12 @@ class GpuSketchStore:
         if t is not None:
             self._bytes -= t.numel()
 
-    def _write(self, path: str, regs: torch.Tensor, p: int, card: float, leaf: bool) -> None:
+    def _write(self, path: str, regs: torch.Tensor, p: int, card: float, leaf: bool, members=None) -> None:
         os.makedirs(os.path.dirname(path), exist_ok=True)
-        if leaf or self.union_files == "full":
+        if leaf or self.union_files == "full" or not members:
             hllfile.write_hll(path, regs.cpu().numpy(), p, card, self.hll_compresslevel)
         else:
-            with open(path, "wb") as f:                       # non-empty marker: header only
-                f.write(hllfile.HEADER.pack(1, 0, hllfile.ERTL_MLE, hllfile.ERTL_JOINT_MLE, p, float(card)))
+            hllfile.write_stub(path, p, card, members)
         self.stats["files_written"] += 1
 
     # ------------------------------------------------------------------ dashing sketch
@@ -136,7 +138,7 @@ class GpuSketchStore:
         for i, k in enumerate(ks):
             regs = unions[i, 0]
             self._remember(out_paths[k], regs)
-            self._write(out_paths[k], regs, p, float(cards[i]), leaf=False)
+            self._write(out_paths[k], regs, p, float(cards[i]), leaf=False, members=list(members_by_k[k]))
             out[k] = float(cards[i])
         return out
 
@@ -181,7 +183,9 @@ class GpuSketchStore:
                             path = out_paths.get((o, st, k))
                             if path and path not in written:
                                 written.add(path)
-                                self._write(path, unions[o - o0, i, st], p, float(cards[o - o0, i, st]), leaf=False)
+                                members = [leaf_paths_by_k[k][g] for g in orderings[o][:st + 1] if g >= 0]
+                                self._write(path, unions[o - o0, i, st], p, float(cards[o - o0, i, st]), leaf=False,
+                                            members=members)
         return out
 
     # ------------------------------------------------------------------ dashing card

@@ -157,6 +157,14 @@ def main():
         run_ref(bindir, ["tree", "-d", data7, "-s", "runD", "-k", "13", "-o", outD, "-n", "3"])
         gold["runs"]["D_tree_nchildren3"] = collect_tree(outD, "runD_7_dashing", os.path.join(outD, "sketchdb"), "dashing")
 
+        # G: config 1 of BASELINE.json -- the example/ tutorial shape (25 mito-like genomes of 16-17 kbp,
+        # `dandd tree -k 14`); the tutorial data itself is not in the reference repository
+        data25 = os.path.join(work, "mito25")
+        make_dataset(data25, 25, 16500, seed=1, sub=0.10, indel=0.003, prefix="mito")
+        outG = os.path.join(work, "outG")
+        run_ref(bindir, ["tree", "-d", data25, "-s", "fish-mito", "-k", "14", "-o", outG])
+        gold["runs"]["G_config1_tree"] = collect_tree(outG, "fish-mito_25_dashing", os.path.join(outG, "sketchdb"), "dashing")
+
         # E: --exact (one reference method patched at run time, see EXACT_WRAPPER)
         outE = os.path.join(work, "outE")
         run_ref(bindir, ["tree", "-d", data5, "-s", "runE", "-k", "14", "-o", outE, "--exact"], exact=True)

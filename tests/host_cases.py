@@ -101,6 +101,15 @@ def scenario_tree_nchildren(tmp):
                         gold_runs()["D_tree_nchildren3"])
 
 
+def scenario_config1_tree(tmp):
+    """BASELINE.json config 1: `dandd tree -k 14` on 25 mito-like genomes (the example/ tutorial shape)."""
+    data = make_dataset(os.path.join(tmp, "mito25"), 25, 16500, seed=1, sub=0.10, indel=0.003, prefix="mito")
+    out = os.path.join(tmp, "outG")
+    run_dandd(["tree", "-d", os.path.dirname(data[0]), "-s", "fish-mito", "-k", "14", "-o", out])
+    assert_tree_matches(collect_tree(out, "fish-mito_25_dashing", os.path.join(out, "sketchdb"), "dashing"),
+                        gold_runs()["G_config1_tree"])
+
+
 def scenario_tree_exact(tmp):
     data = make_dataset(os.path.join(tmp, "data5"), 5, 20000, seed=21)
     out = os.path.join(tmp, "outE")

@@ -72,3 +72,39 @@ def test_single_process_is_identity():
     assert torch.equal(dd_dist.union_over_ranks(t.clone()), t)
     assert torch.equal(dd_dist.gather_registers(t, [[0, 1]]), t)
     assert list(dd_dist.split_work(5)) == [0, 1, 2, 3, 4]
+
+
+def _tree_worker(rank, world, port, tmpdir):
+    """`dandd tree` under two ranks (gloo): leaves are sketched by different ranks into the shared
+    sketchdb, rank 0 builds the tree; the outputs must equal the reference golden."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from dandd_b200 import store as ddstore
+    from tests.oracle_store import OracleStore
+    from tests.host_harness import run_dandd
+    st = OracleStore()
+    ddstore.set_store(st)
+    data = os.path.join(tmpdir, "data5")
+    run_dandd(["tree", "-d", data, "-s", "runA", "-k", "14", "-o", os.path.join(tmpdir, "outA")])
+    with open(os.path.join(tmpdir, f"leafpasses{rank}"), "w") as fh:
+        fh.write(str(st.stats["leaf_passes"]))
+
+
+def test_two_rank_tree_matches_reference(tmp_path):
+    from tests.host_harness import assert_tree_matches, collect_tree, gold_runs
+    from tests.util import make_dataset
+    make_dataset(str(tmp_path / "data5"), 5, 20000, seed=21)
+    mp.spawn(_tree_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    out = str(tmp_path / "outA")
+    ours = collect_tree(out, "runA_5_dashing", os.path.join(out, "sketchdb"), "dashing")
+    gold = gold_runs()["A_tree_hillclimb"]
+    # the ranks pre-sketch a k window around kstart, so the sketchdb may hold MORE leaf sketches than
+    # the reference's hill-climb visited; everything the reference has must be there and agree
+    assert set(gold["files"]) <= set(ours["files"])
+    assert set(gold["cardkey"]) <= set(ours["cardkey"])
+    trimmed = dict(ours, files=gold["files"], cardkey={k: ours["cardkey"][k] for k in gold["cardkey"]},
+                   sketchinfo=gold["sketchinfo"])
+    assert set(gold["sketchinfo"]) <= set(ours["sketchinfo"])
+    assert_tree_matches(trimmed, gold)
+    passes = [int(open(tmp_path / f"leafpasses{r}").read()) for r in (0, 1)]
+    assert passes[0] > 0 and passes[1] > 0      # both ranks sketched leaves; k outside the pre-sketched window costs rank 0 extra passes

@@ -39,6 +39,10 @@ def test_tree_nchildren(tmp_path, gpu_store):
     host_cases.scenario_tree_nchildren(str(tmp_path))
 
 
+def test_config1_tree(tmp_path, gpu_store):
+    host_cases.scenario_config1_tree(str(tmp_path))
+
+
 def test_tree_exact(tmp_path, gpu_store):
     host_cases.scenario_tree_exact(str(tmp_path))
 

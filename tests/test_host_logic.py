@@ -37,6 +37,10 @@ def test_tree_nchildren(tmp_path, oracle_store):
     host_cases.scenario_tree_nchildren(str(tmp_path))
 
 
+def test_config1_tree(tmp_path, oracle_store):
+    host_cases.scenario_config1_tree(str(tmp_path))
+
+
 def test_tree_exact(tmp_path, oracle_store):
     host_cases.scenario_tree_exact(str(tmp_path))
 
