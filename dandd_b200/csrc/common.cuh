@@ -59,6 +59,17 @@ DD_HD int ctz32(uint32_t x) {  // 32 for x == 0
 #endif
 }
 
+DD_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {  // PRMT, selector nibbles 0..7
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t src = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((src >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // Hash + register update (dnbaker/sketch WangHash and hll_t::add)
 // ---------------------------------------------------------------------------------------------
@@ -161,10 +172,15 @@ DD_HD void classify_word(uint32_t x, int wi, ChunkMasks &m) {
     m.nl |= gather_bit7(bytes_eq(x, 0x0a0a0a0au)) << sh;
     m.cr |= gather_bit7(bytes_eq(x, 0x0d0d0d0du)) << sh;
     m.gt |= gather_bit7(bytes_eq(x, 0x3e3e3e3eu)) << sh;
+    // ACGT test with one table lookup: the low three bits of 'A','C','T','G' are 1,3,4,7 -- all
+    // different -- so PRMT with those bits as selectors fetches the only letter each byte could be
+    // (filler 0x01 can never equal a byte whose low bits select it), and one compare finishes it.
     const uint32_t u = x & 0xdfdfdfdfu;  // fold case
-    const uint32_t v = bytes_eq(u, 0x41414141u) | bytes_eq(u, 0x43434343u) | bytes_eq(u, 0x47474747u) |
-                       bytes_eq(u, 0x54545454u);
-    m.acgt |= gather_bit7(v) << sh;
+    const uint32_t y = u & 0x07070707u;
+    const uint32_t t = y | (y >> 4);                        // byte0 = b0|b1<<4, byte2 = b2|b3<<4
+    const uint32_t sel = (t & 0xffu) | ((t >> 8) & 0xff00u);
+    const uint32_t expect = byte_perm(0x43014101u, 0x47010154u, sel);   // [.,A,.,C | T,.,.,G]
+    m.acgt |= gather_bit7(bytes_eq(u, expect)) << sh;
     // code = ((c >> 1) ^ (c >> 2)) & 3 : A->0 C->1 G->2 T->3 for either case
     const uint32_t c = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
     // bytes (b0,b1,b2,b3) 2-bit fields -> bits [1:0],[3:2],[5:4],[7:6]
@@ -227,9 +243,14 @@ DD_HD uint64_t xfer_compose(uint64_t f, uint64_t g) {
                      xfer_end(g, e1));
 }
 DD_HD uint64_t chunk_xfer(const ChunkMasks &m, bool first_at_line_start) {
-    const ChunkSyms a = chunk_symbols(m, first_at_line_start, false);
-    const ChunkSyms b = chunk_symbols(m, first_at_line_start, true);
-    return xfer_make((uint32_t)popc32(a.sym), (uint32_t)popc32(b.sym), a.end_hdr, b.end_hdr);
+    // both incoming states at once (same terms as chunk_symbols; only the "inherited header" bit differs)
+    const uint32_t ls = ((m.nl << 1) | (first_at_line_start ? 1u : 0u)) & 0xFFFFu;
+    const uint32_t hs = ls & m.gt;
+    const uint32_t body = ~(m.nl | m.cr) & 0xFFFFu;
+    const uint32_t span0 = (m.nl - hs) & ~m.nl;
+    const uint32_t span1 = first_at_line_start ? span0 : ((m.nl - (hs | 1u)) & ~m.nl);
+    return xfer_make((uint32_t)popc32((body & ~span0) | hs), (uint32_t)popc32((body & ~span1) | hs), (span0 >> 16) & 1u,
+                     (span1 >> 16) & 1u);
 }
 
 // 16 staged symbol bytes (bits 1:0 code, bit 2 break; 4 per word, first symbol in the low byte)
