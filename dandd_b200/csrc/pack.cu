@@ -203,6 +203,80 @@ __device__ __forceinline__ uint32_t span_prev_byte(const uint8_t *tile, uint32_t
     return tile_base ? (uint32_t)text[tile_base - 1] : entry_last;
 }
 
+// ---- fast path for "simple" tiles ------------------------------------------------------------------
+// A tile is SIMPLE when every byte is either '\n' or has bit 6 set (letters: 0x40-0x7F, 0xC0-0xFF):
+// no '>' (so no header can start), no '\r', no blanks/digits, no padding.  Then the only non-symbol
+// bytes are the newlines, the transition function follows from three block reductions, and pass C
+// needs no per-byte scatter: each 16-byte chunk is validated and 2-bit encoded with SWAR, its
+// newline holes are squeezed out in registers and the result is OR-ed into little-endian bit streams
+// in shared memory.  Everything else (headers, CRLF, the last partial tile) takes the general path.
+constexpr uint64_t kXferSimple = (uint64_t)1 << 62;
+
+// Per-thread summary of a 64-byte span: newline count and whether every byte without bit 6 is a
+// newline (the two byte-wise counters agree exactly then, because a newline itself lacks bit 6).
+struct SimpleSpan {
+    uint32_t nnl;
+    bool simple;
+};
+
+__device__ __forceinline__ SimpleSpan scan_simple(const uint8_t *tile, uint32_t off) {
+    uint32_t acc_nl = 0, acc_low = 0;  // four byte-wide counters each, <= 16 per byte
+#pragma unroll
+    for (int c = 0; c < kSpanChunks; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(tile + off + 16 * c);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            acc_nl += bytes_eq(w[i], 0x0a0a0a0au) >> 7;
+            acc_low += (~w[i] & 0x40404040u) >> 6;
+        }
+    }
+    SimpleSpan sp;
+    sp.simple = acc_nl == acc_low;
+    sp.nnl = (acc_nl * 0x01010101u) >> 24;
+    return sp;
+}
+
+// byte offset of the first '\n' in a 64-byte span that is known to contain one
+__device__ __forceinline__ uint32_t first_newline(const uint8_t *tile, uint32_t off) {
+    for (int i = 0; i < kSpanBytes / 4; ++i) {
+        const uint32_t z = bytes_eq(*reinterpret_cast<const uint32_t *>(tile + off + 4 * i), 0x0a0a0a0au);
+        if (z) return 4 * i + ((__ffs((int)z) - 1) >> 3);
+    }
+    return kSpanBytes;
+}
+
+// block-wide exclusive prefix sum of a small count (blockDim.x == kPackThreads)
+__device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t *s_warp32 /*[8]*/, uint32_t *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp32[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < kPackThreads / 32; ++w) {
+        const uint32_t t = s_warp32[w];
+        if (w < warp) before += t;
+        all += t;
+    }
+    *total = all;
+    return before + incl - v;
+}
+
+// OR `v` into word `idx` of a shared-memory bit stream; words strictly inside the calling thread's
+// own range [lo, hi] belong to it alone, the two end words may be shared with a neighbour thread.
+__device__ __forceinline__ void stream_or(uint32_t *stream, uint32_t idx, uint32_t v, uint32_t lo, uint32_t hi) {
+    if (!v) return;
+    if (idx > lo && idx < hi) stream[idx] |= v;
+    else atomicOr(&stream[idx], v);
+}
+
 // ---- pass A: one transition function per tile -------------------------------------------------
 __global__ void __launch_bounds__(kPackThreads)
 pack_count_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, const dd_pack_state *__restrict__ st,
@@ -231,12 +305,37 @@ pack_count_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
         if (threadIdx.x == 0 && next < ntiles) pipe.issue(next, it + 1);
         const uint8_t *b = pipe.wait(tile, it);
         const uint32_t off = threadIdx.x * kSpanBytes;
-        uint64_t f = kXferIdentity;
-        if (off < pipe.tile_bytes(tile))
-            f = load_span_smem(b, off, span_prev_byte(b, off, text, tile * kTileBytes, entry_last)).f;
-        uint64_t total;
-        block_scan_xfer(f, s_warp, &total);
-        if (threadIdx.x == 0) tile_xfer[tile] = total;
+        const bool full_tile = pipe.tile_bytes(tile) == (uint32_t)kTileBytes;
+        SimpleSpan ss = {0u, false};
+        if (full_tile) ss = scan_simple(b, off);
+        if (__syncthreads_and(full_tile && ss.simple)) {
+            // symbols = every byte that is not a newline; if the text before the tile ended inside a
+            // header, the bytes up to the first newline of the tile belong to that header
+            uint32_t total;
+            block_scan_u32(kSpanBytes - ss.nnl, reinterpret_cast<uint32_t *>(s_warp), &total);
+            // the first newline of the tile matters only if the tile is entered inside a header: the
+            // first thread that holds one looks its position up, nobody else does any work for it
+            __shared__ uint32_t s_first[kPackThreads / 32];
+            const uint32_t holders = __ballot_sync(0xffffffffu, ss.nnl != 0);
+            if ((threadIdx.x & 31) == 0)
+                s_first[threadIdx.x >> 5] = holders ? (threadIdx.x & ~31u) + (uint32_t)(__ffs((int)holders) - 1) : 0xffffffffu;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t t0 = 0xffffffffu;
+                for (int w = 0; w < kPackThreads / 32; ++w) t0 = min(t0, s_first[w]);
+                const bool has_nl = t0 != 0xffffffffu;
+                // no non-symbol byte precedes the first newline, so it is preceded by f0 symbols
+                const uint32_t f0 = has_nl ? t0 * kSpanBytes + first_newline(b, t0 * kSpanBytes) : 0u;
+                tile_xfer[tile] = xfer_make(total, has_nl ? total - f0 : 0u, 0u, has_nl ? 0u : 1u) | kXferSimple;
+            }
+        } else {
+            uint64_t f = kXferIdentity;
+            if (off < pipe.tile_bytes(tile))
+                f = load_span_smem(b, off, span_prev_byte(b, off, text, tile * kTileBytes, entry_last)).f;
+            uint64_t total;
+            block_scan_xfer(f, s_warp, &total);
+            if (threadIdx.x == 0) tile_xfer[tile] = total;
+        }
         __syncthreads();  // buffer it&1 and s_warp are free again
     }
 }
@@ -266,7 +365,7 @@ pack_scan_kernel(const uint8_t *__restrict__ text, size_t n, const uint64_t *__r
     for (size_t t = t0; t < t1; ++t) {
         const uint64_t g = tile_xfer[t];
         tile_out[t].local_off = local;
-        tile_out[t].state = state;
+        tile_out[t].state = state | ((g & kXferSimple) ? 2u : 0u);  // bit 0 header state, bit 1 simple tile
         local += xfer_cnt(g, state);
         state = xfer_end(g, state);
     }
@@ -307,6 +406,13 @@ pack_scan_kernel(const uint8_t *__restrict__ text, size_t n, const uint64_t *__r
 
 // ---- pass C: emit symbols ---------------------------------------------------------------------
 constexpr size_t kWriteSmem = 2 * kTileBytes + (kTileBytes + 64);  // two text buffers + symbol staging
+constexpr int kFastCodeWords = 1040;   // >= (kTileBytes + 31) * 2 / 32 + spill word, multiple of 4
+constexpr int kFastBreakWords = 520;   // >= (kTileBytes + 31) / 32 + spill word, multiple of 4
+// little-endian 2-bit codes (symbol i at bits 2i+1:2i) -> the stream's big-endian order (31-2i:30-2i)
+__device__ __forceinline__ uint32_t codes_le_to_be(uint32_t x) {
+    const uint32_t r = brev32(x);
+    return ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+}
 
 __global__ void __launch_bounds__(kPackThreads)
 pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, const PackTileOut *__restrict__ tile_out,
@@ -339,37 +445,121 @@ pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const size_t next = tile + gridDim.x;
         if (threadIdx.x == 0 && next < ntiles) pipe.issue(next, it + 1);
-        const uint32_t tile_state = (uint32_t)tile_out[tile].state;
+        const uint32_t tile_flags = (uint32_t)tile_out[tile].state;
+        const uint32_t tile_state = tile_flags & 1u;
+        const bool fast = tile_flags == 2u;  // simple tile entered outside a header
         const uint64_t g_tile = stream_base + seg_base[tile / seg_len] + tile_out[tile].local_off;
-
-        // symbols are staged as bytes (bits 1:0 code, bit 2 break) at their position in the output
-        // stream relative to the 32-symbol boundary below g_tile, so that pack-out writes whole words
-        for (int i = threadIdx.x; i < (kTileBytes + 64) / 16; i += kPackThreads)
-            reinterpret_cast<uint4 *>(s_stage)[i] = make_uint4(0, 0, 0, 0);
-
-        const uint8_t *b = pipe.wait(tile, it);
-        const uint32_t off = threadIdx.x * kSpanBytes;
-        const bool active = off < pipe.tile_bytes(tile);
-        Span sp;
-        sp.f = kXferIdentity;
-        if (active) sp = load_span_smem(b, off, span_prev_byte(b, off, text, tile * kTileBytes, entry_last));
-        uint64_t all;
-        const uint64_t pre = block_scan_xfer(sp.f, s_warp, &all);  // its barriers also order the zeroing above
-        const uint32_t tile_cnt = xfer_cnt(all, tile_state);
         const uint32_t lead = (uint32_t)(g_tile & 31);
-        if (active) {
-            uint32_t state = xfer_end(pre, tile_state);
-            uint32_t o = lead + xfer_cnt(pre, tile_state);
+        const uint32_t off = threadIdx.x * kSpanBytes;
+        uint32_t tile_cnt;
+        uint32_t *s_codes = reinterpret_cast<uint32_t *>(s_stage);  // fast path: little-endian bit streams
+        uint32_t *s_brk = s_codes + kFastCodeWords;
+
+        if (fast) {
+            for (int i = threadIdx.x; i < (kFastCodeWords + kFastBreakWords) / 4; i += kPackThreads)
+                reinterpret_cast<uint4 *>(s_stage)[i] = make_uint4(0, 0, 0, 0);
+            const uint8_t *b = pipe.wait(tile, it);
+            // In a simple tile a byte without bit 6 is a newline, so one LOP finds them.  The ACGT test
+            // is classify_word's table lookup with the free slot 2 holding '\n': the XOR below is zero
+            // exactly for ACGTacgt and '\n', so its non-zero bytes are the break symbols.
+            uint32_t acc_nl = 0;
 #pragma unroll
             for (int c = 0; c < kSpanChunks; ++c) {
-                const ChunkSyms cs = chunk_symbols(sp.m[c], (sp.ls >> c) & 1u, state != 0);
-                uint32_t rem = cs.sym;
-                while (rem) {
-                    const int i = __ffs((int)rem) - 1;
-                    rem &= rem - 1;
-                    s_stage[o++] = (uint8_t)(((sp.m[c].codes >> (2 * i)) & 3u) | (((cs.brk >> i) & 1u) << 2));
+                const uint4 v = *reinterpret_cast<const uint4 *>(b + off + 16 * c);
+                acc_nl += ((~v.x & 0x40404040u) >> 6) + ((~v.y & 0x40404040u) >> 6) + ((~v.z & 0x40404040u) >> 6) +
+                          ((~v.w & 0x40404040u) >> 6);
+            }
+            const uint32_t cnt = kSpanBytes - ((acc_nl * 0x01010101u) >> 24);
+            // my first output position (the scan's barriers also order the zeroing above)
+            const uint32_t pos0 = lead + block_scan_u32(cnt, reinterpret_cast<uint32_t *>(s_warp), &tile_cnt);
+            if (cnt) {
+                const uint32_t lo16 = pos0 >> 4, hi16 = (pos0 + cnt - 1) >> 4;
+                const uint32_t lo32 = pos0 >> 5, hi32 = (pos0 + cnt - 1) >> 5;
+                uint32_t wc = lo16, fill_c = 2 * (pos0 & 15), acc_c = 0;
+                uint32_t wb = lo32, fill_b = pos0 & 31, acc_b = 0;
+#pragma unroll
+                for (int c = 0; c < kSpanChunks; ++c) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(b + off + 16 * c);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t nz[4], C = 0, nl = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t u = w[i] & 0xdfdfdfdfu;
+                        const uint32_t y = u & 0x07070707u;
+                        const uint32_t t = y | (y >> 4);
+                        const uint32_t d = u ^ byte_perm(0x430a4101u, 0x47010154u, byte_perm(t, t, 0x0020u));
+                        nz[i] = (((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u;
+                        nl |= ((((~w[i] & 0x40404040u) >> 6) * 0x00204081u >> 21) & 0xFu) << (4 * i);
+                        const uint32_t cc = ((w[i] >> 1) ^ (w[i] >> 2)) & 0x03030303u;
+                        C |= (((cc * 0x00041041u) >> 18) & 0xFFu) << (8 * i);
+                    }
+                    uint32_t B = 0;
+                    if (nz[0] | nz[1] | nz[2] | nz[3])
+                        B = gather_bit7(nz[0]) | (gather_bit7(nz[1]) << 4) | (gather_bit7(nz[2]) << 8) | (gather_bit7(nz[3]) << 12);
+                    const uint32_t n = 16 - __popc(nl);
+                    while (nl) {  // squeeze the newline positions out of both streams
+                        const int h = __ffs((int)nl) - 1;
+                        const uint32_t below = (1u << h) - 1u, below2 = (1u << (2 * h)) - 1u;
+                        B = (B & below) | ((B >> (h + 1)) << h);
+                        C = (C & below2) | (((C >> (2 * h + 1)) >> 1) << (2 * h));
+                        nl = (nl & (nl - 1)) >> 1;
+                    }
+                    if (n) {
+                        // append 2n code bits
+                        acc_c |= C << fill_c;
+                        uint32_t nf = fill_c + 2 * n;
+                        if (nf >= 32) {
+                            if (wc > lo16 && wc < hi16) s_codes[wc] = acc_c;
+                            else atomicOr(&s_codes[wc], acc_c);
+                            ++wc;
+                            acc_c = fill_c ? C >> (32 - fill_c) : 0u;
+                            nf -= 32;
+                        }
+                        fill_c = nf;
+                        // append n break bits
+                        acc_b |= B << fill_b;
+                        nf = fill_b + n;
+                        if (nf >= 32) {
+                            if (wb > lo32 && wb < hi32) s_brk[wb] = acc_b;
+                            else if (acc_b) atomicOr(&s_brk[wb], acc_b);
+                            ++wb;
+                            acc_b = B >> (32 - fill_b);  // fill_b >= 16 here
+                            nf -= 32;
+                        }
+                        fill_b = nf;
+                    }
                 }
-                state = cs.end_hdr;
+                if (fill_c && acc_c) atomicOr(&s_codes[wc], acc_c);
+                if (fill_b && acc_b) atomicOr(&s_brk[wb], acc_b);
+            }
+        } else {
+            // symbols are staged as bytes (bits 1:0 code, bit 2 break) at their position in the output
+            // stream relative to the 32-symbol boundary below g_tile, so that pack-out writes whole words
+            for (int i = threadIdx.x; i < (kTileBytes + 64) / 16; i += kPackThreads)
+                reinterpret_cast<uint4 *>(s_stage)[i] = make_uint4(0, 0, 0, 0);
+
+            const uint8_t *b = pipe.wait(tile, it);
+            const bool active = off < pipe.tile_bytes(tile);
+            Span sp;
+            sp.f = kXferIdentity;
+            if (active) sp = load_span_smem(b, off, span_prev_byte(b, off, text, tile * kTileBytes, entry_last));
+            uint64_t all;
+            const uint64_t pre = block_scan_xfer(sp.f, s_warp, &all);  // its barriers also order the zeroing above
+            tile_cnt = xfer_cnt(all, tile_state);
+            if (active) {
+                uint32_t state = xfer_end(pre, tile_state);
+                uint32_t o = lead + xfer_cnt(pre, tile_state);
+#pragma unroll
+                for (int c = 0; c < kSpanChunks; ++c) {
+                    const ChunkSyms cs = chunk_symbols(sp.m[c], (sp.ls >> c) & 1u, state != 0);
+                    uint32_t rem = cs.sym;
+                    while (rem) {
+                        const int i = __ffs((int)rem) - 1;
+                        rem &= rem - 1;
+                        s_stage[o++] = (uint8_t)(((sp.m[c].codes >> (2 * i)) & 3u) | (((cs.brk >> i) & 1u) << 2));
+                    }
+                    state = cs.end_hdr;
+                }
             }
         }
         __syncthreads();
@@ -378,13 +568,20 @@ pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
         const uint32_t ngroups = (span + 31) >> 5;
         const uint64_t g_base = g_tile - lead;  // multiple of 32
         for (uint32_t g = threadIdx.x; g < ngroups; g += kPackThreads) {
-            const uint4 a = reinterpret_cast<const uint4 *>(s_stage)[2 * g];
-            const uint4 bq = reinterpret_cast<const uint4 *>(s_stage)[2 * g + 1];
-            const uint32_t c0 = (pack_codes4(a.x) << 24) | (pack_codes4(a.y) << 16) | (pack_codes4(a.z) << 8) | pack_codes4(a.w);
-            const uint32_t c1 = (pack_codes4(bq.x) << 24) | (pack_codes4(bq.y) << 16) | (pack_codes4(bq.z) << 8) | pack_codes4(bq.w);
-            const uint32_t iv = (pack_breaks4(a.x) << 28) | (pack_breaks4(a.y) << 24) | (pack_breaks4(a.z) << 20) |
-                                (pack_breaks4(a.w) << 16) | (pack_breaks4(bq.x) << 12) | (pack_breaks4(bq.y) << 8) |
-                                (pack_breaks4(bq.z) << 4) | pack_breaks4(bq.w);
+            uint32_t c0, c1, iv;
+            if (fast) {
+                c0 = codes_le_to_be(s_codes[2 * g]);
+                c1 = codes_le_to_be(s_codes[2 * g + 1]);
+                iv = brev32(s_brk[g]);
+            } else {
+                const uint4 a = reinterpret_cast<const uint4 *>(s_stage)[2 * g];
+                const uint4 bq = reinterpret_cast<const uint4 *>(s_stage)[2 * g + 1];
+                c0 = (pack_codes4(a.x) << 24) | (pack_codes4(a.y) << 16) | (pack_codes4(a.z) << 8) | pack_codes4(a.w);
+                c1 = (pack_codes4(bq.x) << 24) | (pack_codes4(bq.y) << 16) | (pack_codes4(bq.z) << 8) | pack_codes4(bq.w);
+                iv = (pack_breaks4(a.x) << 28) | (pack_breaks4(a.y) << 24) | (pack_breaks4(a.z) << 20) |
+                     (pack_breaks4(a.w) << 16) | (pack_breaks4(bq.x) << 12) | (pack_breaks4(bq.y) << 8) |
+                     (pack_breaks4(bq.z) << 4) | pack_breaks4(bq.w);
+            }
             const uint32_t s0 = 32 * g;
             const uint64_t w32 = (g_base >> 5) + g;
             const uint64_t w16 = w32 * 2;

@@ -331,3 +331,52 @@ def test_pack_unaligned_text_pointer(eng):
         assert nsym == want.size
         got = decode_packed(codes.cpu().numpy().view(np.uint32), inval.cpu().numpy().view(np.uint32), nsym)
         assert np.array_equal(got, want), shift
+
+
+def _simple_tile_cases():
+    rng = np.random.default_rng(77)
+    letters = np.frombuffer(b"ACGTacgtNnRYKMswbdhvUuXx", dtype=np.uint8)
+
+    def noisy(n, frac=0.01):
+        s = np.frombuffer(random_bases(rng, n), dtype=np.uint8).copy()
+        idx = rng.choice(n, size=max(1, int(n * frac)), replace=False)
+        s[idx] = letters[rng.integers(0, letters.size, idx.size)]
+        return s.tobytes()
+
+    def wrap(seq, width):
+        return b"\n".join(seq[i:i + width] for i in range(0, len(seq), width)) + b"\n"
+
+    cases = {}
+    cases["w60"] = b">r1 plain record\n" + wrap(noisy(200_000), 60)
+    cases["w7_multi_newline_per_chunk"] = b">r\n" + wrap(noisy(120_000, 0.05), 7)
+    cases["w1"] = b">r\n" + wrap(noisy(40_000, 0.05), 1)
+    cases["one_line"] = b">r\n" + noisy(150_000) + b"\n"
+    cases["letters_only_header_spanning_tiles"] = b">" + noisy(45_000) + b"\n" + wrap(noisy(100_000), 80)
+    cases["blank_line_runs"] = b">r\n" + wrap(noisy(50_000), 61).replace(b"\n", b"\n\n\n", 300) + wrap(noisy(50_000), 61)
+    hi = np.frombuffer(noisy(100_000), dtype=np.uint8).copy()
+    hi[rng.choice(hi.size, 500, replace=False)] = rng.integers(0xC0, 0x100, 500).astype(np.uint8)
+    cases["high_bytes"] = b">r\n" + wrap(hi.tobytes(), 70)
+    # general tiles (headers, CR, digits, blanks) interleaved with simple ones, at tile-sized distances
+    mixed = b""
+    for i in range(12):
+        mixed += b">rec%d some text\r\n" % i + wrap(noisy(int(rng.integers(10_000, 50_000))), 60)
+        mixed += b"ACGT 12 acgt\n" if i % 3 == 0 else b""
+    cases["mixed"] = mixed
+    cases["no_final_newline"] = (b">r\n" + wrap(noisy(70_000), 60)).rstrip(b"\n")
+    cases["exact_tiles"] = (b">r\n" + wrap(noisy(70_000), 60))[:4 * 16384]
+    return cases
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk", [None, 50_001, 16384, 65536 + 16])
+def test_pack_simple_tiles(eng, chunk):
+    """K1's fast path (tiles holding only letters and newlines) against the oracle, including its
+    seams with general tiles, header state carried into a simple tile, and chunked/unaligned calls."""
+    for name, txt in _simple_tile_cases().items():
+        want = orc.fasta_symbols(txt)
+        seq = eng.pack(txt, chunk_bytes=chunk)
+        assert seq.nsym == want.size, name
+        got = packed_to_numpy(seq)
+        if not np.array_equal(got, want):
+            bad = np.flatnonzero(got != want)
+            raise AssertionError((name, chunk, bad[:10].tolist(), bad.size))
