@@ -340,7 +340,25 @@ pack_count_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
     }
 }
 
-// ---- pass B: scan tile functions, assign output offsets, advance the stream state --------------
+// ---- pass B1: scan tile functions inside groups of kGroupTiles tiles -----------------------------
+// One CTA per group, one tile per thread: tile_xfer[t] becomes the composition of the earlier tiles
+// of its group (exclusive prefix, simple flag kept), group_agg[g] the whole group.  A group emits at
+// most kGroupTiles * kTileBytes = 2^23 symbols, which the 24-bit count fields hold.
+constexpr int kGroupTiles = 512;
+
+__global__ void __launch_bounds__(kGroupTiles)
+pack_scan_groups_kernel(uint64_t *__restrict__ tile_xfer, size_t ntiles, uint64_t *__restrict__ group_agg) {
+    __shared__ uint64_t s_warp[32];
+    const size_t t = (size_t)blockIdx.x * kGroupTiles + threadIdx.x;
+    const uint64_t g = t < ntiles ? tile_xfer[t] : kXferIdentity;
+    uint64_t all;
+    const uint64_t pre = block_scan_xfer(g & ~kXferSimple, s_warp, &all);
+    if (t < ntiles) tile_xfer[t] = pre | (g & kXferSimple);
+    if (threadIdx.x == 0) group_agg[blockIdx.x] = all;
+}
+
+// ---- pass B2: scan the group functions ("tiles" below are groups), assign output offsets,
+// advance the stream state ----------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanThreads)
 pack_scan_kernel(const uint8_t *__restrict__ text, size_t n, const uint64_t *__restrict__ tile_xfer, size_t ntiles,
                  PackTileOut *__restrict__ tile_out, uint64_t *__restrict__ seg_base, PackWsHeader *__restrict__ hdr,
@@ -365,7 +383,7 @@ pack_scan_kernel(const uint8_t *__restrict__ text, size_t n, const uint64_t *__r
     for (size_t t = t0; t < t1; ++t) {
         const uint64_t g = tile_xfer[t];
         tile_out[t].local_off = local;
-        tile_out[t].state = state | ((g & kXferSimple) ? 2u : 0u);  // bit 0 header state, bit 1 simple tile
+        tile_out[t].state = state;
         local += xfer_cnt(g, state);
         state = xfer_end(g, state);
     }
@@ -415,8 +433,8 @@ __device__ __forceinline__ uint32_t codes_le_to_be(uint32_t x) {
 }
 
 __global__ void __launch_bounds__(kPackThreads)
-pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, const PackTileOut *__restrict__ tile_out,
-                  const uint64_t *__restrict__ seg_base, const PackWsHeader *__restrict__ hdr,
+pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, const uint64_t *__restrict__ tile_pre,
+                  const PackTileOut *__restrict__ group_out, const uint64_t *__restrict__ seg_base, const PackWsHeader *__restrict__ hdr,
                   const dd_pack_state *__restrict__ st, uint32_t *__restrict__ codes, uint32_t *__restrict__ invalid,
                   size_t cap_symbols) {
     extern __shared__ __align__(128) uint8_t s_dyn[];
@@ -445,10 +463,12 @@ pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const size_t next = tile + gridDim.x;
         if (threadIdx.x == 0 && next < ntiles) pipe.issue(next, it + 1);
-        const uint32_t tile_flags = (uint32_t)tile_out[tile].state;
-        const uint32_t tile_state = tile_flags & 1u;
-        const bool fast = tile_flags == 2u;  // simple tile entered outside a header
-        const uint64_t g_tile = stream_base + seg_base[tile / seg_len] + tile_out[tile].local_off;
+        const size_t group = tile / kGroupTiles;
+        const uint64_t pre_fn = tile_pre[tile];  // earlier tiles of the group, as a function of the group's entry state
+        const uint32_t group_state = (uint32_t)group_out[group].state;
+        const uint32_t tile_state = xfer_end(pre_fn, group_state);
+        const bool fast = (pre_fn & kXferSimple) && tile_state == 0;  // simple tile entered outside a header
+        const uint64_t g_tile = stream_base + seg_base[group / seg_len] + group_out[group].local_off + xfer_cnt(pre_fn, group_state);
         const uint32_t lead = (uint32_t)(g_tile & 31);
         const uint32_t off = threadIdx.x * kSpanBytes;
         uint32_t tile_cnt;
@@ -473,10 +493,11 @@ pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
             // my first output position (the scan's barriers also order the zeroing above)
             const uint32_t pos0 = lead + block_scan_u32(cnt, reinterpret_cast<uint32_t *>(s_warp), &tile_cnt);
             if (cnt) {
-                const uint32_t lo16 = pos0 >> 4, hi16 = (pos0 + cnt - 1) >> 4;
-                const uint32_t lo32 = pos0 >> 5, hi32 = (pos0 + cnt - 1) >> 5;
-                uint32_t wc = lo16, fill_c = 2 * (pos0 & 15), acc_c = 0;
-                uint32_t wb = lo32, fill_b = pos0 & 31, acc_b = 0;
+                // code bits are collected in a register and OR-ed into the stream one full word at a
+                // time (the tile's stream words are zero and the first/last word of a thread's range is
+                // shared with its neighbours, so every flush is an atomic OR); break bits are rare and
+                // go straight to the stream
+                uint32_t pos = pos0, wc = pos0 >> 4, fill_c = 2 * (pos0 & 15), acc_c = 0;
 #pragma unroll
                 for (int c = 0; c < kSpanChunks; ++c) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(b + off + 16 * c);
@@ -504,33 +525,22 @@ pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
                         C = (C & below2) | (((C >> (2 * h + 1)) >> 1) << (2 * h));
                         nl = (nl & (nl - 1)) >> 1;
                     }
-                    if (n) {
-                        // append 2n code bits
-                        acc_c |= C << fill_c;
-                        uint32_t nf = fill_c + 2 * n;
-                        if (nf >= 32) {
-                            if (wc > lo16 && wc < hi16) s_codes[wc] = acc_c;
-                            else atomicOr(&s_codes[wc], acc_c);
-                            ++wc;
-                            acc_c = fill_c ? C >> (32 - fill_c) : 0u;
-                            nf -= 32;
-                        }
-                        fill_c = nf;
-                        // append n break bits
-                        acc_b |= B << fill_b;
-                        nf = fill_b + n;
-                        if (nf >= 32) {
-                            if (wb > lo32 && wb < hi32) s_brk[wb] = acc_b;
-                            else if (acc_b) atomicOr(&s_brk[wb], acc_b);
-                            ++wb;
-                            acc_b = B >> (32 - fill_b);  // fill_b >= 16 here
-                            nf -= 32;
-                        }
-                        fill_b = nf;
+                    // append 2n code bits
+                    acc_c |= C << fill_c;
+                    if (fill_c + 2 * n >= 32) {
+                        atomicOr(&s_codes[wc++], acc_c);
+                        acc_c = __funnelshift_l(C, 0u, fill_c);  // C >> (32 - fill_c): the bits that did not fit
+                        fill_c -= 32;
                     }
+                    fill_c += 2 * n;
+                    if (B) {
+                        const uint32_t sh = pos & 31;
+                        atomicOr(&s_brk[pos >> 5], B << sh);
+                        if (sh > 16) atomicOr(&s_brk[(pos >> 5) + 1], B >> (32 - sh));
+                    }
+                    pos += n;
                 }
-                if (fill_c && acc_c) atomicOr(&s_codes[wc], acc_c);
-                if (fill_b && acc_b) atomicOr(&s_brk[wb], acc_b);
+                if (acc_c) atomicOr(&s_codes[wc], acc_c);
             }
         } else {
             // symbols are staged as bytes (bits 1:0 code, bit 2 break) at their position in the output
@@ -585,6 +595,11 @@ pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
             const uint32_t s0 = 32 * g;
             const uint64_t w32 = (g_base >> 5) + g;
             const uint64_t w16 = w32 * 2;
+            if (s0 >= lead && s0 + 32 <= span && w16 + 1 < cap_words16 && w32 < cap_words32) {
+                *reinterpret_cast<uint2 *>(codes + w16) = make_uint2(c0, c1);  // wholly this tile's
+                invalid[w32] = iv;
+                continue;
+            }
             // a word wholly produced by this tile is stored; a word shared with a neighbouring tile or
             // chunk is OR-ed (the buffers are zero-filled by dd_pack_reset)
             if (w16 < cap_words16) {
@@ -616,10 +631,12 @@ __global__ void pack_state_init_kernel(dd_pack_state *st) {
 static size_t pack_ntiles(size_t n) { return (n + kTileBytes - 1) / kTileBytes; }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+static size_t pack_ngroups(size_t ntiles) { return (ntiles + kGroupTiles - 1) / kGroupTiles; }
+
 size_t pack_workspace_bytes(size_t chunk_bytes) {
-    const size_t nt = pack_ntiles(chunk_bytes) + 1;
-    return align_up(sizeof(PackWsHeader), 256) + align_up(nt * sizeof(uint64_t), 256) +
-           align_up(nt * sizeof(PackTileOut), 256) + align_up(kScanThreads * sizeof(uint64_t), 256);
+    const size_t nt = pack_ntiles(chunk_bytes) + 1, ng = pack_ngroups(nt) + 1;
+    return align_up(sizeof(PackWsHeader), 256) + align_up(nt * sizeof(uint64_t), 256) + align_up(ng * sizeof(uint64_t), 256) +
+           align_up(ng * sizeof(PackTileOut), 256) + align_up(kScanThreads * sizeof(uint64_t), 256);
 }
 
 cudaError_t pack_reset(uint32_t *d_codes, size_t codes_bytes, uint32_t *d_invalid, size_t invalid_bytes,
@@ -638,10 +655,13 @@ cudaError_t pack_fasta(const uint8_t *d_text, size_t n, uint32_t *d_codes, uint3
     uint8_t *p = static_cast<uint8_t *>(d_ws);
     PackWsHeader *hdr = reinterpret_cast<PackWsHeader *>(p);
     p += align_up(sizeof(PackWsHeader), 256);
+    const size_t ng = pack_ngroups(nt);
     uint64_t *tile_xfer = reinterpret_cast<uint64_t *>(p);
     p += align_up((nt + 1) * sizeof(uint64_t), 256);
-    PackTileOut *tile_out = reinterpret_cast<PackTileOut *>(p);
-    p += align_up((nt + 1) * sizeof(PackTileOut), 256);
+    uint64_t *group_agg = reinterpret_cast<uint64_t *>(p);
+    p += align_up((pack_ngroups(nt + 1) + 1) * sizeof(uint64_t), 256);
+    PackTileOut *group_out = reinterpret_cast<PackTileOut *>(p);
+    p += align_up((pack_ngroups(nt + 1) + 1) * sizeof(PackTileOut), 256);
     uint64_t *seg_base = reinterpret_cast<uint64_t *>(p);
 
     // persistent grids: SM count x resident CTAs (shared memory decides), never more CTAs than tiles
@@ -660,10 +680,10 @@ cudaError_t pack_fasta(const uint8_t *d_text, size_t n, uint32_t *d_codes, uint3
     const unsigned ga = (unsigned)(nt < (size_t)grid_count ? nt : (size_t)grid_count);
     const unsigned gc = (unsigned)(nt < (size_t)grid_write ? nt : (size_t)grid_write);
     pack_count_kernel<<<ga, kPackThreads, 2 * kTileBytes, stream>>>(d_text, n, nt, d_state, tile_xfer);
-    pack_scan_kernel<<<1, kScanThreads, 0, stream>>>(d_text, n, tile_xfer, nt, tile_out, seg_base, hdr, d_state,
-                                                    cap_symbols);
-    pack_write_kernel<<<gc, kPackThreads, kWriteSmem, stream>>>(d_text, n, nt, tile_out, seg_base, hdr, d_state, d_codes,
-                                                               d_invalid, cap_symbols);
+    pack_scan_groups_kernel<<<(unsigned)ng, kGroupTiles, 0, stream>>>(tile_xfer, nt, group_agg);
+    pack_scan_kernel<<<1, kScanThreads, 0, stream>>>(d_text, n, group_agg, ng, group_out, seg_base, hdr, d_state, cap_symbols);
+    pack_write_kernel<<<gc, kPackThreads, kWriteSmem, stream>>>(d_text, n, nt, tile_xfer, group_out, seg_base, hdr, d_state,
+                                                               d_codes, d_invalid, cap_symbols);
     return cudaGetLastError();
 }
 
