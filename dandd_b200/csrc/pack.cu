@@ -482,14 +482,32 @@ pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
             // In a simple tile a byte without bit 6 is a newline, so one LOP finds them.  The ACGT test
             // is classify_word's table lookup with the free slot 2 holding '\n': the XOR below is zero
             // exactly for ACGTacgt and '\n', so its non-zero bytes are the break symbols.
-            uint32_t acc_nl = 0;
+            uint32_t Cw[kSpanChunks], BN[kSpanChunks];  // codes; break mask | newline mask << 16
+            uint32_t nnl = 0;
 #pragma unroll
             for (int c = 0; c < kSpanChunks; ++c) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(b + off + 16 * c);
-                acc_nl += ((~v.x & 0x40404040u) >> 6) + ((~v.y & 0x40404040u) >> 6) + ((~v.z & 0x40404040u) >> 6) +
-                          ((~v.w & 0x40404040u) >> 6);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                uint32_t nz[4], C = 0, nl = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t u = w[i] & 0xdfdfdfdfu;
+                    const uint32_t y = u & 0x07070707u;
+                    const uint32_t t = y | (y >> 4);
+                    const uint32_t d = u ^ byte_perm(0x430a4101u, 0x47010154u, byte_perm(t, t, 0x0020u));
+                    nz[i] = (((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u;
+                    nl |= ((((~w[i] & 0x40404040u) >> 6) * 0x00204081u >> 21) & 0xFu) << (4 * i);
+                    const uint32_t cc = ((w[i] >> 1) ^ (w[i] >> 2)) & 0x03030303u;
+                    C |= (((cc * 0x00041041u) >> 18) & 0xFFu) << (8 * i);
+                }
+                uint32_t B = 0;
+                if (nz[0] | nz[1] | nz[2] | nz[3])
+                    B = gather_bit7(nz[0]) | (gather_bit7(nz[1]) << 4) | (gather_bit7(nz[2]) << 8) | (gather_bit7(nz[3]) << 12);
+                Cw[c] = C;
+                BN[c] = B | (nl << 16);
+                nnl += __popc(nl);
             }
-            const uint32_t cnt = kSpanBytes - ((acc_nl * 0x01010101u) >> 24);
+            const uint32_t cnt = kSpanBytes - nnl;
             // my first output position (the scan's barriers also order the zeroing above)
             const uint32_t pos0 = lead + block_scan_u32(cnt, reinterpret_cast<uint32_t *>(s_warp), &tile_cnt);
             if (cnt) {
@@ -500,23 +518,7 @@ pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
                 uint32_t pos = pos0, wc = pos0 >> 4, fill_c = 2 * (pos0 & 15), acc_c = 0;
 #pragma unroll
                 for (int c = 0; c < kSpanChunks; ++c) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(b + off + 16 * c);
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                    uint32_t nz[4], C = 0, nl = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t u = w[i] & 0xdfdfdfdfu;
-                        const uint32_t y = u & 0x07070707u;
-                        const uint32_t t = y | (y >> 4);
-                        const uint32_t d = u ^ byte_perm(0x430a4101u, 0x47010154u, byte_perm(t, t, 0x0020u));
-                        nz[i] = (((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u;
-                        nl |= ((((~w[i] & 0x40404040u) >> 6) * 0x00204081u >> 21) & 0xFu) << (4 * i);
-                        const uint32_t cc = ((w[i] >> 1) ^ (w[i] >> 2)) & 0x03030303u;
-                        C |= (((cc * 0x00041041u) >> 18) & 0xFFu) << (8 * i);
-                    }
-                    uint32_t B = 0;
-                    if (nz[0] | nz[1] | nz[2] | nz[3])
-                        B = gather_bit7(nz[0]) | (gather_bit7(nz[1]) << 4) | (gather_bit7(nz[2]) << 8) | (gather_bit7(nz[3]) << 12);
+                    uint32_t C = Cw[c], B = BN[c] & 0xFFFFu, nl = BN[c] >> 16;
                     const uint32_t n = 16 - __popc(nl);
                     while (nl) {  // squeeze the newline positions out of both streams
                         const int h = __ffs((int)nl) - 1;
