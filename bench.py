@@ -339,7 +339,7 @@ def run_ours(args):
     sampler.active = True
     ms_step, res = timed(lambda: step_resident(time_k2=True), args.steps)
     sampler.active = False
-    # K2's own duration: with two streams in flight the per-launch events above include time shared
+    # K2's own duration: with several streams in flight the per-launch events above include time shared
     # with the other stream's kernels, so the roofline uses a serialized pass over the same 12
     # genomes taken right after the timed region (same clocks, L2 displaced by the other genomes).
     k2_overlapped_ms = [a.elapsed_time(b) for a, b in k2_events]
@@ -404,7 +404,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "Gbp/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(sum(len(t) for t, _ in texts)) + int(orders.nbytes),
                 "d2h_bytes_per_step": N_GENOMES * nk * 8 + N_ORDERINGS * N_GENOMES * nk * 8 + (nk * 8 if world > 1 else 0),
-                "note": "dd_sketch_fasta_host_async per genome from pinned memory (two files in flight on two streams) + "
+                "note": "dd_sketch_fasta_host_async per genome from pinned memory (%d files in flight on as many streams) + " % NS +
                         "progressive unions; every cardinality is copied back to the host, registers stay in HBM"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
