@@ -27,6 +27,24 @@ import time
 
 import numpy as np
 
+# Rank 0 prints exactly ONE JSON line on stdout.  Libraries chat on fd 1 too (NCCL prints its version
+# banner there), so fd 1 is pointed at stderr for the whole run and the line goes to the saved fd.
+_STDOUT_FD = None
+
+
+def _claim_stdout():
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, data)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -163,7 +181,7 @@ def run_reference(args):
             "config": workload_config(args.gpus),
             "cpu_baseline": {"value": value, "unit": "Gbp/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(n_gpus):
@@ -423,7 +441,7 @@ def run_ours(args):
                          "sample": "1 genome x 5 Mbp x 23 k, p=20, one single-threaded oracle job per (genome,k), "
                                    f"{threads} in flight ({cpu_dt:.2f} s)"},
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -435,6 +453,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
