@@ -108,10 +108,64 @@ __device__ __forceinline__ void count_bucket_sparse(const uint32_t (&P)[4][kPlan
     }
 }
 
+// ---- identical prefixes --------------------------------------------------------------------------
+// Two orderings whose first s+1 entries are the same SET have the same union at step s (always true
+// for the last step of permutations of one set, frequent at the first and last few steps of random
+// ones): only the lowest-numbered ordering of each such class counts, the others get a copy of its
+// histogram row.  Sets are 64-bit masks, so this applies to n_genomes <= 64; beyond that every
+// ordering is its own representative.
+__global__ void __launch_bounds__(1024)
+prefix_dedup_kernel(const int32_t *__restrict__ order, int n_ord, int n_steps, int n_genomes,
+                    unsigned long long *__restrict__ masks, int32_t *__restrict__ rep) {
+    const int total = n_ord * n_steps;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int o = i / n_steps, st = i % n_steps;
+        unsigned long long m = 0ull;
+        for (int j = 0; j <= st; ++j) {
+            const int g = order[(size_t)o * n_steps + j];
+            if (g >= 0 && g < n_genomes && n_genomes <= 64) m |= 1ull << g;
+        }
+        masks[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int o = i / n_steps, st = i % n_steps;
+        int r = o;
+        if (n_genomes <= 64) {
+            const unsigned long long m = masks[i];
+            for (int q = 0; q < o; ++q)
+                if (masks[(size_t)q * n_steps + st] == m) {
+                    r = q;
+                    break;
+                }
+        }
+        rep[i] = r;
+    }
+}
+
+// hist rows of non-representative (ordering, step) pairs <- the representative's rows
+__global__ void prefix_copy_rows_kernel(const int32_t *__restrict__ rep, int n_ord, int n_steps, int nk, int final_only,
+                                        uint32_t *__restrict__ hist) {
+    const int out_steps = final_only ? 1 : n_steps;
+    const size_t rows = (size_t)n_ord * out_steps * nk;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * DD_HIST_BINS; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = i / DD_HIST_BINS, bin = i % DD_HIST_BINS;
+        const int k = (int)(row % nk);
+        const int os = (int)(row / nk);  // o * out_steps + step'
+        const int o = os / out_steps, st = final_only ? n_steps - 1 : os % out_steps;
+        const int r = rep[(size_t)o * n_steps + st];
+        if (r != o) {
+            const size_t src = final_only ? (size_t)r * nk + k : ((size_t)r * n_steps + st) * nk + k;
+            hist[i] = hist[src * DD_HIST_BINS + bin];
+        }
+    }
+}
+
 // grid (n_ord, slices, nk); a thread owns 4 groups (128 registers), a CTA 32768 registers.
-__global__ void __launch_bounds__(kPlThreads, 3)
+__global__ void __launch_bounds__(kPlThreads, 4)
 prefix_union_planes_kernel(const uint32_t *__restrict__ planes, const int32_t *__restrict__ order, int n_steps,
-                           int n_genomes, int nk, int p, int final_only, uint32_t *__restrict__ hist) {
+                           int n_genomes, int nk, int p, int final_only, const int32_t *__restrict__ rep,
+                           uint32_t *__restrict__ hist) {
     __shared__ uint32_t s_cnt[DD_HIST_BINS];
     const size_t ngroups = (size_t)1 << (p - 5);
     const size_t nvec = ngroups >> 2;  // uint4 per plane
@@ -147,6 +201,7 @@ prefix_union_planes_kernel(const uint32_t *__restrict__ planes, const int32_t *_
             plane_max(R[3], X);
         }
         if (final_only && step != n_steps - 1) continue;
+        if (rep[(size_t)o * n_steps + step] != o) continue;  // same set as an earlier ordering: row copied afterwards
         const size_t row = final_only ? (size_t)o * nk + k : ((size_t)o * n_steps + step) * nk + k;
 
         if (threadIdx.x < DD_HIST_BINS) s_cnt[threadIdx.x] = 0u;
@@ -200,7 +255,14 @@ cudaError_t prefix_union_hist_planes(const uint8_t *d_regs, const int32_t *d_ord
         }
         pool_tuned = true;
     }
-    if ((e = cudaMallocAsync(reinterpret_cast<void **>(&planes), planes_bytes(n_genomes * nk, p), stream)) != cudaSuccess) return e;
+    const size_t pl_bytes = (planes_bytes(n_genomes * nk, p) + 255) / 256 * 256;
+    const size_t pairs = (size_t)n_ord * n_steps;
+    if ((e = cudaMallocAsync(reinterpret_cast<void **>(&planes), pl_bytes + pairs * (sizeof(unsigned long long) + sizeof(int32_t)),
+                             stream)) != cudaSuccess)
+        return e;
+    unsigned long long *masks = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(planes) + pl_bytes);
+    int32_t *rep = reinterpret_cast<int32_t *>(masks + pairs);
+    prefix_dedup_kernel<<<1, 1024, 0, stream>>>(d_order, n_ord, n_steps, n_genomes, masks, rep);
     const size_t total_groups = total >> 5;
     size_t blocks = (total_groups + 255) / 256;
     if (blocks > (size_t)148 * 64) blocks = (size_t)148 * 64;
@@ -208,7 +270,12 @@ cudaError_t prefix_union_hist_planes(const uint8_t *d_regs, const int32_t *d_ord
     const size_t nvec = (m >> 5) >> 2;
     const unsigned slices = (unsigned)((nvec + kPlThreads - 1) / kPlThreads);
     prefix_union_planes_kernel<<<dim3((unsigned)n_ord, slices, (unsigned)nk), kPlThreads, 0, stream>>>(
-        planes, d_order, n_steps, n_genomes, nk, p, final_only, d_hist);
+        planes, d_order, n_steps, n_genomes, nk, p, final_only, rep, d_hist);
+    {
+        const size_t cells = rows * DD_HIST_BINS;
+        const unsigned cb = (unsigned)((cells + 255) / 256 < 1184 ? (cells + 255) / 256 : 1184);
+        prefix_copy_rows_kernel<<<cb, 256, 0, stream>>>(rep, n_ord, n_steps, nk, final_only, d_hist);
+    }
     e = cudaGetLastError();
     cudaError_t e2 = cudaFreeAsync(planes, stream);
     return e != cudaSuccess ? e : e2;

@@ -380,3 +380,32 @@ def test_pack_simple_tiles(eng, chunk):
         if not np.array_equal(got, want):
             bad = np.flatnonzero(got != want)
             raise AssertionError((name, chunk, bad[:10].tolist(), bad.size))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,p", [(5, 12), (70, 12)])
+def test_prefix_union_identical_prefix_sets(eng, n, p):
+    """Orderings that share a prefix SET share the histogram row (deduplicated on the device for
+    n <= 64 genomes, counted independently above that); either way every (ordering, step) must carry
+    the cardinality of its own running union."""
+    rng = np.random.default_rng(100 + n)
+    ks = [11, 21]
+    regs, _ = make_sketches(eng, rng, n, ks, p, length=3000)
+    base = [list(rng.permutation(n)) for _ in range(6)]
+    orders = base + [list(reversed(base[0])), base[1][:2][::-1] + base[1][2:], [0] * n, base[2][:-1] + [-1]]
+    orders = [[int(g) for g in o] for o in orders]
+    cards = eng.prefix_union_cards(regs, orders, p).cpu().numpy()
+    fin = eng.prefix_union_cards(regs, orders, p, final_only=True).cpu().numpy()
+    h = regs.cpu().numpy()
+    memo = {}
+    for o, order in enumerate(orders):
+        run = np.zeros_like(h[0])
+        for s, g in enumerate(order):
+            if g >= 0:
+                run = np.maximum(run, h[g])
+            for i in range(len(ks)):
+                key = run[i].tobytes()
+                if key not in memo:
+                    memo[key] = orc.card(run[i], p)
+                assert cards[o, s, i] == pytest.approx(memo[key], rel=CARD_RTOL), (o, s, i)
+        assert np.array_equal(fin[o, 0], cards[o, -1])

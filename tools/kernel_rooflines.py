@@ -64,7 +64,7 @@ def main():
     add("K3 union_max of 12 x [23][2^20]", regs.numel() + nk * m, ms, "n*2^p read + 2^p written per k")
     orders = np.stack([np.random.default_rng(i).permutation(n) for i in range(30)]).astype(np.int32)
     ms = best_ms(lambda: eng.prefix_union_cards(regs, orders, p))
-    add("K3 prefix unions + cards (bit planes), 30 orderings", 30 * regs.numel(), ms, "n*2^p per (ordering,k); DRAM traffic is ~30x lower (L2 sharing)")
+    add("K3 prefix unions + cards (bit planes), 30 orderings", 30 * regs.numel(), ms, "n*2^p per (ordering,k); DRAM traffic is ~30x lower (L2 sharing); rows whose prefix set repeats an earlier ordering are copied, not recounted")
     pairs = np.array([(a, b) for a in range(n) for b in range(a + 1, n)], dtype=np.int32)
     ms = best_ms(lambda: eng.pairwise_cards(regs, pairs, p))
     add("K6 pairwise union cards, 66 pairs x 23 k", len(pairs) * nk * 2 * m, ms, "2*2^p per (pair,k) before tiling")
