@@ -17,7 +17,7 @@ template <int CL>
 __global__ void probe(uint32_t *sink, uint32_t *gtab, int iters, int mode) {
     extern __shared__ __align__(16) uint32_t tab[];
     cg::cluster_group cluster = cg::this_cluster();
-    for (int i = threadIdx.x; i < kTableBytes / 4; i += blockDim.x) tab[i] = 0;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) tab[i] = 0;
     cluster.sync();
     uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(tab);
@@ -27,7 +27,19 @@ __global__ void probe(uint32_t *sink, uint32_t *gtab, int iters, int mode) {
         const uint32_t h = x ^ (x >> 15);
         const uint32_t idx = h >> 12;  // 20 bits
         const uint32_t bit = 1u << (8 * (idx & 3) + (h & 7));
-        if (mode == 2) {
+        if (mode == 3) {   // one-hot byte per register: 4 registers per word, 23 MB table
+            uint32_t *p = gtab + ((h >> 9) % (23u << 18));
+            asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(bit) : "memory");
+        } else if (mode == 4) {   // u32 max over 23 x 2^20 words (92 MB)
+            uint32_t *p = gtab + ((h >> 7) % (23u << 20));
+            asm volatile("red.global.max.u32 [%0], %1;" ::"l"(p), "r"(h & 63u) : "memory");
+        } else if (mode == 5) {   // u32 max over the 46 MB footprint
+            uint32_t *p = gtab + ((h >> 9) % (23u << 19));
+            asm volatile("red.global.max.u32 [%0], %1;" ::"l"(p), "r"(h & 63u) : "memory");
+        } else if (mode == 6) {   // or.b32 over the 46 MB footprint
+            uint32_t *p = gtab + ((h >> 9) % (23u << 19));
+            asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(bit) : "memory");
+        } else if (mode == 2) {
             const uint32_t v = 1u + (h & 7);  // subnormal f16 pattern
             uint32_t *p = gtab + ((h >> 9) % (23u << 19));
             asm volatile("{ .reg .b16 l, h; mov.b32 {l, h}, %1; red.global.max.noftz.v2.f16 [%0], {l, h}; }" ::"l"(p), "r"(v) : "memory");
@@ -41,7 +53,7 @@ __global__ void probe(uint32_t *sink, uint32_t *gtab, int iters, int mode) {
     }
     cluster.sync();
     uint32_t acc = 0;
-    for (int i = threadIdx.x; i < kTableBytes / 4; i += blockDim.x) acc ^= tab[i];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) acc ^= tab[i];
     if (acc == 0xdeadbeefu) sink[0] = acc;
 }
 
@@ -65,7 +77,7 @@ static void run(int threads, int iters, uint32_t *sink, uint32_t *gtab) {
     printf("cluster %d, %d threads: max active clusters %d (%s)\n", CL, threads, maxc, cudaGetErrorString(e));
     if (maxc <= 0) return;
     cfg.gridDim = dim3(CL * maxc);
-    for (int mode = 0; mode < 3; ++mode) {
+    for (int mode = (CL == 8 ? 0 : 2); mode < 7; ++mode) {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
@@ -86,15 +98,35 @@ static void run(int threads, int iters, uint32_t *sink, uint32_t *gtab) {
     }
 }
 
+static void sweep(uint32_t *sink, uint32_t *gtab) {
+    cudaFuncSetAttribute(probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes);
+    for (int threads : {128, 256, 512, 1024})
+        for (int grid : {148, 140, 132, 120, 104, 96, 74, 296}) {
+            const int smem = grid > 148 ? 64 * 1024 : kTableBytes;
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            float best = 1e9f;
+            const int iters = 4096;
+            for (int rep = 0; rep < 4; ++rep) {
+                cudaEventRecord(e0);
+                probe<1><<<grid, threads, smem>>>(sink, gtab, iters, 2);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                float ms;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (rep && ms < best) best = ms;
+            }
+            printf("sweep threads %4d grid %3d: %.3f ms  %.1f G RED/s (%s)\n", threads, grid, best,
+                   (double)grid * threads * iters / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+        }
+}
+
 int main() {
     uint32_t *sink, *gtab;
     cudaMalloc(&sink, 4);
-    cudaMalloc(&gtab, (size_t)(23u << 19) * 4);
-    cudaMemset(gtab, 0, (size_t)(23u << 19) * 4);
-    for (int threads : {256, 512, 1024}) {
-        run<8>(threads, 4096, sink, gtab);
-        run<4>(threads, 4096, sink, gtab);
-        run<16>(threads, 4096, sink, gtab);
-    }
+    cudaMalloc(&gtab, (size_t)(23u << 20) * 4);
+    cudaMemset(gtab, 0, (size_t)(23u << 20) * 4);
+    sweep(sink, gtab);
     return 0;
 }
