@@ -225,7 +225,7 @@ int dd_pairwise_union_card(const uint8_t *d_regs, int n_genomes, int nk, int p, 
 // ---- K5 ------------------------------------------------------------------------------------------
 static int exact_check(int k, uint64_t capacity, const void *ws, size_t ws_bytes, const char *fn) {
     if (!ws) return fail(DD_ERR_ARG, "%s: null workspace", fn);
-    if (k < 1 || k > 32) return fail(DD_ERR_ARG, "%s: k=%d outside [1,32]", fn, k);
+    if (k < 1 || k > DD_EXACT_MAXK) return fail(DD_ERR_ARG, "%s: k=%d outside [1,%d]", fn, k, DD_EXACT_MAXK);
     if (k > DD_EXACT_BITMAP_MAXK && (capacity < 1024 || (capacity & (capacity - 1))))
         return fail(DD_ERR_ARG, "%s: capacity must be a power of two >= 1024", fn);
     if (ws_bytes < dd::exact_workspace_bytes(k, capacity)) return fail(DD_ERR_WORKSPACE, "%s: workspace too small", fn);

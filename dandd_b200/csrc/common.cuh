@@ -145,6 +145,49 @@ DD_HD uint32_t invalid_window(uint32_t i0, uint32_t i1, uint32_t sm) { return fu
 // Number of valid symbols ending at s (saturates at 32).
 DD_HD int valid_run(uint32_t invwin) { return ctz32(invwin); }
 
+// ---- k = 33..64 (exact mode only): 128-bit k-mer values -----------------------------------------
+struct U128 {
+    uint64_t lo, hi;
+};
+DD_HD bool u128_eq(const U128 &a, const U128 &b) { return a.lo == b.lo && a.hi == b.hi; }
+DD_HD bool u128_less(const U128 &a, const U128 &b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+// reverse the order of the 32 two-bit symbols of x
+DD_HD uint64_t rev2_64(uint64_t x) {
+    const uint64_t r = ((uint64_t)brev32((uint32_t)x) << 32) | brev32((uint32_t)(x >> 32));
+    return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+}
+// c[t] = packed word (w - t), t = 0..4; the k-mer (33 <= k <= 64) ends at symbol j of word w.
+// Value = its symbols as a base-4 number, first symbol most significant; canonical = the smaller
+// of that and the same for the reverse complement.
+DD_HD U128 kmer128_at(const uint32_t (&c)[5], int j, int k, bool canon) {
+    const uint32_t sh = 2u * (15u - (uint32_t)j);
+    const uint32_t f0 = funnel_r(c[0], c[1], sh), f1 = funnel_r(c[1], c[2], sh), f2 = funnel_r(c[2], c[3], sh),
+                   f3 = funnel_r(c[3], c[4], sh);
+    U128 fwd = {(uint64_t)f0 | ((uint64_t)f1 << 32), (uint64_t)f2 | ((uint64_t)f3 << 32)};
+    const int drop = 128 - 2 * k;  // 0..62 bits above the k-mer
+    if (drop) fwd.hi &= ~(uint64_t)0 >> drop;
+    if (!canon) return fwd;
+    // complement (the cleared top bits turn into ones), reverse the 64 symbol slots, and shift the
+    // slots that came from above the k-mer out at the bottom
+    U128 rc = {rev2_64(~fwd.hi), rev2_64(~fwd.lo)};
+    if (drop) {
+        rc.lo = (rc.lo >> drop) | (rc.hi << (64 - drop));
+        rc.hi >>= drop;
+    }
+    return u128_less(rc, fwd) ? rc : fwd;
+}
+// Number of valid symbols ending at symbol sm (0..31) of invalid word I[0]; I[t] = invalid word
+// (iw - t), t = 0..4.  Saturates at 128.
+DD_HD int valid_run_long(const uint32_t (&I)[5], uint32_t sm) {
+    int run = 0;
+    for (int t = 0; t < 4; ++t) {
+        const uint32_t win = funnel_r(I[t], I[t + 1], 31u - sm);
+        if (win) return run + ctz32(win);
+        run += 32;
+    }
+    return run;
+}
+
 // ---------------------------------------------------------------------------------------------
 // FASTA text classification for the packer.  16 text bytes -> bit masks
 // (bit i <-> byte i).  A pad byte ('\r') is inert: never a symbol, never changes line state.

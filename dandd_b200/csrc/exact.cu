@@ -7,7 +7,8 @@
 //             with popc -- exact by construction;
 //   k  > 16 : an open-addressing table of 64-bit keys (linear probing, atomicCAS); the key is the
 //             k-mer value itself, so there are no false merges -- exact as long as the table is
-//             not full, which is reported, never ignored.
+//             not full, which is reported, never ignored;
+//   k  > 32 : (to 64; KMC itself goes to 256) the same with 128-bit keys and `atom.cas.b128`.
 // Inserting several genomes into one set gives the union count; reading the count after each
 // insertion gives the progressive exact unions in one sweep (the reference re-merges databases
 // n(n+1)/2 times).
@@ -26,7 +27,7 @@ static size_t exact_table_bytes(int k, uint64_t capacity) {
         const size_t bits = (size_t)1 << (2 * k);
         return bits < 128 ? 16 : bits / 8;
     }
-    return (size_t)capacity * sizeof(unsigned long long);
+    return (size_t)capacity * (k > 32 ? 2 : 1) * sizeof(unsigned long long);
 }
 size_t exact_workspace_bytes(int k, uint64_t capacity) { return 256 + exact_table_bytes(k, capacity); }
 static ExactWsHeader *ex_hdr(void *ws) { return static_cast<ExactWsHeader *>(ws); }
@@ -94,6 +95,63 @@ exact_insert_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restri
     }
 }
 
+// ---- k = 33..64: 128-bit keys ---------------------------------------------------------------------
+__device__ __forceinline__ ulonglong2 cas128(ulonglong2 *addr, ulonglong2 cmp, ulonglong2 val) {
+    ulonglong2 old;
+    asm volatile(
+        "{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\t"
+        "atom.global.cas.b128 o, [%6], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(old.x), "=l"(old.y)
+        : "l"(cmp.x), "l"(cmp.y), "l"(val.x), "l"(val.y), "l"(addr)
+        : "memory");
+    return old;
+}
+
+__global__ void __launch_bounds__(kExactThreads)
+exact_insert_wide_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict__ invalid, uint64_t sym_begin,
+                         uint64_t sym_end, int k, int canon, ExactWsHeader *hdr, ulonglong2 *tab, uint64_t capacity) {
+    const uint64_t w = (sym_begin >> 4) + (uint64_t)blockIdx.x * kExactThreads + threadIdx.x;
+    const uint64_t s0 = w << 4;
+    unsigned long long fresh = 0;
+    if (s0 < sym_end) {
+        uint32_t c[5], I[5];
+        const uint64_t iw = w >> 1;
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            c[t] = w >= (uint64_t)t ? __ldg(codes + w - t) : 0u;
+            I[t] = iw >= (uint64_t)t ? __ldg(invalid + iw - t) : 0xffffffffu;  // before the stream: breaks
+        }
+        const int j_lo = sym_begin > s0 ? (int)(sym_begin - s0) : 0;
+        const int j_hi = sym_end - s0 < 16 ? (int)(sym_end - s0) : 16;
+        const uint32_t sm_base = (uint32_t)(s0 & 31);
+        const ulonglong2 empty = make_ulonglong2(kEmptyKey, kEmptyKey);
+        const uint64_t mask = capacity - 1;
+        for (int j = j_lo; j < j_hi; ++j) {
+            if (valid_run_long(I, sm_base + (uint32_t)j) < k) continue;
+            const U128 v = kmer128_at(c, j, k, canon != 0);
+            if (v.lo == kEmptyKey && v.hi == kEmptyKey) {  // cannot be stored: it is the empty marker
+                if (atomicExch(&hdr->saw_ones, 1ull) == 0ull) ++fresh;
+                continue;
+            }
+            const ulonglong2 key = make_ulonglong2(v.lo, v.hi);
+            uint64_t slot = slot_hash(v.lo ^ slot_hash(v.hi)) & mask;
+            uint64_t probes = 0;
+            for (;;) {
+                // a matching read settles it; anything else is decided by the CAS result alone
+                const ulonglong2 seen = __ldcg(tab + slot);
+                if (seen.x == key.x && seen.y == key.y) break;
+                const ulonglong2 old = cas128(tab + slot, empty, key);
+                if (old.x == kEmptyKey && old.y == kEmptyKey) { ++fresh; break; }
+                if (old.x == key.x && old.y == key.y) break;
+                slot = (slot + 1) & mask;
+                if (++probes > mask) { hdr->overflow = 1; break; }
+            }
+        }
+    }
+    fresh = __reduce_add_sync(0xffffffffu, (unsigned)fresh);
+    if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(&hdr->count, fresh);
+}
+
 __global__ void __launch_bounds__(256) bitmap_count_kernel(const uint32_t *__restrict__ bm, size_t nwords,
                                                            unsigned long long *out) {
     unsigned long long c = 0;
@@ -118,9 +176,13 @@ cudaError_t exact_begin(void *d_ws, int k, uint64_t capacity, cudaStream_t strea
 cudaError_t exact_insert(const uint32_t *d_codes, const uint32_t *d_invalid, uint64_t sym_begin, uint64_t sym_end,
                          int k, int canon, void *d_ws, uint64_t capacity, cudaStream_t stream) {
     if (sym_end <= sym_begin) return cudaSuccess;
-    const size_t nwords = (size_t)((sym_end - sym_begin + 15) / 16 + 2);
+    const size_t nwords = (size_t)((sym_end - sym_begin + 15) / 16 + 2);  // +2: the range need not start on a word boundary
     const unsigned grid = (unsigned)((nwords + kExactThreads - 1) / kExactThreads);
-    if (k <= DD_EXACT_BITMAP_MAXK)
+    if (k > 32)
+        exact_insert_wide_kernel<<<grid, kExactThreads, 0, stream>>>(d_codes, d_invalid, sym_begin, sym_end, k, canon,
+                                                                    ex_hdr(d_ws), static_cast<ulonglong2 *>(ex_tab(d_ws)),
+                                                                    capacity);
+    else if (k <= DD_EXACT_BITMAP_MAXK)
         exact_insert_kernel<true><<<grid, kExactThreads, 0, stream>>>(d_codes, d_invalid, sym_begin, sym_end, k, canon,
                                                                      ex_hdr(d_ws), ex_tab(d_ws), capacity);
     else

@@ -260,8 +260,44 @@ static void orc_radix_sort(uint64_t *a, size_t n) {
     free(tmp);
 }
 
+/* k = 33..64: the same enumeration on 128-bit values (KMC accepts k up to 256; the GPU path and
+ * this oracle stop at 64, two machine words).  Sorted with qsort -- sizes here are test sizes. */
+typedef unsigned __int128 orc_u128;
+static int orc_cmp128(const void *a, const void *b) {
+    const orc_u128 x = *(const orc_u128 *)a, y = *(const orc_u128 *)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+static uint64_t orc_exact_count_wide(const uint8_t *const *sym, const size_t *n, int nseq, int k, int canon) {
+    const orc_u128 mask = (k == 64) ? ~(orc_u128)0 : ((((orc_u128)1) << (2 * k)) - 1);
+    const int rcshift = 2 * (k - 1);
+    size_t cap = 0, cnt = 0;
+    for (int s = 0; s < nseq; ++s) cap += n[s];
+    orc_u128 *a = (orc_u128 *)malloc((cap ? cap : 1) * sizeof(orc_u128));
+    for (int s = 0; s < nseq; ++s) {
+        orc_u128 fwd = 0, rc = 0;
+        int filled = 0;
+        for (size_t i = 0; i < n[s]; ++i) {
+            unsigned c = sym[s][i];
+            if (c > 3) { filled = 0; fwd = rc = 0; continue; }
+            fwd = ((fwd << 2) | c) & mask;
+            rc = (rc >> 2) | ((orc_u128)(3u - c) << rcshift);
+            if (filled < k) ++filled;
+            if (filled == k) a[cnt++] = canon ? (fwd < rc ? fwd : rc) : fwd;
+        }
+    }
+    uint64_t distinct = 0;
+    if (cnt) {
+        qsort(a, cnt, sizeof(orc_u128), orc_cmp128);
+        distinct = 1;
+        for (size_t i = 1; i < cnt; ++i) distinct += (a[i] != a[i - 1]);
+    }
+    free(a);
+    return distinct;
+}
+
 /* Number of distinct (canonical) k-mers in the union of nseq symbol streams. */
 uint64_t orc_exact_count(const uint8_t *const *sym, const size_t *n, int nseq, int k, int canon) {
+    if (k > 32) return orc_exact_count_wide(sym, n, nseq, k, canon);
     struct orc_vec v = {0, 0, 0};
     for (int s = 0; s < nseq; ++s) orc_for_each_kmer(sym[s], n[s], k, canon, orc_vec_cb, &v);
     if (v.n == 0) { free(v.a); return 0; }

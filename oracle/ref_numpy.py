@@ -89,9 +89,30 @@ def hll_sketch_np(sym, k, p=20, canon=True):
 
 def exact_count_np(syms, k, canon=True) -> int:
     """Appendix B: size of the union of the k-mer sets."""
+    if k > 32:
+        return exact_count_strings(syms, k, canon)
     s = set()
     for sym in syms:
         s.update(kmers_np(sym, k, canon).tolist())
+    return len(s)
+
+
+def exact_count_strings(syms, k, canon=True) -> int:
+    """The same on Python strings (any k): a k-mer and its reverse complement are one element
+    when canon.  Small inputs only."""
+    comp = str.maketrans("0123", "3210")
+    s = set()
+    for sym in syms:
+        txt = "".join("N" if c > 3 else str(int(c)) for c in sym)
+        for i in range(len(txt) - k + 1):
+            w = txt[i:i + k]
+            if "N" in w:
+                continue
+            if canon:
+                r = w.translate(comp)[::-1]
+                if r < w:
+                    w = r
+            s.add(w)
     return len(s)
 
 

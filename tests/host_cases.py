@@ -118,6 +118,28 @@ def scenario_tree_exact(tmp):
                         gold_runs()["E_tree_exact"], exact=True)
 
 
+def scenario_exact_sweep_above_k32(tmp):
+    """`--exact --ksweep` across k = 32 (README.md:82: higher ks need --exact): every node's count at
+    every k equals the oracle's distinct canonical k-mer count of its FASTAs."""
+    from oracle import pyoracle as orc
+    data = make_dataset(os.path.join(tmp, "data3"), 3, 12000, seed=33)
+    out = os.path.join(tmp, "outH")
+    run_dandd(["tree", "-d", os.path.dirname(data[0]), "-s", "runH", "-k", "31", "-o", out, "--exact", "--ksweep",
+               "--mink", "30", "--maxk", "36"])
+    with open(os.path.join(out, "runH_3_kmc_dtree.pickle"), "rb") as fh:
+        tree = pickle.load(fh)
+    syms = {f: orc.fasta_symbols(open(f, "rb").read()) for f in tree.fastas}
+    todo, seen = [tree.root], 0
+    while todo:
+        node = todo.pop()
+        todo.extend(node.children)
+        for k in range(30, 37):
+            assert node.ksketches[k] is not None, (node.node_title, k)
+            assert int(node.ksketches[k].card) == orc.exact_count([syms[f] for f in node.fastas], k, True), (node.node_title, k)
+            seen += 1
+    assert seen >= 7 * 4
+
+
 def scenario_pickle_roundtrip(tmp):
     """The dtree pickle names classes by the reference's top-level module names."""
     out = scenario_tree_hillclimb(tmp)

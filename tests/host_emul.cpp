@@ -90,6 +90,32 @@ void emul_sketch(const uint32_t *codes, const uint32_t *invalid, uint64_t sym_be
     }
 }
 
+// Wide exact mode (k = 33..64): same per-word walk as exact_insert_wide_kernel; writes the 128-bit
+// value of every valid k-mer as (lo, hi) pairs and returns how many there were.
+size_t emul_kmers_wide(const uint32_t *codes, const uint32_t *invalid, uint64_t sym_begin, uint64_t sym_end, int k,
+                       int canon, uint64_t *out) {
+    size_t cnt = 0;
+    if (sym_end <= sym_begin) return 0;
+    for (uint64_t w = sym_begin >> 4; (w << 4) < sym_end; ++w) {
+        const uint64_t s0 = w << 4, iw = w >> 1;
+        uint32_t c[5], I[5];
+        for (int t = 0; t < 5; ++t) {
+            c[t] = w >= (uint64_t)t ? codes[w - t] : 0u;
+            I[t] = iw >= (uint64_t)t ? invalid[iw - t] : 0xffffffffu;
+        }
+        const int j_lo = sym_begin > s0 ? (int)(sym_begin - s0) : 0;
+        const int j_hi = sym_end - s0 < 16 ? (int)(sym_end - s0) : 16;
+        for (int j = j_lo; j < j_hi; ++j) {
+            if (valid_run_long(I, (uint32_t)(s0 & 31) + (uint32_t)j) < k) continue;
+            const U128 v = kmer128_at(c, j, k, canon != 0);
+            out[2 * cnt] = v.lo;
+            out[2 * cnt + 1] = v.hi;
+            ++cnt;
+        }
+    }
+    return cnt;
+}
+
 // The kernel computes rank/index from the two hash halves; keep that formulation honest too.
 uint32_t emul_rank_split(uint64_t h, int p) {
     const uint32_t hi = (uint32_t)(h >> 32), lo = (uint32_t)h;

@@ -409,3 +409,36 @@ def test_prefix_union_identical_prefix_sets(eng, n, p):
                     memo[key] = orc.card(run[i], p)
                 assert cards[o, s, i] == pytest.approx(memo[key], rel=CARD_RTOL), (o, s, i)
         assert np.array_equal(fin[o, 0], cards[o, -1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [33, 40, 63, 64])
+@pytest.mark.parametrize("canon", [True, False])
+def test_exact_counts_wide_k(eng, k, canon):
+    """--exact above k = 32 (README.md:82: "to sweep higher ks you must use KMC via --exact"): 128-bit
+    keys, `atom.cas.b128`.  The last text is the reverse complement of part of the first, so the
+    canonical and plain unions differ; poly-T at k = 64 is the all-ones key (the empty marker)."""
+    rng = np.random.default_rng(500 + k)
+    anc = random_bases(rng, 40000)
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+    rc = bytes(comp[b] for b in anc[10000:25000].tolist()[::-1])
+    txts = [to_fasta([(b"a", anc)]), adversarial_fasta(rng, n=20000),
+            to_fasta([(b"m", mutate(rng, anc, sub=0.02))], width=61), b">polyT\n" + b"T" * 200 + b"\n",
+            to_fasta([(b"rc", np.frombuffer(rc, dtype=np.uint8))])]
+    seqs = [eng.pack(t) for t in txts]
+    syms = [orc.fasta_symbols(t) for t in txts]
+    got = eng.exact_counts(seqs, k, canon)
+    want = [orc.exact_count(syms[:i + 1], k, canon) for i in range(len(syms))]
+    assert got == want
+    if canon:
+        assert got[-1] == got[-2]           # the reverse complement adds nothing to a canonical set
+    else:
+        assert got[-1] > got[-2]
+
+
+@pytest.mark.gpu
+def test_exact_k_above_64_is_refused(eng):
+    from dandd_b200._lib import DandDError
+    seq = eng.pack(b">x\n" + b"ACGT" * 100 + b"\n")
+    with pytest.raises(DandDError):
+        eng.exact_counts([seq], 65)

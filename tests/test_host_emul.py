@@ -111,3 +111,41 @@ def test_device_mle_matches_oracle(host_emul):
         hist64 = np.ascontiguousarray(c[:64])
         got = host_emul.emul_mle(hist64.ctypes.data_as(U32P), p)
         assert got == pytest.approx(orc.ertl_mle(c, p), rel=1e-12)
+
+
+@pytest.mark.parametrize("k", [33, 34, 40, 48, 49, 63, 64])
+@pytest.mark.parametrize("canon", [True, False])
+def test_wide_kmer_values_match_big_integers(host_emul, k, canon):
+    """k = 33..64 (exact mode): the 128-bit window extraction / reverse complement / canonical
+    choice of exact_insert_wide_kernel against Python integers on the oracle's symbol stream."""
+    import ctypes as C
+    rng = np.random.default_rng(300 + k)
+    txt = adversarial_fasta(rng, n=3000)
+    sym = orc.fasta_symbols(txt)
+    codes, invalid, nsym = emul_pack(host_emul, txt)
+    out = np.zeros(2 * max(1, nsym), dtype=np.uint64)
+    fn = host_emul.emul_kmers_wide
+    fn.restype = C.c_size_t
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+    cnt = fn(codes.ctypes.data, invalid.ctypes.data, 0, nsym, k, int(canon), out.ctypes.data)
+    got = [int(out[2 * i]) | (int(out[2 * i + 1]) << 64) for i in range(cnt)]
+    want = []
+    run, fwd, rc = 0, 0, 0
+    mask = (1 << (2 * k)) - 1
+    for c in sym.tolist():
+        if c > 3:
+            run, fwd, rc = 0, 0, 0
+            continue
+        fwd = ((fwd << 2) | c) & mask
+        rc = (rc >> 2) | ((3 - c) << (2 * (k - 1)))
+        run += 1
+        if run >= k:
+            want.append(min(fwd, rc) if canon else fwd)
+    assert got == want
+    assert len(set(got)) == orc.exact_count([sym], k, canon)
+    # arbitrary ranges partition the k-mers by end position
+    cuts = [0, 7, 16, 100, 1001, nsym]
+    tot = 0
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        tot += fn(codes.ctypes.data, invalid.ctypes.data, a, b, k, int(canon), out.ctypes.data)
+    assert tot == cnt

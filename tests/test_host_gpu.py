@@ -47,6 +47,10 @@ def test_tree_exact(tmp_path, gpu_store):
     host_cases.scenario_tree_exact(str(tmp_path))
 
 
+def test_exact_sweep_above_k32(tmp_path, gpu_store):
+    host_cases.scenario_exact_sweep_above_k32(str(tmp_path))
+
+
 def test_stub_union_files(tmp_path, gpu_store):
     """DANDD_B200_UNION_FILES=stub keeps union registers in HBM and writes marker files only; the
     reported numbers do not change."""

@@ -45,5 +45,9 @@ def test_tree_exact(tmp_path, oracle_store):
     host_cases.scenario_tree_exact(str(tmp_path))
 
 
+def test_exact_sweep_above_k32(tmp_path, oracle_store):
+    host_cases.scenario_exact_sweep_above_k32(str(tmp_path))
+
+
 def test_pickle_roundtrip(tmp_path, oracle_store):
     host_cases.scenario_pickle_roundtrip(str(tmp_path))

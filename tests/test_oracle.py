@@ -130,3 +130,20 @@ def test_golden_fixtures():
             assert int(np.dot(regs.astype(np.int64), np.arange(regs.size) % 251)) == row["checksum"]
             assert orc.card(regs, case["p"]) == pytest.approx(row["card"], rel=1e-12)
             assert orc.exact_count([sym], row["k"], canon=row["canon"]) == row["exact"]
+
+
+def test_exact_count_wide_k_against_string_sets():
+    """k = 33..64 in the C oracle (128-bit values) against sets of Python strings; the input holds a
+    reverse-complemented copy of part of itself so that canonical and plain counts differ."""
+    rng = np.random.default_rng(64)
+    a = orc.fasta_symbols(to_fasta([(b"a", random_bases(rng, 2500))]))
+    b = a.copy()
+    b[::97] = (b[::97] + 1) % 4
+    rc = (3 - a[500:1500])[::-1].copy()
+    c = np.concatenate([b[:800], np.array([4], dtype=np.uint8), rc])
+    for k in (33, 41, 64):
+        plain = orc.exact_count([a, c], k, canon=False)
+        canon = orc.exact_count([a, c], k, canon=True)
+        assert plain == ref.exact_count_strings([a, c], k, canon=False)
+        assert canon == ref.exact_count_strings([a, c], k, canon=True)
+        assert canon < plain
