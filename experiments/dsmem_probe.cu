@@ -27,7 +27,15 @@ __global__ void probe(uint32_t *sink, uint32_t *gtab, int iters, int mode) {
         const uint32_t h = x ^ (x >> 15);
         const uint32_t idx = h >> 12;  // 20 bits
         const uint32_t bit = 1u << (8 * (idx & 3) + (h & 7));
-        if (mode == 3) {   // one-hot byte per register: 4 registers per word, 23 MB table
+        if (mode == 7 || mode == 8) {   // read filter: load the word, RED only ~45 % of the time
+            uint32_t *p = gtab + ((h >> 9) % (23u << 19));
+            uint32_t cur;
+            asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(cur) : "l"(p) : "memory");
+            const uint32_t v = 1u + (h & 7);
+            const bool go = mode == 7 ? (((cur >> 20) + (h >> 3)) % 100u) < 45u : false;
+            if (go) asm volatile("{ .reg .b16 l, hh; mov.b32 {l, hh}, %1; red.global.max.noftz.v2.f16 [%0], {l, hh}; }" ::"l"(p), "r"(v) : "memory");
+            else if (cur == 0xdeadbeefu) sink[1] = cur;
+        } else if (mode == 3) {   // one-hot byte per register: 4 registers per word, 23 MB table
             uint32_t *p = gtab + ((h >> 9) % (23u << 18));
             asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(bit) : "memory");
         } else if (mode == 4) {   // u32 max over 23 x 2^20 words (92 MB)
@@ -98,11 +106,12 @@ static void run(int threads, int iters, uint32_t *sink, uint32_t *gtab) {
     }
 }
 
+static int g_mode = 2;
 static void sweep(uint32_t *sink, uint32_t *gtab) {
     cudaFuncSetAttribute(probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes);
-    for (int threads : {128, 256, 512, 1024})
-        for (int grid : {148, 140, 132, 120, 104, 96, 74, 296}) {
-            const int smem = grid > 148 ? 64 * 1024 : kTableBytes;
+    for (int threads : {256, 1024})
+        for (int grid : {148, 296, 592}) {
+            const int smem = 16 * 1024;
             cudaEvent_t e0, e1;
             cudaEventCreate(&e0);
             cudaEventCreate(&e1);
@@ -110,14 +119,14 @@ static void sweep(uint32_t *sink, uint32_t *gtab) {
             const int iters = 4096;
             for (int rep = 0; rep < 4; ++rep) {
                 cudaEventRecord(e0);
-                probe<1><<<grid, threads, smem>>>(sink, gtab, iters, 2);
+                probe<1><<<grid, threads, smem>>>(sink, gtab, iters, g_mode);
                 cudaEventRecord(e1);
                 cudaEventSynchronize(e1);
                 float ms;
                 cudaEventElapsedTime(&ms, e0, e1);
                 if (rep && ms < best) best = ms;
             }
-            printf("sweep threads %4d grid %3d: %.3f ms  %.1f G RED/s (%s)\n", threads, grid, best,
+            printf("mode %d ", g_mode); printf("sweep threads %4d grid %3d: %.3f ms  %.1f G RED/s (%s)\n", threads, grid, best,
                    (double)grid * threads * iters / best / 1e6, cudaGetErrorString(cudaGetLastError()));
         }
 }
@@ -127,6 +136,7 @@ int main() {
     cudaMalloc(&sink, 4);
     cudaMalloc(&gtab, (size_t)(23u << 20) * 4);
     cudaMemset(gtab, 0, (size_t)(23u << 20) * 4);
-    sweep(sink, gtab);
+    cudaMalloc(&sink, 64);
+    for (int m : {2, 7, 8}) { g_mode = m; sweep(sink, gtab); }
     return 0;
 }
