@@ -424,6 +424,18 @@ pack_scan_kernel(const uint8_t *__restrict__ text, size_t n, const uint64_t *__r
 
 // ---- pass C: emit symbols ---------------------------------------------------------------------
 constexpr size_t kWriteSmem = 2 * kTileBytes + (kTileBytes + 64);  // two text buffers + symbol staging
+// PRMT without __byte_perm's selector masking (the selectors built here never set a nibble's bit 3)
+__device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+// high half of a 32x32 product, pinned to the FMA pipe: a right shift / multiply-gather off the ALU
+__device__ __forceinline__ uint32_t mulhi_fma(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
 constexpr int kFastCodeWords = 1040;   // >= (kTileBytes + 31) * 2 / 32 + spill word, multiple of 4
 constexpr int kFastBreakWords = 520;   // >= (kTileBytes + 31) / 32 + spill word, multiple of 4
 // little-endian 2-bit codes (symbol i at bits 2i+1:2i) -> the stream's big-endian order (31-2i:30-2i)
@@ -481,33 +493,38 @@ pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
             const uint8_t *b = pipe.wait(tile, it);
             // In a simple tile a byte without bit 6 is a newline, so one LOP finds them.  The ACGT test
             // is classify_word's table lookup with the free slot 2 holding '\n': the XOR below is zero
-            // exactly for ACGTacgt and '\n', so its non-zero bytes are the break symbols.
-            uint32_t Cw[kSpanChunks], BN[kSpanChunks];  // codes; break mask | newline mask << 16
-            uint32_t nnl = 0;
+            // exactly for ACGTacgt and '\n', so its non-zero bytes are the break symbols.  Newline
+            // flags of a chunk are kept transposed (bit 8j+i = byte j of word i; the shifts that put
+            // them there run on the FMA pipe, which is idle here) and only turned into symbol
+            // positions by the few lanes that actually hold one.
+            uint32_t Cw[kSpanChunks], Bw[kSpanChunks / 2], Xw[kSpanChunks / 2];  // codes; break masks; newline flags
+            Bw[0] = Bw[1] = 0u;
 #pragma unroll
             for (int c = 0; c < kSpanChunks; ++c) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(b + off + 16 * c);
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                uint32_t nz[4], C = 0, nl = 0;
+                uint32_t d[4], C = 0, X = 0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const uint32_t u = w[i] & 0xdfdfdfdfu;
-                    const uint32_t y = u & 0x07070707u;
+                    const uint32_t y = w[i] & 0x07070707u;
                     const uint32_t t = y | (y >> 4);
-                    const uint32_t d = u ^ byte_perm(0x430a4101u, 0x47010154u, byte_perm(t, t, 0x0020u));
-                    nz[i] = (((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u;
-                    nl |= ((((~w[i] & 0x40404040u) >> 6) * 0x00204081u >> 21) & 0xFu) << (4 * i);
+                    d[i] = (w[i] & 0xdfdfdfdfu) ^ prmt_raw(0x430a4101u, 0x47010154u, prmt_raw(t, t, 0x0020u));
+                    X |= mulhi_fma(~w[i] & 0x40404040u, 1u << (26 + i));          // >> (6 - i)
                     const uint32_t cc = ((w[i] >> 1) ^ (w[i] >> 2)) & 0x03030303u;
                     C |= (((cc * 0x00041041u) >> 18) & 0xFFu) << (8 * i);
                 }
-                uint32_t B = 0;
-                if (nz[0] | nz[1] | nz[2] | nz[3])
-                    B = gather_bit7(nz[0]) | (gather_bit7(nz[1]) << 4) | (gather_bit7(nz[2]) << 8) | (gather_bit7(nz[3]) << 12);
+                if (d[0] | d[1] | d[2] | d[3]) {  // a letter that is not ACGT: exact per-byte break mask
+                    uint32_t B = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        B |= gather_bit7((((d[i] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d[i]) & 0x80808080u) << (4 * i);
+                    Bw[c >> 1] |= B << (16 * (c & 1));
+                }
                 Cw[c] = C;
-                BN[c] = B | (nl << 16);
-                nnl += __popc(nl);
+                if (c & 1) Xw[c >> 1] |= X << 4;
+                else Xw[c >> 1] = X;
             }
-            const uint32_t cnt = kSpanBytes - nnl;
+            const uint32_t cnt = kSpanBytes - (uint32_t)(__popc(Xw[0]) + __popc(Xw[1]));
             // my first output position (the scan's barriers also order the zeroing above)
             const uint32_t pos0 = lead + block_scan_u32(cnt, reinterpret_cast<uint32_t *>(s_warp), &tile_cnt);
             if (cnt) {
@@ -518,14 +535,27 @@ pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
                 uint32_t pos = pos0, wc = pos0 >> 4, fill_c = 2 * (pos0 & 15), acc_c = 0;
 #pragma unroll
                 for (int c = 0; c < kSpanChunks; ++c) {
-                    uint32_t C = Cw[c], B = BN[c] & 0xFFFFu, nl = BN[c] >> 16;
-                    const uint32_t n = 16 - __popc(nl);
-                    while (nl) {  // squeeze the newline positions out of both streams
-                        const int h = __ffs((int)nl) - 1;
-                        const uint32_t below = (1u << h) - 1u, below2 = (1u << (2 * h)) - 1u;
-                        B = (B & below) | ((B >> (h + 1)) << h);
-                        C = (C & below2) | (((C >> (2 * h + 1)) >> 1) << (2 * h));
-                        nl = (nl & (nl - 1)) >> 1;
+                    uint32_t C = Cw[c], B = (Bw[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
+                    const uint32_t X = (Xw[c >> 1] >> (4 * (c & 1))) & 0x0F0F0F0Fu;
+                    uint32_t n = 16;
+                    if (X) {  // squeeze the newline positions out of both streams
+                        uint32_t nl;
+                        if (X & (X - 1)) {  // several newlines in 16 bytes: symbol-order mask, one at a time
+                            nl = 0;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) nl |= ((((X >> i) & 0x01010101u) * 0x00204081u >> 21) & 0xFu) << (4 * i);
+                        } else {
+                            const int bit = __ffs((int)X) - 1;
+                            nl = 1u << (4 * (bit & 7) + (bit >> 3));
+                        }
+                        n -= __popc(nl);
+                        while (nl) {
+                            const int h = __ffs((int)nl) - 1;
+                            const uint32_t below = (1u << h) - 1u, below2 = (1u << (2 * h)) - 1u;
+                            B = (B & below) | ((B >> (h + 1)) << h);
+                            C = (C & below2) | (((C >> (2 * h + 1)) >> 1) << (2 * h));
+                            nl = (nl & (nl - 1)) >> 1;
+                        }
                     }
                     // append 2n code bits
                     acc_c |= C << fill_c;
