@@ -79,17 +79,29 @@ __device__ __forceinline__ uint32_t match_low4(const uint32_t (&P)[kPlanes], uin
     return t;
 }
 
+// Two values per warp reduction (a lane holds at most 128 registers, so a warp sum fits 16 bits);
+// lane J keeps the warp's count of value J, and the sixteen lanes issue one shared-memory add
+// together at the end -- no branch, vote or atomic per value.
+template <int J>
+__device__ __forceinline__ uint32_t count_pair(const uint32_t (&P)[4][kPlanes], const uint32_t (&mem)[4]) {
+    const uint32_t a = __popc(match_low4<J>(P[0], mem[0])) + __popc(match_low4<J>(P[1], mem[1])) +
+                       __popc(match_low4<J>(P[2], mem[2])) + __popc(match_low4<J>(P[3], mem[3]));
+    const uint32_t b = __popc(match_low4<J + 1>(P[0], mem[0])) + __popc(match_low4<J + 1>(P[1], mem[1])) +
+                       __popc(match_low4<J + 1>(P[2], mem[2])) + __popc(match_low4<J + 1>(P[3], mem[3]));
+    return __reduce_add_sync(0xffffffffu, a | (b << 16));
+}
+
 template <int... Js>
 __device__ __forceinline__ void count_bucket_dense(std::integer_sequence<int, Js...>, const uint32_t (&P)[4][kPlanes],
                                                    const uint32_t (&mem)[4], uint32_t *s_cnt, int lane) {
-    // per value: popc over the thread's four groups, warp sum, one shared-memory add per warp
+    uint32_t mine = 0;
     (([&] {
-         uint32_t c = __popc(match_low4<Js>(P[0], mem[0])) + __popc(match_low4<Js>(P[1], mem[1])) +
-                      __popc(match_low4<Js>(P[2], mem[2])) + __popc(match_low4<Js>(P[3], mem[3]));
-         c = __reduce_add_sync(0xffffffffu, c);
-         if (lane == 0 && c) atomicAdd(&s_cnt[Js], c);
+         const uint32_t both = count_pair<2 * Js>(P, mem);
+         if (lane == 2 * Js) mine = both & 0xFFFFu;
+         if (lane == 2 * Js + 1) mine = both >> 16;
      }()),
      ...);
+    if (lane < 16 && mine) atomicAdd(&s_cnt[lane], mine);
 }
 
 __device__ __forceinline__ void count_bucket_sparse(const uint32_t (&P)[4][kPlanes], const uint32_t (&mem)[4],
@@ -218,7 +230,7 @@ prefix_union_planes_kernel(const uint32_t *__restrict__ planes, const int32_t *_
             if (!__any_sync(0xffffffffu, any != 0u)) continue;  // nobody in the warp has such values
 #pragma unroll
             for (int c = 0; c < 4; ++c) n += __popc(mem[c]);
-            if (__any_sync(0xffffffffu, n > 12u)) count_bucket_dense(std::make_integer_sequence<int, 16>{}, R, mem, s_cnt + 16 * q, lane);
+            if (__any_sync(0xffffffffu, n > 12u)) count_bucket_dense(std::make_integer_sequence<int, 8>{}, R, mem, s_cnt + 16 * q, lane);
             else count_bucket_sparse(R, mem, s_cnt);
         }
         __syncthreads();
