@@ -4,8 +4,8 @@
 // thread-private histogram (extract byte, address, LDS, add, STS).  Here a sketch is first
 // transposed once per call into 6 bit-planes: plane b, word g holds bit b of registers 32g..32g+31
 // (ranks are <= 64-p+1 < 64).  On planes
-//   * the running max of two sketches is a bit-serial compare-and-select, 4 LOP3 per plane
-//     (24 per 32 registers), and
+//   * the running max of two sketches is a bit-serial compare-and-select, 2 LOP3 per plane
+//     (12 per 32 registers), and
 //   * "how many registers equal v" is AND-ing the six planes (or their complements) and a POPC:
 //     1.5 LOP3 + POPC + IADD per value per 32 registers.
 // Values are counted in four buckets of 16 (top two planes); a bucket nobody in the warp populates
@@ -56,16 +56,15 @@ to_planes_kernel(const uint8_t *__restrict__ regs, uint32_t *__restrict__ planes
     }
 }
 
-// running max of bit-sliced values: R = max(R, X), MSB-first compare then select
+// running max of bit-sliced values: R = max(R, X).  "R < X" is the borrow of R - X, carried from the
+// least significant plane up: where the bits differ the higher plane decides, where they agree the
+// verdict so far stands -- a three-input function, one LOP3 per plane; then one select per plane.
 __device__ __forceinline__ void plane_max(uint32_t (&R)[kPlanes], const uint32_t (&X)[kPlanes]) {
-    uint32_t gt = 0u, eq = 0xffffffffu;  // R > X decided / still equal, per register
+    uint32_t lt = 0u;
 #pragma unroll
-    for (int b = kPlanes - 1; b >= 0; --b) {
-        gt |= eq & R[b] & ~X[b];
-        eq &= ~(R[b] ^ X[b]);
-    }
+    for (int b = 0; b < kPlanes; ++b) lt = (~R[b] & X[b]) | (~(R[b] ^ X[b]) & lt);
 #pragma unroll
-    for (int b = 0; b < kPlanes; ++b) R[b] = (R[b] & gt) | (X[b] & ~gt);
+    for (int b = 0; b < kPlanes; ++b) R[b] = (X[b] & lt) | (R[b] & ~lt);
 }
 
 // registers of `members` whose low four bits equal J
