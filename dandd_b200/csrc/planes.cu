@@ -212,7 +212,7 @@ prefix_union_planes_kernel(const uint32_t *__restrict__ planes, const int32_t *_
             plane_max(R[3], X);
         }
         if (final_only && step != n_steps - 1) continue;
-        if (rep[(size_t)o * n_steps + step] != o) continue;  // same set as an earlier ordering: row copied afterwards
+        if (rep && rep[(size_t)o * n_steps + step] != o) continue;  // same set as an earlier ordering: row copied afterwards
         const size_t row = final_only ? (size_t)o * nk + k : ((size_t)o * n_steps + step) * nk + k;
 
         if (threadIdx.x < DD_HIST_BINS) s_cnt[threadIdx.x] = 0u;
@@ -273,7 +273,11 @@ cudaError_t prefix_union_hist_planes(const uint8_t *d_regs, const int32_t *d_ord
         return e;
     unsigned long long *masks = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(planes) + pl_bytes);
     int32_t *rep = reinterpret_cast<int32_t *>(masks + pairs);
-    prefix_dedup_kernel<<<1, 1024, 0, stream>>>(d_order, n_ord, n_steps, n_genomes, masks, rep);
+    // the search for an earlier ordering with the same prefix set is quadratic in n_ord (one CTA):
+    // worth it for tens to hundreds of orderings, pointless for a batch of distinct pairs
+    const bool dedup = n_genomes <= 64 && n_ord > 1 && (double)n_ord * n_ord * n_steps <= 4e6;
+    if (dedup) prefix_dedup_kernel<<<1, 1024, 0, stream>>>(d_order, n_ord, n_steps, n_genomes, masks, rep);
+    else rep = nullptr;
     const size_t total_groups = total >> 5;
     size_t blocks = (total_groups + 255) / 256;
     if (blocks > (size_t)148 * 64) blocks = (size_t)148 * 64;
@@ -282,7 +286,7 @@ cudaError_t prefix_union_hist_planes(const uint8_t *d_regs, const int32_t *d_ord
     const unsigned slices = (unsigned)((nvec + kPlThreads - 1) / kPlThreads);
     prefix_union_planes_kernel<<<dim3((unsigned)n_ord, slices, (unsigned)nk), kPlThreads, 0, stream>>>(
         planes, d_order, n_steps, n_genomes, nk, p, final_only, rep, d_hist);
-    {
+    if (dedup) {
         const size_t cells = rows * DD_HIST_BINS;
         const unsigned cb = (unsigned)((cells + 255) / 256 < 1184 ? (cells + 255) / 256 : 1184);
         prefix_copy_rows_kernel<<<cb, 256, 0, stream>>>(rep, n_ord, n_steps, nk, final_only, d_hist);

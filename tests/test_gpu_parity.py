@@ -442,3 +442,24 @@ def test_exact_k_above_64_is_refused(eng):
     seq = eng.pack(b">x\n" + b"ACGT" * 100 + b"\n")
     with pytest.raises(DandDError):
         eng.exact_counts([seq], 65)
+
+
+@pytest.mark.gpu
+def test_pairwise_union_cards_large_batch(eng):
+    """A batch of distinct pairs large enough that the quadratic identical-prefix search of the prefix
+    kernel is skipped (rep == nullptr path): 60 sketches, all 1830 pairs incl. (a, a)."""
+    rng = np.random.default_rng(19)
+    ks, p, n = [13, 24], 12, 60
+    regs, _ = make_sketches(eng, rng, n, ks, p, length=2500)
+    pairs = [(a, b) for a in range(n) for b in range(a, n)]
+    got = eng.pairwise_cards(regs, pairs, p).cpu().numpy()
+    h = regs.cpu().numpy()
+    memo = {}
+    for j in rng.choice(len(pairs), 150, replace=False).tolist() + [0, len(pairs) - 1]:
+        a, b = pairs[j]
+        for i in range(len(ks)):
+            u = np.maximum(h[a, i], h[b, i])
+            key = u.tobytes()
+            if key not in memo:
+                memo[key] = orc.card(u, p)
+            assert got[j, i] == pytest.approx(memo[key], rel=CARD_RTOL), (a, b, i)
