@@ -173,6 +173,9 @@ __global__ void prefix_copy_rows_kernel(const int32_t *__restrict__ rep, int n_o
 }
 
 // grid (n_ord, slices, nk); a thread owns 4 groups (128 registers), a CTA 32768 registers.
+// kCopyFirst: the first member is copied instead of max-ed with the all-zero start (pairs: half of
+// their max work; for long orderings the extra branch costs more than the one saved step).
+template <bool kCopyFirst>
 __global__ void __launch_bounds__(kPlThreads, 4)
 prefix_union_planes_kernel(const uint32_t *__restrict__ planes, const int32_t *__restrict__ order, int n_steps,
                            int n_genomes, int nk, int p, int final_only, const int32_t *__restrict__ rep,
@@ -197,19 +200,29 @@ prefix_union_planes_kernel(const uint32_t *__restrict__ planes, const int32_t *_
             uint4 x[kPlanes];
 #pragma unroll
             for (int b = 0; b < kPlanes; ++b) x[b] = __ldg(src + (size_t)b * nvec + vec);
-            uint32_t X[kPlanes];
+            if (kCopyFirst && step == 0) {  // max(0, X) = X
 #pragma unroll
-            for (int b = 0; b < kPlanes; ++b) X[b] = x[b].x;
-            plane_max(R[0], X);
+                for (int b = 0; b < kPlanes; ++b) {
+                    R[0][b] = x[b].x;
+                    R[1][b] = x[b].y;
+                    R[2][b] = x[b].z;
+                    R[3][b] = x[b].w;
+                }
+            } else {
+                uint32_t X[kPlanes];
 #pragma unroll
-            for (int b = 0; b < kPlanes; ++b) X[b] = x[b].y;
-            plane_max(R[1], X);
+                for (int b = 0; b < kPlanes; ++b) X[b] = x[b].x;
+                plane_max(R[0], X);
 #pragma unroll
-            for (int b = 0; b < kPlanes; ++b) X[b] = x[b].z;
-            plane_max(R[2], X);
+                for (int b = 0; b < kPlanes; ++b) X[b] = x[b].y;
+                plane_max(R[1], X);
 #pragma unroll
-            for (int b = 0; b < kPlanes; ++b) X[b] = x[b].w;
-            plane_max(R[3], X);
+                for (int b = 0; b < kPlanes; ++b) X[b] = x[b].z;
+                plane_max(R[2], X);
+#pragma unroll
+                for (int b = 0; b < kPlanes; ++b) X[b] = x[b].w;
+                plane_max(R[3], X);
+            }
         }
         if (final_only && step != n_steps - 1) continue;
         if (rep && rep[(size_t)o * n_steps + step] != o) continue;  // same set as an earlier ordering: row copied afterwards
@@ -284,8 +297,13 @@ cudaError_t prefix_union_hist_planes(const uint8_t *d_regs, const int32_t *d_ord
     to_planes_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_regs, planes, p, total_groups);
     const size_t nvec = (m >> 5) >> 2;
     const unsigned slices = (unsigned)((nvec + kPlThreads - 1) / kPlThreads);
-    prefix_union_planes_kernel<<<dim3((unsigned)n_ord, slices, (unsigned)nk), kPlThreads, 0, stream>>>(
-        planes, d_order, n_steps, n_genomes, nk, p, final_only, rep, d_hist);
+    const dim3 grid((unsigned)n_ord, slices, (unsigned)nk);
+    if (final_only && n_steps == 2)
+        prefix_union_planes_kernel<true><<<grid, kPlThreads, 0, stream>>>(planes, d_order, n_steps, n_genomes, nk, p, final_only,
+                                                                         rep, d_hist);
+    else
+        prefix_union_planes_kernel<false><<<grid, kPlThreads, 0, stream>>>(planes, d_order, n_steps, n_genomes, nk, p, final_only,
+                                                                          rep, d_hist);
     if (dedup) {
         const size_t cells = rows * DD_HIST_BINS;
         const unsigned cb = (unsigned)((cells + 255) / 256 < 1184 ? (cells + 255) / 256 : 1184);
