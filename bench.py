@@ -194,6 +194,33 @@ def workload_config(n_gpus):
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPU cores of its GPU's NUMA node before any pinned host buffer exists, so
+    that the per-step host->device copies do not cross sockets (at N=8 half the ranks otherwise do).
+    Best effort: returns the node, or None when the topology cannot be read."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:           # nvml pads the domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -203,6 +230,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank == 0:
         build.build()
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     from dandd_b200 import dist as dd_dist
     if world > 1:
@@ -422,6 +450,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "Gbp/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(sum(len(t) for t, _ in texts)) + int(orders.nbytes),
                 "d2h_bytes_per_step": N_GENOMES * nk * 8 + N_ORDERINGS * N_GENOMES * nk * 8 + (nk * 8 if world > 1 else 0),
+                "host_numa_node": numa_node,   # N>1: each rank is bound to the cores of its GPU's NUMA node
                 "note": "dd_sketch_fasta_host_async per genome from pinned memory (%d files in flight on as many streams) + " % NS +
                         "progressive unions; every cardinality is copied back to the host, registers stay in HBM"},
         "gpu_launches": launches_per_step * args.steps,

@@ -71,3 +71,16 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)
                 assert "liboracle" not in src and "pyoracle" not in src, os.path.join(dirpath, f)
+
+
+def test_cli_startup_trim_is_safe():
+    """The launchers drop torch's queued Triton-operator registration before CUDA initialises; the
+    helper must never raise and must leave torch importable/usable whatever torch's internals are."""
+    import torch
+    from dandd_b200._startup import trim_torch_cuda_init
+    before = len(getattr(torch.cuda, "_queued_calls", []))
+    dropped = trim_torch_cuda_init()
+    after = len(getattr(torch.cuda, "_queued_calls", []))
+    assert isinstance(dropped, bool) and after <= before
+    assert trim_torch_cuda_init() is False or after == len(torch.cuda._queued_calls)   # idempotent
+    assert torch.zeros(2).sum().item() == 0.0
