@@ -9,12 +9,20 @@
 // are persistent kernels (SM count x resident CTAs) that stage their tiles in shared memory with
 // the bulk-copy engine (`cp.async.bulk.shared::cluster.global` + mbarrier complete_tx, SASS
 // UBLKCP.S.G), double-buffered: tile i+1 streams in while tile i is classified, scanned and packed.
-// Text that is not 16-byte aligned falls back to per-thread 128-bit / byte loads (same results).
+// Text that is not 16-byte aligned is staged by a cooperative byte copy instead (same results).
 //
-// The only sequential dependence in FASTA text is "am I inside a header line?".  Each 16-byte
-// chunk is summarised as a transition function over that one bit (dd::chunk_xfer) and the
-// functions are composed with warp-shuffle scans: pass A reduces a 16 KiB tile to one function,
-// pass B scans the tile functions (one CTA), pass C re-scans inside the tile and writes.
+// The only sequential dependence in FASTA text is "am I inside a header line?".  A stretch of text
+// is summarised as a transition function over that one bit plus the symbol counts under both
+// hypotheses (dd::chunk_xfer, packed in a u64) and the functions are composed with warp-shuffle
+// scans: pass A reduces a 16 KiB tile to one function, pass B1 scans the tiles inside groups of
+// 512, pass B2 scans the groups (one CTA), pass C re-scans inside the tile and writes.
+//
+// Two paths per tile.  A tile that holds only letters and '\n' (every tile of a sequence body;
+// one SWAR test per word decides, and pass A records it in the tile's function) takes the FAST
+// path: no per-byte state machine, the symbols of a 16-byte chunk are validated and 2-bit encoded
+// in registers, the newline holes squeezed out, and the result appended to little-endian bit
+// streams in shared memory.  Anything else -- headers, CR, blanks, digits, the last partial tile, a
+// tile entered inside a header -- takes the GENERAL path built on dd::chunk_symbols.
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -30,31 +38,13 @@ constexpr int kScanThreads = 1024;
 
 struct PackWsHeader {
     uint32_t entry_last_byte;  // last text byte before this chunk (for pass C)
-    uint32_t seg_len;          // tiles per pass-B thread segment
+    uint32_t seg_len;          // groups per pass-B2 thread segment
     uint64_t pad;
 };
 struct PackTileOut {
-    uint64_t local_off;  // symbols emitted by earlier tiles of the same pass-B segment
-    uint64_t state;      // header state at the start of the tile
+    uint64_t local_off;  // symbols emitted by earlier groups of the same pass-B2 segment
+    uint64_t state;      // header state at the start of the group
 };
-
-// 16 text bytes at offset off (n = chunk length); beyond the end reads as inert padding.
-__device__ __forceinline__ uint4 load_text16(const uint8_t *__restrict__ text, size_t off, size_t n, bool aligned) {
-    if (aligned && off + 16 <= n) return __ldg(reinterpret_cast<const uint4 *>(text + off));
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint32_t x = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const size_t q = off + 4 * i + b;
-            const uint32_t c = (q < n) ? text[q] : (uint32_t)kPadByte;
-            x |= c << (8 * b);
-        }
-        w[i] = x;
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
 
 __device__ __forceinline__ uint64_t warp_scan_xfer(uint64_t f, int lane) {
 #pragma unroll
@@ -92,28 +82,6 @@ struct Span {
     uint32_t ls;  // bit c: chunk c starts at a line start
     uint64_t f;
 };
-
-__device__ __forceinline__ Span load_span(const uint8_t *__restrict__ text, size_t off, size_t n, bool aligned,
-                                          uint32_t entry_last) {
-    Span sp;
-    sp.f = kXferIdentity;
-    sp.ls = 0;
-    uint4 v[kSpanChunks];
-#pragma unroll
-    for (int c = 0; c < kSpanChunks; ++c)
-        v[c] = (off + 16 * c < n) ? load_text16(text, off + 16 * c, n, aligned)
-                                  : make_uint4(0x0d0d0d0du, 0x0d0d0d0du, 0x0d0d0d0du, 0x0d0d0d0du);
-    uint32_t prev = off == 0 ? entry_last : (off <= n ? (uint32_t)text[off - 1] : (uint32_t)kPadByte);
-#pragma unroll
-    for (int c = 0; c < kSpanChunks; ++c) {
-        sp.m[c] = classify16(v[c].x, v[c].y, v[c].z, v[c].w);
-        const bool ls = prev == '\n';
-        sp.ls |= (ls ? 1u : 0u) << c;
-        sp.f = xfer_compose(sp.f, chunk_xfer(sp.m[c], ls));
-        prev = v[c].w >> 24;
-    }
-    return sp;
-}
 
 // ---- bulk-copy (TMA) staging of text tiles -----------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -267,14 +235,6 @@ __device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t *s_warp3
     }
     *total = all;
     return before + incl - v;
-}
-
-// OR `v` into word `idx` of a shared-memory bit stream; words strictly inside the calling thread's
-// own range [lo, hi] belong to it alone, the two end words may be shared with a neighbour thread.
-__device__ __forceinline__ void stream_or(uint32_t *stream, uint32_t idx, uint32_t v, uint32_t lo, uint32_t hi) {
-    if (!v) return;
-    if (idx > lo && idx < hi) stream[idx] |= v;
-    else atomicOr(&stream[idx], v);
 }
 
 // ---- pass A: one transition function per tile -------------------------------------------------
