@@ -15,6 +15,7 @@ compute stream are the right tool; there is no compute kernel to fuse them into.
 import os
 from typing import List, Sequence
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -97,3 +98,76 @@ def split_work(n_items: int) -> range:
     lo = (n_items * rank) // n
     hi = (n_items * (rank + 1)) // n
     return range(lo, hi)
+
+
+# ---- one genome over several ranks -------------------------------------------------------------------
+def split_fasta(text, nparts: int, overlap_symbols: int = 63) -> List[bytes]:
+    """Cut ONE FASTA text into `nparts` FASTA texts whose sketches merge to the sketch of the whole
+    ("genomes < GPUs"): register-wise max for HLL, set union for exact counts.
+
+    k-mers never span records, so whole records can go anywhere; a record larger than its fair
+    share is cut inside its sequence body and every later piece starts `overlap_symbols` symbols
+    early (>= k-1 for every k <= 64 by default) behind a synthetic header line, so each k-mer of the
+    record lies wholly inside at least one piece.  Seeing a k-mer twice is harmless for a max / a
+    set.  Pieces are assigned to parts largest-first; a part may be empty."""
+    buf = text if isinstance(text, np.ndarray) else np.frombuffer(text, dtype=np.uint8)
+    n = int(buf.size)
+    nparts = max(1, int(nparts))
+    if nparts == 1 or n == 0:
+        return [buf.tobytes()] + [b""] * (nparts - 1)
+    gt = np.flatnonzero(buf == 62)                                   # '>'
+    starts = [int(i) for i in gt if i == 0 or buf[i - 1] == 10]      # ... at a line start: a record
+    if not starts:                                                   # no record at all: nothing is sequence
+        return [buf.tobytes()] + [b""] * (nparts - 1)
+    bounds = starts + [n]
+    total = n - starts[0]
+    target = max(1, -(-total // nparts))
+    pieces = []                                                      # (begin, end, needs_header)
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        nl = np.flatnonzero(buf[a:b] == 10)
+        body = a + int(nl[0]) + 1 if nl.size else b                  # first byte after the header line
+        grain = max(target // 4, 4096)                               # pieces of a quarter share balance well
+        if b - a <= grain + grain // 4 or body >= b:
+            pieces.append((a, b, False))
+            continue
+        ncut = -(-(b - body) // grain)
+        cuts = [body + (b - body) * i // ncut for i in range(1, ncut)]
+        prev = a
+        for c in cuts:
+            pieces.append((prev, c, prev != a))
+            # step back over at least overlap_symbols sequence bytes (newlines / CRs do not count)
+            back, span = c, 2 * overlap_symbols + 64
+            while True:
+                lo = max(body, c - span)
+                seg = buf[lo:c]
+                is_sym = (seg != 10) & (seg != 13)
+                have = int(is_sym.sum())
+                if have >= overlap_symbols:
+                    idx = np.flatnonzero(is_sym)
+                    back = lo + int(idx[have - overlap_symbols])
+                    break
+                if lo == body:
+                    back = body
+                    break
+                span *= 2
+            prev = back
+        pieces.append((prev, b, True))
+    order = sorted(range(len(pieces)), key=lambda i: (-(pieces[i][1] - pieces[i][0]), i))
+    load = [0] * nparts
+    owned = [[] for _ in range(nparts)]
+    for i in order:
+        r = min(range(nparts), key=lambda j: (load[j], j))
+        owned[r].append(i)
+        load[r] += pieces[i][1] - pieces[i][0]
+    out = []
+    for r in range(nparts):
+        chunks = []
+        for i in sorted(owned[r]):
+            a, b, hdr = pieces[i]
+            if hdr:
+                chunks.append(b">part\n")
+            chunks.append(buf[a:b].tobytes())
+            if b > a and buf[b - 1] != 10:
+                chunks.append(b"\n")                                 # keep the next header at a line start
+        out.append(b"".join(chunks))
+    return out

@@ -663,6 +663,9 @@ def presketch_leaves_sharded(fastas, speciesinfo, experiment, kstart, halfwidth=
     import torch.distributed as tdist
     lo, hi = experiment["ksweep"] if experiment["ksweep"] is not None else (kstart - halfwidth, kstart + halfwidth)
     lo, hi = max(1, int(lo)), min(HLL_MAX_K, int(hi))
+    if len(fastas) < world:
+        _presketch_split(fastas, speciesinfo, experiment, lo, hi, rank, world)
+        return rank
     owners = dd_dist.shard_by_size([os.path.getsize(f) for f in fastas], world)
     mine = [fastas[i] for i in owners[rank]]
     ingest.prefetch(mine)
@@ -684,6 +687,37 @@ def presketch_leaves_sharded(fastas, speciesinfo, experiment, kstart, halfwidth=
         for key, value in hexes.items():
             speciesinfo.fastahex.setdefault(key, value)
     return rank
+
+
+def _presketch_split(fastas, speciesinfo, experiment, lo, hi, rank, world) -> None:
+    """Fewer genomes than GPUs: every rank sketches its PART of every genome (records, or overlapping
+    pieces of a large record -- dandd_b200.dist.split_fasta), the registers are max-reduced over the
+    ranks and rank 0 writes the leaf sketches and remembers their cardinalities.  Which k are still
+    missing on disk is decided by rank 0 alone and broadcast, so that all ranks enter the same
+    collectives."""
+    import torch.distributed as tdist
+    store = get_store()
+    scratch = dict(experiment, baseset=set())
+    registers, canon = int(experiment["registers"]), bool(experiment["canonicalize"])
+    for path in fastas:
+        template = SketchFilePath(filenames=[path], kval=0, speciesinfo=speciesinfo, experiment=scratch)
+        paths = {k: template.full.replace("{}", str(k)) for k in range(lo, hi + 1)}
+        missing = None
+        if rank == 0:
+            probe = _sketch_class("dashing")(kval=0, sfp=template, speciesinfo=speciesinfo, experiment=scratch)
+            missing = []
+            for k in range(lo, hi + 1):
+                os.makedirs(template.dir.replace("{}", str(k)), exist_ok=True)
+                if not probe.sketch_check(path=paths[k]):
+                    missing.append(k)
+        box = [missing]
+        tdist.broadcast_object_list(box, src=0)
+        missing = box[0]
+        if missing:
+            cards = store.leaf_sketches(path, missing, registers, canon, {k: paths[k] for k in missing}, split=(rank, world))
+            if rank == 0:
+                for k, card in cards.items():
+                    speciesinfo.cardkey[paths[k]] = card
 
 
 def create_delta_tree(tag: str, genomedir: str, sketchdir: str, kstart: int, nchildren=None, registers=0, flist_loc=None,

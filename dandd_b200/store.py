@@ -15,7 +15,7 @@ One store per process; it talks to one Engine (one GPU).  There is no CPU path h
 """
 import os
 from collections import OrderedDict
-from typing import Dict, List, Sequence
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -95,17 +95,31 @@ class GpuSketchStore:
             self._packed[fasta] = seq
         return seq
 
-    def leaf_sketches(self, fasta: str, ks: Sequence[int], p: int, canon: bool, out_paths: Dict[int, str]) -> Dict[int, float]:
+    def leaf_sketches(self, fasta: str, ks: Sequence[int], p: int, canon: bool, out_paths: Dict[int, str],
+                      split: Optional[Tuple[int, int]] = None) -> Dict[int, float]:
         """Sketch `fasta` for every k in `ks` (one fused pass), write each sketch to out_paths[k]
         and return {k: cardinality}.  With prefetch_all_k the pass covers k = 1..32 once and later
-        requests for other k of the same FASTA are served from HBM."""
+        requests for other k of the same FASTA are served from HBM.
+
+        split=(rank, world): a COLLECTIVE call -- every rank sketches its part of the file
+        (dist.split_fasta), the registers are max-reduced over the ranks, every rank gets the
+        cardinalities of the whole file and rank 0 writes the sketch files (fewer
+        genomes than GPUs)."""
         key = (fasta, int(p), bool(canon))
         ent = self._leaf_all.get(key)
         need = [int(k) for k in ks]
-        if ent is None or any(k not in ent["ks"] for k in need):
+        if split is not None or ent is None or any(k not in ent["ks"] for k in need):
             run_ks = list(ALL_HLL_KS) if self.prefetch_all_k else sorted(set(need) | set(ent["ks"] if ent else ()))
-            seq = self.engine.pack(read_fasta_bytes(fasta))
+            text = read_fasta_bytes(fasta)
+            if split is not None:
+                from dandd_b200 import dist as dd_dist
+                run_ks = sorted(need)                      # identical on every rank, whatever each one has cached
+                text = dd_dist.split_fasta(text, split[1])[split[0]]
+            seq = self.engine.pack(text)
             regs, cards = self.engine.sketch(seq, run_ks, p=p, canon=canon)
+            if split is not None:
+                dd_dist.union_over_ranks(regs)
+                cards = self.engine.cards(regs, p)
             ent = {"regs": regs, "cards": cards.cpu().numpy(), "ks": {k: i for i, k in enumerate(run_ks)}}
             self._leaf_all[key] = ent
             self.stats["leaf_passes"] += 1
@@ -114,7 +128,8 @@ class GpuSketchStore:
             i = ent["ks"][k]
             card = float(ent["cards"][i])
             self._remember(out_paths[k], ent["regs"][i])
-            self._write(out_paths[k], ent["regs"][i], p, card, leaf=True)
+            if split is None or split[0] == 0:
+                self._write(out_paths[k], ent["regs"][i], p, card, leaf=True)
             out[k] = card
         return out
 

@@ -45,13 +45,23 @@ class OracleStore:
         self._regs[path] = regs
         self.stats["files_written"] += 1
 
-    def leaf_sketches(self, fasta, ks, p, canon, out_paths):
+    def leaf_sketches(self, fasta, ks, p, canon, out_paths, split=None):
         self.stats["leaf_passes"] += 1
         out = {}
-        for k in ks:
-            regs = orc.hll_sketch(self.symbols(fasta), int(k), p, canon)
+        sym = self.symbols(fasta)
+        if split is not None:   # collective: my part of the file, registers max-reduced over the ranks (gloo)
+            import torch
+            from dandd_b200 import dist as dd_dist
+            sym = orc.fasta_symbols(dd_dist.split_fasta(_read_fasta(fasta), split[1])[split[0]])
+        for k in sorted(ks):
+            regs = orc.hll_sketch(sym, int(k), p, canon)
+            if split is not None:
+                t = torch.from_numpy(regs.copy())
+                dd_dist.union_over_ranks(t)
+                regs = t.numpy()
             out[k] = orc.card(regs, p)
-            self._write(out_paths[k], regs, p, out[k])
+            if split is None or split[0] == 0:
+                self._write(out_paths[k], regs, p, out[k])
         return out
 
     def union_sketches(self, members_by_k, p, out_paths):

@@ -108,3 +108,69 @@ def test_two_rank_tree_matches_reference(tmp_path):
     assert_tree_matches(trimmed, gold)
     passes = [int(open(tmp_path / f"leafpasses{r}").read()) for r in (0, 1)]
     assert passes[0] > 0 and passes[1] > 0      # both ranks sketched leaves; k outside the pre-sketched window costs rank 0 extra passes
+
+
+# ---- one genome over several ranks -------------------------------------------------------------------
+def _split_cases():
+    import numpy as np
+    from tests.util import adversarial_fasta, random_bases, to_fasta
+    rng = np.random.default_rng(3)
+    big = to_fasta([(b"chr1", random_bases(rng, 120000)), (b"chr2", random_bases(rng, 30000)),
+                    (b"chr3", random_bases(rng, 5000))], width=60)
+    one = to_fasta([(b"x", random_bases(rng, 90000))], width=10 ** 9)
+    w1 = b">r\n" + b"\n".join(bytes([c]) for c in random_bases(rng, 3000)) + b"\n"
+    return {"three_records": big, "adversarial": adversarial_fasta(rng, n=40000), "one_line": one,
+            "one_line_crlf": one.replace(b"\n", b"\r\n"), "width1": w1, "header_only": b">only header", "empty": b"",
+            "no_records": b"ACGT\nno records\n", "no_final_newline": b">a\nACGTACGTAC"}
+
+
+@pytest.mark.parametrize("nparts", [2, 3, 8])
+def test_split_fasta_parts_merge_to_the_whole(nparts):
+    """dist.split_fasta: the parts' HLL registers max-merge, and their k-mer sets union, to exactly
+    those of the whole file, for every k up to 64 (record cuts, overlapping cuts inside a record)."""
+    import numpy as np
+    from oracle import pyoracle as orc
+    for name, txt in _split_cases().items():
+        parts = dd_dist.split_fasta(txt, nparts)
+        assert len(parts) == nparts, name
+        whole = orc.fasta_symbols(txt)
+        syms = [orc.fasta_symbols(t) for t in parts]
+        for k in (1, 5, 21, 32):
+            want = orc.hll_sketch(whole, k, 10)
+            got = orc.union_max([orc.hll_sketch(s, k, 10) for s in syms])
+            assert np.array_equal(want, got), (name, k)
+        for k in (1, 21, 32, 64):
+            assert orc.exact_count([whole], k) == orc.exact_count(syms, k), (name, k)
+    sizes = [len(t) for t in dd_dist.split_fasta(_split_cases()["three_records"], nparts)]
+    assert max(sizes) <= 1.35 * (sum(sizes) / nparts)      # balanced by size
+
+
+def _split_tree_worker(rank, world, port, tmpdir, outname):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from dandd_b200 import store as ddstore
+    from tests.oracle_store import OracleStore
+    from tests.host_harness import run_dandd
+    st = OracleStore()
+    ddstore.set_store(st)
+    run_dandd(["tree", "-d", os.path.join(tmpdir, "data2"), "-s", "runS", "-k", "14", "-o", os.path.join(tmpdir, outname),
+               "--ksweep", "--mink", "12", "--maxk", "16"])
+    with open(os.path.join(tmpdir, f"{outname}_passes{rank}"), "w") as fh:
+        fh.write(str(st.stats["leaf_passes"]))
+
+
+def test_fewer_genomes_than_ranks_split_each_genome(tmp_path):
+    """`dandd tree` on 2 genomes under 3 ranks (gloo): every rank sketches a part of each genome,
+    registers are max-reduced, rank 0 builds the tree -- same outputs as one process."""
+    from tests.host_harness import collect_tree
+    from tests.util import make_dataset
+    make_dataset(str(tmp_path / "data2"), 2, 30000, seed=5)
+    _split_tree_worker(0, 1, _free_port(), str(tmp_path), "out1")
+    mp.spawn(_split_tree_worker, args=(3, _free_port(), str(tmp_path), "out3"), nprocs=3, join=True)
+    one = collect_tree(str(tmp_path / "out1"), "runS_2_dashing", str(tmp_path / "out1" / "sketchdb"), "dashing")
+    three = collect_tree(str(tmp_path / "out3"), "runS_2_dashing", str(tmp_path / "out3" / "sketchdb"), "dashing")
+    assert one["deltas"] == three["deltas"]
+    assert one["files"] == three["files"]
+    assert one["cardkey"] == three["cardkey"]
+    passes = [int(open(tmp_path / f"out3_passes{r}").read()) for r in range(3)]
+    assert all(p >= 2 for p in passes)          # every rank took part in both genomes
