@@ -101,7 +101,7 @@ def split_work(n_items: int) -> range:
 
 
 # ---- one genome over several ranks -------------------------------------------------------------------
-def split_fasta(text, nparts: int, overlap_symbols: int = 63) -> List[bytes]:
+def split_fasta(text, nparts: int, overlap_symbols: int = 63, only: int = None) -> List[bytes]:
     """Cut ONE FASTA text into `nparts` FASTA texts whose sketches merge to the sketch of the whole
     ("genomes < GPUs"): register-wise max for HLL, set union for exact counts.
 
@@ -109,23 +109,29 @@ def split_fasta(text, nparts: int, overlap_symbols: int = 63) -> List[bytes]:
     share is cut inside its sequence body and every later piece starts `overlap_symbols` symbols
     early (>= k-1 for every k <= 64 by default) behind a synthetic header line, so each k-mer of the
     record lies wholly inside at least one piece.  Seeing a k-mer twice is harmless for a max / a
-    set.  Pieces are assigned to parts largest-first; a part may be empty."""
-    buf = text if isinstance(text, np.ndarray) else np.frombuffer(text, dtype=np.uint8)
-    n = int(buf.size)
+    set.  Pieces are assigned to parts largest-first; a part may be empty.  `only=r` materialises
+    part r alone (the others come back as None) -- a rank needs just its own bytes."""
+    raw = text.tobytes() if isinstance(text, np.ndarray) else bytes(text) if not isinstance(text, bytes) else text
+    buf = np.frombuffer(raw, dtype=np.uint8)
+    n = len(raw)
     nparts = max(1, int(nparts))
     if nparts == 1 or n == 0:
-        return [buf.tobytes()] + [b""] * (nparts - 1)
-    gt = np.flatnonzero(buf == 62)                                   # '>'
-    starts = [int(i) for i in gt if i == 0 or buf[i - 1] == 10]      # ... at a line start: a record
+        return [raw] + [b""] * (nparts - 1)
+    starts = []                                                      # '>' at a line start: a record
+    at = raw.find(b">")                                              # (single-byte find runs at memchr speed)
+    while at >= 0:
+        if at == 0 or raw[at - 1] == 10:
+            starts.append(at)
+        at = raw.find(b">", at + 1)
     if not starts:                                                   # no record at all: nothing is sequence
-        return [buf.tobytes()] + [b""] * (nparts - 1)
+        return [raw] + [b""] * (nparts - 1)
     bounds = starts + [n]
     total = n - starts[0]
     target = max(1, -(-total // nparts))
     pieces = []                                                      # (begin, end, needs_header)
     for a, b in zip(bounds[:-1], bounds[1:]):
-        nl = np.flatnonzero(buf[a:b] == 10)
-        body = a + int(nl[0]) + 1 if nl.size else b                  # first byte after the header line
+        nl = raw.find(b"\n", a, b)
+        body = nl + 1 if nl >= 0 else b                              # first byte after the header line
         grain = max(target // 4, 4096)                               # pieces of a quarter share balance well
         if b - a <= grain + grain // 4 or body >= b:
             pieces.append((a, b, False))
@@ -160,14 +166,18 @@ def split_fasta(text, nparts: int, overlap_symbols: int = 63) -> List[bytes]:
         owned[r].append(i)
         load[r] += pieces[i][1] - pieces[i][0]
     out = []
+    view = memoryview(raw)
     for r in range(nparts):
+        if only is not None and r != only:
+            out.append(None)
+            continue
         chunks = []
         for i in sorted(owned[r]):
             a, b, hdr = pieces[i]
             if hdr:
                 chunks.append(b">part\n")
-            chunks.append(buf[a:b].tobytes())
-            if b > a and buf[b - 1] != 10:
+            chunks.append(view[a:b])
+            if b > a and raw[b - 1] != 10:
                 chunks.append(b"\n")                                 # keep the next header at a line start
         out.append(b"".join(chunks))
     return out

@@ -114,7 +114,7 @@ class GpuSketchStore:
             if split is not None:
                 from dandd_b200 import dist as dd_dist
                 run_ks = sorted(need)                      # identical on every rank, whatever each one has cached
-                text = dd_dist.split_fasta(text, split[1])[split[0]]
+                text = dd_dist.split_fasta(text, split[1], only=split[0])[split[0]]
             seq = self.engine.pack(text)
             regs, cards = self.engine.sketch(seq, run_ks, p=p, canon=canon)
             if split is not None:

@@ -52,7 +52,7 @@ class OracleStore:
         if split is not None:   # collective: my part of the file, registers max-reduced over the ranks (gloo)
             import torch
             from dandd_b200 import dist as dd_dist
-            sym = orc.fasta_symbols(dd_dist.split_fasta(_read_fasta(fasta), split[1])[split[0]])
+            sym = orc.fasta_symbols(dd_dist.split_fasta(_read_fasta(fasta), split[1], only=split[0])[split[0]])
         for k in sorted(ks):
             regs = orc.hll_sketch(sym, int(k), p, canon)
             if split is not None:

@@ -28,7 +28,7 @@ def main():
     ks, p = list(range(10, 33)), 20
     text = synth_fasta(bases, records, seed=7, device=eng.device).cpu().numpy()     # same text on every rank
     t0 = time.perf_counter()
-    part = dd_dist.split_fasta(text, world)[rank]
+    part = dd_dist.split_fasta(text, world, only=rank)[rank]
     t_split = time.perf_counter() - t0
     dev_part = torch.from_numpy(np.frombuffer(part, dtype=np.uint8).copy()).to(eng.device)
     for _ in range(2):      # second pass is the timed one (NCCL channels, lazy kernel loading)
