@@ -51,6 +51,7 @@ SIGNATURES = {
     "dd_exact_workspace_bytes": (_sz, [_i, _u64]),
     "dd_exact_begin": (_i, [_vp, _sz, _i, _u64, _vp]),
     "dd_exact_insert": (_i, [_vp, _vp, _u64, _u64, _i, _i, _vp, _sz, _u64, _vp]),
+    "dd_exact_insert_shard": (_i, [_vp, _vp, _u64, _u64, _i, _i, _vp, _sz, _u64, _u32, _u32, _vp]),
     "dd_exact_count": (_i, [_vp, _sz, _i, _u64, _vp, _vp]),
     "dd_sketch_fasta_host_workspace_bytes": (_sz, [_sz, _i, _i]),
     "dd_sketch_fasta_host": (_i, [_vp, _sz, _u32, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -238,12 +238,21 @@ int dd_exact_begin(void *d_ws, size_t ws_bytes, int k, uint64_t capacity, dd_str
     DD_CUDA(dd::exact_begin(d_ws, k, capacity, S(stream)), "dd_exact_begin");
     return DD_OK;
 }
+int dd_exact_insert_shard(const uint32_t *d_codes, const uint32_t *d_invalid, uint64_t sym_begin, uint64_t sym_end, int k,
+                          int canon, void *d_ws, size_t ws_bytes, uint64_t capacity, uint32_t shard_rank,
+                          uint32_t shard_world, dd_stream stream) {
+    if (!d_codes || !d_invalid) return fail(DD_ERR_ARG, "dd_exact_insert: null pointer");
+    if (shard_world < 1 || shard_rank >= shard_world || shard_world > 65536)
+        return fail(DD_ERR_ARG, "dd_exact_insert: shard %u of %u", shard_rank, shard_world);
+    if (int rc = exact_check(k, capacity, d_ws, ws_bytes, "dd_exact_insert")) return rc;
+    DD_CUDA(dd::exact_insert(d_codes, d_invalid, sym_begin, sym_end, k, canon, d_ws, capacity, shard_rank, shard_world,
+                             S(stream)),
+            "dd_exact_insert");
+    return DD_OK;
+}
 int dd_exact_insert(const uint32_t *d_codes, const uint32_t *d_invalid, uint64_t sym_begin, uint64_t sym_end, int k,
                     int canon, void *d_ws, size_t ws_bytes, uint64_t capacity, dd_stream stream) {
-    if (!d_codes || !d_invalid) return fail(DD_ERR_ARG, "dd_exact_insert: null pointer");
-    if (int rc = exact_check(k, capacity, d_ws, ws_bytes, "dd_exact_insert")) return rc;
-    DD_CUDA(dd::exact_insert(d_codes, d_invalid, sym_begin, sym_end, k, canon, d_ws, capacity, S(stream)), "dd_exact_insert");
-    return DD_OK;
+    return dd_exact_insert_shard(d_codes, d_invalid, sym_begin, sym_end, k, canon, d_ws, ws_bytes, capacity, 0, 1, stream);
 }
 int dd_exact_count(void *d_ws, size_t ws_bytes, int k, uint64_t capacity, uint64_t *d_count, dd_stream stream) {
     if (!d_count) return fail(DD_ERR_ARG, "dd_exact_count: null pointer");

@@ -41,10 +41,18 @@ __device__ __forceinline__ uint64_t slot_hash(uint64_t x) {
     return x;
 }
 
+// Key-range sharding over ranks: a k-mer belongs to rank (hash >> 40) % world -- the
+// high hash bits, so the low bits that pick the slot stay uniform inside every shard.  Each rank
+// scans everything but stores only its own keys; the per-rank distinct counts add up exactly.
+__device__ __forceinline__ bool mine(uint64_t h, uint32_t shard_rank, uint32_t shard_world) {
+    return shard_world <= 1u || (uint32_t)(h >> 40) % shard_world == shard_rank;
+}
+
 template <bool kBitmap>
 __global__ void __launch_bounds__(kExactThreads)
 exact_insert_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict__ invalid, uint64_t sym_begin,
-                    uint64_t sym_end, int k, int canon, ExactWsHeader *hdr, void *table, uint64_t capacity) {
+                    uint64_t sym_end, int k, int canon, ExactWsHeader *hdr, void *table, uint64_t capacity,
+                    uint32_t shard_rank, uint32_t shard_world) {
     const uint64_t w = (sym_begin >> 4) + (uint64_t)blockIdx.x * kExactThreads + threadIdx.x;
     const uint64_t s0 = w << 4;
     unsigned long long fresh = 0;
@@ -63,6 +71,7 @@ exact_insert_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restri
             if (valid_run(invalid_window(i0, i1, sm_base + (uint32_t)j)) < k) continue;
             const Window win = window_at(w0, w1, w2, r0, r1, r2, j);
             const uint64_t v = kmer_value_rt(win, k, canon != 0);
+            if (!mine(slot_hash(v), shard_rank, shard_world)) continue;  // another rank's key range
             if (kBitmap) {
                 uint32_t *bm = static_cast<uint32_t *>(table);
                 const uint32_t bit = 1u << (v & 31);
@@ -109,7 +118,8 @@ __device__ __forceinline__ ulonglong2 cas128(ulonglong2 *addr, ulonglong2 cmp, u
 
 __global__ void __launch_bounds__(kExactThreads)
 exact_insert_wide_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict__ invalid, uint64_t sym_begin,
-                         uint64_t sym_end, int k, int canon, ExactWsHeader *hdr, ulonglong2 *tab, uint64_t capacity) {
+                         uint64_t sym_end, int k, int canon, ExactWsHeader *hdr, ulonglong2 *tab, uint64_t capacity,
+                         uint32_t shard_rank, uint32_t shard_world) {
     const uint64_t w = (sym_begin >> 4) + (uint64_t)blockIdx.x * kExactThreads + threadIdx.x;
     const uint64_t s0 = w << 4;
     unsigned long long fresh = 0;
@@ -129,12 +139,14 @@ exact_insert_wide_kernel(const uint32_t *__restrict__ codes, const uint32_t *__r
         for (int j = j_lo; j < j_hi; ++j) {
             if (valid_run_long(I, sm_base + (uint32_t)j) < k) continue;
             const U128 v = kmer128_at(c, j, k, canon != 0);
-            if (v.lo == kEmptyKey && v.hi == kEmptyKey) {  // cannot be stored: it is the empty marker
-                if (atomicExch(&hdr->saw_ones, 1ull) == 0ull) ++fresh;
+            if (v.lo == kEmptyKey && v.hi == kEmptyKey) {  // cannot be stored: it is the empty marker (rank 0's)
+                if (shard_rank == 0u && atomicExch(&hdr->saw_ones, 1ull) == 0ull) ++fresh;
                 continue;
             }
+            const uint64_t hv = slot_hash(v.lo ^ slot_hash(v.hi));
+            if (!mine(hv, shard_rank, shard_world)) continue;
             const ulonglong2 key = make_ulonglong2(v.lo, v.hi);
-            uint64_t slot = slot_hash(v.lo ^ slot_hash(v.hi)) & mask;
+            uint64_t slot = hv & mask;
             uint64_t probes = 0;
             for (;;) {
                 // a matching read settles it; anything else is decided by the CAS result alone
@@ -174,20 +186,22 @@ cudaError_t exact_begin(void *d_ws, int k, uint64_t capacity, cudaStream_t strea
 }
 
 cudaError_t exact_insert(const uint32_t *d_codes, const uint32_t *d_invalid, uint64_t sym_begin, uint64_t sym_end,
-                         int k, int canon, void *d_ws, uint64_t capacity, cudaStream_t stream) {
+                         int k, int canon, void *d_ws, uint64_t capacity, uint32_t shard_rank, uint32_t shard_world,
+                         cudaStream_t stream) {
     if (sym_end <= sym_begin) return cudaSuccess;
     const size_t nwords = (size_t)((sym_end - sym_begin + 15) / 16 + 2);  // +2: the range need not start on a word boundary
     const unsigned grid = (unsigned)((nwords + kExactThreads - 1) / kExactThreads);
     if (k > 32)
         exact_insert_wide_kernel<<<grid, kExactThreads, 0, stream>>>(d_codes, d_invalid, sym_begin, sym_end, k, canon,
                                                                     ex_hdr(d_ws), static_cast<ulonglong2 *>(ex_tab(d_ws)),
-                                                                    capacity);
+                                                                    capacity, shard_rank, shard_world);
     else if (k <= DD_EXACT_BITMAP_MAXK)
         exact_insert_kernel<true><<<grid, kExactThreads, 0, stream>>>(d_codes, d_invalid, sym_begin, sym_end, k, canon,
-                                                                     ex_hdr(d_ws), ex_tab(d_ws), capacity);
+                                                                     ex_hdr(d_ws), ex_tab(d_ws), capacity, shard_rank, shard_world);
     else
         exact_insert_kernel<false><<<grid, kExactThreads, 0, stream>>>(d_codes, d_invalid, sym_begin, sym_end, k,
-                                                                      canon, ex_hdr(d_ws), ex_tab(d_ws), capacity);
+                                                                      canon, ex_hdr(d_ws), ex_tab(d_ws), capacity, shard_rank,
+                                                                      shard_world);
     return cudaGetLastError();
 }
 

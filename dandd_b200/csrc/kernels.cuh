@@ -60,7 +60,8 @@ struct ExactWsHeader {
 size_t exact_workspace_bytes(int k, uint64_t capacity);
 cudaError_t exact_begin(void *d_ws, int k, uint64_t capacity, cudaStream_t stream);
 cudaError_t exact_insert(const uint32_t *d_codes, const uint32_t *d_invalid, uint64_t sym_begin, uint64_t sym_end,
-                         int k, int canon, void *d_ws, uint64_t capacity, cudaStream_t stream);
+                         int k, int canon, void *d_ws, uint64_t capacity, uint32_t shard_rank, uint32_t shard_world,
+                         cudaStream_t stream);
 cudaError_t exact_count(void *d_ws, int k, uint64_t capacity, uint64_t *d_count, cudaStream_t stream);
 
 }  // namespace dd

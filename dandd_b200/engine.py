@@ -301,13 +301,17 @@ class Engine:
         return cards
 
     # ---- K5 ---------------------------------------------------------------------------------
-    def exact_counts(self, seqs: Sequence[PackedSeq], k: int, canon: bool = True, capacity: Optional[int] = None) -> List[int]:
+    def exact_counts(self, seqs: Sequence[PackedSeq], k: int, canon: bool = True, capacity: Optional[int] = None,
+                     shard: Optional[tuple] = None) -> List[int]:
         """Insert the sequences one after another into one k-mer set and return the number of
-        distinct (canonical) k-mers after each: [|S1|, |S1 u S2|, ...] (exact, KMC semantics)."""
+        distinct (canonical) k-mers after each: [|S1|, |S1 u S2|, ...] (exact, KMC semantics).
+        shard=(rank, world): only the k-mers of this rank's key range are stored and counted; the
+        ranks' results add up to the unsharded counts (dandd_b200.dist.sum_counts)."""
         nsyms = [s.nsym for s in seqs]
+        srank, sworld = (int(shard[0]), int(shard[1])) if shard is not None else (0, 1)
         if capacity is None:
             capacity = 1024
-            while capacity < 2 * max(1, sum(nsyms)):
+            while capacity < 2 * max(1, sum(nsyms)) // sworld + 1024:
                 capacity *= 2
         wsb = self.lib.dd_exact_workspace_bytes(k, capacity)
         ws = self._buf(wsb, "exact")
@@ -315,8 +319,8 @@ class Engine:
         counts = torch.zeros(len(seqs), dtype=torch.int64, device=self.device)
         check(self.lib.dd_exact_begin(ws.data_ptr(), ws.numel(), k, capacity, st), "dd_exact_begin")
         for i, (s, n) in enumerate(zip(seqs, nsyms)):
-            check(self.lib.dd_exact_insert(s.codes.data_ptr(), s.invalid.data_ptr(), 0, n, k, int(canon), ws.data_ptr(),
-                                           ws.numel(), capacity, st), "dd_exact_insert")
+            check(self.lib.dd_exact_insert_shard(s.codes.data_ptr(), s.invalid.data_ptr(), 0, n, k, int(canon), ws.data_ptr(),
+                                                 ws.numel(), capacity, srank, sworld, st), "dd_exact_insert_shard")
             check(self.lib.dd_exact_count(ws.data_ptr(), ws.numel(), k, capacity, counts[i:].data_ptr(), st), "dd_exact_count")
         out = counts.cpu().numpy().astype(np.uint64)
         if (out == np.uint64(0xFFFFFFFFFFFFFFFF)).any():

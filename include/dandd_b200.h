@@ -186,6 +186,13 @@ DD_API size_t dd_exact_workspace_bytes(int k, uint64_t capacity);
 DD_API int dd_exact_begin(void *d_ws, size_t ws_bytes, int k, uint64_t capacity, dd_stream stream);
 DD_API int dd_exact_insert(const uint32_t *d_codes, const uint32_t *d_invalid, uint64_t sym_begin, uint64_t sym_end, int k,
                     int canon, void *d_ws, size_t ws_bytes, uint64_t capacity, dd_stream stream);
+/* Multi-GPU exact mode ("per-range local distinct + all-reduce SUM"): the same insert
+ * restricted to the k-mers of key range `shard_rank` of `shard_world` (a hash of the k-mer decides).
+ * Every rank scans the same streams with its own rank; the per-rank dd_exact_count values add up to
+ * the count a single dd_exact_insert pass would give, with 1/shard_world of the table per rank. */
+DD_API int dd_exact_insert_shard(const uint32_t *d_codes, const uint32_t *d_invalid, uint64_t sym_begin, uint64_t sym_end,
+                          int k, int canon, void *d_ws, size_t ws_bytes, uint64_t capacity, uint32_t shard_rank,
+                          uint32_t shard_world, dd_stream stream);
 /* Distinct k-mers inserted since dd_exact_begin -> *d_count (device u64); cumulative, so calling
  * it after each genome gives the progressive exact unions. */
 DD_API int dd_exact_count(void *d_ws, size_t ws_bytes, int k, uint64_t capacity, uint64_t *d_count, dd_stream stream);

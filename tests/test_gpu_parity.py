@@ -463,3 +463,25 @@ def test_pairwise_union_cards_large_batch(eng):
             if key not in memo:
                 memo[key] = orc.card(u, p)
             assert got[j, i] == pytest.approx(memo[key], rel=CARD_RTOL), (a, b, i)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [9, 16, 21, 32, 40, 64])
+def test_exact_counts_key_range_shards_add_up(eng, k):
+    """dd_exact_insert_shard: the distinct counts of the world's key ranges add up to the unsharded
+    progressive counts (what sum_counts() all-reduces over ranks), for the bitmap, 64-bit and 128-bit sets."""
+    rng = np.random.default_rng(700 + k)
+    anc = random_bases(rng, 30000)
+    txts = [to_fasta([(b"a", anc)]), to_fasta([(b"m", mutate(rng, anc, sub=0.03))], width=70),
+            adversarial_fasta(rng, n=15000), b">polyT\n" + b"T" * 150 + b"\n"]
+    seqs = [eng.pack(t) for t in txts]
+    want = eng.exact_counts(seqs, k)
+    assert want == [orc.exact_count([orc.fasta_symbols(t) for t in txts[:i + 1]], k) for i in range(len(txts))]
+    for world in (2, 3, 8):
+        parts = [eng.exact_counts(seqs, k, shard=(r, world)) for r in range(world)]
+        assert [sum(col) for col in zip(*parts)] == want, world
+        if k >= 16:
+            assert all(p[-1] > 0 for p in parts)      # every shard holds a share of the keys
+    from dandd_b200._lib import DandDError
+    with pytest.raises(DandDError):
+        eng.exact_counts(seqs, k, shard=(2, 2))
