@@ -24,7 +24,7 @@
 
 namespace dd {
 
-constexpr int kPlThreads = 256;
+constexpr int kPlThreads = 128;   // measured: 128 -> 1.54 ms, 256 -> 1.60 ms, 512 -> 1.74 ms (bench prefix unions)
 constexpr int kPlanes = 6;
 
 // ---- u8 registers -> bit planes -------------------------------------------------------------------
@@ -172,11 +172,11 @@ __global__ void prefix_copy_rows_kernel(const int32_t *__restrict__ rep, int n_o
     }
 }
 
-// grid (n_ord, slices, nk); a thread owns 4 groups (128 registers), a CTA 32768 registers.
+// grid (n_ord, slices, nk); a thread owns 4 groups (128 registers), a CTA 128 x kPlThreads registers.
 // kCopyFirst: the first member is copied instead of max-ed with the all-zero start (pairs: half of
 // their max work; for long orderings the extra branch costs more than the one saved step).
 template <bool kCopyFirst>
-__global__ void __launch_bounds__(kPlThreads, 4)
+__global__ void __launch_bounds__(kPlThreads, 1024 / kPlThreads)
 prefix_union_planes_kernel(const uint32_t *__restrict__ planes, const int32_t *__restrict__ order, int n_steps,
                            int n_genomes, int nk, int p, int final_only, const int32_t *__restrict__ rep,
                            uint32_t *__restrict__ hist) {
