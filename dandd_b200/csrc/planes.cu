@@ -122,9 +122,11 @@ __device__ __forceinline__ void count_bucket_sparse(const uint32_t (&P)[4][kPlan
 // ---- identical prefixes --------------------------------------------------------------------------
 // Two orderings whose first s+1 entries are the same SET have the same union at step s (always true
 // for the last step of permutations of one set, frequent at the first and last few steps of random
-// ones): only the lowest-numbered ordering of each such class counts, the others get a copy of its
-// histogram row.  Sets are 64-bit masks, so this applies to n_genomes <= 64; beyond that every
+// ones): only the lowest-numbered ordering of each such class (among the first kDedupWindow orderings)
+// counts, the others get a copy of its histogram row.  Sets are 64-bit masks, so this applies to n_genomes <= 64; beyond that every
 // ordering is its own representative.
+constexpr int kDedupWindow = 256;   // representatives are looked for among the first 256 orderings
+
 __global__ void __launch_bounds__(1024)
 prefix_dedup_kernel(const int32_t *__restrict__ order, int n_ord, int n_steps, int n_genomes,
                     unsigned long long *__restrict__ masks, int32_t *__restrict__ rep) {
@@ -144,7 +146,8 @@ prefix_dedup_kernel(const int32_t *__restrict__ order, int n_ord, int n_steps, i
         int r = o;
         if (n_genomes <= 64) {
             const unsigned long long m = masks[i];
-            for (int q = 0; q < o; ++q)
+            const int qmax = o < kDedupWindow ? o : kDedupWindow;   // bounded search: linear in n_ord
+            for (int q = 0; q < qmax; ++q)
                 if (masks[(size_t)q * n_steps + st] == m) {
                     r = q;
                     break;
@@ -286,9 +289,10 @@ cudaError_t prefix_union_hist_planes(const uint8_t *d_regs, const int32_t *d_ord
         return e;
     unsigned long long *masks = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(planes) + pl_bytes);
     int32_t *rep = reinterpret_cast<int32_t *>(masks + pairs);
-    // the search for an earlier ordering with the same prefix set is quadratic in n_ord (one CTA):
-    // worth it for tens to hundreds of orderings, pointless for a batch of distinct pairs
-    const bool dedup = n_genomes <= 64 && n_ord > 1 && (double)n_ord * n_ord * n_steps <= 4e6;
+    // one CTA compares every (ordering, step) with the first kDedupWindow orderings: the big classes
+    // (last steps, first steps) are always found there; pointless for a batch of distinct pairs
+    const bool dedup = n_genomes <= 64 && n_ord > 1 && !(final_only && n_steps == 2) &&
+                       (double)n_ord * (n_ord < kDedupWindow ? n_ord : kDedupWindow) * n_steps <= 5e7;
     if (dedup) prefix_dedup_kernel<<<1, 1024, 0, stream>>>(d_order, n_ord, n_steps, n_genomes, masks, rep);
     else rep = nullptr;
     const size_t total_groups = total >> 5;

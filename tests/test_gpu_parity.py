@@ -485,3 +485,26 @@ def test_exact_counts_key_range_shards_add_up(eng, k):
     from dandd_b200._lib import DandDError
     with pytest.raises(DandDError):
         eng.exact_counts(seqs, k, shard=(2, 2))
+
+
+@pytest.mark.gpu
+def test_prefix_union_many_orderings(eng):
+    """More orderings than the identical-prefix search window (256): rows beyond it either find
+    their class among the first 256 orderings or are counted themselves -- all must be right."""
+    rng = np.random.default_rng(321)
+    n, p, ks = 6, 12, [15]
+    regs, _ = make_sketches(eng, rng, n, ks, p, length=2500)
+    orders = [[int(g) for g in rng.permutation(n)] for _ in range(400)]
+    orders[300] = [5, 5, 5, 4, 4, 4]           # a class that first appears beyond the window
+    orders[350] = [5, 5, 5, 4, 4, 4]
+    cards = eng.prefix_union_cards(regs, orders, p).cpu().numpy()
+    h = regs.cpu().numpy()
+    memo = {}
+    for o, order in enumerate(orders):
+        run = np.zeros_like(h[0, 0])
+        for s, g in enumerate(order):
+            run = np.maximum(run, h[g, 0])
+            key = run.tobytes()
+            if key not in memo:
+                memo[key] = orc.card(run, p)
+            assert cards[o, s, 0] == pytest.approx(memo[key], rel=CARD_RTOL), (o, s)
