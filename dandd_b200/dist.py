@@ -181,3 +181,54 @@ def split_fasta(text, nparts: int, overlap_symbols: int = 63, only: int = None) 
                 chunks.append(b"\n")                                 # keep the next header at a line start
         out.append(b"".join(chunks))
     return out
+
+
+# ---- rank 0 drives, the other ranks serve (exact mode from the command line) -----------------------
+def broadcast_object(obj, src: int = 0):
+    """Small Python object from rank `src` to everyone; returns it on every rank."""
+    _, n = world()
+    if n < 2:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+class ExactWorkers:
+    """`dandd tree --exact` under torchrun: rank 0 runs the (inherently sequential) tree logic; every
+    exact count it needs is announced to the other ranks, all ranks insert their key range of the
+    k-mer set (`shard=(rank, world)`) and the counts are summed.  Ranks > 0 sit in serve() until
+    rank 0 calls stop()."""
+
+    def __init__(self, counter):
+        self.counter = counter          # callable(fastas, k, canon, shard) -> list of progressive counts (this rank's shard)
+        self.rank, self.world = world()
+        self.active = self.world > 1
+
+    def counts(self, fastas, k, canon):
+        """Called on rank 0: progressive distinct counts of the union of fastas[:i+1], all ranks helping."""
+        if not self.active:
+            return self.counter(fastas, k, canon, None)
+        broadcast_object(("exact", list(fastas), int(k), bool(canon)))
+        return self._collective(fastas, k, canon)
+
+    def _collective(self, fastas, k, canon):
+        mine = torch.tensor(self.counter(fastas, k, canon, (self.rank, self.world)), dtype=torch.int64)
+        if dist.get_backend() == "nccl":
+            mine = mine.cuda()
+        return [int(v) for v in sum_counts(mine).cpu().tolist()]
+
+    def serve(self) -> int:
+        """Ranks > 0: answer requests until rank 0 says stop; returns how many were served."""
+        served = 0
+        while True:
+            req = broadcast_object(None)
+            if not req or req[0] == "stop":
+                return served
+            self._collective(req[1], req[2], req[3])
+            served += 1
+
+    def stop(self) -> None:
+        if self.active and self.rank == 0:
+            broadcast_object(("stop",))
+        self.active = False

@@ -123,13 +123,20 @@ def tree_command(args):
         tool, args.registers = "kmc", 20
     if args.ksweep:
         args.ksweep = (int(args.mink), int(args.maxk))
-    dtree = huffman_dandd.create_delta_tree(
-        tag=args.tag, genomedir=args.genomedir, sketchdir=args.sketchdir, kstart=args.kstart, nchildren=args.nchildren,
-        registers=args.registers, flist_loc=args.flist_loc, canonicalize=args.canonicalize, tool=tool, debug=args.debug,
-        nthreads=int(args.nthreads), safety=args.safety, fast=args.fast, verbose=args.verbose, ksweep=args.ksweep,
-        lowmem=args.lowmem)
-    if dtree is not None:   # rank 0 (or the only process)
-        dtree.save(fileprefix=dtree.make_prefix(outdir=args.outdir, tag=args.tag, label=args.label), fast=args.fast)
+    try:
+        dtree = huffman_dandd.create_delta_tree(
+            tag=args.tag, genomedir=args.genomedir, sketchdir=args.sketchdir, kstart=args.kstart, nchildren=args.nchildren,
+            registers=args.registers, flist_loc=args.flist_loc, canonicalize=args.canonicalize, tool=tool, debug=args.debug,
+            nthreads=int(args.nthreads), safety=args.safety, fast=args.fast, verbose=args.verbose, ksweep=args.ksweep,
+            lowmem=args.lowmem)
+        if dtree is not None:   # rank 0 (or the only process)
+            dtree.save(fileprefix=dtree.make_prefix(outdir=args.outdir, tag=args.tag, label=args.label), fast=args.fast)
+    finally:
+        if world > 1:           # release the ranks that serve exact-count requests, also when rank 0 fails
+            from dandd_b200.store import get_store
+            workers = getattr(get_store(), "exact_workers", None)
+            if workers is not None:
+                workers.stop()
     _finish_ranks(world)
 
 

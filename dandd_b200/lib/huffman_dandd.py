@@ -659,7 +659,12 @@ def presketch_leaves_sharded(fastas, speciesinfo, experiment, kstart, halfwidth=
     if world < 2:
         return 0
     if experiment["tool"] != "dashing":
-        return rank           # exact mode: rank 0 does everything (k-mer sets are not mergeable files)
+        # exact mode: k-mer sets are not mergeable files; rank 0 walks the tree, every count it needs is
+        # computed by all ranks on key-range shards of the set (dandd_b200.dist.ExactWorkers)
+        workers = get_store().start_exact_workers()
+        if rank > 0:
+            workers.serve()
+        return rank
     import torch.distributed as tdist
     lo, hi = experiment["ksweep"] if experiment["ksweep"] is not None else (kstart - halfwidth, kstart + halfwidth)
     lo, hi = max(1, int(lo)), min(HLL_MAX_K, int(hi))

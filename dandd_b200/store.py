@@ -47,6 +47,7 @@ class GpuSketchStore:
         self._packed: Dict[str, object] = {}                           # fasta -> PackedSeq
         self._bytes = 0
         self.stats = {"leaf_passes": 0, "union_launches": 0, "files_written": 0, "files_read": 0, "exact_calls": 0}
+        self.exact_workers = None   # set by start_exact_workers() for `--exact` under torchrun
 
     # ------------------------------------------------------------------ cache plumbing
     def _remember(self, path: str, regs: torch.Tensor) -> None:
@@ -212,12 +213,22 @@ class GpuSketchStore:
     # ------------------------------------------------------------------ kmc / kmc_tools
     def exact_count(self, fastas: Sequence[str], k: int, canon: bool) -> int:
         """Number of distinct (canonical) k-mers in the union of the FASTAs (KMC semantics)."""
-        self.stats["exact_calls"] += 1
-        return self.engine.exact_counts([self.packed(f) for f in fastas], int(k), canon)[-1]
+        return self.exact_prefix_counts(fastas, k, canon)[-1]
 
     def exact_prefix_counts(self, fastas: Sequence[str], k: int, canon: bool) -> List[int]:
         self.stats["exact_calls"] += 1
-        return self.engine.exact_counts([self.packed(f) for f in fastas], int(k), canon)
+        if self.exact_workers is not None:
+            return self.exact_workers.counts(list(fastas), int(k), bool(canon))
+        return self._exact_shard_counts(fastas, k, canon, None)
+
+    def _exact_shard_counts(self, fastas, k, canon, shard):
+        return self.engine.exact_counts([self.packed(f) for f in fastas], int(k), canon, shard=shard)
+
+    def start_exact_workers(self):
+        """Multi-rank exact mode (dandd_b200.dist.ExactWorkers): rank 0 keeps going, the others serve."""
+        from dandd_b200 import dist as dd_dist
+        self.exact_workers = dd_dist.ExactWorkers(self._exact_shard_counts)
+        return self.exact_workers
 
 
 _store = None

@@ -24,6 +24,7 @@ class OracleStore:
         self._regs = {}
         self._syms = {}
         self.stats = {"leaf_passes": 0, "union_launches": 0, "files_written": 0, "files_read": 0, "exact_calls": 0}
+        self.exact_workers = None
 
     def symbols(self, fasta):
         if fasta not in self._syms:
@@ -95,8 +96,23 @@ class OracleStore:
         return orc.card(regs, int(regs.size).bit_length() - 1)
 
     def exact_count(self, fastas, k, canon):
-        self.stats["exact_calls"] += 1
-        return orc.exact_count([self.symbols(f) for f in fastas], int(k), canon)
+        return self.exact_prefix_counts(fastas, k, canon)[-1]
 
     def exact_prefix_counts(self, fastas, k, canon):
+        self.stats["exact_calls"] += 1
+        if self.exact_workers is not None:
+            return self.exact_workers.counts(list(fastas), int(k), bool(canon))
+        return self._exact_shard_counts(fastas, k, canon, None)
+
+    def _exact_shard_counts(self, fastas, k, canon, shard):
+        """The CPU oracle has no key-range filter: rank 0's "shard" is the whole set, the other ranks
+        contribute zeros -- enough to exercise the request / serve / sum protocol."""
+        self.stats["shard_calls"] = self.stats.get("shard_calls", 0) + 1
+        if shard is not None and shard[0] != 0:
+            return [0] * len(fastas)
         return [orc.exact_count([self.symbols(f) for f in fastas[:i + 1]], int(k), canon) for i in range(len(fastas))]
+
+    def start_exact_workers(self):
+        from dandd_b200 import dist as dd_dist
+        self.exact_workers = dd_dist.ExactWorkers(self._exact_shard_counts)
+        return self.exact_workers

@@ -174,3 +174,31 @@ def test_fewer_genomes_than_ranks_split_each_genome(tmp_path):
     assert one["cardkey"] == three["cardkey"]
     passes = [int(open(tmp_path / f"out3_passes{r}").read()) for r in range(3)]
     assert all(p >= 2 for p in passes)          # every rank took part in both genomes
+
+
+def _exact_tree_worker(rank, world, port, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from dandd_b200 import store as ddstore
+    from tests.oracle_store import OracleStore
+    from tests.host_harness import run_dandd
+    st = OracleStore()
+    ddstore.set_store(st)
+    run_dandd(["tree", "-d", os.path.join(tmpdir, "data5"), "-s", "runE", "-k", "14", "-o", os.path.join(tmpdir, "outE"),
+               "--exact"])
+    with open(os.path.join(tmpdir, f"shardcalls{rank}"), "w") as fh:
+        fh.write(str(st.stats.get("shard_calls", 0)))
+
+
+def test_two_rank_exact_tree_matches_reference(tmp_path):
+    """`dandd tree --exact` under two ranks: rank 0 walks the tree, rank 1 serves every exact-count
+    request on its key-range shard until rank 0 says stop; outputs equal the reference golden."""
+    from tests.host_harness import assert_tree_matches, collect_tree, gold_runs
+    from tests.util import make_dataset
+    make_dataset(str(tmp_path / "data5"), 5, 20000, seed=21)
+    mp.spawn(_exact_tree_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    out = str(tmp_path / "outE")
+    assert_tree_matches(collect_tree(out, "runE_5_kmc", os.path.join(out, "sketchdb"), "kmc"), gold_runs()["E_tree_exact"],
+                        exact=True)
+    calls = [int(open(tmp_path / f"shardcalls{r}").read()) for r in (0, 1)]
+    assert calls[0] > 0 and calls[0] == calls[1]       # every request of rank 0 was served by rank 1
