@@ -97,6 +97,16 @@ def _select_device(args):
         os.environ["LOCAL_RANK"] = str(args.device)
 
 
+def _single_rank_command(name) -> bool:
+    """`progressive` and `kij` run on one GPU (their device work is milliseconds once the leaves are
+    in HBM).  Started under torchrun, every rank but the first steps aside instead of repeating
+    the job and racing on the output files.  Returns True if this process should return."""
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and int(os.environ.get("RANK", "0")) > 0:
+        print(f"dandd {name}: rank {os.environ.get('RANK')} idle (single-GPU command)")
+        return True
+    return False
+
+
 def _load_tree(path):
     with open(path, "rb") as fh:
         return pickle.load(fh)
@@ -157,6 +167,8 @@ def _finish_ranks(world):
 
 def progressive_command(args):
     """reference :65-87"""
+    if _single_rank_command("progressive"):
+        return
     _select_device(args)
     dtree = _load_tree(args.delta_tree)
     args.tag = args.tag or dtree.speciesinfo.tag
@@ -173,6 +185,8 @@ def progressive_command(args):
 
 def kij_command(args):
     """reference :107-132"""
+    if _single_rank_command("kij"):
+        return
     _select_device(args)
     dtree = _load_tree(args.delta_tree)
     dtree.speciesinfo.update(tool=dtree.experiment["tool"])
