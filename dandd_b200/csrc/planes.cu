@@ -24,7 +24,7 @@
 
 namespace dd {
 
-constexpr int kPlThreads = 128;   // measured: 128 -> 1.54 ms, 256 -> 1.60 ms, 512 -> 1.74 ms (bench prefix unions)
+constexpr int kPlThreads = 64;   // measured (bench prefix unions): 64 -> 1.51 ms, 128 -> 1.54, 256 -> 1.60, 512 -> 1.74
 constexpr int kPlanes = 6;
 
 // ---- u8 registers -> bit planes -------------------------------------------------------------------
