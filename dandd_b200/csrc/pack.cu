@@ -307,14 +307,35 @@ pack_count_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
 constexpr int kGroupTiles = 512;
 
 __global__ void __launch_bounds__(kGroupTiles)
-pack_scan_groups_kernel(uint64_t *__restrict__ tile_xfer, size_t ntiles, uint64_t *__restrict__ group_agg) {
+pack_scan_groups_kernel(uint64_t *__restrict__ tile_xfer, size_t ntiles, uint64_t *__restrict__ group_agg,
+                        const uint8_t *__restrict__ text, size_t n, PackTileOut *__restrict__ group_out,
+                        uint64_t *__restrict__ seg_base, PackWsHeader *__restrict__ hdr, dd_pack_state *__restrict__ st,
+                        size_t cap_symbols) {
     __shared__ uint64_t s_warp[32];
     const size_t t = (size_t)blockIdx.x * kGroupTiles + threadIdx.x;
     const uint64_t g = t < ntiles ? tile_xfer[t] : kXferIdentity;
     uint64_t all;
     const uint64_t pre = block_scan_xfer(g & ~kXferSimple, s_warp, &all);
     if (t < ntiles) tile_xfer[t] = pre | (g & kXferSimple);
-    if (threadIdx.x == 0) group_agg[blockIdx.x] = all;
+    if (threadIdx.x == 0) {
+        group_agg[blockIdx.x] = all;
+        if (gridDim.x == 1) {
+            // a single group (<= 8 MiB of text): there is nothing left to scan, so this kernel also does
+            // pass B2's bookkeeping and the host skips that launch
+            const uint32_t entry_state = st->in_header;
+            group_out[0].local_off = 0;
+            group_out[0].state = entry_state;
+            seg_base[0] = 0;
+            hdr->entry_last_byte = st->last_byte;
+            hdr->seg_len = 1;
+            const uint64_t before = st->nsym, run = xfer_cnt(all, entry_state);
+            st->prev_nsym = before;
+            st->nsym = before + run;
+            st->in_header = xfer_end(all, entry_state);
+            if (n > 0) st->last_byte = text[n - 1];
+            if (before + run > cap_symbols) st->reserved |= 1;  // overflow: symbols past capacity are dropped
+        }
+    }
 }
 
 // ---- pass B2: scan the group functions ("tiles" below are groups), assign output offsets,
@@ -672,8 +693,11 @@ cudaError_t pack_fasta(const uint8_t *d_text, size_t n, uint32_t *d_codes, uint3
     const unsigned ga = (unsigned)(nt < (size_t)grid_count ? nt : (size_t)grid_count);
     const unsigned gc = (unsigned)(nt < (size_t)grid_write ? nt : (size_t)grid_write);
     pack_count_kernel<<<ga, kPackThreads, 2 * kTileBytes, stream>>>(d_text, n, nt, d_state, tile_xfer);
-    pack_scan_groups_kernel<<<(unsigned)ng, kGroupTiles, 0, stream>>>(tile_xfer, nt, group_agg);
-    pack_scan_kernel<<<1, kScanThreads, 0, stream>>>(d_text, n, group_agg, ng, group_out, seg_base, hdr, d_state, cap_symbols);
+    pack_scan_groups_kernel<<<(unsigned)ng, kGroupTiles, 0, stream>>>(tile_xfer, nt, group_agg, d_text, n, group_out, seg_base,
+                                                                      hdr, d_state, cap_symbols);
+    if (ng > 1)
+        pack_scan_kernel<<<1, kScanThreads, 0, stream>>>(d_text, n, group_agg, ng, group_out, seg_base, hdr, d_state,
+                                                        cap_symbols);
     pack_write_kernel<<<gc, kPackThreads, kWriteSmem, stream>>>(d_text, n, nt, tile_xfer, group_out, seg_base, hdr, d_state,
                                                                d_codes, d_invalid, cap_symbols);
     return cudaGetLastError();
