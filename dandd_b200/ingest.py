@@ -36,11 +36,65 @@ def _key(path):
     return (os.path.abspath(path), st.st_size, st.st_mtime_ns)
 
 
+# ---- BGZF (bgzip) ------------------------------------------------------------------------------------
+# A plain .gz stream can only be inflated front to back.  bgzip output -- common for genome FASTAs --
+# is a series of independent <= 64 KiB gzip members whose header carries the member's size in a
+# "BC" extra field, so the members can be found without inflating and inflated in parallel
+# (zlib releases the GIL).  Anything that is not BGZF goes through gzip.decompress as before.
+_inflate_pool = None
+_BGZF_BATCH = 256          # members per task (~16 MiB of text)
+
+
+def _bgzf_members(raw: bytes):
+    """[(payload_begin, payload_end, isize, crc32)] of every member if `raw` is BGZF from end to end, else None."""
+    out, at, n = [], 0, len(raw)
+    while at < n:
+        if n - at < 18 or raw[at:at + 4] != b"\x1f\x8b\x08\x04":
+            return None
+        xlen = int.from_bytes(raw[at + 10:at + 12], "little")
+        extra, bsize, q = raw[at + 12:at + 12 + xlen], None, 0
+        while q + 4 <= len(extra):
+            slen = int.from_bytes(extra[q + 2:q + 4], "little")
+            if extra[q:q + 2] == b"BC" and slen == 2:
+                bsize = int.from_bytes(extra[q + 4:q + 6], "little") + 1
+            q += 4 + slen
+        if bsize is None or at + bsize > n or bsize < 12 + xlen + 8:
+            return None
+        out.append((at + 12 + xlen, at + bsize - 8, int.from_bytes(raw[at + bsize - 4:at + bsize], "little"),
+                    int.from_bytes(raw[at + bsize - 8:at + bsize - 4], "little")))
+        at += bsize
+    return out
+
+
+def _inflate_batch(raw, members):
+    import zlib
+    parts = []
+    for begin, end, isize, crc in members:
+        data = zlib.decompress(raw[begin:end], wbits=-15, bufsize=max(isize, 1))
+        if len(data) != isize or zlib.crc32(data) != crc:
+            raise ValueError("corrupt BGZF member (size or CRC-32 does not match its trailer)")
+        parts.append(data)
+    return b"".join(parts)
+
+
+def gunzip(raw: bytes) -> bytes:
+    """gzip -> bytes; BGZF input is inflated by a pool of threads."""
+    global _inflate_pool
+    members = _bgzf_members(raw) if raw[:4] == b"\x1f\x8b\x08\x04" else None
+    if not members or len(members) <= _BGZF_BATCH:
+        return gzip.decompress(raw)
+    if _inflate_pool is None:      # its own pool: _load itself runs on the ingest pool
+        _inflate_pool = ThreadPoolExecutor(max_workers=max(2, min(32, os.cpu_count() or 4)), thread_name_prefix="dd-inflate")
+    view = memoryview(raw)
+    jobs = [_inflate_pool.submit(_inflate_batch, view, members[i:i + _BGZF_BATCH]) for i in range(0, len(members), _BGZF_BATCH)]
+    return b"".join(j.result() for j in jobs)
+
+
 def _load(path):
     with open(path, "rb") as fh:
         raw = fh.read()
     dig = hashlib.blake2b(raw).hexdigest()
-    text = gzip.decompress(raw) if raw[:2] == b"\x1f\x8b" else raw
+    text = gunzip(raw) if raw[:2] == b"\x1f\x8b" else raw
     return text, dig
 
 
