@@ -2,6 +2,14 @@
 work inside ~5 s of interpreter, torch and CUDA start-up)."""
 import os
 
+TRIM_REQUESTED = False   # set by the command-line launchers; honoured by dandd_b200.store.get_store()
+
+
+def request_trim() -> None:
+    """Ask for trim_torch_cuda_init() right before the store starts CUDA -- without importing torch now."""
+    global TRIM_REQUESTED
+    TRIM_REQUESTED = True
+
 
 def trim_torch_cuda_init() -> bool:
     """torch queues, for its lazy CUDA initialisation, the registration of two sparse-BSR Triton

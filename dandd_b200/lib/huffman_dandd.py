@@ -29,7 +29,15 @@ from sketch_classes import DashSketchObj, KMCSketchObj, SketchFilePath, SketchOb
 from species_specifics import SpeciesSpecifics
 
 from dandd_b200 import ingest
-from dandd_b200.store import get_store
+
+
+def get_store():
+    """The process-wide sketch store (dandd_b200.store), imported on first use: a run that is served
+    entirely from the sketch database -- or ends in an argument error -- never pays for importing
+    torch and starting CUDA."""
+    from dandd_b200.store import get_store as _get
+    return _get()
+
 
 HLL_MAX_K = 32      # "maxk<=32 for estimation" (reference README.md:82, lib/huffman_dandd.py:109-110)
 MIN_KSLOTS = 100    # default length of DeltaTreeNode.ksketches (index = k, slot 0 = sweep template)
@@ -654,6 +662,8 @@ def presketch_leaves_sharded(fastas, speciesinfo, experiment, kstart, halfwidth=
     left after this call is the unions.  Returns this process's rank.  HLL merge is exact, so the results are
     identical to a single-GPU run.  k range: the sweep if one was asked for, else a
     window around kstart (anything the hill-climb visits outside it is sketched on demand)."""
+    if int(os.environ.get("WORLD_SIZE", "1")) < 2:
+        return 0              # (and torch.distributed is never imported in the single-process case)
     from dandd_b200 import dist as dd_dist
     rank, world = dd_dist.world()
     if world < 2:

@@ -18,7 +18,15 @@ import os
 from species_specifics import SpeciesSpecifics
 
 from dandd_b200 import ingest
-from dandd_b200.store import get_store
+
+
+def get_store():
+    """The process-wide sketch store (dandd_b200.store), imported on first use: a run that is served
+    entirely from the sketch database -- or ends in an argument error -- never pays for importing
+    torch and starting CUDA."""
+    from dandd_b200.store import get_store as _get
+    return _get()
+
 
 DASHINGLOC = "dashing"   # kept for API compatibility; only ever used inside the recorded .cmd text
 

@@ -237,6 +237,9 @@ _store = None
 def get_store():
     global _store
     if _store is None:
+        from dandd_b200 import _startup
+        if _startup.TRIM_REQUESTED:          # command-line start-up trim, see _startup.py
+            _startup.trim_torch_cuda_init()
         _store = GpuSketchStore()
     return _store
 

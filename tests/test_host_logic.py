@@ -2,6 +2,8 @@
 (tests/golden/reference_runs.json), on the CPU: the store is replaced by the oracle-backed double
 so that naming, caching, the k hill-climb, tree shapes and every output table are exercised in a
 container without a GPU.  tests/test_host_gpu.py runs the same scenarios on the real store."""
+import os
+
 import pytest
 
 from dandd_b200 import store as ddstore
@@ -51,3 +53,37 @@ def test_exact_sweep_above_k32(tmp_path, oracle_store):
 
 def test_pickle_roundtrip(tmp_path, oracle_store):
     host_cases.scenario_pickle_roundtrip(str(tmp_path))
+
+
+def test_cached_rerun_never_touches_the_store(tmp_path, oracle_store):
+    """A second identical `tree` run is answered from the sketch database alone: with no store
+    installed (creating the real one would need CUDA and fail loudly here) it must still succeed --
+    which is what lets such runs skip importing torch and starting CUDA altogether."""
+    import sys
+    from dandd_b200 import store as ddstore
+    from tests.host_harness import run_dandd
+    out = host_cases.scenario_tree_hillclimb(str(tmp_path))
+    first = open(os.path.join(out, "runA_5_dashing_deltas.csv")).read()
+    ddstore.set_store(None)
+    try:
+        run_dandd(["tree", "-d", os.path.join(str(tmp_path), "data5"), "-s", "runA", "-k", "14", "-o", out])
+        assert ddstore._store is None
+    finally:
+        ddstore.set_store(oracle_store)
+    assert open(os.path.join(out, "runA_5_dashing_deltas.csv")).read() == first
+
+
+def test_cached_rerun_as_a_process_imports_no_torch(tmp_path, oracle_store):
+    """The real launcher, as a subprocess, on a fully cached sketch database: exits 0 in a container
+    without a GPU and never imports torch (that is the whole start-up cost of such a run)."""
+    import subprocess
+    import sys
+    out = host_cases.scenario_tree_hillclimb(str(tmp_path))
+    launcher = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dandd_b200", "lib", "dandd")
+    argv = [launcher, "tree", "-d", os.path.join(str(tmp_path), "data5"), "-s", "runA", "-k", "14", "-o", out]
+    code = ("import sys, runpy\nsys.argv = %r\ntry:\n    runpy.run_path(sys.argv[0], run_name='__main__')\n"
+            "except SystemExit as e:\n    assert not e.code, e.code\nprint('TORCH_IMPORTED', 'torch' in sys.modules)\n" % (argv,))
+    env = dict(os.environ, WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "TORCH_IMPORTED False" in r.stdout
