@@ -25,7 +25,7 @@ from math import factorial
 from random import sample, shuffle
 from typing import Dict, List, Set, Tuple
 
-from sketch_classes import DashSketchObj, KMCSketchObj, SketchFilePath, SketchObj  # noqa: F401
+from sketch_classes import DashSketchObj, KMCSketchObj, SketchFilePath, SketchObj, ensure_dir  # noqa: F401
 from species_specifics import SpeciesSpecifics
 
 from dandd_b200 import ingest
@@ -180,7 +180,7 @@ class DeltaTreeNode:
         paths = {k: template.full.replace("{}", str(k)) for k in range(lo, hi + 1)}
         sketchlist = []
         for k in range(lo, hi + 1):
-            os.makedirs(template.dir.replace("{}", str(k)), exist_ok=True)
+            ensure_dir(template.dir.replace("{}", str(k)))
             sketchlist.append(paths[k])
             self.experiment["baseset"].add(template.base.replace("{}", str(k)))
 
@@ -520,7 +520,7 @@ class DeltaTree:
                     path = template.full.replace("{}", str(k))
                     cells[(o, i - 1, k)] = path
                     if not probe.sketch_check(path=path):
-                        os.makedirs(os.path.dirname(path), exist_ok=True)
+                        ensure_dir(os.path.dirname(path))
                         out_paths[(o, i - 1, k)] = path
         if not out_paths and all(float(cardkey.get(path) or 0) > 0 for path in cells.values()):
             return   # everything cached already: a repeated run issues no GPU work
@@ -722,7 +722,7 @@ def _presketch_split(fastas, speciesinfo, experiment, lo, hi, rank, world) -> No
             probe = _sketch_class("dashing")(kval=0, sfp=template, speciesinfo=speciesinfo, experiment=scratch)
             missing = []
             for k in range(lo, hi + 1):
-                os.makedirs(template.dir.replace("{}", str(k)), exist_ok=True)
+                ensure_dir(template.dir.replace("{}", str(k)))
                 if not probe.sketch_check(path=paths[k]):
                     missing.append(k)
         box = [missing]

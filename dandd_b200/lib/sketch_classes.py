@@ -30,6 +30,24 @@ def get_store():
 
 DASHINGLOC = "dashing"   # kept for API compatibility; only ever used inside the recorded .cmd text
 
+_made_dirs = set()
+
+
+def ensure_dir(path: str) -> None:
+    """os.makedirs(exist_ok=True), once per directory and process (a progressive run asks for the
+    same few hundred ngen*/k* directories tens of thousands of times)."""
+    if path and path not in _made_dirs:
+        os.makedirs(path, exist_ok=True)
+        _made_dirs.add(path)
+
+
+def nonempty_file(path: str) -> bool:
+    """exists-and-not-empty with a single stat (the reference's sketch existence test, :331)."""
+    try:
+        return os.stat(path).st_size != 0
+    except OSError:
+        return False
+
 
 def blake2b(fname):
     """Hex digest of the file bytes that names a FASTA (reference :12-18).  Computed by the ingest
@@ -65,7 +83,7 @@ class SketchFilePath:
         self.relative = os.path.join("ngen" + str(self.ngen), "k" + str(kval), self.base) + ext
         self.full = os.path.join(self.dir, self.base) + ext
         if kval != 0:
-            os.makedirs(self.dir, exist_ok=True)
+            ensure_dir(self.dir)
 
     def __repr__(self):
         return (f"{self.__class__.__name__}[basename: {self.base}, 'fullpath inputs: {self.ffiles}', "
@@ -298,7 +316,7 @@ class DashSketchObj(SketchObj):
 
     def sketch_check(self, path=None) -> bool:
         path = path or self.sfp.full
-        return os.path.exists(path) and os.stat(path).st_size != 0
+        return nonempty_file(path)
 
     def remove_sketch(self, delete_me: str = None):
         pattern = delete_me or self.sfp.full
@@ -359,7 +377,7 @@ class KMCSketchObj(SketchObj):
         `full` + .kmc_pre/.kmc_suf and cache the count -- `kmc` (one FASTA) or `kmc_tools complex`
         (several) followed by `kmc_tools info`, in one step."""
         count = get_store().exact_count(list(fastas), kval, canon)
-        os.makedirs(os.path.dirname(full), exist_ok=True)
+        ensure_dir(os.path.dirname(full))
         body = (cls.MAGIC + f"k={kval}\ncanonical={int(canon)}\ntotal k-mers={count}\n".encode()
                 + "".join(f"input={f}\n" for f in fastas).encode())
         for ext in (".kmc_pre", ".kmc_suf"):
@@ -391,7 +409,7 @@ class KMCSketchObj(SketchObj):
         check_cardinality() here, which calls sketch_check() again: a RecursionError as shipped,
         SURVEY.md App. B; the intended existence test is what is implemented.)"""
         path = path or self.sfp.full
-        return all(os.path.exists(path + ext) and os.stat(path + ext).st_size != 0 for ext in (".kmc_pre", ".kmc_suf"))
+        return all(nonempty_file(path + ext) for ext in (".kmc_pre", ".kmc_suf"))
 
     def remove_sketch(self, delete_me: str = None):
         pattern = delete_me or self.sfp.full
