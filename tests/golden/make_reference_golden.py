@@ -93,6 +93,46 @@ def collect_tree(outdir, prefix, sketchdir, tool):
     return {"deltas": rows, "files": files, "cardkey": cardkey, "fastahex": fastahex, "sketchinfo": sketchinfo}
 
 
+def prog_rows(path):
+    return [{"ngen": int(r["ngen"]), "kval": int(r["kval"]), "delta": float(r["delta"]), "fastas": norm_fastas(r["fastas"], ",")}
+            for r in read_csv(path)]
+
+
+def more_runs(work, bindir, data5, dtreeA, outA, gold):
+    """Option coverage: --no-canon / --registers, -f file lists, --safe, --fast, progressive -f and
+    --step, kij --afproject.  (`--lowmem` and `kij -f` fail in the reference as shipped -- a runaway
+    hill-climb after the union sketches are deleted, and strings where nodes are expected,
+    lib/huffman_dandd.py:685 -- so there is nothing to pin for them.)"""
+    # H: non-canonical k-mers, 2^12 registers
+    outH = os.path.join(work, "outH")
+    run_ref(bindir, ["tree", "-d", data5, "-s", "runH", "-k", "12", "-o", outH, "-C", "-r", "12"])
+    gold["runs"]["H_tree_noncanon_p12"] = collect_tree(outH, "runH_5_dashing", os.path.join(outH, "sketchdb"), "dashing")
+    # I: a file list instead of a directory (3 of the 5 FASTAs), with --safe
+    flist = os.path.join(work, "flist.txt")
+    with open(flist, "w") as fh:
+        fh.write("\n".join(os.path.join(data5, f) for f in sorted(os.listdir(data5))[1:4]) + "\n")
+    outI = os.path.join(work, "outI")
+    run_ref(bindir, ["tree", "-f", flist, "-s", "runI", "-k", "14", "-o", outI, "--safe"])
+    gold["runs"]["I_tree_flist_safe"] = collect_tree(outI, "runI_3_dashing", os.path.join(outI, "sketchdb"), "dashing")
+    # K: --fast writes the deltas table only
+    outK = os.path.join(work, "outK")
+    run_ref(bindir, ["tree", "-d", data5, "-s", "runK", "-k", "14", "-o", outK, "--fast"])
+    gold["runs"]["K_tree_fast"] = {"outputs": sorted(f for f in os.listdir(outK) if f != "sketchdb"),
+                                   "deltas": [{"title": r["title"], "ngen": int(r["ngen"]), "k": int(r["k"]),
+                                               "delta": float(r["delta"]), "card": float(r["card"])}
+                                              for r in read_csv(os.path.join(outK, "runK_5_dashing_deltas.csv"))]}
+    # L: progressive over a subset of the tree's FASTAs; N: --step 2
+    run_ref(bindir, ["progressive", "-d", dtreeA, "-f", flist, "-n", "1", "-o", outA, "-s", "sub"])
+    gold["runs"]["L_progressive_subset"] = {"rows": prog_rows(os.path.join(outA, "sub_progu1_5_dashing.csv"))}
+    run_ref(bindir, ["progressive", "-d", dtreeA, "-n", "1", "--step", "2", "-o", outA, "-s", "st2"])
+    gold["runs"]["N_progressive_step2"] = {"rows": prog_rows(os.path.join(outA, "st2_progu1_5_dashing.csv"))}
+    # O: kij --afproject (the tuples handed to the AFproject helper)
+    run_ref(bindir, ["kij", "-d", dtreeA, "-o", outA, "--afproject", "-s", "af"])
+    with open(os.path.join(outA, "af_5_dashing_AFtuples.pickle"), "rb") as fh:
+        tuples = pickle.load(fh)
+    gold["runs"]["O_kij_afproject"] = {"type": type(tuples).__name__, "tuples": json.loads(json.dumps(tuples, default=list))}
+
+
 def main():
     work = tempfile.mkdtemp(prefix="dandd_golden_")
     bindir = pyoracle.install_shims(os.path.join(work, "bin"))
@@ -169,6 +209,7 @@ def main():
         outE = os.path.join(work, "outE")
         run_ref(bindir, ["tree", "-d", data5, "-s", "runE", "-k", "14", "-o", outE, "--exact"], exact=True)
         gold["runs"]["E_tree_exact"] = collect_tree(outE, "runE_5_kmc", os.path.join(outE, "sketchdb"), "kmc")
+        more_runs(work, bindir, data5, dtreeA, outA, gold)
     finally:
         shutil.rmtree(work, ignore_errors=True)
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_runs.json")

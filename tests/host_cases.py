@@ -140,6 +140,58 @@ def scenario_exact_sweep_above_k32(tmp):
     assert seen >= 7 * 4
 
 
+def scenario_option_coverage(tmp):
+    """--no-canon / --registers, -f file lists with --safe, --fast, progressive -f and --step, kij --afproject:
+    the same commands the golden generator ran through the unmodified reference."""
+    gold = gold_runs()
+    data = make_dataset(os.path.join(tmp, "data5"), 5, 20000, seed=21)
+    ddir = os.path.dirname(data[0])
+    outH = os.path.join(tmp, "outH")
+    run_dandd(["tree", "-d", ddir, "-s", "runH", "-k", "12", "-o", outH, "-C", "-r", "12"])
+    assert_tree_matches(collect_tree(outH, "runH_5_dashing", os.path.join(outH, "sketchdb"), "dashing"), gold["H_tree_noncanon_p12"])
+
+    flist = os.path.join(tmp, "flist.txt")
+    with open(flist, "w") as fh:
+        fh.write("\n".join(os.path.join(ddir, f) for f in sorted(os.listdir(ddir))[1:4]) + "\n")
+    outI = os.path.join(tmp, "outI")
+    run_dandd(["tree", "-f", flist, "-s", "runI", "-k", "14", "-o", outI, "--safe"])
+    assert_tree_matches(collect_tree(outI, "runI_3_dashing", os.path.join(outI, "sketchdb"), "dashing"), gold["I_tree_flist_safe"])
+
+    outK = os.path.join(tmp, "outK")
+    run_dandd(["tree", "-d", ddir, "-s", "runK", "-k", "14", "-o", outK, "--fast"])
+    want = gold["K_tree_fast"]
+    assert sorted(f for f in os.listdir(outK) if f != "sketchdb") == want["outputs"]
+    rows = read_csv(os.path.join(outK, "runK_5_dashing_deltas.csv"))
+    assert [(r["title"], int(r["ngen"]), int(r["k"])) for r in rows] == [(r["title"], r["ngen"], r["k"]) for r in want["deltas"]]
+    for a, b in zip(rows, want["deltas"]):
+        assert close(float(a["delta"]), b["delta"]) and close(float(a["card"]), b["card"])
+
+    outA = os.path.join(tmp, "outA")
+    run_dandd(["tree", "-d", ddir, "-s", "runA", "-k", "14", "-o", outA])
+    dtree = os.path.join(outA, "runA_5_dashing_dtree.pickle")
+
+    def prog_matches(csv_name, want_rows):
+        got = read_csv(os.path.join(outA, csv_name))
+        assert [(int(r["ngen"]), int(r["kval"]), norm_fastas(r["fastas"], ",")) for r in got] == \
+               [(r["ngen"], r["kval"], r["fastas"]) for r in want_rows]
+        for a, b in zip(got, want_rows):
+            assert close(float(a["delta"]), b["delta"])
+
+    run_dandd(["progressive", "-d", dtree, "-f", flist, "-n", "1", "-o", outA, "-s", "sub"])
+    prog_matches("sub_progu1_5_dashing.csv", gold["L_progressive_subset"]["rows"])
+    run_dandd(["progressive", "-d", dtree, "-n", "1", "--step", "2", "-o", outA, "-s", "st2"])
+    prog_matches("st2_progu1_5_dashing.csv", gold["N_progressive_step2"]["rows"])
+
+    run_dandd(["kij", "-d", dtree, "-o", outA, "--afproject", "-s", "af"])
+    with open(os.path.join(outA, "af_5_dashing_AFtuples.pickle"), "rb") as fh:
+        tuples = pickle.load(fh)
+    want = gold["O_kij_afproject"]
+    assert type(tuples).__name__ == want["type"] and len(tuples) == len(want["tuples"])
+    key = lambda t: (t[1], t[2])
+    for a, b in zip(sorted((list(t) for t in tuples), key=key), sorted(want["tuples"], key=key)):
+        assert a[:4] == b[:4] and a[5:] == b[5:] and close(float(a[4]), float(b[4]))
+
+
 def scenario_pickle_roundtrip(tmp):
     """The dtree pickle names classes by the reference's top-level module names."""
     out = scenario_tree_hillclimb(tmp)

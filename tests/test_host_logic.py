@@ -51,6 +51,10 @@ def test_exact_sweep_above_k32(tmp_path, oracle_store):
     host_cases.scenario_exact_sweep_above_k32(str(tmp_path))
 
 
+def test_option_coverage(tmp_path, oracle_store):
+    host_cases.scenario_option_coverage(str(tmp_path))
+
+
 def test_pickle_roundtrip(tmp_path, oracle_store):
     host_cases.scenario_pickle_roundtrip(str(tmp_path))
 
