@@ -133,6 +133,26 @@ def more_runs(work, bindir, data5, dtreeA, outA, gold):
     gold["runs"]["O_kij_afproject"] = {"type": type(tuples).__name__, "tuples": json.loads(json.dumps(tuples, default=list))}
 
 
+def exact_runs(work, bindir, data5, gold):
+    """--exact beyond the hill-climb: a k sweep, progressive unions with and without the sweep
+    (all with the one-method run-time patch described at EXACT_WRAPPER), and a binary tree."""
+    outP = os.path.join(work, "outP")
+    sweep = ["--ksweep", "--mink", "12", "--maxk", "15"]
+    run_ref(bindir, ["tree", "-d", data5, "-s", "runP", "-k", "14", "-o", outP, "--exact"] + sweep, exact=True)
+    gold["runs"]["P_tree_exact_ksweep"] = collect_tree(outP, "runP_5_kmc", os.path.join(outP, "sketchdb"), "kmc")
+    dtreeP = os.path.join(outP, "runP_5_kmc_dtree.pickle")
+    run_ref(bindir, ["progressive", "-d", dtreeP, "-n", "1", "-o", outP] + sweep, exact=True)
+    summ = read_csv(os.path.join(outP, "runP_progu1_5_kmcsummary.csv"))
+    gold["runs"]["Q_progressive_exact_ksweep"] = {
+        "summary": [{"ngen": int(r["ngen"]), "kval": int(r["kval"]), "card": float(r["card"]), "delta_pos": float(r["delta_pos"]),
+                     "title": r["title"]} for r in summ]}
+    run_ref(bindir, ["progressive", "-d", dtreeP, "-n", "1", "-o", outP, "-s", "hc"], exact=True)
+    gold["runs"]["Q_progressive_exact_hillclimb"] = {"rows": prog_rows(os.path.join(outP, "hc_progu1_5_kmc.csv"))}
+    outS = os.path.join(work, "outS")
+    run_ref(bindir, ["tree", "-d", data5, "-s", "runS", "-k", "13", "-o", outS, "-n", "2"])
+    gold["runs"]["S_tree_nchildren2"] = collect_tree(outS, "runS_5_dashing", os.path.join(outS, "sketchdb"), "dashing")
+
+
 def main():
     work = tempfile.mkdtemp(prefix="dandd_golden_")
     bindir = pyoracle.install_shims(os.path.join(work, "bin"))
@@ -210,6 +230,7 @@ def main():
         run_ref(bindir, ["tree", "-d", data5, "-s", "runE", "-k", "14", "-o", outE, "--exact"], exact=True)
         gold["runs"]["E_tree_exact"] = collect_tree(outE, "runE_5_kmc", os.path.join(outE, "sketchdb"), "kmc")
         more_runs(work, bindir, data5, dtreeA, outA, gold)
+        exact_runs(work, bindir, data5, gold)
     finally:
         shutil.rmtree(work, ignore_errors=True)
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_runs.json")

@@ -192,6 +192,38 @@ def scenario_option_coverage(tmp):
         assert a[:4] == b[:4] and a[5:] == b[5:] and close(float(a[4]), float(b[4]))
 
 
+def scenario_exact_sweep_progressive_and_binary_tree(tmp):
+    """--exact with a k sweep, progressive exact unions (with the sweep and with the hill-climb) and a
+    2-children tree, against the goldens of the unmodified reference."""
+    gold = gold_runs()
+    data = make_dataset(os.path.join(tmp, "data5"), 5, 20000, seed=21)
+    ddir = os.path.dirname(data[0])
+    outP = os.path.join(tmp, "outP")
+    sweep = ["--ksweep", "--mink", "12", "--maxk", "15"]
+    run_dandd(["tree", "-d", ddir, "-s", "runP", "-k", "14", "-o", outP, "--exact"] + sweep)
+    assert_tree_matches(collect_tree(outP, "runP_5_kmc", os.path.join(outP, "sketchdb"), "kmc"), gold["P_tree_exact_ksweep"],
+                        exact=True)
+    dtree = os.path.join(outP, "runP_5_kmc_dtree.pickle")
+    run_dandd(["progressive", "-d", dtree, "-n", "1", "-o", outP] + sweep)
+    summ = read_csv(os.path.join(outP, "runP_progu1_5_kmcsummary.csv"))
+    want = gold["Q_progressive_exact_ksweep"]["summary"]
+    assert [(int(r["ngen"]), int(r["kval"]), r["title"], float(r["card"])) for r in summ] == \
+           [(r["ngen"], r["kval"], r["title"], r["card"]) for r in want]
+    for a, b in zip(summ, want):
+        assert close(float(a["delta_pos"]), b["delta_pos"])
+    run_dandd(["progressive", "-d", dtree, "-n", "1", "-o", outP, "-s", "hc"])
+    got = read_csv(os.path.join(outP, "hc_progu1_5_kmc.csv"))
+    want = gold["Q_progressive_exact_hillclimb"]["rows"]
+    assert [(int(r["ngen"]), int(r["kval"]), norm_fastas(r["fastas"], ",")) for r in got] == \
+           [(r["ngen"], r["kval"], r["fastas"]) for r in want]
+    for a, b in zip(got, want):
+        assert close(float(a["delta"]), b["delta"])
+
+    outS = os.path.join(tmp, "outS")
+    run_dandd(["tree", "-d", ddir, "-s", "runS", "-k", "13", "-o", outS, "-n", "2"])
+    assert_tree_matches(collect_tree(outS, "runS_5_dashing", os.path.join(outS, "sketchdb"), "dashing"), gold["S_tree_nchildren2"])
+
+
 def scenario_pickle_roundtrip(tmp):
     """The dtree pickle names classes by the reference's top-level module names."""
     out = scenario_tree_hillclimb(tmp)
