@@ -149,3 +149,31 @@ def test_wide_kmer_values_match_big_integers(host_emul, k, canon):
     for a, b in zip(cuts[:-1], cuts[1:]):
         tot += fn(codes.ctypes.data, invalid.ctypes.data, a, b, k, int(canon), out.ctypes.data)
     assert tot == cnt
+
+
+def test_pack_fuzz_against_oracle(host_emul):
+    """Property test (hypothesis): any byte string over a FASTA-ish alphabet, cut into chunks of any
+    16-byte multiple, packs to exactly the oracle's symbol stream -- the transition-function algebra
+    (dd::chunk_xfer / xfer_compose) and the per-chunk emission (dd::chunk_symbols) shipped in the kernels."""
+    from hypothesis import given, settings, strategies as st
+    alphabet = b">ACGTNacgtn\n\n\r x;-"
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.integers(0, len(alphabet) - 1), min_size=0, max_size=400), st.integers(1, 12),
+           st.booleans())
+    def run(idx, chunk16, lead_header):
+        txt = bytes(alphabet[i] for i in idx)
+        if lead_header:
+            txt = b">h\n" + txt
+        want = orc.fasta_symbols(txt)
+        # the kernels are handed the text from its first '>' on, wherever that is (Engine.skip_preamble;
+        # kseq skips to the first record marker and treats it as opening a header line)
+        start = txt.find(b">")
+        if start < 0:
+            assert want.size == 0
+            return
+        codes, invalid, nsym = emul_pack(host_emul, txt[start:], 16 * chunk16)
+        assert nsym == want.size
+        assert np.array_equal(decode_packed(codes, invalid, nsym), want)
+
+    run()
