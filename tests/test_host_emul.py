@@ -177,3 +177,27 @@ def test_pack_fuzz_against_oracle(host_emul):
         assert np.array_equal(decode_packed(codes, invalid, nsym), want)
 
     run()
+
+
+def test_sketch_fuzz_against_oracle(host_emul):
+    """Property test: random short FASTA texts (breaks, lower case, odd line widths), random k, p,
+    strand mode and update ranges -- the window extraction / canonical choice / hash / rank of the
+    kernels (host emulation) against the oracle's rolling formulation."""
+    from hypothesis import given, settings, strategies as st
+    alphabet = b"ACGTACGTACGTacgtN\n"
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(st.integers(0, len(alphabet) - 1), min_size=1, max_size=300), st.integers(1, 32), st.integers(4, 12),
+           st.booleans(), st.lists(st.integers(0, 300), min_size=0, max_size=4))
+    def run(idx, k, p, canon, cuts):
+        txt = b">r\n" + bytes(alphabet[i] for i in idx) + b"\n"
+        sym = orc.fasta_symbols(txt)
+        codes, invalid, nsym = emul_pack(host_emul, txt)
+        assert nsym == sym.size
+        want = orc.hll_sketch(sym, k, p, canon)
+        assert np.array_equal(emul_sketch(host_emul, codes, invalid, nsym, k, p, canon), want)
+        pts = sorted({0, nsym} | {min(c, nsym) for c in cuts})
+        ranges = list(zip(pts[:-1], pts[1:]))
+        assert np.array_equal(emul_sketch(host_emul, codes, invalid, nsym, k, p, canon, ranges=ranges), want)
+
+    run()
