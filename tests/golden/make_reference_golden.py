@@ -151,6 +151,12 @@ def exact_runs(work, bindir, data5, gold):
     outS = os.path.join(work, "outS")
     run_ref(bindir, ["tree", "-d", data5, "-s", "runS", "-k", "13", "-o", outS, "-n", "2"])
     gold["runs"]["S_tree_nchildren2"] = collect_tree(outS, "runS_5_dashing", os.path.join(outS, "sketchdb"), "dashing")
+    # T: the default sweep (k = 2..32) -- small k included -- on three short genomes
+    data3 = os.path.join(work, "data3")
+    make_dataset(data3, 3, 6000, seed=23, prefix="s")
+    outT = os.path.join(work, "outT")
+    run_ref(bindir, ["tree", "-d", data3, "-s", "runT", "-k", "10", "-o", outT, "--ksweep"])
+    gold["runs"]["T_tree_default_sweep"] = collect_tree(outT, "runT_3_dashing", os.path.join(outT, "sketchdb"), "dashing")
 
 
 def main():

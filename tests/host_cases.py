@@ -224,6 +224,15 @@ def scenario_exact_sweep_progressive_and_binary_tree(tmp):
     assert_tree_matches(collect_tree(outS, "runS_5_dashing", os.path.join(outS, "sketchdb"), "dashing"), gold["S_tree_nchildren2"])
 
 
+def scenario_default_sweep(tmp):
+    """`tree --ksweep` with the default range k = 2..32 (small k included) on three short genomes."""
+    data = make_dataset(os.path.join(tmp, "data3"), 3, 6000, seed=23, prefix="s")
+    out = os.path.join(tmp, "outT")
+    run_dandd(["tree", "-d", os.path.dirname(data[0]), "-s", "runT", "-k", "10", "-o", out, "--ksweep"])
+    assert_tree_matches(collect_tree(out, "runT_3_dashing", os.path.join(out, "sketchdb"), "dashing"),
+                        gold_runs()["T_tree_default_sweep"])
+
+
 def scenario_pickle_roundtrip(tmp):
     """The dtree pickle names classes by the reference's top-level module names."""
     out = scenario_tree_hillclimb(tmp)

@@ -59,6 +59,10 @@ def test_exact_sweep_progressive_and_binary_tree(tmp_path, oracle_store):
     host_cases.scenario_exact_sweep_progressive_and_binary_tree(str(tmp_path))
 
 
+def test_default_sweep(tmp_path, oracle_store):
+    host_cases.scenario_default_sweep(str(tmp_path))
+
+
 def test_pickle_roundtrip(tmp_path, oracle_store):
     host_cases.scenario_pickle_roundtrip(str(tmp_path))
 
