@@ -51,6 +51,18 @@ def test_exact_sweep_above_k32(tmp_path, gpu_store):
     host_cases.scenario_exact_sweep_above_k32(str(tmp_path))
 
 
+def test_option_coverage(tmp_path, gpu_store):
+    host_cases.scenario_option_coverage(str(tmp_path))
+
+
+def test_exact_sweep_progressive_and_binary_tree(tmp_path, gpu_store):
+    host_cases.scenario_exact_sweep_progressive_and_binary_tree(str(tmp_path))
+
+
+def test_default_sweep(tmp_path, gpu_store):
+    host_cases.scenario_default_sweep(str(tmp_path))
+
+
 def test_stub_union_files(tmp_path, gpu_store):
     """DANDD_B200_UNION_FILES=stub keeps union registers in HBM and writes marker files only; the
     reported numbers do not change."""
