@@ -95,9 +95,16 @@ class Engine:
         if isinstance(text, torch.Tensor):
             hit = (text == 62).nonzero()
             return int(hit[0]) if hit.numel() else int(text.numel())
-        arr = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.asarray(text)
-        hit = np.flatnonzero(arr == 62)
-        return int(hit[0]) if hit.size else int(arr.size)
+        if isinstance(text, (bytes, bytearray)):
+            at = text.find(b">")                      # memchr: the marker is almost always byte 0
+            return at if at >= 0 else len(text)
+        arr = np.frombuffer(text, dtype=np.uint8) if isinstance(text, memoryview) else np.asarray(text)
+        block = 1 << 24                               # scan in blocks instead of materialising a 3 GB mask
+        for off in range(0, int(arr.size), block):
+            hit = np.flatnonzero(arr[off:off + block] == 62)
+            if hit.size:
+                return off + int(hit[0])
+        return int(arr.size)
 
     def pack(self, text, chunk_bytes: Optional[int] = None, start: Optional[int] = None, ws_tag: str = "pack") -> PackedSeq:
         """FASTA text (bytes / numpy / torch uint8) -> PackedSeq.  `chunk_bytes` packs in several
