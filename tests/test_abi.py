@@ -84,3 +84,16 @@ def test_cli_startup_trim_is_safe():
     assert isinstance(dropped, bool) and after <= before
     assert trim_torch_cuda_init() is False or after == len(torch.cuda._queued_calls)   # idempotent
     assert torch.zeros(2).sum().item() == 0.0
+
+
+def test_skip_preamble_host_variants():
+    """Engine.skip_preamble on host inputs (bytes: memchr; numpy / memoryview: blockwise scan)."""
+    import numpy as np
+    from dandd_b200.engine import Engine
+    f = Engine.skip_preamble
+    assert f(b">abc") == 0 and f(b"xx\n>abc") == 3 and f(b"none") == 4 and f(b"") == 0 and f(bytearray(b"a>")) == 1
+    a = np.frombuffer(b"xx\n>abc", dtype=np.uint8)
+    assert f(a) == 3 and f(memoryview(b"xx\n>abc")) == 3 and f(np.zeros(5, dtype=np.uint8)) == 5
+    big = np.zeros((1 << 24) + 100, dtype=np.uint8)
+    big[(1 << 24) + 7] = 62
+    assert f(big) == (1 << 24) + 7
