@@ -101,7 +101,7 @@ def split_work(n_items: int) -> range:
 
 
 # ---- one genome over several ranks -------------------------------------------------------------------
-def split_fasta(text, nparts: int, overlap_symbols: int = 63, only: int = None) -> List[bytes]:
+def split_fasta(text, nparts: int, overlap_symbols: int = 63, only: int = None, min_grain: int = 4096) -> List[bytes]:
     """Cut ONE FASTA text into `nparts` FASTA texts whose sketches merge to the sketch of the whole
     ("genomes < GPUs"): register-wise max for HLL, set union for exact counts.
 
@@ -110,7 +110,8 @@ def split_fasta(text, nparts: int, overlap_symbols: int = 63, only: int = None) 
     early (>= k-1 for every k <= 64 by default) behind a synthetic header line, so each k-mer of the
     record lies wholly inside at least one piece.  Seeing a k-mer twice is harmless for a max / a
     set.  Pieces are assigned to parts largest-first; a part may be empty.  `only=r` materialises
-    part r alone (the others come back as None) -- a rank needs just its own bytes."""
+    part r alone (the others come back as None) -- a rank needs just its own bytes.  Records are not
+    cut into pieces smaller than `min_grain` bytes."""
     raw = text.tobytes() if isinstance(text, np.ndarray) else bytes(text) if not isinstance(text, bytes) else text
     buf = np.frombuffer(raw, dtype=np.uint8)
     n = len(raw)
@@ -132,7 +133,7 @@ def split_fasta(text, nparts: int, overlap_symbols: int = 63, only: int = None) 
     for a, b in zip(bounds[:-1], bounds[1:]):
         nl = raw.find(b"\n", a, b)
         body = nl + 1 if nl >= 0 else b                              # first byte after the header line
-        grain = max(target // 4, 4096)                               # pieces of a quarter share balance well
+        grain = max(target // 4, min_grain)                          # pieces of a quarter share balance well
         if b - a <= grain + grain // 4 or body >= b:
             pieces.append((a, b, False))
             continue
@@ -142,15 +143,21 @@ def split_fasta(text, nparts: int, overlap_symbols: int = 63, only: int = None) 
         for c in cuts:
             pieces.append((prev, c, prev != a))
             # step back over at least overlap_symbols sequence bytes (newlines / CRs do not count)
-            back, span = c, 2 * overlap_symbols + 64
+            # ... and never start on a '>' (junk inside a sequence line): behind the synthetic header
+            # it would sit at a line start and turn the rest of its line into a header
+            back, span, need = c, 2 * overlap_symbols + 64, overlap_symbols
             while True:
                 lo = max(body, c - span)
                 seg = buf[lo:c]
                 is_sym = (seg != 10) & (seg != 13)
                 have = int(is_sym.sum())
-                if have >= overlap_symbols:
+                if have >= need:
                     idx = np.flatnonzero(is_sym)
-                    back = lo + int(idx[have - overlap_symbols])
+                    at = lo + int(idx[have - need])
+                    if buf[at] == 62 and at > body:
+                        need += 1
+                        continue
+                    back = at
                     break
                 if lo == body:
                     back = body

@@ -202,3 +202,45 @@ def test_two_rank_exact_tree_matches_reference(tmp_path):
                         exact=True)
     calls = [int(open(tmp_path / f"shardcalls{r}").read()) for r in (0, 1)]
     assert calls[0] > 0 and calls[0] == calls[1]       # every request of rank 0 was served by rank 1
+
+
+def test_split_fasta_fuzz():
+    """Property test: for ANY FASTA-ish byte string, number of parts and overlap >= k-1, the parts'
+    k-mer sets union to the whole text's (and so do HLL registers) -- including '>' inside lines,
+    CR/LF mixes, empty records, text before the first record and tiny inputs."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import pyoracle as orc
+    alphabet = b">ACGTACGTNacgt\n\n\r x"
+
+    @settings(max_examples=250, deadline=None)
+    @given(st.lists(st.integers(0, len(alphabet) - 1), min_size=0, max_size=600), st.integers(1, 6), st.integers(1, 24),
+           st.booleans(), st.sampled_from([8, 16, 64, 4096]))
+    def run(idx, nparts, k, lead_header, min_grain):
+        txt = bytes(alphabet[i] for i in idx)
+        if lead_header:
+            txt = b">h\n" + txt
+        parts = dd_dist.split_fasta(txt, nparts, overlap_symbols=k - 1 if k > 1 else 1, min_grain=min_grain)
+        assert len(parts) == nparts
+        whole = orc.fasta_symbols(txt)
+        syms = [orc.fasta_symbols(t) for t in parts]
+        assert orc.exact_count([whole], k) == orc.exact_count(syms, k)
+        want = orc.hll_sketch(whole, k, 8)
+        assert np.array_equal(want, orc.union_max([orc.hll_sketch(s, k, 8) for s in syms]))
+
+    run()
+
+
+def test_split_fasta_never_starts_a_piece_on_a_midline_marker():
+    """'>' inside a sequence line is junk (a break symbol), but right behind a piece's synthetic
+    header it would open a header line and swallow the rest of its line; pieces therefore step back
+    past it.  (Without that rule ~40 % of these cases lose k-mers.)"""
+    from oracle import pyoracle as orc
+    rng = np.random.default_rng(4)
+    for _ in range(300):
+        seq = bytearray(b"ACGT"[i] for i in rng.integers(0, 4, 300))
+        for pos in rng.choice(300, 25, replace=False):
+            seq[pos] = 62
+        txt = b">r\n" + bytes(seq) + b"\n"
+        k, n = int(rng.integers(2, 8)), int(rng.integers(2, 6))
+        parts = dd_dist.split_fasta(txt, n, overlap_symbols=k - 1, min_grain=8)
+        assert orc.exact_count([orc.fasta_symbols(txt)], k) == orc.exact_count([orc.fasta_symbols(t) for t in parts], k)
