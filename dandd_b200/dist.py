@@ -118,10 +118,12 @@ def split_fasta(text, nparts: int, overlap_symbols: int = 63, only: int = None, 
     nparts = max(1, int(nparts))
     if nparts == 1 or n == 0:
         return [raw] + [b""] * (nparts - 1)
-    starts = []                                                      # '>' at a line start: a record
+    # records: the FIRST '>' of the file wherever it is (kseq skips to the first marker and takes it
+    # as a header line), afterwards every '>' at a line start
+    starts = []
     at = raw.find(b">")                                              # (single-byte find runs at memchr speed)
     while at >= 0:
-        if at == 0 or raw[at - 1] == 10:
+        if not starts or raw[at - 1] == 10:
             starts.append(at)
         at = raw.find(b">", at + 1)
     if not starts:                                                   # no record at all: nothing is sequence

@@ -213,7 +213,7 @@ def test_split_fasta_fuzz():
     alphabet = b">ACGTACGTNacgt\n\n\r x"
 
     @settings(max_examples=250, deadline=None)
-    @given(st.lists(st.integers(0, len(alphabet) - 1), min_size=0, max_size=600), st.integers(1, 6), st.integers(1, 24),
+    @given(st.lists(st.integers(0, len(alphabet) - 1), min_size=0, max_size=600), st.integers(1, 6), st.integers(1, 10),
            st.booleans(), st.sampled_from([8, 16, 64, 4096]))
     def run(idx, nparts, k, lead_header, min_grain):
         txt = bytes(alphabet[i] for i in idx)
