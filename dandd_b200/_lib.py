@@ -10,7 +10,9 @@ LIB_PATH = os.path.join(_HERE, "libdandd_b200.so")
 
 DD_HIST_BINS = 64
 DD_EXACT_BITMAP_MAXK = 16
-ABI_VERSION = 1
+ABI_VERSION = 2
+DD_PACK_FLAG_OVERFLOW, DD_PACK_FLAG_FASTQ = 1, 2
+DD_ERR_FORMAT = -5
 
 
 class DandDError(RuntimeError):
@@ -36,6 +38,9 @@ SIGNATURES = {
     "dd_pack_workspace_bytes": (_sz, [_sz]),
     "dd_pack_reset": (_i, [_vp, _sz, _vp, _sz, _vp, _vp]),
     "dd_pack_fasta": (_i, [_vp, _sz, _vp, _vp, _sz, _vp, _vp, _sz, _vp]),
+    "dd_pack_polyt_sentinel": (_i, [_vp, _vp, _vp, _u64, _u64, _sz, _vp]),
+    "dd_fastq_to_fasta_host": (_sz, [_vp, _sz, _vp]),
+    "dd_fasta_first_record_host": (_sz, [_vp, _sz]),
     "dd_sketch_workspace_bytes": (_sz, [_i, _i]),
     "dd_sketch_begin": (_i, [_vp, _sz, _i, _i, _vp]),
     "dd_sketch_update": (_i, [_vp, _vp, _vp, _sz, _u32, _i, _i, _vp, _sz, _vp]),
@@ -45,9 +50,14 @@ SIGNATURES = {
     "dd_card_ertl_mle": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "dd_mle_from_hist": (_i, [_vp, _i, _i, _vp, _vp]),
     "dd_union_max": (_i, [_vp, _i, _sz, _vp, _vp]),
-    "dd_prefix_union_card": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dd_prefix_union_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "dd_prefix_union_card": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dd_planes_bytes": (_sz, [_i64, _i]),
+    "dd_to_planes": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "dd_prefix_union_card_planes": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "dd_union_sets_card": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "dd_pairwise_union_card": (_i, [_vp, _i, _i, _i, _vp, _i64, _vp, _vp, _vp]),
+    "dd_pairwise_union_card": (_i, [_vp, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "dd_pairwise_union_card_planes": (_i, [_vp, _i, _i, _i, _vp, _i64, _vp, _vp, _vp]),
     "dd_exact_workspace_bytes": (_sz, [_i, _u64]),
     "dd_exact_begin": (_i, [_vp, _sz, _i, _u64, _vp]),
     "dd_exact_insert": (_i, [_vp, _vp, _u64, _u64, _i, _i, _vp, _sz, _u64, _vp]),

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -79,6 +80,10 @@ int dd_set_option(const char *name, long value) {
         dd::g_prefix_planes = value != 0;
         return DD_OK;
     }
+    if (!strcmp(name, "polyt_sentinel")) {
+        dd::g_polyt_sentinel = value != 0;
+        return DD_OK;
+    }
     return fail(DD_ERR_ARG, "dd_set_option: unknown option '%s'", name);
 }
 
@@ -103,6 +108,92 @@ int dd_pack_fasta(const uint8_t *d_text, size_t n_bytes, uint32_t *d_codes, uint
         return fail(DD_ERR_WORKSPACE, "dd_pack_fasta: workspace %zu < %zu", ws_bytes, dd::pack_workspace_bytes(n_bytes));
     DD_CUDA(dd::pack_fasta(d_text, n_bytes, d_codes, d_invalid, cap_symbols, d_state, d_ws, S(stream)), "dd_pack_fasta");
     return DD_OK;
+}
+
+int dd_pack_polyt_sentinel(const uint32_t *d_codes, uint32_t *d_invalid, const dd_pack_state *d_state, uint64_t sym_begin,
+                           uint64_t sym_end, size_t max_symbols, dd_stream stream) {
+    if (!d_codes || !d_invalid) return fail(DD_ERR_ARG, "dd_pack_polyt_sentinel: null pointer");
+    if (!d_state && sym_end < sym_begin) return fail(DD_ERR_ARG, "dd_pack_polyt_sentinel: end < begin");
+    DD_CUDA(dd::pack_polyt_sentinel(d_codes, d_invalid, d_state, sym_begin, sym_end, max_symbols, S(stream)),
+            "dd_pack_polyt_sentinel");
+    return DD_OK;
+}
+
+// ---- host-side text helpers (no GPU work) ---------------------------------------------------------
+size_t dd_fasta_first_record_host(const uint8_t *h_text, size_t n_bytes) {
+    if (!h_text) return 0;
+    // kseq looks for '>' or '@' (klib kseq.h: `while ((c = ks_getc(ks)) != -1 && c != '>' && c != '@');`)
+    const uint8_t *gt = static_cast<const uint8_t *>(memchr(h_text, '>', n_bytes));
+    const size_t lim = gt ? (size_t)(gt - h_text) : n_bytes;   // '@' only matters if it comes first
+    const uint8_t *at = static_cast<const uint8_t *>(memchr(h_text, '@', lim));
+    return at ? (size_t)(at - h_text) : lim;
+}
+
+// The walk of kseq_read() over FASTA/FASTQ text, emitting plain FASTA: ">\n" per record, sequence
+// lines verbatim.  One record per iteration of the outer loop.
+size_t dd_fastq_to_fasta_host(const uint8_t *h_in, size_t n, uint8_t *h_out) {
+    if (!h_in || !h_out) return 0;
+    const uint8_t *p = h_in, *const end = h_in + n;
+    uint8_t *o = h_out;
+    auto line_end = [&](const uint8_t *from) {   // one past the line's '\n', or `end`
+        const uint8_t *nl = static_cast<const uint8_t *>(memchr(from, '\n', (size_t)(end - from)));
+        return nl ? nl + 1 : end;
+    };
+    bool marker_taken = false;   // the previous record ended on the next record's marker
+    while (true) {
+        if (!marker_taken) {
+            p += dd_fasta_first_record_host(p, (size_t)(end - p));
+            if (p >= end) break;
+            ++p;
+        }
+        marker_taken = false;
+        uint8_t *const record_out = o;
+        *o++ = '>';
+        *o++ = '\n';
+        p = line_end(p);   // name and comment
+        size_t seq_len = 0;
+        int stop = -1;
+        while (p < end) {
+            const uint8_t c = *p;
+            if (c == '>' || c == '@' || c == '+') {
+                stop = c;
+                ++p;
+                break;
+            }
+            const uint8_t *le = line_end(p);
+            for (const uint8_t *q = p; q < le; ++q)
+                if (*q != '\n' && *q != '\r') ++seq_len;
+            memcpy(o, p, (size_t)(le - p));
+            o += le - p;
+            p = le;
+        }
+        if (o > record_out + 2 && o[-1] != '\n') *o++ = '\n';   // text ended without a newline
+        if (stop == '>' || stop == '@') {
+            marker_taken = true;
+            continue;
+        }
+        if (stop != '+') break;   // end of text
+        const uint8_t *le = line_end(p);   // the rest of the '+' line
+        if (le == end && (le == p || le[-1] != '\n')) {   // no quality string: kseq_read fails
+            o = record_out;
+            break;
+        }
+        p = le;
+        size_t qual_len = 0;
+        bool first = true;
+        while (p < end && (first || qual_len < seq_len)) {
+            le = line_end(p);
+            for (const uint8_t *q = p; q < le; ++q)
+                if (*q != '\n' && *q != '\r') ++qual_len;
+            p = le;
+            first = false;
+        }
+        if (qual_len != seq_len) {   // kseq_read returns -2: this record and the rest are not read
+            o = record_out;
+            break;
+        }
+    }
+    return (size_t)(o - h_out);
 }
 
 // ---- K2 ------------------------------------------------------------------------------------------
@@ -181,21 +272,72 @@ int dd_union_max(const uint8_t *const *d_in, int n_in, size_t len, uint8_t *d_ou
     return DD_OK;
 }
 
+size_t dd_prefix_union_workspace_bytes(int n_ord, int n_steps, int n_genomes, int nk, int p) {
+    if (n_ord < 0 || n_steps < 0 || n_genomes < 0 || nk < 0 || bad_p(p)) return 0;
+    return dd::prefix_union_workspace_bytes(n_ord, n_steps, n_genomes, nk, p);
+}
+size_t dd_planes_bytes(int64_t n_sketches, int p) {
+    if (n_sketches < 0 || bad_p(p)) return 0;
+    return dd::planes_bytes(n_sketches, p);
+}
+
+int dd_to_planes(const uint8_t *d_regs, int64_t n_sketches, int p, uint32_t *d_planes, dd_stream stream) {
+    if (n_sketches == 0) return DD_OK;
+    if (!d_regs || !d_planes || n_sketches < 0 || bad_p(p) || !dd::planes_supported(p))
+        return fail(DD_ERR_ARG, "dd_to_planes: bad argument (bit planes need p >= 12)");
+    DD_CUDA(dd::to_planes(d_regs, n_sketches, p, d_planes, S(stream)), "dd_to_planes");
+    return DD_OK;
+}
+
+static int prefix_args_ok(const void *data, const int32_t *d_order, const double *d_cards, const uint32_t *d_hist, int n_ord,
+                          int n_steps, int n_genomes, int nk, int p) {
+    return data && d_order && d_cards && d_hist && n_ord >= 0 && n_steps >= 0 && n_genomes >= 1 && nk >= 1 && nk <= 65535 &&
+           !bad_p(p) && (((size_t)1 << p) + 32767) / 32768 <= 65535;
+}
+
 int dd_prefix_union_card(const uint8_t *d_regs, const int32_t *d_order, int n_ord, int n_steps, int n_genomes, int nk,
-                         int p, int final_only, double *d_cards, uint32_t *d_hist, uint8_t *d_unions, dd_stream stream) {
+                         int p, int final_only, double *d_cards, uint32_t *d_hist, uint8_t *d_unions, void *d_ws,
+                         size_t ws_bytes, dd_stream stream) {
     if (n_ord == 0 || n_steps == 0) return DD_OK;
-    if (!d_regs || !d_order || !d_cards || !d_hist || n_ord < 0 || n_steps < 0 || n_genomes < 1 || nk < 1 || nk > 65535 ||
-        bad_p(p) || (((size_t)1 << p) + 32767) / 32768 > 65535)
+    if (!prefix_args_ok(d_regs, d_order, d_cards, d_hist, n_ord, n_steps, n_genomes, nk, p))
         return fail(DD_ERR_ARG, "dd_prefix_union_card: bad argument");
-    if (!d_unions && dd::g_prefix_planes && dd::planes_supported(p))
-        DD_CUDA(dd::prefix_union_hist_planes(d_regs, d_order, n_ord, n_steps, n_genomes, nk, p, final_only, d_hist, S(stream)),
-                "dd_prefix_union_card(planes)");
-    else
-        DD_CUDA(dd::prefix_union_hist(d_regs, d_order, n_ord, n_steps, n_genomes, nk, p, final_only, d_hist, d_unions, S(stream)),
-                "dd_prefix_union_card(hist)");
     const size_t rows = (size_t)n_ord * (final_only ? 1 : n_steps) * nk;
     if (rows > 0x7fffffff) return fail(DD_ERR_ARG, "dd_prefix_union_card: too many (ordering, step, k) rows");
+    if (!d_unions && d_ws && dd::g_prefix_planes && dd::planes_supported(p)) {
+        void *base = reinterpret_cast<void *>(align_up(reinterpret_cast<uintptr_t>(d_ws), 256));
+        const size_t lost = (size_t)(static_cast<uint8_t *>(base) - static_cast<uint8_t *>(d_ws));
+        if (ws_bytes < lost + dd::prefix_union_workspace_bytes(n_ord, n_steps, n_genomes, nk, p) - 256)
+            return fail(DD_ERR_WORKSPACE, "dd_prefix_union_card: workspace %zu < %zu", ws_bytes,
+                        dd::prefix_union_workspace_bytes(n_ord, n_steps, n_genomes, nk, p));
+        DD_CUDA(dd::prefix_union_hist_planes(d_regs, d_order, n_ord, n_steps, n_genomes, nk, p, final_only, d_hist, base, S(stream)),
+                "dd_prefix_union_card(planes)");
+    } else {
+        DD_CUDA(dd::prefix_union_hist(d_regs, d_order, n_ord, n_steps, n_genomes, nk, p, final_only, d_hist, d_unions, S(stream)),
+                "dd_prefix_union_card(hist)");
+    }
     DD_CUDA(dd::mle_from_hist(d_hist, (int)rows, p, d_cards, S(stream)), "dd_prefix_union_card(mle)");
+    return DD_OK;
+}
+
+int dd_prefix_union_card_planes(const uint32_t *d_planes, const int32_t *d_order, int n_ord, int n_steps, int n_genomes,
+                                int nk, int p, int final_only, double *d_cards, uint32_t *d_hist, void *d_ws, size_t ws_bytes,
+                                dd_stream stream) {
+    if (n_ord == 0 || n_steps == 0) return DD_OK;
+    if (!prefix_args_ok(d_planes, d_order, d_cards, d_hist, n_ord, n_steps, n_genomes, nk, p) || !dd::planes_supported(p))
+        return fail(DD_ERR_ARG, "dd_prefix_union_card_planes: bad argument (bit planes need p >= 12)");
+    const size_t rows = (size_t)n_ord * (final_only ? 1 : n_steps) * nk;
+    if (rows > 0x7fffffff) return fail(DD_ERR_ARG, "dd_prefix_union_card_planes: too many (ordering, step, k) rows");
+    void *scratch = nullptr;
+    if (d_ws) {
+        scratch = reinterpret_cast<void *>(align_up(reinterpret_cast<uintptr_t>(d_ws), 256));
+        const size_t lost = (size_t)(static_cast<uint8_t *>(scratch) - static_cast<uint8_t *>(d_ws));
+        if (ws_bytes < lost + dd::prefix_union_workspace_bytes(n_ord, n_steps, 0, 0, p) - 256)
+            return fail(DD_ERR_WORKSPACE, "dd_prefix_union_card_planes: workspace too small");
+    }
+    DD_CUDA(dd::prefix_union_hist_from_planes(d_planes, d_order, n_ord, n_steps, n_genomes, nk, p, final_only, d_hist, scratch,
+                                              S(stream)),
+            "dd_prefix_union_card_planes");
+    DD_CUDA(dd::mle_from_hist(d_hist, (int)rows, p, d_cards, S(stream)), "dd_prefix_union_card_planes(mle)");
     return DD_OK;
 }
 
@@ -212,14 +354,25 @@ int dd_union_sets_card(const uint8_t *const *d_members, int n_sets, int n_steps,
     return DD_OK;
 }
 
+static int pair_count_ok(int64_t n_pairs, int nk) {
+    return n_pairs >= 0 && n_pairs <= 0x7fffffff / (2 * (int64_t)(nk > 0 ? nk : 1));
+}
+
 int dd_pairwise_union_card(const uint8_t *d_regs, int n_genomes, int nk, int p, const int32_t *d_pairs, int64_t n_pairs,
-                           double *d_cards, uint32_t *d_hist, dd_stream stream) {
+                           double *d_cards, uint32_t *d_hist, void *d_ws, size_t ws_bytes, dd_stream stream) {
     if (n_pairs == 0) return DD_OK;
-    if (n_pairs < 0 || n_pairs > 0x7fffffff / (2 * (int64_t)(nk > 0 ? nk : 1)))
-        return fail(DD_ERR_ARG, "dd_pairwise_union_card: bad pair count");
+    if (!pair_count_ok(n_pairs, nk)) return fail(DD_ERR_ARG, "dd_pairwise_union_card: bad pair count");
     // a pair is a 2-step ordering of which only the full union is estimated
     return dd_prefix_union_card(d_regs, d_pairs, (int)n_pairs, 2, n_genomes, nk, p, /*final_only=*/1, d_cards, d_hist,
-                                nullptr, stream);
+                                nullptr, d_ws, ws_bytes, stream);
+}
+
+int dd_pairwise_union_card_planes(const uint32_t *d_planes, int n_genomes, int nk, int p, const int32_t *d_pairs,
+                                  int64_t n_pairs, double *d_cards, uint32_t *d_hist, dd_stream stream) {
+    if (n_pairs == 0) return DD_OK;
+    if (!pair_count_ok(n_pairs, nk)) return fail(DD_ERR_ARG, "dd_pairwise_union_card_planes: bad pair count");
+    return dd_prefix_union_card_planes(d_planes, d_pairs, (int)n_pairs, 2, n_genomes, nk, p, /*final_only=*/1, d_cards, d_hist,
+                                       nullptr, 0, stream);
 }
 
 // ---- K5 ------------------------------------------------------------------------------------------
@@ -307,6 +460,13 @@ size_t dd_sketch_fasta_host_workspace_bytes(size_t n_bytes, int nk, int p) {
     return carve(nullptr, n_bytes, nk, p).total + 256;
 }
 
+// cards <- NaN when the packer saw a line beginning with '+': the registers built from FASTQ text
+// without dd_fastq_to_fasta_host are not what kseq would have produced, and an asynchronous caller
+// has no other way of learning it.
+__global__ void fastq_poison_kernel(const dd_pack_state *st, double *cards, int nk) {
+    if ((st->reserved & DD_PACK_FLAG_FASTQ) && threadIdx.x < (unsigned)nk) cards[threadIdx.x] = nan("");
+}
+
 static int sketch_fasta_host_impl(const uint8_t *h_text, size_t n_bytes, uint32_t kmask, int p, int canon, uint8_t *h_regs,
                                   double *h_cards, uint8_t *d_regs_or_null, void *d_ws, size_t ws_bytes, dd_stream stream,
                                   bool synchronize) {
@@ -321,8 +481,7 @@ static int sketch_fasta_host_impl(const uint8_t *h_text, size_t n_bytes, uint32_
     cudaStream_t st = S(stream);
 
     // kseq ignores everything before the first record marker
-    const uint8_t *first = static_cast<const uint8_t *>(memchr(h_text, '>', n_bytes));
-    const size_t skip = first ? (size_t)(first - h_text) : n_bytes;
+    const size_t skip = dd_fasta_first_record_host(h_text, n_bytes);
     const uint8_t *text = h_text + skip;
     const size_t n = n_bytes - skip;
 
@@ -332,6 +491,9 @@ static int sketch_fasta_host_impl(const uint8_t *h_text, size_t n_bytes, uint32_
     const size_t nchunks = n ? (n + chunk - 1) / chunk : 0;
     const size_t floor_after = (size_t)16 << p;  // start filtering once registers have seen ~16 items each
     // More than one chunk: copies run on their own stream, double-buffered against pack + sketch.
+    // The stream and the events are created here and destroyed before returning WITHOUT waiting:
+    // CUDA releases a destroyed stream / event once the work already enqueued on it has completed,
+    // so the call stays asynchronous however large the file is.
     cudaStream_t cs = st;
     cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr}, entry = nullptr;
     const bool overlap = nchunks > 1;
@@ -372,24 +534,39 @@ static int sketch_fasta_host_impl(const uint8_t *h_text, size_t n_bytes, uint32_
         }
         DD_TRY(dd::pack_fasta(d_text, len, w.codes, w.invalid, n_bytes, w.state, w.pack_ws, st), "pack_fasta");
         if (overlap) DD_TRY(cudaEventRecord(freed[b], st), "event record");
+        if (dd::g_polyt_sentinel) DD_TRY(dd::pack_polyt_sentinel(w.codes, w.invalid, w.state, 0, 0, len, st), "polyt_sentinel");
         DD_TRY(dd::sketch_update(w.codes, w.invalid, w.state, 0, 0, len, kmask, p, canon, w.sketch_ws, st), "sketch_update");
         done += len;
         if (done >= floor_after && done < n) DD_TRY(dd::sketch_refresh_floor(w.sketch_ws, kmask, p, st), "refresh_floor");
     }
-    if (overlap) DD_TRY(cudaStreamSynchronize(cs), "synchronize copy stream");
     cleanup();
 #undef DD_TRY
     DD_CUDA(dd::sketch_end(w.sketch_ws, nk, p, d_regs, w.hist, w.cards, st), "sketch_end");
+    fastq_poison_kernel<<<1, 32, 0, st>>>(w.state, w.cards, nk);
+    DD_CUDA(cudaGetLastError(), "fastq_poison");
     DD_CUDA(cudaMemcpyAsync(h_cards, w.cards, (size_t)nk * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H cards");
     if (h_regs) DD_CUDA(cudaMemcpyAsync(h_regs, d_regs, (size_t)nk << p, cudaMemcpyDeviceToHost, st), "D2H regs");
-    if (synchronize) DD_CUDA(cudaStreamSynchronize(st), "synchronize");
+    if (synchronize) {
+        dd_pack_state hs;
+        DD_CUDA(cudaMemcpyAsync(&hs, w.state, sizeof hs, cudaMemcpyDeviceToHost, st), "D2H state");
+        DD_CUDA(cudaStreamSynchronize(st), "synchronize");
+        if (hs.reserved & DD_PACK_FLAG_FASTQ) return DD_ERR_FORMAT;   // the caller normalises and retries
+    }
     return DD_OK;
 }
 
 int dd_sketch_fasta_host(const uint8_t *h_text, size_t n_bytes, uint32_t kmask, int p, int canon, uint8_t *h_regs,
                          double *h_cards, uint8_t *d_regs_or_null, void *d_ws, size_t ws_bytes, dd_stream stream) {
-    return sketch_fasta_host_impl(h_text, n_bytes, kmask, p, canon, h_regs, h_cards, d_regs_or_null, d_ws, ws_bytes, stream,
-                                  true);
+    int rc = sketch_fasta_host_impl(h_text, n_bytes, kmask, p, canon, h_regs, h_cards, d_regs_or_null, d_ws, ws_bytes, stream,
+                                    true);
+    if (rc != DD_ERR_FORMAT) return rc;
+    // FASTQ (a line begins with '+'): rewrite to FASTA the way kseq walks it, then sketch that
+    std::vector<uint8_t> fasta(n_bytes + 16);
+    const size_t m = dd_fastq_to_fasta_host(h_text, n_bytes, fasta.data());
+    rc = sketch_fasta_host_impl(fasta.data(), m, kmask, p, canon, h_regs, h_cards, d_regs_or_null, d_ws, ws_bytes, stream,
+                                true);
+    if (rc == DD_ERR_FORMAT) return fail(DD_ERR_FORMAT, "dd_sketch_fasta_host: text still looks like FASTQ after normalisation");
+    return rc;
 }
 
 int dd_sketch_fasta_host_async(const uint8_t *h_text, size_t n_bytes, uint32_t kmask, int p, int canon, uint8_t *h_regs,

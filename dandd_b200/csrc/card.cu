@@ -56,16 +56,75 @@ hist_kernel(const uint8_t *__restrict__ regs, int p, uint32_t *__restrict__ hist
 }
 
 // -------------------------------------------------------------------------------------------------
-// K4b: Ertl MLE, one thread per sketch (f64, a few hundred flops each)
+// K4b: Ertl MLE, one WARP per sketch.  dd::ertl_mle (common.cuh) walks the ranks one after another
+// with a doubling identity -- ~45 dependent f64 divisions per secant step, ~10 us for a lone thread.
+// Here lane L owns ranks L and L+32: it evaluates h(t) = 1 - t/(e^t - 1) at t = x 2^-j directly
+// (Taylor series below 2^-3, expm1 above) and the weighted sum is a butterfly reduction, so a
+// secant step is one expm1 deep.  Same equation, same starting point, same stopping rule; the
+// results differ from the sequential form by rounding only (<= 1e-14 relative, tests/ pin 1e-9).
 // -------------------------------------------------------------------------------------------------
-__global__ void mle_kernel(const uint32_t *__restrict__ hist, int nsk, int p, double *__restrict__ cards) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nsk) return;
-    uint32_t c[DD_HIST_BINS + 2];
+__device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
-    for (int j = 0; j < DD_HIST_BINS; ++j) c[j] = hist[(size_t)i * DD_HIST_BINS + j];
-    c[DD_HIST_BINS] = c[DD_HIST_BINS + 1] = 0;
-    cards[i] = ertl_mle(c, p);
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ double mle_h(double t) {
+    if (t < 0.125) {
+        const double y = 0.5 * t, y2 = y * y;
+        return y - y2 * (1.0 / 3.0 - y2 * (1.0 / 45.0 - y2 * (1.0 / 472.5 - y2 * (1.0 / 4725.0 - y2 * (1.0 / 46777.5)))));
+    }
+    return 1.0 - t / expm1(t);
+}
+__device__ double ertl_mle_warp(uint32_t c_lo, uint32_t c_hi, int p, int lane) {
+    const unsigned full = 0xffffffffu;
+    const int q = 64 - p;
+    const double m = ldexp(1.0, p);
+    auto count_at = [&](int j) { return __shfl_sync(full, j < 32 ? c_lo : c_hi, j & 31); };
+    const double c0 = (double)count_at(0), ctop_reg = (double)count_at(q + 1);
+    if (ctop_reg == m) return INFINITY;  // every register saturated
+    unsigned long long nz = (unsigned long long)__ballot_sync(full, c_lo != 0u) |
+                            ((unsigned long long)__ballot_sync(full, c_hi != 0u) << 32);
+    if (q + 2 < 64) nz &= (1ull << (q + 2)) - 1ull;
+    if (nz == 0ull) return nan("");      // not a histogram of 2^p registers
+    const int lo = __ffsll((long long)nz) - 1, hi = 63 - __clzll((long long)nz);
+    const int jlo = lo < 1 ? 1 : lo, jhi = hi > q ? q : hi;
+    const double occupied = m - c0;
+    if (occupied == 0.0 || jhi < jlo) return 0.0;  // empty sketch
+    const double c_jhi = (double)count_at(jhi);
+    const double ctop = ctop_reg + c_jhi;
+    // my two ranks and their weights in z (plain counts) and in g (the top rank carries ctop)
+    const int j1 = lane, j2 = lane + 32;
+    const bool in1 = j1 >= jlo && j1 <= jhi, in2 = j2 >= jlo && j2 <= jhi;
+    const double n1 = in1 ? (double)c_lo : 0.0, n2 = in2 ? (double)c_hi : 0.0;
+    const double w1 = in1 ? (j1 == jhi ? ctop : n1) : 0.0, w2 = in2 ? (j2 == jhi ? ctop : n2) : 0.0;
+    const double z = warp_sum_f64(ldexp(n1, -j1) + ldexp(n2, -j2));
+    const double a = z + c0;
+    const double b = z + ldexp(ctop_reg, -q);
+    double x = (b <= 1.5 * a) ? occupied / (0.5 * b + a) : occupied / b * log1p(b / a);
+    double step = x, g_prev = 0.0;
+    const double tol = 1e-2 / sqrt(m);
+    while (step > x * tol) {  // warp-uniform: every lane holds the same x and step
+        double part = 0.0;
+        if (in1) part += w1 * mle_h(ldexp(x, -j1));
+        if (in2) part += w2 * mle_h(ldexp(x, -j2));
+        const double g = warp_sum_f64(part) + x * a;
+        if (g_prev < g && g <= occupied) step *= (g - occupied) / (g_prev - g);
+        else step = 0.0;
+        x += step;
+        g_prev = g;
+    }
+    return x * m;
+}
+
+constexpr int kMleWarps = 4;
+__global__ void __launch_bounds__(32 * kMleWarps)
+mle_kernel(const uint32_t *__restrict__ hist, int nsk, int p, double *__restrict__ cards) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kMleWarps + (threadIdx.x >> 5);
+    if (i >= nsk) return;  // whole warps leave together
+    const uint32_t *row = hist + (size_t)i * DD_HIST_BINS;
+    const double card = ertl_mle_warp(row[lane], row[lane + 32], p, lane);
+    if (lane == 0) cards[i] = card;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -195,7 +254,7 @@ cudaError_t card_hist(const uint8_t *d_regs, int nsk, int p, uint32_t *d_hist, c
 
 cudaError_t mle_from_hist(const uint32_t *d_hist, int nsk, int p, double *d_cards, cudaStream_t stream) {
     if (nsk == 0) return cudaSuccess;
-    mle_kernel<<<(nsk + 63) / 64, 64, 0, stream>>>(d_hist, nsk, p, d_cards);
+    mle_kernel<<<(nsk + kMleWarps - 1) / kMleWarps, 32 * kMleWarps, 0, stream>>>(d_hist, nsk, p, d_cards);
     return cudaGetLastError();
 }
 

@@ -191,13 +191,19 @@ DD_HD int valid_run_long(const uint32_t (&I)[5], uint32_t sm) {
 // ---------------------------------------------------------------------------------------------
 // FASTA text classification for the packer.  16 text bytes -> bit masks
 // (bit i <-> byte i).  A pad byte ('\r') is inert: never a symbol, never changes line state.
+// Line rules follow klib's kseq_read(): the first byte of a line decides -- '>' or '@' opens a
+// record (header line), '+' opens a FASTQ quality section.  Quality sections are not a finite-state
+// matter (their length depends on the record's sequence length), so the packer only REPORTS a
+// line-initial '+' (dd_pack_state.reserved bit DD_PACK_FLAG_FASTQ); such text goes through
+// dd_fastq_to_fasta_host first.
 // ---------------------------------------------------------------------------------------------
 constexpr uint8_t kPadByte = 0x0D;
 
 struct ChunkMasks {
     uint32_t nl;     // '\n'
     uint32_t cr;     // '\r'
-    uint32_t gt;     // '>'
+    uint32_t gt;     // '>' or '@': a record marker when it is the first byte of a line (kseq)
+    uint32_t plus;   // '+': first byte of a line => FASTQ quality section (flagged, never packed here)
     uint32_t acgt;   // one of ACGTacgt
     uint32_t codes;  // 2-bit code of byte i at bits [2i+1:2i] (meaningful where acgt is set)
 };
@@ -214,7 +220,8 @@ DD_HD void classify_word(uint32_t x, int wi, ChunkMasks &m) {
     const int sh = 4 * wi;
     m.nl |= gather_bit7(bytes_eq(x, 0x0a0a0a0au)) << sh;
     m.cr |= gather_bit7(bytes_eq(x, 0x0d0d0d0du)) << sh;
-    m.gt |= gather_bit7(bytes_eq(x, 0x3e3e3e3eu)) << sh;
+    m.gt |= gather_bit7(bytes_eq(x, 0x3e3e3e3eu) | bytes_eq(x, 0x40404040u)) << sh;
+    m.plus |= gather_bit7(bytes_eq(x, 0x2b2b2b2bu)) << sh;
     // ACGT test with one table lookup: the low three bits of 'A','C','T','G' are 1,3,4,7 -- all
     // different -- so PRMT with those bits as selectors fetches the only letter each byte could be
     // (filler 0x01 can never equal a byte whose low bits select it), and one compare finishes it.
@@ -232,7 +239,7 @@ DD_HD void classify_word(uint32_t x, int wi, ChunkMasks &m) {
 }
 
 DD_HD ChunkMasks classify16(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) {
-    ChunkMasks m = {0, 0, 0, 0, 0};
+    ChunkMasks m = {0, 0, 0, 0, 0, 0};
     classify_word(x0, 0, m);
     classify_word(x1, 1, m);
     classify_word(x2, 2, m);
@@ -284,6 +291,10 @@ DD_HD uint64_t xfer_compose(uint64_t f, uint64_t g) {
     const uint32_t e0 = xfer_end(f, 0), e1 = xfer_end(f, 1);
     return xfer_make(xfer_cnt(f, 0) + xfer_cnt(g, e0), xfer_cnt(f, 1) + xfer_cnt(g, e1), xfer_end(g, e0),
                      xfer_end(g, e1));
+}
+// bytes of the chunk that are a line-initial '+'
+DD_HD uint32_t chunk_fastq_marks(const ChunkMasks &m, bool first_at_line_start) {
+    return ((m.nl << 1) | (first_at_line_start ? 1u : 0u)) & 0xFFFFu & m.plus;
 }
 DD_HD uint64_t chunk_xfer(const ChunkMasks &m, bool first_at_line_start) {
     // both incoming states at once (same terms as chunk_symbols; only the "inherited header" bit differs)

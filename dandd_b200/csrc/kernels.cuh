@@ -15,6 +15,9 @@ cudaError_t pack_reset(uint32_t *d_codes, size_t codes_bytes, uint32_t *d_invali
                        dd_pack_state *d_state, cudaStream_t stream);
 cudaError_t pack_fasta(const uint8_t *d_text, size_t n, uint32_t *d_codes, uint32_t *d_invalid, size_t cap_symbols,
                        dd_pack_state *d_state, void *d_ws, cudaStream_t stream);
+cudaError_t pack_polyt_sentinel(const uint32_t *d_codes, uint32_t *d_invalid, const dd_pack_state *d_state,
+                                uint64_t sym_begin, uint64_t sym_end, size_t max_symbols, cudaStream_t stream);
+extern int g_polyt_sentinel;  // dd_set_option("polyt_sentinel"): the *_host entry points apply the pass
 
 // ---- K2 (sketch.cu).  Workspace = [SketchWsHeader | u16 accumulators [nk][2^p]]
 extern int g_k_per_pass;
@@ -44,8 +47,14 @@ cudaError_t prefix_union_hist(const uint8_t *d_regs, const int32_t *d_order, int
 
 // planes.cu: the same contract as prefix_union_hist (without materialised unions) on bit-sliced sketches
 bool planes_supported(int p);
+size_t planes_bytes(int64_t n_sketches, int p);
+size_t prefix_union_workspace_bytes(int n_ord, int n_steps, int n_genomes, int nk, int p);
+cudaError_t to_planes(const uint8_t *d_regs, int64_t n_sketches, int p, uint32_t *d_planes, cudaStream_t stream);
+cudaError_t prefix_union_hist_from_planes(const uint32_t *d_planes, const int32_t *d_order, int n_ord, int n_steps,
+                                          int n_genomes, int nk, int p, int final_only, uint32_t *d_hist, void *d_scratch,
+                                          cudaStream_t stream);
 cudaError_t prefix_union_hist_planes(const uint8_t *d_regs, const int32_t *d_order, int n_ord, int n_steps, int n_genomes,
-                                     int nk, int p, int final_only, uint32_t *d_hist, cudaStream_t stream);
+                                     int nk, int p, int final_only, uint32_t *d_hist, void *d_ws, cudaStream_t stream);
 extern int g_prefix_planes;  // tuning knob: 1 = use the bit-plane kernel where it applies (default)
 cudaError_t union_sets_hist(const uint8_t *const *d_members, int n_sets, int n_steps, int p, int final_only,
                             uint32_t *d_hist, uint8_t *d_unions, cudaStream_t stream);

@@ -80,6 +80,7 @@ __device__ __forceinline__ uint64_t block_scan_xfer(uint64_t f, uint64_t *s_warp
 struct Span {
     ChunkMasks m[kSpanChunks];
     uint32_t ls;  // bit c: chunk c starts at a line start
+    uint32_t fastq;  // non-zero: the span holds a line that begins with '+'
     uint64_t f;
 };
 
@@ -149,6 +150,7 @@ __device__ __forceinline__ Span load_span_smem(const uint8_t *tile, uint32_t off
     Span sp;
     sp.f = kXferIdentity;
     sp.ls = 0;
+    sp.fastq = 0;
     uint4 v[kSpanChunks];
 #pragma unroll
     for (int c = 0; c < kSpanChunks; ++c) v[c] = *reinterpret_cast<const uint4 *>(tile + off_in_tile + 16 * c);
@@ -159,6 +161,7 @@ __device__ __forceinline__ Span load_span_smem(const uint8_t *tile, uint32_t off
         const bool ls = prev == '\n';
         sp.ls |= (ls ? 1u : 0u) << c;
         sp.f = xfer_compose(sp.f, chunk_xfer(sp.m[c], ls));
+        sp.fastq |= chunk_fastq_marks(sp.m[c], ls);
         prev = v[c].w >> 24;
     }
     return sp;
@@ -172,8 +175,9 @@ __device__ __forceinline__ uint32_t span_prev_byte(const uint8_t *tile, uint32_t
 }
 
 // ---- fast path for "simple" tiles ------------------------------------------------------------------
-// A tile is SIMPLE when every byte is either '\n' or has bit 6 set (letters: 0x40-0x7F, 0xC0-0xFF):
-// no '>' (so no header can start), no '\r', no blanks/digits, no padding.  Then the only non-symbol
+// A tile is SIMPLE when every byte is either '\n' or has bit 6 set and a non-zero low part (letters:
+// 0x41-0x7F, 0xC1-0xFF; '@' = 0x40 is excluded because a line-initial '@' is a record marker):
+// no '>' / '@' (so no header can start), no '+', no '\r', no blanks/digits, no padding.  Then the only non-symbol
 // bytes are the newlines, the transition function follows from three block reductions, and pass C
 // needs no per-byte scatter: each 16-byte chunk is validated and 2-bit encoded with SWAR, its
 // newline holes are squeezed out in registers and the result is OR-ed into little-endian bit streams
@@ -189,6 +193,7 @@ struct SimpleSpan {
 
 __device__ __forceinline__ SimpleSpan scan_simple(const uint8_t *tile, uint32_t off) {
     uint32_t acc_nl = 0, acc_low = 0;  // four byte-wide counters each, <= 16 per byte
+    uint32_t at = 0;                   // bit 7 of a byte set if (byte & 0x3f) == 0 there or in a lower byte
 #pragma unroll
     for (int c = 0; c < kSpanChunks; ++c) {
         const uint4 v = *reinterpret_cast<const uint4 *>(tile + off + 16 * c);
@@ -197,10 +202,11 @@ __device__ __forceinline__ SimpleSpan scan_simple(const uint8_t *tile, uint32_t 
         for (int i = 0; i < 4; ++i) {
             acc_nl += bytes_eq(w[i], 0x0a0a0a0au) >> 7;
             acc_low += (~w[i] & 0x40404040u) >> 6;
+            at |= (w[i] & 0x3f3f3f3fu) - 0x01010101u;   // zero-byte test; a borrow only adds false alarms
         }
     }
     SimpleSpan sp;
-    sp.simple = acc_nl == acc_low;
+    sp.simple = acc_nl == acc_low && (at & 0x80808080u) == 0u;
     sp.nnl = (acc_nl * 0x01010101u) >> 24;
     return sp;
 }
@@ -239,7 +245,7 @@ __device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t *s_warp3
 
 // ---- pass A: one transition function per tile -------------------------------------------------
 __global__ void __launch_bounds__(kPackThreads)
-pack_count_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, const dd_pack_state *__restrict__ st,
+pack_count_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, dd_pack_state *__restrict__ st,
                   uint64_t *__restrict__ tile_xfer) {
     extern __shared__ __align__(128) uint8_t s_dyn[];
     __shared__ uint64_t s_warp[32];
@@ -290,8 +296,12 @@ pack_count_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
             }
         } else {
             uint64_t f = kXferIdentity;
-            if (off < pipe.tile_bytes(tile))
-                f = load_span_smem(b, off, span_prev_byte(b, off, text, tile * kTileBytes, entry_last)).f;
+            if (off < pipe.tile_bytes(tile)) {
+                const Span sp = load_span_smem(b, off, span_prev_byte(b, off, text, tile * kTileBytes, entry_last));
+                f = sp.f;
+                // a line that begins with '+': FASTQ.  Reported, not interpreted (see common.cuh).
+                if (sp.fastq) atomicOr(reinterpret_cast<unsigned long long *>(&st->reserved), (unsigned long long)DD_PACK_FLAG_FASTQ);
+            }
             uint64_t total;
             block_scan_xfer(f, s_warp, &total);
             if (threadIdx.x == 0) tile_xfer[tile] = total;
@@ -333,7 +343,7 @@ pack_scan_groups_kernel(uint64_t *__restrict__ tile_xfer, size_t ntiles, uint64_
             st->nsym = before + run;
             st->in_header = xfer_end(all, entry_state);
             if (n > 0) st->last_byte = text[n - 1];
-            if (before + run > cap_symbols) st->reserved |= 1;  // overflow: symbols past capacity are dropped
+            if (before + run > cap_symbols) st->reserved |= DD_PACK_FLAG_OVERFLOW;  // symbols past capacity are dropped
         }
     }
 }
@@ -399,7 +409,7 @@ pack_scan_kernel(const uint8_t *__restrict__ text, size_t n, const uint64_t *__r
         st->nsym = before + run;
         st->in_header = xfer_end(all, entry_state);
         if (n > 0) st->last_byte = text[n - 1];
-        if (before + run > cap_symbols) st->reserved |= 1;  // overflow: symbols past capacity are dropped
+        if (before + run > cap_symbols) st->reserved |= DD_PACK_FLAG_OVERFLOW;  // symbols past capacity are dropped
     }
 }
 
@@ -632,6 +642,44 @@ pack_write_kernel(const uint8_t *__restrict__ text, size_t n, size_t ntiles, con
     }
 }
 
+// ---- optional: the all-ones accumulator quirk (UNVERIFIED, off by default) ---------
+// Every 32nd T of a run of valid T symbols becomes a break.  One thread per 16-symbol word looks
+// for run starts among its symbols; the thread that owns a run's start walks the run (runs of T
+// are short in real text; a pathological all-T genome is walked by one thread -- this pass is an
+// emulation switch, not part of the default path).  Breaks inserted by an earlier call (the range
+// grows chunk by chunk) look like run boundaries to a later one, which yields the same positions
+// because they are 32 apart by construction; a run that began before `begin` is continued by the
+// thread of symbol `begin`, which first counts the at most 31 T behind it.
+__device__ __forceinline__ bool sym_is_valid_t(const uint32_t *codes, const uint32_t *invalid, uint64_t s) {
+    const uint32_t code = (codes[s >> 4] >> (30u - 2u * (uint32_t)(s & 15))) & 3u;
+    const uint32_t bad = (invalid[s >> 5] >> (31u - (uint32_t)(s & 31))) & 1u;
+    return code == 3u && !bad;
+}
+__global__ void __launch_bounds__(256)
+pack_polyt_kernel(const uint32_t *__restrict__ codes, uint32_t *invalid, const dd_pack_state *__restrict__ st,
+                  uint64_t sym_begin, uint64_t sym_end) {
+    if (st) {
+        sym_begin = st->prev_nsym;
+        sym_end = st->nsym;
+    }
+    const uint64_t w = (sym_begin >> 4) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int j = 0; j < 16; ++j) {
+        const uint64_t s = (w << 4) + j;
+        if (s < sym_begin || s >= sym_end) continue;
+        if (!sym_is_valid_t(codes, invalid, s)) continue;
+        const bool prev_t = s > 0 && sym_is_valid_t(codes, invalid, s - 1);
+        if (prev_t && s != sym_begin) continue;       // not a run start, and not the continuation point
+        uint32_t run = 0;
+        if (prev_t)                                    // s == sym_begin inside a run: count what lies behind
+            for (uint64_t b = s; b > 0 && sym_is_valid_t(codes, invalid, b - 1); --b) run = (run + 1) & 31u;
+        for (uint64_t t = s; t < sym_end && sym_is_valid_t(codes, invalid, t); ++t)
+            if (++run == 32u) {
+                atomicOr(&invalid[t >> 5], 1u << (31u - (uint32_t)(t & 31)));
+                run = 0;
+            }
+    }
+}
+
 __global__ void pack_state_init_kernel(dd_pack_state *st) {
     st->nsym = 0;
     st->prev_nsym = 0;
@@ -700,6 +748,17 @@ cudaError_t pack_fasta(const uint8_t *d_text, size_t n, uint32_t *d_codes, uint3
                                                         cap_symbols);
     pack_write_kernel<<<gc, kPackThreads, kWriteSmem, stream>>>(d_text, n, nt, tile_xfer, group_out, seg_base, hdr, d_state,
                                                                d_codes, d_invalid, cap_symbols);
+    return cudaGetLastError();
+}
+
+int g_polyt_sentinel = 0;
+
+cudaError_t pack_polyt_sentinel(const uint32_t *d_codes, uint32_t *d_invalid, const dd_pack_state *d_state,
+                                uint64_t sym_begin, uint64_t sym_end, size_t max_symbols, cudaStream_t stream) {
+    const size_t nsym = d_state ? max_symbols : (size_t)(sym_end - sym_begin);
+    if (nsym == 0) return cudaSuccess;
+    const size_t nwords = (nsym + 15) / 16 + 2;   // the range may start and end inside a word
+    pack_polyt_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, stream>>>(d_codes, d_invalid, d_state, sym_begin, sym_end);
     return cudaGetLastError();
 }
 

@@ -259,63 +259,72 @@ prefix_union_planes_kernel(const uint32_t *__restrict__ planes, const int32_t *_
 
 // ---- host side ----------------------------------------------------------------------------------
 bool planes_supported(int p) { return p >= 12; }   // whole uint4s of groups per plane, >= 1 CTA of work
-size_t planes_bytes(int n_sketches, int p) { return (size_t)n_sketches * kPlanes * (((size_t)1 << p) / 8); }
+size_t planes_bytes(int64_t n_sketches, int p) { return (size_t)n_sketches * kPlanes * (((size_t)1 << p) / 8); }
 
-cudaError_t prefix_union_hist_planes(const uint8_t *d_regs, const int32_t *d_order, int n_ord, int n_steps, int n_genomes,
-                                     int nk, int p, int final_only, uint32_t *d_hist, cudaStream_t stream) {
+static size_t dedup_bytes(int n_ord, int n_steps) {
+    return (size_t)n_ord * n_steps * (sizeof(unsigned long long) + sizeof(int32_t));
+}
+// scratch of the register-input entry: [planes | identical-prefix masks | representatives]
+size_t prefix_union_workspace_bytes(int n_ord, int n_steps, int n_genomes, int nk, int p) {
+    const size_t pl = (planes_bytes((int64_t)n_genomes * nk, p) + 255) / 256 * 256;
+    return pl + (dedup_bytes(n_ord, n_steps) + 255) / 256 * 256 + 256;
+}
+
+cudaError_t to_planes(const uint8_t *d_regs, int64_t n_sketches, int p, uint32_t *d_planes, cudaStream_t stream) {
+    const size_t total_groups = ((size_t)n_sketches << p) >> 5;
+    if (total_groups == 0) return cudaSuccess;
+    size_t blocks = (total_groups + 255) / 256;
+    if (blocks > (size_t)148 * 64) blocks = (size_t)148 * 64;
+    to_planes_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_regs, d_planes, p, total_groups);
+    return cudaGetLastError();
+}
+
+// d_scratch: dedup_bytes(n_ord, n_steps) bytes, or nullptr (no identical-prefix search)
+cudaError_t prefix_union_hist_from_planes(const uint32_t *d_planes, const int32_t *d_order, int n_ord, int n_steps,
+                                          int n_genomes, int nk, int p, int final_only, uint32_t *d_hist, void *d_scratch,
+                                          cudaStream_t stream) {
     const int out_steps = final_only ? 1 : n_steps;
     const size_t rows = (size_t)n_ord * out_steps * nk;
     cudaError_t e = cudaMemsetAsync(d_hist, 0, rows * DD_HIST_BINS * sizeof(uint32_t), stream);
     if (e != cudaSuccess || rows == 0) return e;
     const size_t m = (size_t)1 << p;
-    const size_t total = (size_t)n_genomes * nk * m;
-    uint32_t *planes = nullptr;
-    // scratch lives only for this call: stream-ordered allocation, released behind the kernels.
-    // Let the default pool keep freed blocks (otherwise every call pays ~1 ms of OS allocation).
-    static bool pool_tuned = false;
-    if (!pool_tuned) {
-        int dev = 0;
-        cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        pool_tuned = true;
-    }
-    const size_t pl_bytes = (planes_bytes(n_genomes * nk, p) + 255) / 256 * 256;
     const size_t pairs = (size_t)n_ord * n_steps;
-    if ((e = cudaMallocAsync(reinterpret_cast<void **>(&planes), pl_bytes + pairs * (sizeof(unsigned long long) + sizeof(int32_t)),
-                             stream)) != cudaSuccess)
-        return e;
-    unsigned long long *masks = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(planes) + pl_bytes);
-    int32_t *rep = reinterpret_cast<int32_t *>(masks + pairs);
+    unsigned long long *masks = reinterpret_cast<unsigned long long *>(d_scratch);
+    int32_t *rep = d_scratch ? reinterpret_cast<int32_t *>(masks + pairs) : nullptr;
     // one CTA compares every (ordering, step) with the first kDedupWindow orderings: the big classes
     // (last steps, first steps) are always found there; pointless for a batch of distinct pairs
-    const bool dedup = n_genomes <= 64 && n_ord > 1 && !(final_only && n_steps == 2) &&
+    const bool dedup = d_scratch && n_genomes <= 64 && n_ord > 1 && !(final_only && n_steps == 2) &&
                        (double)n_ord * (n_ord < kDedupWindow ? n_ord : kDedupWindow) * n_steps <= 5e7;
     if (dedup) prefix_dedup_kernel<<<1, 1024, 0, stream>>>(d_order, n_ord, n_steps, n_genomes, masks, rep);
     else rep = nullptr;
-    const size_t total_groups = total >> 5;
-    size_t blocks = (total_groups + 255) / 256;
-    if (blocks > (size_t)148 * 64) blocks = (size_t)148 * 64;
-    to_planes_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_regs, planes, p, total_groups);
     const size_t nvec = (m >> 5) >> 2;
     const unsigned slices = (unsigned)((nvec + kPlThreads - 1) / kPlThreads);
+    // the ordering / pair index is the fastest grid dimension (co-resident CTAs share slices in L2);
+    // gridDim.x has room for 2^31-1 of them
     const dim3 grid((unsigned)n_ord, slices, (unsigned)nk);
     if (final_only && n_steps == 2)
-        prefix_union_planes_kernel<true><<<grid, kPlThreads, 0, stream>>>(planes, d_order, n_steps, n_genomes, nk, p, final_only,
+        prefix_union_planes_kernel<true><<<grid, kPlThreads, 0, stream>>>(d_planes, d_order, n_steps, n_genomes, nk, p, final_only,
                                                                          rep, d_hist);
     else
-        prefix_union_planes_kernel<false><<<grid, kPlThreads, 0, stream>>>(planes, d_order, n_steps, n_genomes, nk, p, final_only,
+        prefix_union_planes_kernel<false><<<grid, kPlThreads, 0, stream>>>(d_planes, d_order, n_steps, n_genomes, nk, p, final_only,
                                                                           rep, d_hist);
     if (dedup) {
         const size_t cells = rows * DD_HIST_BINS;
         const unsigned cb = (unsigned)((cells + 255) / 256 < 1184 ? (cells + 255) / 256 : 1184);
         prefix_copy_rows_kernel<<<cb, 256, 0, stream>>>(rep, n_ord, n_steps, nk, final_only, d_hist);
     }
-    e = cudaGetLastError();
-    cudaError_t e2 = cudaFreeAsync(planes, stream);
-    return e != cudaSuccess ? e : e2;
+    return cudaGetLastError();
+}
+
+// register input: transpose into the caller's workspace, then the planes path
+cudaError_t prefix_union_hist_planes(const uint8_t *d_regs, const int32_t *d_order, int n_ord, int n_steps, int n_genomes,
+                                     int nk, int p, int final_only, uint32_t *d_hist, void *d_ws, cudaStream_t stream) {
+    uint32_t *planes = reinterpret_cast<uint32_t *>(d_ws);
+    const size_t pl = (planes_bytes((int64_t)n_genomes * nk, p) + 255) / 256 * 256;
+    cudaError_t e = to_planes(d_regs, (int64_t)n_genomes * nk, p, planes, stream);
+    if (e != cudaSuccess) return e;
+    return prefix_union_hist_from_planes(planes, d_order, n_ord, n_steps, n_genomes, nk, p, final_only, d_hist,
+                                         static_cast<uint8_t *>(d_ws) + pl, stream);
 }
 
 }  // namespace dd

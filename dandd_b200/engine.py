@@ -12,7 +12,12 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DD_EXACT_BITMAP_MAXK, DD_HIST_BINS, DandDError, check
+from ._lib import DD_EXACT_BITMAP_MAXK, DD_HIST_BINS, DD_PACK_FLAG_FASTQ, DD_PACK_FLAG_OVERFLOW, DandDError, check
+
+
+class FastqInput(DandDError):
+    """The packed text holds a line beginning with '+': FASTQ.  The caller rewrites the text with
+    Engine.fastq_to_fasta (kseq's walk of the records, on the host) and packs that instead."""
 
 
 def kmask_of(ks: Iterable[int]) -> int:
@@ -46,10 +51,17 @@ class PackedSeq:
         """Number of symbols (reads the device state: synchronises)."""
         if self._nsym is None:
             st = self.state.cpu().numpy().view(np.uint64)
-            if int(st[3]) & 1:
+            if int(st[3]) & DD_PACK_FLAG_OVERFLOW:
                 raise DandDError("packed stream overflowed its capacity")
+            if int(st[3]) & DD_PACK_FLAG_FASTQ:
+                raise FastqInput("FASTQ text (a line begins with '+') must go through Engine.fastq_to_fasta first")
             self._nsym = int(st[0])
         return self._nsym
+
+    def check(self) -> "PackedSeq":
+        """Raise if the packer flagged the text (overflow, FASTQ).  Synchronises."""
+        self.nsym  # noqa: B018
+        return self
 
 
 class Engine:
@@ -64,6 +76,9 @@ class Engine:
         check(self.lib.dd_device_info(int(device), C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(l2), C.byref(mem)))
         self.sm_count, self.cc, self.l2_bytes, self.total_mem = sm.value, (maj.value, mnr.value), l2.value, mem.value
         self._ws = {}
+        # SURVEY.md A.6 (UNVERIFIED encoder quirk): opt-in emulation, for every entry point of this engine
+        self.polyt_sentinel = os.environ.get("DANDD_B200_POLYT_SENTINEL", "0") not in ("", "0")
+        check(self.lib.dd_set_option(b"polyt_sentinel", int(self.polyt_sentinel)), "dd_set_option")
 
     # ---- plumbing ---------------------------------------------------------------------------
     @property
@@ -91,20 +106,34 @@ class Engine:
     # ---- K1 ---------------------------------------------------------------------------------
     @staticmethod
     def skip_preamble(text) -> int:
-        """Offset of the first '>' (kseq ignores everything before it); len if none."""
+        """Offset of the first '>' or '@' (kseq ignores everything before the first record marker,
+        SURVEY.md A.1); len if there is none."""
+        if isinstance(text, torch.Tensor) and text.is_cuda:
+            n = int(text.numel())
+            block = 1 << 26
+            for off in range(0, n, block):            # the marker is almost always in the first block
+                part = text[off:off + block]
+                hit = ((part == 62) | (part == 64)).nonzero()
+                if hit.numel():
+                    return off + int(hit[0])
+            return n
         if isinstance(text, torch.Tensor):
-            hit = (text == 62).nonzero()
-            return int(hit[0]) if hit.numel() else int(text.numel())
-        if isinstance(text, (bytes, bytearray)):
-            at = text.find(b">")                      # memchr: the marker is almost always byte 0
-            return at if at >= 0 else len(text)
-        arr = np.frombuffer(text, dtype=np.uint8) if isinstance(text, memoryview) else np.asarray(text)
-        block = 1 << 24                               # scan in blocks instead of materialising a 3 GB mask
-        for off in range(0, int(arr.size), block):
-            hit = np.flatnonzero(arr[off:off + block] == 62)
-            if hit.size:
-                return off + int(hit[0])
-        return int(arr.size)
+            ptr, n = text.data_ptr(), int(text.numel())
+        else:
+            arr = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else \
+                np.ascontiguousarray(text, dtype=np.uint8).reshape(-1)
+            ptr, n = arr.ctypes.data, int(arr.size)
+        return int(_lib.load().dd_fasta_first_record_host(ptr, n)) if n else 0
+
+    @staticmethod
+    def fastq_to_fasta(text) -> bytes:
+        """kseq_read()'s walk over FASTA/FASTQ text, written back as plain FASTA (host side, no GPU):
+        what the packer must be given when it reports DD_PACK_FLAG_FASTQ."""
+        arr = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else \
+            np.ascontiguousarray(text, dtype=np.uint8).reshape(-1)
+        out = np.empty(arr.size + 16, dtype=np.uint8)
+        n = _lib.load().dd_fastq_to_fasta_host(arr.ctypes.data, arr.size, out.ctypes.data) if arr.size else 0
+        return out[:n].tobytes()
 
     def pack(self, text, chunk_bytes: Optional[int] = None, start: Optional[int] = None, ws_tag: str = "pack") -> PackedSeq:
         """FASTA text (bytes / numpy / torch uint8) -> PackedSeq.  `chunk_bytes` packs in several
@@ -138,6 +167,9 @@ class Engine:
                 part = part.clone()
             check(self.lib.dd_pack_fasta(part.data_ptr(), ln, codes.data_ptr(), invalid.data_ptr(), max(n, 1),
                                          state.data_ptr(), ws.data_ptr(), ws.numel(), st), "dd_pack_fasta")
+            if self.polyt_sentinel:
+                check(self.lib.dd_pack_polyt_sentinel(codes.data_ptr(), invalid.data_ptr(), state.data_ptr(), 0, 0, ln, st),
+                      "dd_pack_polyt_sentinel")
             pos += ln
         return PackedSeq(codes, invalid, state, max(n, 1), n)
 
@@ -272,11 +304,43 @@ class Engine:
         hist = torch.empty((n_ord, osteps, nk, DD_HIST_BINS), dtype=torch.int32, device=self.device)
         cards = torch.empty((n_ord, osteps, nk), dtype=torch.float64, device=self.device)
         unions = torch.empty((n_ord, osteps, nk, m), dtype=torch.uint8, device=self.device) if materialize else None
+        ws = None
+        if not materialize and p >= 12:   # scratch for the bit-plane kernel (transposed sketches + identical-prefix table)
+            ws = self._buf(self.lib.dd_prefix_union_workspace_bytes(n_ord, n_steps, n_g, nk, p), "prefix")
         check(self.lib.dd_prefix_union_card(regs.data_ptr(), order.data_ptr(), n_ord, n_steps, n_g, nk, p, int(final_only),
                                             cards.data_ptr(), hist.data_ptr(), unions.data_ptr() if materialize else None,
+                                            ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
                                             self.stream), "dd_prefix_union_card")
         self._keep = order
         return (cards, unions) if materialize else cards
+
+    # ---- bit planes (K3/K6 on sketches that are unioned many times) -------------------------------
+    def to_planes(self, regs: torch.Tensor, p: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """regs [..., 2^p] uint8 -> bit planes [n_sketches, 6, 2^p/32] int32 (dd_to_planes), once;
+        prefix_union_cards_planes / pairwise_cards(planes=...) then never transpose again."""
+        m = 1 << p
+        flat = regs.contiguous().view(-1, m)
+        nsk = flat.shape[0]
+        if out is None:
+            out = torch.empty((nsk, 6, m // 32), dtype=torch.int32, device=self.device)
+        assert out.is_contiguous() and out.numel() * 4 == self.lib.dd_planes_bytes(nsk, p)
+        check(self.lib.dd_to_planes(flat.data_ptr(), nsk, p, out.data_ptr(), self.stream), "dd_to_planes")
+        return out
+
+    def prefix_union_cards_planes(self, planes: torch.Tensor, n_genomes: int, nk: int, orders, p: int,
+                                  final_only: bool = False) -> torch.Tensor:
+        """prefix_union_cards on sketches already transposed by to_planes ([n_genomes * nk, 6, 2^p/32])."""
+        order = torch.as_tensor(np.asarray(orders, dtype=np.int32)).to(self.device).contiguous()
+        n_ord, n_steps = order.shape
+        osteps = 1 if final_only else n_steps
+        hist = torch.empty((n_ord, osteps, nk, DD_HIST_BINS), dtype=torch.int32, device=self.device)
+        cards = torch.empty((n_ord, osteps, nk), dtype=torch.float64, device=self.device)
+        ws = self._buf(self.lib.dd_prefix_union_workspace_bytes(n_ord, n_steps, 0, 0, p), "prefix_dedup")
+        check(self.lib.dd_prefix_union_card_planes(planes.data_ptr(), order.data_ptr(), n_ord, n_steps, n_genomes, nk, p,
+                                                   int(final_only), cards.data_ptr(), hist.data_ptr(), ws.data_ptr(),
+                                                   ws.numel(), self.stream), "dd_prefix_union_card_planes")
+        self._keep = order
+        return cards
 
     def union_sets(self, member_ptrs, p: int, final_only: bool = True, materialize: bool = False):
         """member_ptrs: int64 [n_sets, n_steps] device addresses of 2^p-byte sketches (0 = skip).
@@ -295,15 +359,31 @@ class Engine:
         self._keep = ptrs
         return (cards, unions) if materialize else cards
 
-    def pairwise_cards(self, regs: torch.Tensor, pairs, p: int) -> torch.Tensor:
-        """card(A u B) for every listed pair and every k: [n_pairs, nk] f64."""
-        n_g, nk, m = regs.shape
-        pr = torch.as_tensor(np.asarray(pairs, dtype=np.int32).reshape(-1, 2)).to(self.device).contiguous()
+    def pairwise_cards(self, regs: Optional[torch.Tensor], pairs, p: int, planes: Optional[torch.Tensor] = None,
+                       n_genomes: Optional[int] = None, nk: Optional[int] = None,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """card(A u B) for every listed pair and every k: [n_pairs, nk] f64.  Either `regs`
+        [n_genomes, nk, 2^p] (transposed into scratch on every call) or `planes` from to_planes()
+        with n_genomes / nk given (tiles of a big pair matrix share one transpose)."""
+        if isinstance(pairs, torch.Tensor):
+            pr = pairs.to(self.device, dtype=torch.int32).contiguous().view(-1, 2)
+        else:
+            pr = torch.as_tensor(np.asarray(pairs, dtype=np.int32).reshape(-1, 2)).to(self.device).contiguous()
         n_pairs = pr.shape[0]
-        hist = torch.empty((n_pairs, nk, DD_HIST_BINS), dtype=torch.int32, device=self.device)
-        cards = torch.empty((n_pairs, nk), dtype=torch.float64, device=self.device)
-        check(self.lib.dd_pairwise_union_card(regs.data_ptr(), n_g, nk, p, pr.data_ptr(), n_pairs, cards.data_ptr(),
-                                              hist.data_ptr(), self.stream), "dd_pairwise_union_card")
+        if planes is None:
+            n_genomes, nk, m = regs.shape
+        hist = self._buf(n_pairs * nk * DD_HIST_BINS * 4, "pair_hist")
+        cards = out if out is not None else torch.empty((n_pairs, nk), dtype=torch.float64, device=self.device)
+        assert cards.is_contiguous() and cards.numel() == n_pairs * nk and cards.dtype == torch.float64
+        if planes is not None:
+            check(self.lib.dd_pairwise_union_card_planes(planes.data_ptr(), n_genomes, nk, p, pr.data_ptr(), n_pairs,
+                                                         cards.data_ptr(), hist.data_ptr(), self.stream),
+                  "dd_pairwise_union_card_planes")
+        else:
+            ws = self._buf(self.lib.dd_prefix_union_workspace_bytes(0, 0, n_genomes, nk, p), "prefix") if p >= 12 else None
+            check(self.lib.dd_pairwise_union_card(regs.data_ptr(), n_genomes, nk, p, pr.data_ptr(), n_pairs, cards.data_ptr(),
+                                                  hist.data_ptr(), ws.data_ptr() if ws is not None else None,
+                                                  ws.numel() if ws is not None else 0, self.stream), "dd_pairwise_union_card")
         self._keep = pr
         return cards
 

@@ -1,12 +1,18 @@
 """Dashing-v1 style `.hll` sketch files: a (possibly gzip-compressed) stream of
-    uint32[4] flags (is_calculated, clamp, estimation method, joint estimation method)
+    uint32[N] flags (is_calculated, clamp, estimation method, joint estimation method[, nthreads])
     uint32    p
     float64   cached estimate
     2^p bytes registers
 DandD itself never opens these files -- it only tests that they exist and are non-empty
-(reference lib/sketch_classes.py:323-334) -- but writing the real layout lets a sketchdb made here
-be read by Dashing's own `card`/`union` (its reader goes through zlib, which passes uncompressed
-files through unchanged) and lets sketches cached by real Dashing be re-used here."""
+(reference lib/sketch_classes.py:323-334).  The layout above is a RECOLLECTION of dnbaker/sketch
+hll_t::write (no Dashing source or binary is available here), so interoperability
+with real Dashing is a goal, not a tested fact.  What is uncertain is kept in one place:
+    HEADER_FLAG_WORDS   how many uint32 flags precede p: 4 as the survey recalls, or 5 if the
+                        writer also stores its thread count.  The WRITER uses this constant; the
+                        READER accepts both widths (the file size, 28 or 32 + 2^p bytes, says which).
+    JESTIM_*            the estimator enum values written into the flags (informational: this
+                        package always re-estimates with the Ertl MLE from the registers).
+tools/crosscheck_dashing.py diffs this module against a real `dashing` when one is on PATH."""
 import gzip
 import os
 import struct
@@ -14,8 +20,32 @@ import zlib
 
 import numpy as np
 
-HEADER = struct.Struct("<4I I d")
-ERTL_MLE, ERTL_JOINT_MLE = 2, 2
+HEADER_FLAG_WORDS = int(os.environ.get("DANDD_B200_HLL_FLAG_WORDS", "4"))   # 4 (28-byte header) or 5 (32-byte)
+if HEADER_FLAG_WORDS not in (4, 5):
+    raise ValueError("DANDD_B200_HLL_FLAG_WORDS must be 4 or 5")
+HEADERS = {4: struct.Struct("<4I I d"), 5: struct.Struct("<5I I d")}
+HEADER = HEADERS[HEADER_FLAG_WORDS]
+JESTIM_ERTL_MLE = 2          # value recalled for hll::EstimationMethod::ERTL_MLE (unconfirmed)
+ERTL_MLE = ERTL_JOINT_MLE = JESTIM_ERTL_MLE   # older names, kept for callers
+
+
+def _pack_header(known: int, p: int, card: float) -> bytes:
+    flags = [known, 0, JESTIM_ERTL_MLE, JESTIM_ERTL_MLE] + ([1] if HEADER_FLAG_WORDS == 5 else [])
+    return HEADER.pack(*flags, p, card)
+
+
+def _unpack_header(raw: bytes):
+    """-> (header size, known, p, value) or None.  Both header widths are tried; the one whose p is
+    consistent with the file size (header + 2^p register bytes) wins."""
+    for words in (HEADER_FLAG_WORDS, 9 - HEADER_FLAG_WORDS):
+        h = HEADERS[words]
+        if len(raw) < h.size:
+            continue
+        fields = h.unpack_from(raw)
+        known, p, value = fields[0], fields[words], fields[words + 1]
+        if 4 <= p <= 32 and len(raw) == h.size + (1 << p):
+            return h.size, known, p, value
+    return None
 
 
 def write_hll(path: str, regs: np.ndarray, p: int, card: float = 0.0, compresslevel: int = 0) -> None:
@@ -24,7 +54,7 @@ def write_hll(path: str, regs: np.ndarray, p: int, card: float = 0.0, compressle
     if regs.size != 1 << p:
         raise ValueError(f"expected {1 << p} registers, got {regs.size}")
     known = 1 if card and np.isfinite(card) else 0
-    head = HEADER.pack(known, 0, ERTL_MLE, ERTL_JOINT_MLE, p, float(card) if known else 0.0)
+    head = _pack_header(known, p, float(card) if known else 0.0)
     tmp = f"{path}.tmp{os.getpid()}"
     if compresslevel > 0:
         with gzip.open(tmp, "wb", compresslevel=compresslevel) as f:
@@ -54,24 +84,26 @@ def write_stub(path: str, p: int, card: float, members) -> None:
     registers can be rebuilt on demand."""
     tmp = f"{path}.tmp{os.getpid()}"
     with open(tmp, "wb") as f:
-        f.write(HEADER.pack(1, 0, ERTL_MLE, ERTL_JOINT_MLE, p, float(card)))
+        f.write(_pack_header(1, p, float(card)))
         f.write(STUB_MAGIC + "\n".join(members).encode())
     os.replace(tmp, path)
 
 
 def read_hll(path: str):
-    """-> (registers uint8[2^p], p, cached estimate or None); raises StubSketch for a union marker."""
+    """-> (registers uint8[2^p], p, cached estimate or None); raises StubSketch for a union marker.
+    Accepts 28- and 32-byte headers, gzip-compressed or raw."""
     with open(path, "rb") as f:
         raw = f.read()
-    if raw[HEADER.size:HEADER.size + len(STUB_MAGIC)] == STUB_MAGIC:
-        known, _c, _e, _j, p, value = HEADER.unpack_from(raw)
-        raise StubSketch(path, p, value, raw[HEADER.size + len(STUB_MAGIC):].decode().split("\n"))
+    for h in HEADERS.values():
+        if raw[h.size:h.size + len(STUB_MAGIC)] == STUB_MAGIC:
+            fields = h.unpack_from(raw)
+            words = len(fields) - 2
+            raise StubSketch(path, fields[words], fields[words + 1], raw[h.size + len(STUB_MAGIC):].decode().split("\n"))
     if raw[:2] == b"\x1f\x8b":
         raw = zlib.decompress(raw, 16 + zlib.MAX_WBITS)
-    if len(raw) < HEADER.size:
-        raise ValueError(f"{path}: too short for a sketch header")
-    known, _clamp, _est, _jest, p, value = HEADER.unpack_from(raw)
-    if not 4 <= p <= 32 or len(raw) != HEADER.size + (1 << p):
-        raise ValueError(f"{path}: not a 2^p-register sketch (p={p}, {len(raw)} bytes)")
-    regs = np.frombuffer(raw, dtype=np.uint8, offset=HEADER.size).copy()
+    got = _unpack_header(raw)
+    if got is None:
+        raise ValueError(f"{path}: not a 2^p-register sketch ({len(raw)} bytes: neither a 28- nor a 32-byte header fits)")
+    size, known, p, value = got
+    regs = np.frombuffer(raw, dtype=np.uint8, offset=size).copy()
     return regs, p, (value if known else None)

@@ -558,6 +558,7 @@ class DeltaTree:
                 print("WARNING: If BOTH minimum AND maximum k are not provided either by the input delta-tree or using "
                       "--mink and --maxk, the --jaccard flag will be ignored.")
                 jaccard = False
+        self._prefetch_pair_unions(leaves)
         kij_rows, j_rows = [], []
         for i, first in enumerate(leaves):
             for second in leaves[i + 1:]:
@@ -568,6 +569,24 @@ class DeltaTree:
                     pair.ksweep(mink=mink, maxk=maxk)
                     j_rows.extend(pair.jaccard_summarize(mink=mink, maxk=maxk))
         return kij_rows, j_rows
+
+    def _prefetch_pair_unions(self, leaves) -> None:
+        """K6: the union cardinality of every pair of leaves at every k the leaves hold is computed by
+        ONE batched device job (sketches transposed once, pair matrix tiled) and kept by the store;
+        the per-pair SubSpiders below then find every two-leaf union already evaluated and issue no
+        device work of their own.  HLL mode only; exact mode goes pair by pair (k-mer sets are not
+        mergeable sketches)."""
+        if self.experiment["tool"] != "dashing" or len(leaves) < 3 or not all(hasattr(leaf, "ksketches") for leaf in leaves):
+            return
+        store = get_store()
+        if not hasattr(store, "pair_unions"):
+            return
+        ks = [k for k in range(1, HLL_MAX_K + 1)
+              if all(k < len(leaf.ksketches) and leaf.ksketches[k] is not None for leaf in leaves)]
+        if not ks:
+            return
+        leaf_paths = {k: [leaf.ksketches[k].sketch for leaf in leaves] for k in ks}
+        store.pair_unions(leaf_paths, int(self.experiment["registers"]))
 
     def prepare_AFproject(self, kijsummary, jsummary) -> List[Tuple]:
         """(tool, name1, name2, k, value, k1, k2, k12) tuples for helpers/AFproject.py: k = 0 rows carry

@@ -42,27 +42,41 @@ class GpuSketchStore:
         # 'full': union sketches are written out like `dashing union -o` does; 'stub': a header-only
         # marker file (registers stay in HBM / are recomputed from the leaves on demand)
         self.union_files = union_files or os.environ.get("DANDD_B200_UNION_FILES", "full")
-        self._regs: "OrderedDict[str, torch.Tensor]" = OrderedDict()   # sketch path -> [2^p] u8 (device)
-        self._leaf_all: Dict[tuple, dict] = {}                         # (fasta, p, canon) -> {"regs","cards","ks"}
-        self._packed: Dict[str, object] = {}                           # fasta -> PackedSeq
+        # One LRU over everything resident in HBM, keyed by kind: ("sketch", path) -> [2^p] u8,
+        # ("leaf", fasta, p, canon) -> {"regs","cards","ks"}, ("packed", fasta) -> PackedSeq.  A sketch that
+        # is a VIEW of a leaf block costs nothing by itself (the block is what occupies memory).
+        self._lru: "OrderedDict[tuple, object]" = OrderedDict()
+        self._cost: Dict[tuple, int] = {}
         self._bytes = 0
+        self.pair_table = None   # cardinalities of every two-leaf union, filled by one batched K6 job (pair_unions)
         self.stats = {"leaf_passes": 0, "union_launches": 0, "files_written": 0, "files_read": 0, "exact_calls": 0}
         self.exact_workers = None   # set by start_exact_workers() for `--exact` under torchrun
 
     # ------------------------------------------------------------------ cache plumbing
-    def _remember(self, path: str, regs: torch.Tensor) -> None:
-        old = self._regs.pop(path, None)
-        if old is not None:
-            self._bytes -= old.numel()
-        self._regs[path] = regs
-        self._bytes += regs.numel()
-        while self._bytes > self.cache_bytes and len(self._regs) > 1:
-            _, ev = self._regs.popitem(last=False)
-            self._bytes -= ev.numel()
+    def _put(self, key: tuple, value, cost: int) -> None:
+        if key in self._lru:
+            self._bytes -= self._cost.pop(key)
+            del self._lru[key]
+        self._lru[key] = value
+        self._cost[key] = int(cost)
+        self._bytes += int(cost)
+        while self._bytes > self.cache_bytes and len(self._lru) > 1:
+            old, _ = self._lru.popitem(last=False)
+            self._bytes -= self._cost.pop(old)
+
+    def _get(self, key: tuple):
+        value = self._lru.get(key)
+        if value is not None:
+            self._lru.move_to_end(key)
+        return value
+
+    def _remember(self, path: str, regs: torch.Tensor, view_of_block: bool = False) -> None:
+        self._put(("sketch", path), regs, 0 if view_of_block else regs.numel())
 
     def registers(self, path: str) -> torch.Tensor:
-        """Device registers of the sketch stored at `path` (HBM cache, else read the file)."""
-        t = self._regs.get(path)
+        """Device registers of the sketch stored at `path` (HBM cache, else read the file).  The
+        returned tensor stays valid for as long as the caller holds it, whatever the cache evicts."""
+        t = self._get(("sketch", path))
         if t is None:
             try:
                 regs, _p, _ = hllfile.read_hll(path)
@@ -71,14 +85,13 @@ class GpuSketchStore:
                 t = self.engine.union([self.registers(m) for m in stub.members])
             self.stats["files_read"] += 1
             self._remember(path, t)
-        else:
-            self._regs.move_to_end(path)
         return t
 
     def forget(self, path: str) -> None:
-        t = self._regs.pop(path, None)
-        if t is not None:
-            self._bytes -= t.numel()
+        key = ("sketch", path)
+        if key in self._lru:
+            del self._lru[key]
+            self._bytes -= self._cost.pop(key)
 
     def _write(self, path: str, regs: torch.Tensor, p: int, card: float, leaf: bool, members=None) -> None:
         os.makedirs(os.path.dirname(path), exist_ok=True)
@@ -89,11 +102,20 @@ class GpuSketchStore:
         self.stats["files_written"] += 1
 
     # ------------------------------------------------------------------ dashing sketch
+    def _pack_text(self, text):
+        """K1, with the FASTQ detour: the packer only reports a line beginning with '+'; the text is
+        then rewritten record by record the way kseq reads it (host side) and packed again."""
+        from .engine import FastqInput
+        try:
+            return self.engine.pack(text).check()
+        except FastqInput:
+            return self.engine.pack(self.engine.fastq_to_fasta(text)).check()
+
     def packed(self, fasta: str):
-        seq = self._packed.get(fasta)
+        seq = self._get(("packed", fasta))
         if seq is None:
-            seq = self.engine.pack(read_fasta_bytes(fasta))
-            self._packed[fasta] = seq
+            seq = self._pack_text(read_fasta_bytes(fasta))
+            self._put(("packed", fasta), seq, seq.codes.numel() + seq.invalid.numel())
         return seq
 
     def leaf_sketches(self, fasta: str, ks: Sequence[int], p: int, canon: bool, out_paths: Dict[int, str],
@@ -106,8 +128,8 @@ class GpuSketchStore:
         (dist.split_fasta), the registers are max-reduced over the ranks, every rank gets the
         cardinalities of the whole file and rank 0 writes the sketch files (fewer
         genomes than GPUs)."""
-        key = (fasta, int(p), bool(canon))
-        ent = self._leaf_all.get(key)
+        key = ("leaf", fasta, int(p), bool(canon))
+        ent = self._get(key)
         need = [int(k) for k in ks]
         if split is not None or ent is None or any(k not in ent["ks"] for k in need):
             run_ks = list(ALL_HLL_KS) if self.prefetch_all_k else sorted(set(need) | set(ent["ks"] if ent else ()))
@@ -116,19 +138,19 @@ class GpuSketchStore:
                 from dandd_b200 import dist as dd_dist
                 run_ks = sorted(need)                      # identical on every rank, whatever each one has cached
                 text = dd_dist.split_fasta(text, split[1], only=split[0])[split[0]]
-            seq = self.engine.pack(text)
+            seq = self._pack_text(text)
             regs, cards = self.engine.sketch(seq, run_ks, p=p, canon=canon)
             if split is not None:
                 dd_dist.union_over_ranks(regs)
                 cards = self.engine.cards(regs, p)
             ent = {"regs": regs, "cards": cards.cpu().numpy(), "ks": {k: i for i, k in enumerate(run_ks)}}
-            self._leaf_all[key] = ent
+            self._put(key, ent, regs.numel())
             self.stats["leaf_passes"] += 1
         out = {}
         for k in need:
             i = ent["ks"][k]
             card = float(ent["cards"][i])
-            self._remember(out_paths[k], ent["regs"][i])
+            self._remember(out_paths[k], ent["regs"][i], view_of_block=True)
             if split is None or split[0] == 0:
                 self._write(out_paths[k], ent["regs"][i], p, card, leaf=True)
             out[k] = card
@@ -138,9 +160,14 @@ class GpuSketchStore:
     def union_sketches(self, members_by_k: Dict[int, List[str]], p: int, out_paths: Dict[int, str]) -> Dict[int, float]:
         """For every k: union of the sketches stored at members_by_k[k]; written to out_paths[k];
         returns {k: cardinality}.  One launch for all k."""
-        ks = sorted(members_by_k)
+        out = {}
+        for k in sorted(members_by_k):   # cells a batched pair job (pair_unions) has already evaluated
+            card = self._pair_lookup(members_by_k[k], p)
+            if card is not None:
+                out[k] = self._materialize_precomputed(out_paths[k], p, card, members_by_k[k])
+        ks = sorted(k for k in members_by_k if k not in out)
         if not ks:
-            return {}
+            return out
         width = max(len(members_by_k[k]) for k in ks)
         tensors = [[self.registers(pth) for pth in members_by_k[k]] for k in ks]
         ptrs = np.zeros((len(ks), width), dtype=np.int64)
@@ -150,7 +177,6 @@ class GpuSketchStore:
         cards, unions = self.engine.union_sets(ptrs, p, final_only=True, materialize=True)
         self.stats["union_launches"] += 1
         cards = cards.cpu().numpy().reshape(len(ks))
-        out = {}
         for i, k in enumerate(ks):
             regs = unions[i, 0]
             self._remember(out_paths[k], regs)
@@ -170,7 +196,10 @@ class GpuSketchStore:
         orderings = np.asarray(orderings, dtype=np.int64)
         n_ord, n_steps = orderings.shape
         m = 1 << p
-        base = np.array([[self.registers(pth).data_ptr() for pth in leaf_paths_by_k[k]] for k in ks], dtype=np.int64)  # [nk, n]
+        # hold every leaf tensor for the duration of the call: a cache miss further down this list may
+        # evict (and free) sketches whose addresses are already in the table
+        held = [[self.registers(pth) for pth in leaf_paths_by_k[k]] for k in ks]
+        base = np.array([[t.data_ptr() for t in row] for row in held], dtype=np.int64)  # [nk, n]
         # rows are laid out [ordering-chunk][k][ordering] at launch time: sets that read the same
         # sketches (same k, different ordering) are adjacent, which is what keeps them in L2
         ptrs = np.zeros((n_ord, len(ks), n_steps), dtype=np.int64)
@@ -202,7 +231,66 @@ class GpuSketchStore:
                                 members = [leaf_paths_by_k[k][g] for g in orderings[o][:st + 1] if g >= 0]
                                 self._write(path, unions[o - o0, i, st], p, float(cards[o - o0, i, st]), leaf=False,
                                             members=members)
+        del held   # every launch above was followed by a device->host read of its results, so nothing still uses them
         return out
+
+    # ------------------------------------------------------------------ all pairs (K6)
+    def pair_unions(self, leaf_paths_by_k: Dict[int, List[str]], p: int, tile_pairs: int = 1 << 16,
+                    remember: bool = True) -> np.ndarray:
+        """Cardinality of the union of EVERY unordered pair of leaves, for every k: [n(n-1)/2, nk], pairs
+        in the order (0,1), (0,2) .. (n-2,n-1), k sorted.  leaf_paths_by_k[k] lists the leaf sketches in
+        leaf-index order.  The sketches are transposed into bit planes ONCE; the pair list then goes
+        through K6 in tiles.  With `remember` the table also answers later union_sketches() calls for
+        two-leaf unions (`dandd kij` builds one SubSpider per pair: reference lib/huffman_dandd.py:666-695)."""
+        ks = sorted(leaf_paths_by_k)
+        n = len(leaf_paths_by_k[ks[0]])
+        m = 1 << p
+        eng = self.engine
+        regs = torch.empty((n, len(ks), m), dtype=torch.uint8, device=eng.device)
+        for i, k in enumerate(ks):
+            for g, pth in enumerate(leaf_paths_by_k[k]):
+                regs[g, i].copy_(self.registers(pth))
+        iu = np.triu_indices(n, 1)
+        pairs = np.stack(iu, axis=1).astype(np.int32)
+        out = np.empty((pairs.shape[0], len(ks)), dtype=np.float64)
+        planes = eng.to_planes(regs, p) if p >= 12 else None
+        for t0 in range(0, pairs.shape[0], tile_pairs):
+            tile = pairs[t0:t0 + tile_pairs]
+            if planes is not None:
+                cards = eng.pairwise_cards(None, tile, p, planes=planes, n_genomes=n, nk=len(ks))
+            else:
+                cards = eng.pairwise_cards(regs, tile, p)
+            out[t0:t0 + tile.shape[0]] = cards.cpu().numpy()
+            self.stats["union_launches"] += 1
+        if remember:
+            self.pair_table = {"p": int(p), "n": n, "col": {k: i for i, k in enumerate(ks)}, "cards": out,
+                               "leaf": {pth: (g, k) for k in ks for g, pth in enumerate(leaf_paths_by_k[k])}}
+        return out
+
+    def _pair_lookup(self, members: Sequence[str], p: int):
+        """Cardinality of the union of two leaf sketches if the last pair_unions() job covered it."""
+        tab = self.pair_table
+        if tab is None or len(members) != 2 or tab["p"] != int(p):
+            return None
+        a, b = tab["leaf"].get(members[0]), tab["leaf"].get(members[1])
+        if a is None or b is None or a[1] != b[1] or a[0] == b[0]:
+            return None
+        i, j = (a[0], b[0]) if a[0] < b[0] else (b[0], a[0])
+        n = tab["n"]
+        return float(tab["cards"][i * n - i * (i + 1) // 2 + (j - i - 1), tab["col"][a[1]]])
+
+    def _materialize_precomputed(self, path: str, p: int, card: float, members) -> float:
+        """A union whose cardinality a batched job already produced is asked for as a FILE: write the
+        marker (or, with union_files == 'full', build the registers from the members) -- no estimator run."""
+        if self.union_files == "full":
+            regs = self.engine.union([self.registers(mb) for mb in members])
+            self._remember(path, regs)
+            self._write(path, regs, p, card, leaf=False, members=list(members))
+        else:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            hllfile.write_stub(path, p, card, list(members))
+            self.stats["files_written"] += 1
+        return float(card)
 
     # ------------------------------------------------------------------ dashing card
     def card_of_file(self, path: str, p: int = None) -> float:

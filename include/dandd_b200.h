@@ -33,13 +33,14 @@
 extern "C" {
 #endif
 
-#define DD_ABI_VERSION 1
+#define DD_ABI_VERSION 2
 
 #define DD_OK 0
 #define DD_ERR_ARG (-1)       /* bad argument (null pointer, k/p out of range, ...) */
 #define DD_ERR_CUDA (-2)      /* a CUDA runtime call or kernel launch failed        */
 #define DD_ERR_WORKSPACE (-3) /* workspace smaller than *_workspace_bytes() says    */
 #define DD_ERR_DEVICE (-4)    /* no usable sm_100 device                            */
+#define DD_ERR_FORMAT (-5)    /* input text needs dd_fastq_to_fasta_host first      */
 
 #define DD_HIST_BINS 64 /* register-value histogram: bin j = #registers == j (j <= 64-p+1 < 64) */
 
@@ -58,7 +59,8 @@ DD_API int dd_init(int device);
 /* Tuning knobs (never change results).  "sketch_k_per_pass" = n: K2 updates at most n k values per
  * kernel launch (0 = all in one), trading re-reads of the packed stream for L2 residency of the
  * accumulators.  "prefix_planes" = 0/1: dd_prefix_union_card uses the bit-sliced kernel (default 1)
- * or the byte kernel. */
+ * or the byte kernel.  "polyt_sentinel" = 0/1: the dd_*_host entry points apply dd_pack_polyt_sentinel
+ * (this one DOES change results: it selects the SURVEY.md A.6 encoder behaviour; default 0). */
 DD_API int dd_set_option(const char *name, long value);
 DD_API int dd_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes, size_t *total_mem);
 
@@ -74,16 +76,32 @@ DD_API int dd_device_info(int device, int *sm_count, int *cc_major, int *cc_mino
  *             means "k-mer windows restart here" (any byte other than ACGTacgt, and one synthetic
  *             symbol per '>' header line so that k-mers never span records);
  *   state   : dd_pack_state, carried from chunk to chunk so a FASTA can be streamed.
- * Text rules: a line whose first byte is '>' is a header; '\n' and '\r' are not
- * sequence; text before the first '>' of a file must be skipped by the caller (dd_*_host do it).
+ * Text rules (klib kseq_read() as used by Dashing and by KMC's -fm mode): a line
+ * whose first byte is '>' or '@' is a record header; '\n' and '\r' are not sequence; text before
+ * the first '>' / '@' of a file must be skipped by the caller (dd_*_host do it).  A line whose
+ * first byte is '+' opens a FASTQ quality section, whose extent depends on the record's sequence
+ * length: the packer does not interpret it, it sets DD_PACK_FLAG_FASTQ in dd_pack_state.reserved and
+ * the caller must pass such text through dd_fastq_to_fasta_host first (dd_sketch_fasta_host does).
  * =========================================================================================== */
+#define DD_PACK_FLAG_OVERFLOW 1u /* more symbols than cap_symbols: the excess was dropped            */
+#define DD_PACK_FLAG_FASTQ 2u    /* a line begins with '+': FASTQ, results are NOT what kseq yields  */
 typedef struct dd_pack_state {
     uint64_t nsym;      /* symbols in the stream so far                                   */
     uint64_t prev_nsym; /* value of nsym before the most recent dd_pack_fasta call        */
     uint32_t in_header; /* 1 if the text consumed so far ends inside a header line        */
     uint32_t last_byte; /* last text byte consumed ('\n' initially: start of a line)      */
-    uint64_t reserved;
+    uint64_t reserved;  /* DD_PACK_FLAG_* bits (sticky)                                   */
 } dd_pack_state;
+
+/* HOST helper, no GPU work: rewrite FASTA/FASTQ text the way kseq_read() walks it into plain
+ * FASTA that dd_pack_fasta packs to the same symbols -- record markers found anywhere while no
+ * record is open, '+' lines and quality lines (as many bytes as the record has sequence bytes, at
+ * least one line) dropped, a record with a quality/sequence length mismatch and everything after
+ * it dropped (kseq_read returns an error there and the reader loop ends).  h_out must hold
+ * n_bytes + 16 bytes and may not overlap h_in; returns the number of bytes written. */
+DD_API size_t dd_fastq_to_fasta_host(const uint8_t *h_in, size_t n_bytes, uint8_t *h_out);
+/* Offset of the first record marker ('>' or '@') in host text, n_bytes if there is none. */
+DD_API size_t dd_fasta_first_record_host(const uint8_t *h_text, size_t n_bytes);
 
 DD_API size_t dd_pack_codes_bytes(size_t max_text_bytes);
 DD_API size_t dd_pack_invalid_bytes(size_t max_text_bytes);
@@ -94,6 +112,16 @@ DD_API int dd_pack_reset(uint32_t *d_codes, size_t codes_bytes, uint32_t *d_inva
  * 16-byte aligned for full speed.  cap_symbols = capacity of codes/invalid in symbols. */
 DD_API int dd_pack_fasta(const uint8_t *d_text, size_t n_bytes, uint32_t *d_codes, uint32_t *d_invalid,
                   size_t cap_symbols, dd_pack_state *d_state, void *d_ws, size_t ws_bytes, dd_stream stream);
+
+/* Optional emulation of the encoder quirk recalled in SURVEY.md A.6 (UNVERIFIED, off by default):
+ * bonsai's unwindowed encoder tests its 64-bit accumulator against all-ones to detect an invalid
+ * base, and 32 consecutive 'T' make a legitimate accumulator all-ones too.  With this pass every
+ * 32nd 'T' of a run of T/t becomes a break symbol, for symbols [sym_begin, sym_end) -- or
+ * [d_state->prev_nsym, d_state->nsym) when d_state != NULL (max_symbols bounds the grid) -- so
+ * call it after each dd_pack_fasta, before dd_sketch_update.  dd_set_option("polyt_sentinel", 1)
+ * makes the dd_*_host entry points do so. */
+DD_API int dd_pack_polyt_sentinel(const uint32_t *d_codes, uint32_t *d_invalid, const dd_pack_state *d_state, uint64_t sym_begin,
+                           uint64_t sym_end, size_t max_symbols, dd_stream stream);
 
 /* ===========================================================================================
  * K2  fused all-k canonical-k-mer HyperLogLog sketch.
@@ -157,18 +185,41 @@ DD_API int dd_mle_from_hist(const uint32_t *d_hist, int nsk, int p, double *d_ca
 DD_API int dd_union_sets_card(const uint8_t *const *d_members, int n_sets, int n_steps, int p, int final_only,
                               double *d_cards, uint32_t *d_hist, uint8_t *d_unions, dd_stream stream);
 DD_API int dd_union_max(const uint8_t *const *d_in, int n_in, size_t len, uint8_t *d_out, dd_stream stream);
+/* Scratch: (d_ws, ws_bytes) sized by dd_prefix_union_workspace_bytes() lets the call use the bit-plane
+ * kernel (it holds the transposed sketches and the identical-prefix table); with d_ws == NULL, or when
+ * d_unions != NULL, the byte kernel runs, which needs no scratch. */
+DD_API size_t dd_prefix_union_workspace_bytes(int n_ord, int n_steps, int n_genomes, int nk, int p);
 DD_API int dd_prefix_union_card(const uint8_t *d_regs, const int32_t *d_order, int n_ord, int n_steps, int n_genomes,
                          int nk, int p, int final_only, double *d_cards, uint32_t *d_hist, uint8_t *d_unions,
-                         dd_stream stream);
+                         void *d_ws, size_t ws_bytes, dd_stream stream);
+
+/* Bit planes: a sketch of 2^p one-byte registers transposed into 6 planes of 2^p bits (plane b, word
+ * g = bit b of registers 32g..32g+31; ranks are <= 64-p+1 < 64), 0.75 bytes per register.  A caller
+ * that unions the same sketches many times (all pairs, many orderings) transposes them ONCE with
+ * dd_to_planes and passes the planes to the *_planes entry points; p >= 12.
+ *   d_planes [n_sketches][6][2^p / 32] u32,  dd_planes_bytes(n_sketches, p) bytes
+ * dd_prefix_union_card_planes: d_planes laid out [n_genomes][nk]; scratch only for the
+ * identical-prefix table, dd_prefix_union_workspace_bytes(n_ord, n_steps, 0, 0, p) bytes (NULL = none). */
+DD_API size_t dd_planes_bytes(int64_t n_sketches, int p);
+DD_API int dd_to_planes(const uint8_t *d_regs, int64_t n_sketches, int p, uint32_t *d_planes, dd_stream stream);
+DD_API int dd_prefix_union_card_planes(const uint32_t *d_planes, const int32_t *d_order, int n_ord, int n_steps,
+                                int n_genomes, int nk, int p, int final_only, double *d_cards, uint32_t *d_hist,
+                                void *d_ws, size_t ws_bytes, dd_stream stream);
 
 /* ===========================================================================================
  * K6  all-pairs union cardinalities (the shape of lib/huffman_dandd.py:666-695 and
  * helpers/allpairs.py:360-370): for each listed pair (a,b) and each of the nk sketches,
  * card(max(regs[a], regs[b])).
  *   d_pairs [n_pairs][2] int32      d_cards [n_pairs][nk] f64     d_hist [n_pairs][nk][64] u32
+ * dd_pairwise_union_card transposes d_regs into (d_ws, ws_bytes) -- dd_prefix_union_workspace_bytes(0, 0,
+ * n_genomes, nk, p) bytes -- on every call (NULL: byte kernel); dd_pairwise_union_card_planes takes
+ * sketches already transposed by dd_to_planes, so tiles of a large pair matrix share one transpose.
  * =========================================================================================== */
 DD_API int dd_pairwise_union_card(const uint8_t *d_regs, int n_genomes, int nk, int p, const int32_t *d_pairs,
-                           int64_t n_pairs, double *d_cards, uint32_t *d_hist, dd_stream stream);
+                           int64_t n_pairs, double *d_cards, uint32_t *d_hist, void *d_ws, size_t ws_bytes,
+                           dd_stream stream);
+DD_API int dd_pairwise_union_card_planes(const uint32_t *d_planes, int n_genomes, int nk, int p, const int32_t *d_pairs,
+                                  int64_t n_pairs, double *d_cards, uint32_t *d_hist, dd_stream stream);
 
 /* ===========================================================================================
  * K5  --exact: number of distinct (canonical) k-mers, KMC semantics.
@@ -201,7 +252,9 @@ DD_API int dd_exact_count(void *d_ws, size_t ws_bytes, int k, uint64_t capacity,
  * Host-buffer convenience path (what bench.py's e2e number times): one FASTA held in host memory
  * -> H2D copy -> K1 -> K2 -> K4 -> D2H of cardinalities (and registers if h_regs != NULL);
  * synchronises the stream before returning.  Equivalent to the reference running
- * `dashing sketch` + `dashing card` for every k of the mask on that file.
+ * `dashing sketch` + `dashing card` for every k of the mask on that file.  FASTQ text (a line
+ * beginning with '+') is detected by the packer, rewritten with dd_fastq_to_fasta_host and sketched
+ * again, so the result is what kseq-based readers produce for it.
  * =========================================================================================== */
 DD_API size_t dd_sketch_fasta_host_workspace_bytes(size_t n_bytes, int nk, int p);
 DD_API int dd_sketch_fasta_host(const uint8_t *h_text, size_t n_bytes, uint32_t kmask, int p, int canon,
@@ -211,7 +264,10 @@ DD_API int dd_sketch_fasta_host(const uint8_t *h_text, size_t n_bytes, uint32_t 
 /* Same, but returns as soon as the work is enqueued: h_text must stay valid, and h_cards / h_regs
  * must not be read, until `stream` has been synchronised by the caller (pinned host memory makes
  * the copies truly asynchronous).  Lets a caller keep several FASTAs in flight on different streams
- * (one workspace per stream) so that H2D copies overlap the kernels of the previous file. */
+ * (one workspace per stream) so that H2D copies overlap the kernels of the previous file.  Nothing
+ * in the call waits for the device, whatever the file size.  FASTQ text cannot be handled without
+ * a host round trip: h_cards[] is then filled with NaN, and the caller falls back to
+ * dd_sketch_fasta_host for that file. */
 DD_API int dd_sketch_fasta_host_async(const uint8_t *h_text, size_t n_bytes, uint32_t kmask, int p, int canon,
                                       uint8_t *h_regs, double *h_cards, uint8_t *d_regs_or_null, void *d_ws,
                                       size_t ws_bytes, dd_stream stream);

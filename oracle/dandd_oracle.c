@@ -32,19 +32,31 @@
 #define ORC_BREAK 4u /* symbol value for "k-mer window must restart here" */
 
 /* ------------------------------------------------------------------------------------------
- * A.1 sequence model.  FASTA text -> symbol stream.
+ * A.1 sequence model.  FASTA / FASTQ text -> symbol stream.
  *   0..3 = A,C,G,T (either case); 4 = break.
- * Restates what kseq (the parser inside both Dashing/bonsai and KMC's -fm mode) hands to the
- * k-mer encoder:
- *   - everything before the first '>' is ignored (kseq scans for the record marker);
- *   - a line whose FIRST byte is '>' is a header: it contributes no bases and ends the previous
- *     record, so exactly one break symbol is emitted per header (k-mers never span records);
- *   - '\n' is never part of the sequence; '\r' is dropped (CRLF files; modern kseq strips it);
- *   - every other byte is a sequence character: ACGTacgt map to 0..3, anything else (N, IUPAC,
- *     blanks, '>' in the middle of a line ...) is a break  (bonsai cstr_lut == -1  /  KMC "symbols
- *     other than ACGT break k-mers").
- * Returns the number of symbols written; out must hold n bytes (a header is >= 1 byte long, so
- * the stream can never be longer than the text).
+ * Restates what kseq_read() (klib kseq.h, the parser inside both Dashing/bonsai and KMC's -fm
+ * mode) hands to the k-mer encoder, step for step:
+ *   - with no record pending, kseq scans forward for the next '>' OR '@' ANYWHERE in the text
+ *     (`while ((c = ks_getc(ks)) != -1 && c != '>' && c != '@');`): everything before the first
+ *     marker of a file is ignored, and so is everything between the end of a FASTQ record and the
+ *     next marker -- even when that marker sits in the middle of a line;
+ *   - the rest of the marker's line is the record name/comment: it contributes no bases and ends
+ *     the previous record, so exactly one break symbol is emitted per record (k-mers never span
+ *     records);
+ *   - sequence lines follow; the FIRST byte of each line decides: '>' or '@' opens the next record,
+ *     '+' starts the quality section of a FASTQ record, an empty line is skipped, anything else
+ *     makes the whole line sequence ('>', '@' or '+' in the middle of a line are sequence bytes);
+ *   - '\n' is never part of the sequence; '\r' is dropped (kseq strips the '\r' of a CRLF line
+ *     end; a '\r' elsewhere does not occur in practice and is dropped here as well -- one rule);
+ *   - every other sequence byte: ACGTacgt map to 0..3, anything else (N, IUPAC, blanks ...) is a
+ *     break  (bonsai cstr_lut == -1  /  KMC "symbols other than ACGT break k-mers");
+ *   - after a '+' line kseq reads whole lines as quality until it holds at least as many quality
+ *     bytes as the record has sequence bytes (at least one line), whatever those lines start with;
+ *     if the two lengths then differ, or the text ends right after the '+' line, kseq_read returns
+ *     an error: the caller's `while (kseq_read(ks) >= 0)` loop stops, so that record and the rest
+ *     of the file contribute nothing.
+ * Returns the number of symbols written; out must hold n bytes (a record marker is >= 1 byte
+ * long, so the stream can never be longer than the text).
  * ------------------------------------------------------------------------------------------ */
 static inline unsigned orc_base_code(uint8_t c) {
     switch (c) {
@@ -58,27 +70,60 @@ static inline unsigned orc_base_code(uint8_t c) {
 
 size_t orc_fasta_symbols(const uint8_t *buf, size_t n, uint8_t *out) {
     size_t i = 0, o = 0;
-    /* preamble: skip to the first record marker */
-    while (i < n && buf[i] != '>') ++i;
-    int at_line_start = 1; /* the marker we stopped at is treated as opening a header line */
-    int in_header = 0;
-    for (; i < n; ++i) {
-        uint8_t c = buf[i];
-        if (in_header) {
-            if (c == '\n') { in_header = 0; at_line_start = 1; }
-            continue;
+    int pending = 0; /* kseq's last_char: a record marker has already been consumed */
+    for (;;) {
+        if (!pending) { /* scan for the next record marker, anywhere */
+            while (i < n && buf[i] != '>' && buf[i] != '@') ++i;
+            if (i >= n) break;
+            ++i;
         }
-        if (c == '\n') { at_line_start = 1; continue; }
-        if (at_line_start && c == '>') {
-            in_header = 1; at_line_start = 0;
-            out[o++] = ORC_BREAK;
-            continue;
+        pending = 0;
+        const size_t record_start = o;
+        out[o++] = ORC_BREAK;
+        while (i < n && buf[i] != '\n') ++i; /* name + comment: the rest of the marker's line */
+        if (i < n) ++i;
+        /* sequence lines */
+        size_t seq_len = 0; /* kseq's seq.l: sequence bytes kept ('\r' excluded) */
+        int c = -1;
+        while (i < n) {
+            c = buf[i];
+            if (c == '>' || c == '+' || c == '@') { ++i; break; }
+            c = -1;
+            if (buf[i] == '\n') { ++i; continue; } /* empty line */
+            while (i < n && buf[i] != '\n') {
+                if (buf[i] != '\r') { out[o++] = (uint8_t)orc_base_code(buf[i]); ++seq_len; }
+                ++i;
+            }
+            if (i < n) ++i;
         }
-        at_line_start = 0;
-        if (c == '\r') continue;
-        out[o++] = (uint8_t)orc_base_code(c);
+        if (c == '>' || c == '@') { pending = 1; continue; }
+        if (c != '+') break; /* end of text: last FASTA record */
+        /* FASTQ: skip the rest of the '+' line, then read quality lines */
+        while (i < n && buf[i] != '\n') ++i;
+        if (i >= n) { o = record_start; break; } /* error: no quality string */
+        ++i;
+        size_t qual_len = 0;
+        do {
+            if (i >= n) break; /* ks_getuntil2 < 0 at end of text */
+            while (i < n && buf[i] != '\n') { if (buf[i] != '\r') ++qual_len; ++i; }
+            if (i < n) ++i;
+        } while (qual_len < seq_len);
+        if (qual_len != seq_len) { o = record_start; break; } /* error: record and the rest are not read */
     }
     return o;
+}
+
+/* A.6 (UNVERIFIED, optional): bonsai's unwindowed encoder is recalled to test its 64-bit rolling
+ * accumulator against all-ones to detect an invalid base; 32 consecutive T (code 3) make a
+ * legitimate accumulator all-ones as well, so the 32nd T of such a run would be taken for an
+ * invalid base and the accumulator reset.  This turns every 32nd T of a run of T into a break, in
+ * place -- the behaviour dd_pack_polyt_sentinel emulates when switched on. */
+void orc_polyt_sentinel(uint8_t *sym, size_t n) {
+    unsigned run = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (sym[i] != 3) { run = 0; continue; }
+        if (++run == 32) { sym[i] = ORC_BREAK; run = 0; }
+    }
 }
 
 /* ------------------------------------------------------------------------------------------

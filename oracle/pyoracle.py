@@ -33,6 +33,8 @@ def lib():
         u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
         L.orc_fasta_symbols.restype = C.c_size_t
         L.orc_fasta_symbols.argtypes = [u8p, C.c_size_t, u8p]
+        L.orc_polyt_sentinel.restype = None
+        L.orc_polyt_sentinel.argtypes = [u8p, C.c_size_t]
         L.orc_wang.restype = C.c_uint64
         L.orc_wang.argtypes = [C.c_uint64]
         L.orc_revcomp.restype = C.c_uint64
@@ -67,6 +69,13 @@ def fasta_symbols(text: bytes) -> np.ndarray:
     out = np.empty(max(1, buf.size), dtype=np.uint8)
     n = lib().orc_fasta_symbols(bp, buf.size, out.ctypes.data_as(C.POINTER(C.c_uint8)))
     return out[:n].copy()
+
+
+def polyt_sentinel(sym: np.ndarray) -> np.ndarray:
+    """SURVEY.md A.6 switched ON: a copy of the symbol stream with every 32nd T of a T run broken."""
+    out, op = _u8(np.array(sym, dtype=np.uint8, copy=True))
+    lib().orc_polyt_sentinel(op, out.size)
+    return out
 
 
 def wang(x: int) -> int:

@@ -14,21 +14,59 @@ M64 = (1 << 64) - 1
 
 
 def fasta_symbols_py(text: bytes) -> np.ndarray:
-    """Line-oriented FASTA reader (A.1): records start at lines beginning with '>', text before the
-    first '>' is ignored, line terminators are not sequence, other bytes are sequence characters."""
-    start = text.find(b">")
-    if start < 0:
-        return np.zeros(0, dtype=np.uint8)
-    out = []
+    """Line-oriented FASTA/FASTQ reader (A.1), written as a state machine over LINES where the C
+    oracle walks bytes.  Records open at the first '>' or '@' found anywhere while no record is
+    open, afterwards at lines BEGINNING with '>' or '@'; a line beginning with '+' switches to
+    quality lines, consumed until they hold as many bytes as the record's sequence; a record whose
+    quality length differs ends the parse (kseq_read error); line terminators are not sequence."""
     lut = {ord(c): v for c, v in zip("ACGTacgt", [0, 1, 2, 3, 0, 1, 2, 3])}
-    for line in text[start:].split(b"\n"):
-        if line.startswith(b">"):
-            out.append(4)
-            continue
-        for ch in line:
-            if ch == 13:      # '\r'
+    out = []
+    pos, n = 0, len(text)
+
+    def next_line(at):
+        """(line bytes without the terminator, offset after it, whether a terminator was seen)"""
+        end = text.find(b"\n", at)
+        return (text[at:], n, False) if end < 0 else (text[at:end], end + 1, True)
+
+    while True:
+        marks = [m for m in (text.find(b">", pos), text.find(b"@", pos)) if m >= 0]
+        if not marks:
+            break
+        _, pos, _ = next_line(min(marks) + 1)       # header: rest of the marker's line
+        mark = len(out)
+        out.append(4)
+        while True:                                  # one iteration per record opened at a line start
+            seq_len, kind = 0, None
+            while pos < n:
+                first = text[pos:pos + 1]
+                if first in (b">", b"@", b"+"):
+                    kind = first
+                    break
+                line, pos, _ = next_line(pos)
+                for ch in line:
+                    if ch != 13:                     # '\r'
+                        out.append(lut.get(ch, 4))
+                        seq_len += 1
+            if kind in (b">", b"@"):
+                _, pos, _ = next_line(pos + 1)
+                mark = len(out)
+                out.append(4)
                 continue
-            out.append(lut.get(ch, 4))
+            break
+        if kind != b"+":
+            break                                    # end of text after a FASTA record
+        _, pos, terminated = next_line(pos)          # the '+' line
+        if not terminated:
+            del out[mark:]
+            break
+        qual_len, first_line = 0, True
+        while pos < n and (first_line or qual_len < seq_len):
+            line, pos, _ = next_line(pos)
+            qual_len += len(line) - line.count(b"\r")
+            first_line = False
+        if qual_len != seq_len:
+            del out[mark:]
+            break
     return np.asarray(out, dtype=np.uint8)
 
 

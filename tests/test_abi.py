@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_size_queries(lib):
-    assert lib.dd_abi_version() == 1
+    assert lib.dd_abi_version() == 2
     assert lib.dd_pack_codes_bytes(1 << 20) >= (1 << 20) // 4
     assert lib.dd_pack_invalid_bytes(1 << 20) >= (1 << 20) // 8
     assert lib.dd_sketch_workspace_bytes(23, 20) >= 23 * 2 * (1 << 20)
@@ -97,3 +97,37 @@ def test_skip_preamble_host_variants():
     big = np.zeros((1 << 24) + 100, dtype=np.uint8)
     big[(1 << 24) + 7] = 62
     assert f(big) == (1 << 24) + 7
+
+
+# ---- host-side text helpers of the library (no GPU work, so they run everywhere) ------------------
+def _normalise(lib, text: bytes) -> bytes:
+    import ctypes as C
+    src = (C.c_uint8 * max(1, len(text))).from_buffer_copy(text or b"\0")
+    dst = (C.c_uint8 * (len(text) + 16))()
+    n = lib.dd_fastq_to_fasta_host(C.addressof(src), len(text), C.addressof(dst))
+    assert n <= len(text) + 16
+    return bytes(dst[:n])
+
+
+def test_first_record_marker(lib):
+    import ctypes as C
+    for text, want in [(b">a\nAC", 0), (b"xx\n@r\nAC", 3), (b"junk>a", 4), (b"a@b>c", 1), (b"none", 4), (b"", 0)]:
+        buf = (C.c_uint8 * max(1, len(text))).from_buffer_copy(text or b"\0")
+        assert lib.dd_fasta_first_record_host(C.addressof(buf), len(text)) == want, text
+
+
+def test_fastq_normaliser_matches_the_oracle_walk(lib):
+    """dd_fastq_to_fasta_host is the product's restatement of kseq_read(); the oracle is another.
+    Feeding the normalised text back through the oracle must give the symbols of the raw text, and
+    the normalised text must be plain FASTA (no line begins with '+' or '@')."""
+    import numpy as np
+    from oracle import pyoracle as orc
+    from tests.test_oracle import KSEQ_CASES
+    texts = [t for t, _ in KSEQ_CASES]
+    rng = np.random.default_rng(5)
+    alpha = np.frombuffer(b"ACGTacgtN>@+\n\n\n\r I", dtype=np.uint8)
+    texts += [alpha[rng.integers(0, alpha.size, int(rng.integers(0, 80)))].tobytes() for _ in range(4000)]
+    for text in texts:
+        fasta = _normalise(lib, text)
+        assert orc.fasta_symbols(fasta).tolist() == orc.fasta_symbols(text).tolist(), (text, fasta)
+        assert all(not ln.startswith((b"+", b"@")) for ln in fasta.split(b"\n")), (text, fasta)

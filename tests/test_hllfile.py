@@ -44,3 +44,18 @@ def test_stub_and_bad_files(tmp_path):
     trunc.write_bytes(trunc.read_bytes()[:-5])
     with pytest.raises(ValueError):
         hllfile.read_hll(str(trunc))
+
+
+def test_reader_accepts_both_header_widths(tmp_path):
+    """The recalled dnbaker/sketch layout has four or five uint32 flags before p (28- or 32-byte
+    header); the writer uses HEADER_FLAG_WORDS, the reader takes whichever fits the file size."""
+    p = 10
+    regs = np.arange(1 << p, dtype=np.uint32).astype(np.uint8) % 50
+    for words in (4, 5):
+        raw = struct.pack(f"<{words}I I d", 1, 0, 2, 2, *([8] if words == 5 else []), p, 4242.5) + regs.tobytes()
+        for packer in (lambda b: b, gzip.compress):
+            path = tmp_path / f"w{words}.hll"
+            path.write_bytes(packer(raw))
+            got, gp, card = hllfile.read_hll(str(path))
+            assert np.array_equal(got, regs) and gp == p and card == 4242.5
+    assert hllfile.HEADER.size == 12 + 4 * hllfile.HEADER_FLAG_WORDS

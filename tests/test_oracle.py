@@ -147,3 +147,43 @@ def test_exact_count_wide_k_against_string_sets():
         assert plain == ref.exact_count_strings([a, c], k, canon=False)
         assert canon == ref.exact_count_strings([a, c], k, canon=True)
         assert canon < plain
+
+
+# ---- kseq record rules ('@' headers, '+' quality sections) and the A.6 switch ---------------------
+KSEQ_CASES = [
+    # (text, expected symbols) -- hand-derived from klib kseq_read()
+    (b"@r1\nACGT\n+\nIIII\n@r2\nGGCC\n+r2\nJJJJ\n", [4, 0, 1, 2, 3, 4, 2, 2, 1, 1]),          # 4-line FASTQ
+    (b"@r1\nACGT\nAC\n+\nII\n@III\n>x\nACGT\n", [4, 0, 1, 2, 3, 0, 1, 4, 0, 1, 2, 3]),          # multi-line; a quality line starting with '@'
+    (b"xx@r1\nACGT\n+\nIIII\njunk>r2 c\nAAAA\n@r3\nCC\n", [4, 0, 1, 2, 3, 4, 0, 0, 0, 0, 4, 1, 1]),  # markers found mid-line after a FASTQ record
+    (b"@r1\nACGT\n+\nII\n>r2\nAAAA\n", []),                 # quality longer than sequence: kseq_read fails, nothing is read
+    (b">ok\nAC\n@r1\nACGT\n+\nII\n", [4, 0, 1]),            # ... but records before the bad one stand
+    (b"@r1\nACGT\n+", []),                                     # no quality string
+    (b"@r1\n+\n\n>r2\nACGT", [4, 4, 0, 1, 2, 3]),            # empty read, one (empty) quality line
+    (b">a\nAC\n+\nxx\n>b\nGG\n", [4, 0, 1, 4, 2, 2]),        # '+' line inside a FASTA file
+    (b">a\nACGT\n@b\nTTTT\n", [4, 0, 1, 2, 3, 4, 3, 3, 3, 3]),  # '@' line is a header
+    (b">a\nAC@GT+A>C\n", [4, 0, 1, 4, 2, 3, 4, 0, 4, 1]),       # the same bytes in the middle of a line are sequence
+]
+
+
+@pytest.mark.parametrize("text,want", KSEQ_CASES)
+def test_kseq_record_rules(text, want):
+    assert orc.fasta_symbols(text).tolist() == want
+    assert ref.fasta_symbols_py(text).tolist() == want
+
+
+def test_kseq_rules_fuzz_c_vs_numpy():
+    rng = np.random.default_rng(11)
+    alpha = np.frombuffer(b"ACGTacgtN>@+\n\n\n\r I", dtype=np.uint8)
+    for _ in range(3000):
+        txt = alpha[rng.integers(0, alpha.size, int(rng.integers(0, 60)))].tobytes()
+        assert orc.fasta_symbols(txt).tolist() == ref.fasta_symbols_py(txt).tolist(), txt
+
+
+def test_polyt_sentinel_switch():
+    sym = np.array([0] + [3] * 70 + [4] + [3] * 31 + [1] + [3] * 32, dtype=np.uint8)
+    out = orc.polyt_sentinel(sym)
+    broken = np.flatnonzero(out != sym).tolist()
+    assert broken == [32, 64, 135]            # every 32nd T of a run; a run of 31 is untouched
+    assert (out[broken] == 4).all()
+    # with the switch on, a k=32 poly-T window never reaches the sketch
+    assert orc.kmers(sym, 32, True).size > 0 and not np.any(orc.kmers(out, 32, False) == np.uint64(0xFFFFFFFFFFFFFFFF))
