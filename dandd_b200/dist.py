@@ -118,14 +118,17 @@ def split_fasta(text, nparts: int, overlap_symbols: int = 63, only: int = None, 
     nparts = max(1, int(nparts))
     if nparts == 1 or n == 0:
         return [raw] + [b""] * (nparts - 1)
-    # records: the FIRST '>' of the file wherever it is (kseq skips to the first marker and takes it
-    # as a header line), afterwards every '>' at a line start
+    # records: the FIRST '>' / '@' of the file wherever it is (kseq skips to the first marker and takes
+    # it as a header line), afterwards every '>' / '@' at a line start.  (FASTQ text --
+    # a line beginning with '+' -- must be rewritten with Engine.fastq_to_fasta before it gets here.)
     starts = []
-    at = raw.find(b">")                                              # (single-byte find runs at memchr speed)
-    while at >= 0:
-        if not starts or raw[at - 1] == 10:
+    for mark in (b">", b"@"):
+        at = raw.find(mark)                                          # (single-byte find runs at memchr speed)
+        while at >= 0:
             starts.append(at)
-        at = raw.find(b">", at + 1)
+            at = raw.find(mark, at + 1)
+    starts.sort()
+    starts = [at for i, at in enumerate(starts) if i == 0 or raw[at - 1] == 10]
     if not starts:                                                   # no record at all: nothing is sequence
         return [raw] + [b""] * (nparts - 1)
     bounds = starts + [n]
@@ -145,8 +148,8 @@ def split_fasta(text, nparts: int, overlap_symbols: int = 63, only: int = None, 
         for c in cuts:
             pieces.append((prev, c, prev != a))
             # step back over at least overlap_symbols sequence bytes (newlines / CRs do not count)
-            # ... and never start on a '>' (junk inside a sequence line): behind the synthetic header
-            # it would sit at a line start and turn the rest of its line into a header
+            # ... and never start on a '>', '@' or '+' (junk inside a sequence line): behind the synthetic
+            # header it would sit at a line start and turn the rest of its line into a header / quality
             back, span, need = c, 2 * overlap_symbols + 64, overlap_symbols
             while True:
                 lo = max(body, c - span)
@@ -156,7 +159,7 @@ def split_fasta(text, nparts: int, overlap_symbols: int = 63, only: int = None, 
                 if have >= need:
                     idx = np.flatnonzero(is_sym)
                     at = lo + int(idx[have - need])
-                    if buf[at] == 62 and at > body:
+                    if buf[at] in (62, 64, 43) and at > body:
                         need += 1
                         continue
                     back = at

@@ -137,6 +137,8 @@ class GpuSketchStore:
             if split is not None:
                 from dandd_b200 import dist as dd_dist
                 run_ks = sorted(need)                      # identical on every rank, whatever each one has cached
+                if b"\n+" in text or text[:1] == b"+":     # FASTQ: records as kseq reads them, then split
+                    text = self.engine.fastq_to_fasta(text)
                 text = dd_dist.split_fasta(text, split[1], only=split[0])[split[0]]
             seq = self._pack_text(text)
             regs, cards = self.engine.sketch(seq, run_ks, p=p, canon=canon)

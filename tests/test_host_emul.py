@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle as orc
-from tests.util import adversarial_fasta, decode_packed, random_bases, to_fasta
+from tests.util import adversarial_fasta, decode_packed, kseq_fasta, random_bases, to_fasta
 
 U8P, U32P = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
 
@@ -53,6 +53,19 @@ def test_pack_matches_oracle_symbols(host_emul, seed, chunk):
         txt = to_fasta([(b"one-line", random_bases(rng, 5000))], width=100000)  # single long line
     want = orc.fasta_symbols(txt)
     codes, invalid, nsym = emul_pack(host_emul, txt, chunk)
+    assert nsym == want.size
+    assert np.array_equal(decode_packed(codes, invalid, nsym), want)
+
+
+@pytest.mark.parametrize("chunk", [None, 16, 80, 4096])
+def test_pack_kseq_markers(host_emul, chunk):
+    """'@' at the start of a line opens a record like '>' does; '@', '+', '>' inside a line are
+    plain (invalid) sequence characters."""
+    rng = np.random.default_rng(7)
+    txt = kseq_fasta(rng, n=4000)
+    want = orc.fasta_symbols(txt)
+    start = min(i for i in (txt.find(b">"), txt.find(b"@")) if i >= 0)
+    codes, invalid, nsym = emul_pack(host_emul, txt[start:], chunk)
     assert nsym == want.size
     assert np.array_equal(decode_packed(codes, invalid, nsym), want)
 

@@ -68,6 +68,30 @@ def adversarial_fasta(rng, n=6000):
     return txt.replace(b">tiny", b"\n\n>tiny")  # blank lines between records
 
 
+def kseq_fasta(rng, n=6000, fastq=False):
+    """Text that exercises kseq's record rules: '@' header lines between '>' ones,
+    '@' / '+' / '>' in the middle of sequence lines, junk before the first marker; with fastq=True
+    also FASTQ records -- single- and multi-line, quality lines that begin with '@' and '>'."""
+    a = random_bases(rng, n)
+    width = 67
+    a[width * 3 + 5] = ord("@")          # columns 5, 7, 9: never the first byte of a line
+    a[width * 7 + 7] = ord("+")
+    b = a[n // 2:]
+    b[width * 2 + 9] = ord(">")
+    recs = [(b"r0 first", a[:n // 2]), (b"r1", b)]
+    txt = to_fasta(recs, width=width).replace(b">r1", b"@r1")
+    out = b"junk line\nmore junk " + txt
+    if fastq:
+        s1 = random_bases(rng, 150).tobytes()
+        s2 = random_bases(rng, 301).tobytes()
+        q2 = bytes(rng.integers(33, 74, 301).astype(np.uint8))
+        q2 = b"@" + q2[1:100] + b"\n>" + q2[101:200] + b"\n+" + q2[201:]          # quality lines starting with @ > +
+        out += (b"@read1 desc\n" + s1 + b"\n+\n" + b"I" * 150 + b"\n"
+                b"@read2\n" + s2[:100] + b"\n" + s2[100:200] + b"\n" + s2[200:] + b"\n+read2\n" + q2 + b"\n"
+                b"stray text >late record\n" + random_bases(rng, 200).tobytes() + b"\n")
+    return out
+
+
 def decode_packed(codes, invalid, nsym):
     """Packed stream (include/dandd_b200.h layout) -> oracle symbol stream (0..3, 4 = break)."""
     codes = np.asarray(codes, dtype=np.uint32)
