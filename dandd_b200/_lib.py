@@ -45,6 +45,7 @@ SIGNATURES = {
     "dd_sketch_begin": (_i, [_vp, _sz, _i, _i, _vp]),
     "dd_sketch_update": (_i, [_vp, _vp, _vp, _sz, _u32, _i, _i, _vp, _sz, _vp]),
     "dd_sketch_update_range": (_i, [_vp, _vp, _u64, _u64, _u32, _i, _i, _vp, _sz, _vp]),
+    "dd_sketch_update_sched": (_i, [_vp, _vp, _vp, _u64, _u64, _sz, _u64, _u32, _i, _i, _vp, _sz, _vp]),
     "dd_sketch_refresh_floor": (_i, [_vp, _sz, _u32, _i, _vp]),
     "dd_sketch_end": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp]),
     "dd_card_ertl_mle": (_i, [_vp, _i, _i, _vp, _vp, _vp]),

@@ -13,7 +13,7 @@ LIB = os.path.join(HERE, "libdandd_b200.so")
 SOURCES = ["pack.cu", "sketch.cu", "card.cu", "planes.cu", "exact.cu", "api.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "hist.cuh", os.path.join("..", "..", "include", "dandd_b200.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + os.environ.get("DD_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

@@ -233,6 +233,17 @@ int dd_sketch_update_range(const uint32_t *d_codes, const uint32_t *d_invalid, u
     return DD_OK;
 }
 
+int dd_sketch_update_sched(const uint32_t *d_codes, const uint32_t *d_invalid, const dd_pack_state *d_state, uint64_t sym_begin,
+                           uint64_t sym_end, size_t max_new_symbols, uint64_t seen_before, uint32_t kmask, int p, int canon,
+                           void *d_ws, size_t ws_bytes, dd_stream stream) {
+    if (int rc = sketch_check(d_codes, d_invalid, kmask, p, d_ws, ws_bytes, "dd_sketch_update_sched")) return rc;
+    if (!d_state && sym_end < sym_begin) return fail(DD_ERR_ARG, "dd_sketch_update_sched: end < begin");
+    DD_CUDA(dd::sketch_update_sched(d_codes, d_invalid, d_state, sym_begin, sym_end, max_new_symbols, seen_before, kmask, p, canon,
+                                    d_ws, S(stream)),
+            "dd_sketch_update_sched");
+    return DD_OK;
+}
+
 int dd_sketch_refresh_floor(void *d_ws, size_t ws_bytes, uint32_t kmask, int p, dd_stream stream) {
     if (!d_ws || kmask == 0 || bad_p(p)) return fail(DD_ERR_ARG, "dd_sketch_refresh_floor: bad argument");
     if (ws_bytes < dd::sketch_workspace_bytes(popc(kmask), p)) return fail(DD_ERR_WORKSPACE, "dd_sketch_refresh_floor: workspace too small");
@@ -489,7 +500,6 @@ static int sketch_fasta_host_impl(const uint8_t *h_text, size_t n_bytes, uint32_
     DD_CUDA(dd::sketch_begin(w.sketch_ws, nk, p, st), "sketch_begin");
     const size_t chunk = n_bytes < kHostChunk ? n_bytes : kHostChunk;
     const size_t nchunks = n ? (n + chunk - 1) / chunk : 0;
-    const size_t floor_after = (size_t)16 << p;  // start filtering once registers have seen ~16 items each
     // More than one chunk: copies run on their own stream, double-buffered against pack + sketch.
     // The stream and the events are created here and destroyed before returning WITHOUT waiting:
     // CUDA releases a destroyed stream / event once the work already enqueued on it has completed,
@@ -535,9 +545,10 @@ static int sketch_fasta_host_impl(const uint8_t *h_text, size_t n_bytes, uint32_
         DD_TRY(dd::pack_fasta(d_text, len, w.codes, w.invalid, n_bytes, w.state, w.pack_ws, st), "pack_fasta");
         if (overlap) DD_TRY(cudaEventRecord(freed[b], st), "event record");
         if (dd::g_polyt_sentinel) DD_TRY(dd::pack_polyt_sentinel(w.codes, w.invalid, w.state, 0, 0, len, st), "polyt_sentinel");
-        DD_TRY(dd::sketch_update(w.codes, w.invalid, w.state, 0, 0, len, kmask, p, canon, w.sketch_ws, st), "sketch_update");
+        // (text bytes stand in for symbols in the floor schedule: the cuts move by ~1 %, the result does not)
+        DD_TRY(dd::sketch_update_sched(w.codes, w.invalid, w.state, 0, 0, len, done, kmask, p, canon, w.sketch_ws, st),
+               "sketch_update");
         done += len;
-        if (done >= floor_after && done < n) DD_TRY(dd::sketch_refresh_floor(w.sketch_ws, kmask, p, st), "refresh_floor");
     }
     cleanup();
 #undef DD_TRY

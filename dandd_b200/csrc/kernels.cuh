@@ -29,11 +29,17 @@ struct SketchWsHeader {
 size_t sketch_workspace_bytes(int nk, int p);
 cudaError_t sketch_begin(void *d_ws, int nk, int p, cudaStream_t stream);
 // Either d_state != nullptr (range read on the device: [prev_nsym, nsym), grid sized from
-// max_new_symbols) or an explicit host-known range.
+// max_new_symbols; a non-empty [sym_begin, sym_end) then selects a sub-range RELATIVE to prev_nsym)
+// or an explicit host-known range.
 cudaError_t sketch_update(const uint32_t *d_codes, const uint32_t *d_invalid, const dd_pack_state *d_state,
                           uint64_t sym_begin, uint64_t sym_end, size_t max_new_symbols, uint32_t kmask, int p,
                           int canon, void *d_ws, cudaStream_t stream);
 cudaError_t sketch_refresh_floor(void *d_ws, uint32_t kmask, int p, cudaStream_t stream);
+// sketch_update cut at the floor schedule's boundaries, with the refreshes in between (sketch.cu).
+// d_state != nullptr: [sym_begin, sym_end) is ignored, the range is the last pack call's.
+cudaError_t sketch_update_sched(const uint32_t *d_codes, const uint32_t *d_invalid, const dd_pack_state *d_state,
+                                uint64_t sym_begin, uint64_t sym_end, size_t max_new_symbols, uint64_t seen_before,
+                                uint32_t kmask, int p, int canon, void *d_ws, cudaStream_t stream);
 cudaError_t sketch_end(void *d_ws, int nk, int p, uint8_t *d_regs, uint32_t *d_hist, double *d_cards,
                        cudaStream_t stream);
 

@@ -40,7 +40,18 @@
 
 namespace dd {
 
-constexpr int kSketchThreads = 256;
+// CTA shapes, measured on B200 (profiles/r02_k2_variants.md).  Sweeps without a small k (no presence
+// bitmaps, short genomes dominate: config 2) run best as 256-thread CTAs, one tile each; sweeps with
+// small k are persistent and share one 43.7 KB bitmap set among the 32 warps of a 1024-thread CTA
+// (two CTAs per SM instead of five 256-thread ones: 64 resident warps instead of 40).
+#ifndef DD_SKETCH_THREADS_PLAIN
+#define DD_SKETCH_THREADS_PLAIN 256
+#endif
+#ifndef DD_SKETCH_THREADS_SMALLK
+#define DD_SKETCH_THREADS_SMALLK 1024
+#endif
+constexpr int kThreadsPlain = DD_SKETCH_THREADS_PLAIN, kThreadsSmallK = DD_SKETCH_THREADS_SMALLK;
+constexpr int min_ctas_for(int threads) { return threads >= 1024 ? 2 : threads >= 512 ? 3 : 5; }
 #ifndef DD_XORSHIFT_ON_FMA
 #define DD_XORSHIFT_ON_FMA 0  // measured: no gain (3.1 Gbp 210 vs 203 ms); IMAD.WIDE is not cheaper than SHF here
 #endif
@@ -55,7 +66,7 @@ struct SketchArgs {
     int p;
     uint32_t *acc;                // [nk][2^p / 2] words, two u16 registers per word
     const SketchWsHeader *hdr;
-    uint32_t ntiles;              // upper bound on the 256-word tiles of the symbol range
+    uint32_t ntiles;              // upper bound on the (CTA size)-word tiles of the symbol range
 };
 
 // Presence bitmaps for k = 1..kBitmapMaxK: 4^k bits each (at least one word).
@@ -111,6 +122,29 @@ __device__ __forceinline__ uint64_t xorshr_fma(uint64_t h) {
     return r;
 }
 
+// h ^= h >> S with only the HIGH word's shift moved to the FMA pipe (mul.hi by 2^(32-S) == >> S):
+// one ALU instruction less per xor-shift, one IMAD.HI more.
+#ifndef DD_K2_MULHI
+#define DD_K2_MULHI 0
+#endif
+#ifndef DD_K2_VOTE_TAIL
+#define DD_K2_VOTE_TAIL 0
+#endif
+template <int S>
+__device__ __forceinline__ uint64_t xorshr(uint64_t h) {
+#if DD_K2_MULHI
+    uint32_t hl, hh, sh;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(hl), "=r"(hh) : "l"(h));
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(sh) : "r"(hh), "r"(1u << (32 - S)));
+    const uint32_t nl = hl ^ __funnelshift_r(hl, hh, S), nh = hh ^ sh;
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(nl), "r"(nh));
+    return r;
+#else
+    return h ^ (h >> S);
+#endif
+}
+
 // Canonical (or forward) k-mer ending at the current symbol.  For K <= 16 the whole k-mer lives in
 // one 32-bit register: mask, shift and min are single instructions.
 template <int K, bool kCanon>
@@ -125,95 +159,124 @@ __device__ __forceinline__ uint64_t kmer_of(const Window &win) {
     }
 }
 
+// Per-k constants of one launch, in shared memory (a load with an immediate address per use; kept
+// in registers they cost 64 of them): thresh[k-1] = largest value of the top 32 remainder bits whose
+// rank still exceeds the floor of k (rank > floor <=> clz(t) >= floor <=> t <= 0xffffffff >> floor),
+// floor[k-1] itself for the exact re-check that only matters when floor > 32.
+struct KConsts {
+    uint32_t thresh[32];
+    uint32_t floor[32];
+};
+
 // One (symbol, k) update.  `live` says whether this lane has a valid k-mer of this length; the
 // warp stays converged (dead lanes are only predicated off the shared-memory and global updates),
 // so the small-k early exit is a plain full-warp vote.
-template <int K, bool kCanon>
+// kStaticMask != 0: the set of k values is known at compile time (no per-k mask tests, table slot a
+// constant); 0: generic, driven by kmask / kmask_run.
+// Cost after the hash (SASS, profiles/r02_k2_sass.md): the common case -- rank <= floor on a long
+// genome -- is one funnel shift, one compare and one branch; rank, register index and address are
+// only computed by the lanes that actually update.
+template <int K, bool kCanon, uint32_t kStaticMask>
 __device__ __forceinline__ void update_one_k(const Window &win, int run, uint32_t kmask, uint32_t kmask_run, int p,
-                                             uint32_t *acc, uint32_t &off_k, const uint32_t (&floor4)[8],
-                                             uint32_t *s_seen) {
-    if (!((kmask >> (K - 1)) & 1u)) return;  // warp-uniform
-    if ((kmask_run >> (K - 1)) & 1u) {       // warp-uniform
-        const uint64_t v = kmer_of<K, kCanon>(win);
-        bool live = run >= K;
-        if (K <= kBitmapMaxK) {
-            // already sent by this CTA?  (a racing duplicate only repeats an idempotent update)
-            uint32_t *word = s_seen + bitmap_offset(K) + ((uint32_t)v >> 5);
-            const uint32_t bit = 1u << ((uint32_t)v & 31u);
-            live = live && !(*word & bit);
-            if (live) atomicOr(word, bit);
-            if (!__any_sync(0xffffffffu, live)) {
-                off_k += 1u << (p - 1);
-                return;
-            }
+                                             uint32_t *acc, uint32_t &off_k, const KConsts &kc, uint32_t *s_seen,
+                                             uint64_t minus_one) {
+    constexpr uint32_t bit = 1u << (K - 1);
+    if (kStaticMask) {
+        if (!(kStaticMask & bit)) return;    // compile time
+    } else {
+        if (!(kmask & bit)) return;          // warp-uniform
+        if (!(kmask_run & bit)) {
+            off_k += 1u << (p - 1);
+            return;
         }
-        // dd::wang64 (common.cuh) with the multiplications pinned to the FMA pipe
-        uint64_t h = mad64x32(v, 0x1FFFFFu, 0xFFFFFFFFFFFFFFFFull);
+    }
+    const uint64_t v = kmer_of<K, kCanon>(win);
+    bool live = run >= K;
+    if (K <= kBitmapMaxK) {
+        // already sent by this CTA?  (a racing duplicate only repeats an idempotent update)
+        uint32_t *word = s_seen + bitmap_offset(K) + ((uint32_t)v >> 5);
+        const uint32_t seen_bit = 1u << ((uint32_t)v & 31u);
+        live = live && !(*word & seen_bit);
+        if (live) atomicOr(word, seen_bit);
+        if (!__any_sync(0xffffffffu, live)) {
+            if (!kStaticMask) off_k += 1u << (p - 1);
+            return;
+        }
+    }
+    // dd::wang64 (common.cuh) with the multiplications pinned to the FMA pipe
+    uint64_t h = mad64x32(v, 0x1FFFFFu, minus_one);
 #if DD_XORSHIFT_ON_FMA
-        h = xorshr_fma<24>(h);
-        h = mul64x32(h, 265u);
-        h = xorshr_fma<14>(h);
-        h = mul64x32(h, 21u);
-        h = xorshr_fma<28>(h);
+    h = xorshr_fma<24>(h);
+    h = mul64x32(h, 265u);
+    h = xorshr_fma<14>(h);
+    h = mul64x32(h, 21u);
+    h = xorshr_fma<28>(h);
 #else
-        h ^= h >> 24;
-        h = mul64x32(h, 265u);
-        h ^= h >> 14;
-        h = mul64x32(h, 21u);
-        h ^= h >> 28;
+    h = xorshr<24>(h);
+    h = mul64x32(h, 265u);
+    h = xorshr<14>(h);
+    h = mul64x32(h, 21u);
+    h = xorshr<28>(h);
 #endif
-        h = mul64x32(h, 0x80000001u);
-        const uint32_t hi = (uint32_t)(h >> 32), lo = (uint32_t)h;
-        // rank = 1 + leading zeros of the low (64-p) bits, capped at 64-p+1
-        const uint32_t rem_hi = hi & (0xffffffffu >> p);
-        const uint32_t rank = (rem_hi ? (uint32_t)__clz((int)rem_hi) : 32u + (uint32_t)__clz((int)lo)) + 1u - (uint32_t)p;
-        const uint32_t floor_k = (floor4[(K - 1) >> 2] >> (8 * ((K - 1) & 3))) & 0xffu;
-        if (live && rank > floor_k) {
+    h = mul64x32(h, 0x80000001u);
+    const uint32_t hi = (uint32_t)(h >> 32), lo = (uint32_t)h;
+    // t = the 32 bits below the register index; rank = clz(t) + 1 unless they are all zero
+    const uint32_t t = __funnelshift_l(lo, hi, (uint32_t)p);
+    const bool pass = live && t <= kc.thresh[K - 1];
+#if DD_K2_VOTE_TAIL
+    if (__any_sync(0xffffffffu, pass))   // warp-uniform branch (no reconvergence barrier); the tail is predicated
+#endif
+    if (pass) {
+        const uint32_t rank = t ? (uint32_t)__clz((int)t) + 1u : 33u + (uint32_t)__clz((int)((lo << p) | (1u << (p - 1))));
+        if (rank > kc.floor[K - 1]) {
             // register idx = hi >> (32-p) lives in word idx>>1, half idx&1
             const uint32_t val = rank << ((hi >> (28 - p)) & 16u);
-            uint32_t *word = acc + (off_k + (hi >> (33 - p)));
+            const uint32_t slot_off = kStaticMask ? (uint32_t)__popc(kStaticMask & (bit - 1u)) << (p - 1) : off_k;
+            uint32_t *word = acc + (slot_off + (hi >> (33 - p)));
             asm volatile("{ .reg .b16 l, h; mov.b32 {l, h}, %1; red.global.max.noftz.v2.f16 [%0], {l, h}; }" ::"l"(word), "r"(val)
                          : "memory");
         }
     }
-    off_k += 1u << (p - 1);
+    if (!kStaticMask) off_k += 1u << (p - 1);
 }
 
-template <bool kCanon, int... Ks>
+template <bool kCanon, uint32_t kStaticMask, int... Ks>
 __device__ __forceinline__ void update_all_k(std::integer_sequence<int, Ks...>, const Window &win, int run,
                                              uint32_t kmask, uint32_t kmask_run, int p, uint32_t *acc,
-                                             const uint32_t (&floor4)[8], uint32_t *s_seen) {
+                                             const KConsts &kc, uint32_t *s_seen, uint64_t minus_one) {
     uint32_t off_k = 0;
-    (update_one_k<Ks + 1, kCanon>(win, run, kmask, kmask_run, p, acc, off_k, floor4, s_seen), ...);
+    (update_one_k<Ks + 1, kCanon, kStaticMask>(win, run, kmask, kmask_run, p, acc, off_k, kc, s_seen, minus_one), ...);
 }
 
-template <bool kCanon>
-__global__ void __launch_bounds__(kSketchThreads) sketch_allk_kernel(SketchArgs a) {
+template <bool kCanon, uint32_t kStaticMask, int kThreads>
+__global__ void __launch_bounds__(kThreads, min_ctas_for(kThreads)) sketch_allk_kernel(SketchArgs a) {
     extern __shared__ uint32_t s_seen[];  // presence bitmaps, only allocated when a k <= 9 is requested
-    const bool small_k = (a.kmask_run & kSmallKMask) != 0u;
+    const bool small_k = ((kStaticMask ? kStaticMask : a.kmask_run) & kSmallKMask) != 0u;
     if (small_k) {
-        for (uint32_t i = threadIdx.x; i < kBitmapWords; i += kSketchThreads) s_seen[i] = 0u;
+        for (uint32_t i = threadIdx.x; i < kBitmapWords; i += kThreads) s_seen[i] = 0u;
         __syncthreads();
     }
-    // per-k floors (indexed by k-1), four to a register
-    uint32_t floor4[8];
-    {
-        const uint4 f0 = __ldg(reinterpret_cast<const uint4 *>(a.hdr->floor));
-        const uint4 f1 = __ldg(reinterpret_cast<const uint4 *>(a.hdr->floor) + 1);
-        floor4[0] = f0.x; floor4[1] = f0.y; floor4[2] = f0.z; floor4[3] = f0.w;
-        floor4[4] = f1.x; floor4[5] = f1.y; floor4[6] = f1.z; floor4[7] = f1.w;
+    // per-k floors (indexed by k-1) and the remainder thresholds derived from them
+    __shared__ KConsts kc;
+    if (threadIdx.x < 32) {
+        const uint32_t f = a.hdr->floor[threadIdx.x];
+        kc.floor[threadIdx.x] = f;
+        kc.thresh[threadIdx.x] = f >= 32u ? 0u : 0xffffffffu >> f;
     }
+    __syncthreads();
+    const uint64_t minus_one = ~0ull;   // (ptxas splits the addend off the IMAD.WIDE whether or not it can see its value)
     uint64_t sym_begin = a.sym_begin, sym_end = a.sym_end;
-    if (a.state) {
-        sym_begin = a.state->prev_nsym;
-        sym_end = a.state->nsym;
+    if (a.state) {   // the range of the last pack call; a.sym_begin / a.sym_end select a sub-range of it, relative to its start
+        const uint64_t first = a.state->prev_nsym, last = a.state->nsym;
+        sym_begin = first + a.sym_begin < last ? first + a.sym_begin : last;
+        sym_end = a.sym_end < last - first ? first + a.sym_end : last;
     }
 
 #pragma unroll 1
     for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        const uint64_t w = (sym_begin >> 4) + (uint64_t)tile * kSketchThreads + threadIdx.x;
+        const uint64_t w = (sym_begin >> 4) + (uint64_t)tile * kThreads + threadIdx.x;
         const uint64_t s0 = w << 4;
-        if ((uint64_t)((sym_begin >> 4) + (uint64_t)tile * kSketchThreads) << 4 >= sym_end) break;  // CTA-uniform
+        if ((uint64_t)((sym_begin >> 4) + (uint64_t)tile * kThreads) << 4 >= sym_end) break;  // CTA-uniform
         const bool in_range = s0 < sym_end;   // lanes past the end stay in the loop, predicated off
 
         const uint32_t w0 = in_range ? __ldg(a.codes + w) : 0u;
@@ -235,8 +298,8 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_allk_kernel(SketchArgs 
             int run = all_valid ? 32 : valid_run(invalid_window(i0, i1, sm_base + (uint32_t)j));
             if (j < j_lo || j >= j_hi) run = 0;
             if (!__any_sync(0xffffffffu, run != 0)) continue;  // warp-uniform
-            update_all_k<kCanon>(std::make_integer_sequence<int, 32>{}, win, run, a.kmask, a.kmask_run, a.p, a.acc,
-                                 floor4, s_seen);
+            update_all_k<kCanon, kStaticMask>(std::make_integer_sequence<int, 32>{}, win, run, a.kmask, a.kmask_run, a.p,
+                                              a.acc, kc, s_seen, minus_one);
         }
     }
 }
@@ -306,16 +369,50 @@ finalize_kernel(const uint32_t *__restrict__ acc, int p, uint8_t *__restrict__ r
 // ---- host side ----------------------------------------------------------------------------------
 int g_k_per_pass = 0;  // tuning knob, see dd_set_option("sketch_k_per_pass", n)
 
-// SM count x resident CTAs per SM for the persistent (small-k) launch, cached per variant.
-static unsigned persistent_grid(bool canon, size_t smem) {
-    static unsigned cached[2] = {0, 0};
-    unsigned &g = cached[canon ? 1 : 0];
+// The k sets that get their own instantiation (no per-k mask tests, constant table slots): the sweeps
+// DandD actually runs -- config 2 (10..32), `--ksweep` default (2..32), the store's all-k prefetch
+// (1..32).  Anything else takes the generic kernel.
+constexpr uint32_t kMask10to32 = 0xFFFFFE00u, kMask2to32 = 0xFFFFFFFEu, kMask1to32 = 0xFFFFFFFFu;
+
+using SketchKernel = void (*)(SketchArgs);
+struct SketchVariant {
+    SketchKernel fn;
+    int threads;
+    int id;   // index into the occupancy cache
+};
+static SketchVariant pick_kernel(bool canon, uint32_t kmask, uint32_t kmask_run) {
+    int v = 0;
+    if (kmask == kmask_run) v = kmask == kMask10to32 ? 1 : kmask == kMask2to32 ? 2 : kmask == kMask1to32 ? 3 : 0;
+    const bool small_k = (kmask_run & kSmallKMask) != 0u;
+    if (v == 0 && small_k) v = 4;   // generic mask with a small k: the wide persistent CTA
+    const int id = 2 * v + (canon ? 1 : 0);
+    switch (id) {
+        case 0: return {sketch_allk_kernel<false, 0u, kThreadsPlain>, kThreadsPlain, id};
+        case 1: return {sketch_allk_kernel<true, 0u, kThreadsPlain>, kThreadsPlain, id};
+        case 2: return {sketch_allk_kernel<false, kMask10to32, kThreadsPlain>, kThreadsPlain, id};
+        case 3: return {sketch_allk_kernel<true, kMask10to32, kThreadsPlain>, kThreadsPlain, id};
+        case 4: return {sketch_allk_kernel<false, kMask2to32, kThreadsSmallK>, kThreadsSmallK, id};
+        case 5: return {sketch_allk_kernel<true, kMask2to32, kThreadsSmallK>, kThreadsSmallK, id};
+        case 6: return {sketch_allk_kernel<false, kMask1to32, kThreadsSmallK>, kThreadsSmallK, id};
+        case 7: return {sketch_allk_kernel<true, kMask1to32, kThreadsSmallK>, kThreadsSmallK, id};
+        case 8: return {sketch_allk_kernel<false, 0u, kThreadsSmallK>, kThreadsSmallK, id};
+        default: return {sketch_allk_kernel<true, 0u, kThreadsSmallK>, kThreadsSmallK, id};
+    }
+}
+
+// SM count x resident CTAs per SM for the persistent (small-k) launch, cached per (device, variant).
+static unsigned persistent_grid(const SketchVariant &v, size_t smem) {
+    constexpr int kMaxDev = 64;
+    static unsigned cached[kMaxDev][10] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    unsigned local = 0;
+    unsigned &g = (dev >= 0 && dev < kMaxDev) ? cached[dev][v.id] : local;
     if (g == 0) {
-        int dev = 0, sms = 148, per_sm = 1;
-        cudaGetDevice(&dev);
+        int sms = 148, per_sm = 1;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (canon) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_allk_kernel<true>, kSketchThreads, smem);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_allk_kernel<false>, kSketchThreads, smem);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, v.threads, smem);
         g = (unsigned)(sms * (per_sm > 0 ? per_sm : 1));
     }
     return g;
@@ -346,13 +443,19 @@ cudaError_t sketch_update(const uint32_t *d_codes, const uint32_t *d_invalid, co
     a.p = p;
     a.acc = ws_acc(d_ws);
     a.hdr = ws_hdr(d_ws);
-    const size_t nsym = d_state ? max_new_symbols : (size_t)(sym_end - sym_begin);
+    if (d_state && sym_end <= sym_begin) {   // state-relative range not given: the whole last pack call
+        a.sym_begin = 0;
+        a.sym_end = ~0ull;
+    }
+    size_t nsym = d_state ? max_new_symbols : (size_t)(sym_end - sym_begin);
+    if (d_state && a.sym_end != ~0ull) {      // grid sized for the sub-range only
+        const uint64_t hi = a.sym_end < (uint64_t)max_new_symbols ? a.sym_end : (uint64_t)max_new_symbols;
+        nsym = hi > a.sym_begin ? (size_t)(hi - a.sym_begin) : 0;
+    }
     if (nsym == 0) return cudaSuccess;
     // +2 words: the range may start and end in the middle of a word
     const size_t nwords = (nsym + 15) / 16 + 2;
-    const size_t ntiles = (nwords + kSketchThreads - 1) / kSketchThreads;
-    if (ntiles > 0xffffffffull) return cudaErrorInvalidValue;
-    a.ntiles = (uint32_t)ntiles;
+
     // Optionally split the k set over several launches so that the accumulators touched by one
     // launch (2^(p+1) bytes per k) stay L2-resident; 0 = all k in one launch.
     const int per_pass = g_k_per_pass > 0 ? g_k_per_pass : 32;
@@ -369,15 +472,50 @@ cudaError_t sketch_update(const uint32_t *d_codes, const uint32_t *d_invalid, co
         // the bitmaps in dynamic shared memory; otherwise one CTA per tile and no shared memory.
         const bool small_k = (run & kSmallKMask) != 0u;
         const size_t smem = small_k ? kBitmapWords * sizeof(uint32_t) : 0;
+        const SketchVariant v = pick_kernel(canon != 0, kmask, run);
+        const size_t ntiles = (nwords + v.threads - 1) / v.threads;
+        if (ntiles > 0xffffffffull) return cudaErrorInvalidValue;
+        a.ntiles = (uint32_t)ntiles;
         unsigned grid = (unsigned)ntiles;
         if (small_k) {
-            const unsigned resident = persistent_grid(canon != 0, smem);
+            const unsigned resident = persistent_grid(v, smem);
             if (grid > resident) grid = resident;
         }
-        if (canon) sketch_allk_kernel<true><<<grid, kSketchThreads, smem, stream>>>(a);
-        else sketch_allk_kernel<false><<<grid, kSketchThreads, smem, stream>>>(a);
+        v.fn<<<grid, v.threads, smem, stream>>>(a);
     }
     return cudaGetLastError();
+}
+
+// Update + floor schedule.  The per-k floor (min register) rises by one each time the number of
+// k-mers seen doubles, first reaching 1 at about 14 x 2^p k-mers (every register occupied), and an
+// update whose rank does not exceed it is dropped before the reduction.  So the range is cut at
+// 16 x 2^p x 2^i symbols (i = 0, 1, ...) counted from the start of the sketch and the floor is
+// refreshed at each cut: a handful of 10 us refreshes turn most of a long genome's reductions into
+// one compare.  `seen_before` = symbols sketched into this workspace by earlier calls (host-side
+// count; an estimate only shifts the cuts, never the result).
+cudaError_t sketch_update_sched(const uint32_t *d_codes, const uint32_t *d_invalid, const dd_pack_state *d_state,
+                                uint64_t sym_begin, uint64_t sym_end, size_t max_new_symbols, uint64_t seen_before,
+                                uint32_t kmask, int p, int canon, void *d_ws, cudaStream_t stream) {
+    const uint64_t total = d_state ? (uint64_t)max_new_symbols : sym_end - sym_begin;
+    const uint64_t origin = d_state ? 0 : sym_begin;   // state mode: ranges are relative to the pack call's first symbol
+    uint64_t pos = 0;                       // symbols of this call already issued
+    uint64_t cut = (uint64_t)16 << p;       // next cut, counted from the start of the sketch
+    while (cut <= seen_before) cut <<= 1;
+    cudaError_t e;
+    while (pos < total) {
+        const uint64_t to_cut = cut - (seen_before + pos);
+        const bool refresh = to_cut <= total - pos;
+        const uint64_t upto = refresh ? pos + to_cut : total;
+        if ((e = sketch_update(d_codes, d_invalid, d_state, origin + pos, origin + upto, max_new_symbols, kmask, p, canon, d_ws,
+                               stream)) != cudaSuccess)
+            return e;
+        pos = upto;
+        if (refresh) {
+            if ((e = sketch_refresh_floor(d_ws, kmask, p, stream)) != cudaSuccess) return e;
+            cut <<= 1;
+        }
+    }
+    return cudaSuccess;
 }
 
 cudaError_t sketch_refresh_floor(void *d_ws, uint32_t kmask, int p, cudaStream_t stream) {

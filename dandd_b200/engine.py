@@ -223,8 +223,11 @@ class Engine:
         # the pack state says [prev_nsym, nsym); for a whole-stream sketch rewind prev_nsym to 0
         state = seq.state.clone()
         state.view(torch.int64)[1] = 0
-        check(self.lib.dd_sketch_update(seq.codes.data_ptr(), seq.invalid.data_ptr(), state.data_ptr(), seq.text_bytes,
-                                        kmask, p, int(canon), ws.data_ptr(), ws.numel(), st), "dd_sketch_update")
+        # (dd_sketch_update_sched == dd_sketch_update for streams shorter than 16 x 2^p symbols; longer ones
+        # are cut at the floor schedule's boundaries with a refresh at each)
+        check(self.lib.dd_sketch_update_sched(seq.codes.data_ptr(), seq.invalid.data_ptr(), state.data_ptr(), 0, 0,
+                                              seq.text_bytes, 0, kmask, p, int(canon), ws.data_ptr(), ws.numel(), st),
+              "dd_sketch_update_sched")
         self._keep = state  # keep alive until the stream has consumed it
 
     def sketch_fasta_host(self, text: bytes, ks: Sequence[int], p: int = 20, canon: bool = True,

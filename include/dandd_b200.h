@@ -144,6 +144,15 @@ DD_API int dd_sketch_update(const uint32_t *d_codes, const uint32_t *d_invalid, 
                      dd_stream stream);
 DD_API int dd_sketch_update_range(const uint32_t *d_codes, const uint32_t *d_invalid, uint64_t sym_begin, uint64_t sym_end,
                            uint32_t kmask, int p, int canon, void *d_ws, size_t ws_bytes, dd_stream stream);
+/* dd_sketch_update plus the floor schedule: the per-k lower bound min(register) rises by one every
+ * time the number of k-mers seen doubles (first at about 14 x 2^p), and an update that cannot exceed
+ * it is dropped before the reduction.  This entry cuts the range at 16 x 2^p x 2^i symbols counted
+ * from the start of the sketch and refreshes the bound at each cut.  seen_before = symbols sketched
+ * into this workspace by earlier calls (a host-side count; an estimate only moves the cuts).  With
+ * d_state != NULL the range is the last dd_pack_fasta call's and [sym_begin, sym_end) is ignored. */
+DD_API int dd_sketch_update_sched(const uint32_t *d_codes, const uint32_t *d_invalid, const dd_pack_state *d_state,
+                           uint64_t sym_begin, uint64_t sym_end, size_t max_new_symbols, uint64_t seen_before,
+                           uint32_t kmask, int p, int canon, void *d_ws, size_t ws_bytes, dd_stream stream);
 /* Recompute the per-k lower bound min(register) used to skip no-op updates (long genomes). */
 DD_API int dd_sketch_refresh_floor(void *d_ws, size_t ws_bytes, uint32_t kmask, int p, dd_stream stream);
 DD_API int dd_sketch_end(void *d_ws, size_t ws_bytes, int nk, int p, uint8_t *d_regs, uint32_t *d_hist /*[nk][64] or NULL*/,

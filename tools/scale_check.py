@@ -73,12 +73,13 @@ def main():
         seq, t_pack = timed(lambda: eng.pack(text, start=0))
         nsym = seq.nsym
         eng.sketch(seq, [21], p=p)                                       # warm-up
-        (r_floor, c_floor), t_floor = timed(lambda: eng.sketch(seq, ks, p=p, floor_every=int(args.chunk)))
+        # default path: dd_sketch_update_sched (floor refreshed at 16 x 2^p x 2^i symbols)
+        (r_floor, c_floor), t_floor = timed(lambda: eng.sketch(seq, ks, p=p))
         row = {"bases": size, "text_bytes": int(text.numel()), "symbols": nsym, "pack_ms": t_pack,
                "sketch_floor_ms": t_floor, "gbp_s_floor": size / t_floor / 1e6, "chunk": int(args.chunk),
                "pack_gb_s": text.numel() / t_pack / 1e6}
         if size <= 1.2e9:
-            (r_plain, _), t_plain = timed(lambda: eng.sketch(seq, ks, p=p))
+            (r_plain, _), t_plain = timed(lambda: eng.sketch(seq, ks, p=p, ranges=[(0, nsym)]))   # no floor filter at all
             row.update(sketch_plain_ms=t_plain, gbp_s_plain=size / t_plain / 1e6,
                        floor_equals_plain=bool((r_plain == r_floor).all()))
             del r_plain
@@ -92,7 +93,7 @@ def main():
         if args.per_k:
             row["per_k_ms"] = {}
             for k in ks:
-                _, t = timed(lambda: eng.sketch(seq, [k], p=p, floor_every=int(args.chunk)))
+                _, t = timed(lambda: eng.sketch(seq, [k], p=p))
                 row["per_k_ms"][k] = round(t, 2)
         cards = c_floor.cpu().numpy()
         deltas = cards / np.array(ks)
