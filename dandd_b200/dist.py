@@ -39,17 +39,7 @@ def world() -> (int, int):
     return 0, 1
 
 
-def shard_by_size(sizes: Sequence[int], nranks: int) -> List[List[int]]:
-    """Greedy longest-processing-time assignment of genomes (by byte size) to ranks; deterministic,
-    every rank computes the same table.  Returns the genome indices of each rank, ascending."""
-    order = sorted(range(len(sizes)), key=lambda i: (-int(sizes[i]), i))
-    load = [0] * nranks
-    out = [[] for _ in range(nranks)]
-    for i in order:
-        r = min(range(nranks), key=lambda j: (load[j], j))
-        out[r].append(i)
-        load[r] += int(sizes[i])
-    return [sorted(x) for x in out]
+from .shard import shard_by_size  # noqa: E402,F401  (re-exported: the table every rank computes)
 
 
 def union_over_ranks(regs: torch.Tensor) -> torch.Tensor:

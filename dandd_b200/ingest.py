@@ -5,7 +5,8 @@ by the time a leaf is sketched its bytes and its name are already there, and fil
 prepared while the GPU works on file i.
 
     prefetch(paths)          start background work for these files (idempotent)
-    fasta_bytes(path)        decompressed bytes (waits for the worker if needed; drops the cache entry)
+    fasta_bytes(path)        decompressed bytes (waits for the READ only; drops the cache entry)
+    drop(path)               release a prefetched file whose bytes are not needed after all
     digest(path)             blake2b hex digest of the FILE bytes (what the reference hashes, compressed
                              or not: lib/sketch_classes.py:12-18)
 """
@@ -90,12 +91,40 @@ def gunzip(raw: bytes) -> bytes:
     return b"".join(j.result() for j in jobs)
 
 
+def _read(path):
+    from . import timing
+    with timing.span("prefetch_read"):
+        with open(path, "rb") as fh:
+            return fh.read()
+
+
+def _hash(raw_job):
+    from . import timing
+    raw = raw_job.result()
+    with timing.span("prefetch_blake2b"):
+        return hashlib.blake2b(raw).hexdigest()
+
+
+def _text(raw_job):
+    raw = raw_job.result()
+    return gunzip(raw) if raw[:2] == b"\x1f\x8b" else raw
+
+
 def _load(path):
-    with open(path, "rb") as fh:
-        raw = fh.read()
-    dig = hashlib.blake2b(raw).hexdigest()
-    text = gunzip(raw) if raw[:2] == b"\x1f\x8b" else raw
-    return text, dig
+    """(decompressed text, blake2b hex digest of the file bytes), in the calling thread."""
+    raw = _read(path)
+    return (gunzip(raw) if raw[:2] == b"\x1f\x8b" else raw), hashlib.blake2b(raw).hexdigest()
+
+
+class _Job:
+    """Background work for one file: the text becomes available as soon as the file is read (and
+    inflated), the digest -- the slow part, one core at ~0.6-1 GB/s -- on its own thread, so a sketch
+    can start before the name is known."""
+
+    def __init__(self, path, pool):
+        raw = pool.submit(_read, path)
+        self.text = pool.submit(_text, raw)
+        self.digest = pool.submit(_hash, raw)
 
 
 def prefetch(paths: Iterable[str]) -> None:
@@ -108,25 +137,60 @@ def prefetch(paths: Iterable[str]) -> None:
             if _cached + size > _MAX_CACHED_BYTES:
                 break                         # the rest is loaded on demand
             _cached += size
-            _jobs[p] = _pool_get().submit(_load, p)
+            _jobs[p] = _Job(p, _pool_get())
 
 
 def _take(path):
+    """(text, digest-or-None).  A prefetched file gives its text as soon as it is read; its digest is
+    remembered as a future so that digest() can wait for it separately."""
     global _cached
     with _lock:
         job = _jobs.pop(path, None)
     if job is None:
         return _load(path)
-    text, dig = job.result()
+    text = job.text.result()
     with _lock:
         _cached = max(0, _cached - os.path.getsize(path))
-    return text, dig
+        _digest_jobs[_key(path)] = job.digest
+    return text, None
+
+
+_digest_jobs: Dict[tuple, Future] = {}
+
+
+def is_prefetched(path: str) -> bool:
+    with _lock:
+        return path in _jobs
 
 
 def fasta_bytes(path: str) -> bytes:
     text, dig = _take(path)
-    _digests[_key(path)] = dig
+    if dig is not None:
+        _digests[_key(path)] = dig
     return text
+
+
+def set_digest(path: str, hexdigest: str) -> None:
+    """Record a digest computed elsewhere (the streaming sketch hashes the chunks it reads)."""
+    _digests[_key(path)] = hexdigest
+
+
+def drop(path: str) -> None:
+    """Forget the cached bytes of a prefetched file that turned out not to be needed (its sketches
+    were already in the database); the digest, once computed, is kept."""
+    global _cached
+    with _lock:
+        job = _jobs.pop(path, None)
+        if job is not None:
+            _cached = max(0, _cached - os.path.getsize(path))
+            _digest_jobs[_key(path)] = job.digest
+
+
+def drop_all() -> None:
+    with _lock:
+        paths = list(_jobs)
+    for p in paths:
+        drop(p)
 
 
 def digest(path: str) -> str:
@@ -135,8 +199,12 @@ def digest(path: str) -> str:
     if d is None:
         with _lock:
             job = _jobs.get(path)
-        if job is not None:
-            d = job.result()[1]               # keep the bytes cached for the sketch that follows
+            fut = job.digest if job is not None else _digest_jobs.get(k)
+        if fut is not None:
+            from . import timing
+            with timing.span("digest_wait"):
+                d = fut.result()              # (the text stays cached for the sketch that follows)
+            _digest_jobs.pop(k, None)
         else:
             h = hashlib.blake2b()
             with open(path, "rb") as fh:

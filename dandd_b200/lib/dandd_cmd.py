@@ -123,9 +123,13 @@ def tree_command(args):
         print("ERROR: You must provide either a datadirectory or a fasta file list!")
         sys.exit(1)
     _select_device(args)
-    rank, world = _init_ranks()
     if not args.sketchdir:
         args.sketchdir = os.path.join(args.outdir, "sketchdb")
+    from dandd_b200 import timing
+    _early_prefetch(args)       # file reads + blake2b start now, under the ~4 s of torch import / CUDA start-up
+    timing.mark("prefetch_started")
+    with timing.span("init_ranks"):
+        rank, world = _init_ranks()
     os.makedirs(args.sketchdir, exist_ok=True)
     os.makedirs(args.outdir, exist_ok=True)
     tool = "dashing"
@@ -134,20 +138,50 @@ def tree_command(args):
     if args.ksweep:
         args.ksweep = (int(args.mink), int(args.maxk))
     try:
+        timing.mark("tree_start")
         dtree = huffman_dandd.create_delta_tree(
             tag=args.tag, genomedir=args.genomedir, sketchdir=args.sketchdir, kstart=args.kstart, nchildren=args.nchildren,
             registers=args.registers, flist_loc=args.flist_loc, canonicalize=args.canonicalize, tool=tool, debug=args.debug,
             nthreads=int(args.nthreads), safety=args.safety, fast=args.fast, verbose=args.verbose, ksweep=args.ksweep,
             lowmem=args.lowmem)
+        timing.mark("tree_built")
         if dtree is not None:   # rank 0 (or the only process)
-            dtree.save(fileprefix=dtree.make_prefix(outdir=args.outdir, tag=args.tag, label=args.label), fast=args.fast)
+            with timing.span("save_outputs"):
+                dtree.save(fileprefix=dtree.make_prefix(outdir=args.outdir, tag=args.tag, label=args.label), fast=args.fast)
     finally:
         if world > 1:           # release the ranks that serve exact-count requests, also when rank 0 fails
             from dandd_b200.store import get_store
             workers = getattr(get_store(), "exact_workers", None)
             if workers is not None:
                 workers.stop()
-    _finish_ranks(world)
+    with timing.span("finish_ranks"):
+        _finish_ranks(world)
+
+
+def _early_prefetch(args) -> None:
+    """Start reading (and hashing) this process's share of the FASTAs in background threads before
+    anything imports torch.  Only files the sketch database has never seen: a cached re-run reads
+    nothing, like the reference (its fastahex pickle short-circuits the hash)."""
+    from dandd_b200 import ingest
+    from dandd_b200.shard import shard_by_size
+    try:
+        fastas = huffman_dandd.list_fastas(args.genomedir, args.flist_loc)
+    except (OSError, ValueError):
+        return                  # create_delta_tree reports the problem
+    known = set()
+    try:
+        with open(os.path.join(args.sketchdir, "dandd_fastahex.pickle"), "rb") as fh:
+            known = set(pickle.load(fh))
+    except Exception:  # noqa: BLE001 -- no database yet (or unreadable): everything is new
+        pass
+    fastas = [f for f in fastas if os.path.isfile(f)]
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world > 1 and len(fastas) >= world and not args.exact:
+        owners = shard_by_size([os.path.getsize(f) for f in fastas], world)
+        fastas = [fastas[i] for i in owners[rank]]
+    elif world > 1 and rank > 0:
+        return                  # split-genome and exact modes: rank 0 hashes, every rank reads on demand
+    ingest.prefetch([f for f in fastas if os.path.basename(f) not in known])
 
 
 def _init_ranks():

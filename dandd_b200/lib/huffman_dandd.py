@@ -28,7 +28,7 @@ from typing import Dict, List, Set, Tuple
 from sketch_classes import DashSketchObj, KMCSketchObj, SketchFilePath, SketchObj, ensure_dir  # noqa: F401
 from species_specifics import SpeciesSpecifics
 
-from dandd_b200 import ingest
+from dandd_b200 import ingest, timing
 
 
 def get_store():
@@ -702,12 +702,13 @@ def presketch_leaves_sharded(fastas, speciesinfo, experiment, kstart, halfwidth=
         return rank
     owners = dd_dist.shard_by_size([os.path.getsize(f) for f in fastas], world)
     mine = [fastas[i] for i in owners[rank]]
-    ingest.prefetch(mine)
+    ingest.prefetch([f for f in mine if os.path.basename(f) not in speciesinfo.fastahex])   # (usually started already: dandd_cmd._early_prefetch)
     found = {}
     scratch = dict(experiment, baseset=set())   # pre-sketching must not leak names into the tree's own bookkeeping
     for path in mine:
         leaf = DeltaTreeNode(node_title=path, children=[], speciesinfo=speciesinfo, experiment=scratch, progeny=[])
-        leaf.ksweep_update_node(mink=lo, maxk=hi)
+        with timing.span("presketch_leaves"):
+            leaf.ksweep_update_node(mink=lo, maxk=hi)
         template = leaf.ksketches[0].sfp.full if leaf.ksketches[0] is not None else None
         for k in range(lo, hi + 1):
             if template:
@@ -715,7 +716,8 @@ def presketch_leaves_sharded(fastas, speciesinfo, experiment, kstart, halfwidth=
                 if key in speciesinfo.cardkey:
                     found[key] = speciesinfo.cardkey[key]
     bucket = [None] * world
-    tdist.all_gather_object(bucket, (found, {k: v for k, v in speciesinfo.fastahex.items()}))
+    with timing.span("exchange_cards"):      # also where a fast rank waits for the slowest one
+        tdist.all_gather_object(bucket, (found, {k: v for k, v in speciesinfo.fastahex.items()}))
     for cards, hexes in bucket:
         speciesinfo.cardkey.update(cards)
         for key, value in hexes.items():
@@ -754,6 +756,20 @@ def _presketch_split(fastas, speciesinfo, experiment, lo, hi, rank, world) -> No
                     speciesinfo.cardkey[paths[k]] = card
 
 
+def list_fastas(genomedir, flist_loc) -> List[str]:
+    """The sorted FASTA list of a `tree` run: the lines of --fastas, else every file of --datadir
+    (reference :858-868)."""
+    if flist_loc:
+        with open(flist_loc) as fh:
+            fastas = [line.strip() for line in fh]
+    elif genomedir and os.path.exists(genomedir):
+        fastas = [os.path.join(genomedir, n) for n in os.listdir(genomedir)]
+    else:
+        raise ValueError("no FASTA directory or list")
+    fastas.sort()
+    return fastas
+
+
 def create_delta_tree(tag: str, genomedir: str, sketchdir: str, kstart: int, nchildren=None, registers=0, flist_loc=None,
                       canonicalize=True, tool="dashing", debug=False, nthreads=0, safety=False, fast=False, verbose=False,
                       ksweep=None, lowmem=False):
@@ -775,11 +791,14 @@ def create_delta_tree(tag: str, genomedir: str, sketchdir: str, kstart: int, nch
     fastas.sort()
     if presketch_leaves_sharded(fastas, speciesinfo, experiment, kstart) > 0:
         return None           # ranks > 0 only contribute leaf sketches; rank 0 builds and saves the tree
-    ingest.prefetch(fastas)   # read / gunzip / blake2b in the background while the GPU works
+    # read / gunzip / blake2b in the background while the GPU works -- only files the database has never
+    # named (a cached re-run reads nothing; usually started already by dandd_cmd._early_prefetch)
+    ingest.prefetch([f for f in fastas if os.path.basename(f) not in speciesinfo.fastahex])
     if nchildren:
         dtree = DeltaTree(fasta_files=fastas, speciesinfo=speciesinfo, nchildren=nchildren, experiment=experiment)
     else:
         dtree = DeltaSpider(fasta_files=fastas, speciesinfo=speciesinfo, experiment=experiment)
     speciesinfo.save_cardkey(tool=tool, fast=fast)
     speciesinfo.save_references(fast=fast)
+    ingest.drop_all()         # prefetched bytes nobody asked for (their sketches were cached)
     return dtree

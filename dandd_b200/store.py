@@ -20,10 +20,11 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from . import hllfile, ingest
+from . import hllfile, ingest, timing
 from .engine import Engine, get_engine
 
 ALL_HLL_KS = tuple(range(1, 33))
+STREAM_MIN_BYTES = int(os.environ.get("DANDD_B200_STREAM_MIN", str(32 << 20)))   # larger FASTAs take the chunked pipeline
 
 
 def read_fasta_bytes(path: str) -> bytes:
@@ -51,6 +52,7 @@ class GpuSketchStore:
         self.pair_table = None   # cardinalities of every two-leaf union, filled by one batched K6 job (pair_unions)
         self.stats = {"leaf_passes": 0, "union_launches": 0, "files_written": 0, "files_read": 0, "exact_calls": 0}
         self.exact_workers = None   # set by start_exact_workers() for `--exact` under torchrun
+        self.stream_stats: List[dict] = []   # per streamed FASTA: stage times (read, blake2b, GPU span, wall)
 
     # ------------------------------------------------------------------ cache plumbing
     def _put(self, key: tuple, value, cost: int) -> None:
@@ -78,11 +80,12 @@ class GpuSketchStore:
         returned tensor stays valid for as long as the caller holds it, whatever the cache evicts."""
         t = self._get(("sketch", path))
         if t is None:
-            try:
-                regs, _p, _ = hllfile.read_hll(path)
-                t = torch.from_numpy(regs).to(self.engine.device)
-            except hllfile.StubSketch as stub:       # union marker: rebuild from its members
-                t = self.engine.union([self.registers(m) for m in stub.members])
+            with timing.span("read_sketch_files"):
+                try:
+                    regs, _p, _ = hllfile.read_hll(path)
+                    t = torch.from_numpy(regs).to(self.engine.device)
+                except hllfile.StubSketch as stub:       # union marker: rebuild from its members
+                    t = self.engine.union([self.registers(m) for m in stub.members])
             self.stats["files_read"] += 1
             self._remember(path, t)
         return t
@@ -94,11 +97,12 @@ class GpuSketchStore:
             self._bytes -= self._cost.pop(key)
 
     def _write(self, path: str, regs: torch.Tensor, p: int, card: float, leaf: bool, members=None) -> None:
-        os.makedirs(os.path.dirname(path), exist_ok=True)
-        if leaf or self.union_files == "full" or not members:
-            hllfile.write_hll(path, regs.cpu().numpy(), p, card, self.hll_compresslevel)
-        else:
-            hllfile.write_stub(path, p, card, members)
+        with timing.span("write_sketch_files"):
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            if leaf or self.union_files == "full" or not members:
+                hllfile.write_hll(path, regs.cpu().numpy(), p, card, self.hll_compresslevel)
+            else:
+                hllfile.write_stub(path, p, card, members)
         self.stats["files_written"] += 1
 
     # ------------------------------------------------------------------ dashing sketch
@@ -133,19 +137,26 @@ class GpuSketchStore:
         need = [int(k) for k in ks]
         if split is not None or ent is None or any(k not in ent["ks"] for k in need):
             run_ks = list(ALL_HLL_KS) if self.prefetch_all_k else sorted(set(need) | set(ent["ks"] if ent else ()))
-            text = read_fasta_bytes(fasta)
+            streamed = None
+            if split is None and os.path.getsize(fasta) >= STREAM_MIN_BYTES:
+                streamed = self._stream_leaf(fasta, run_ks, p, canon)
+            text = read_fasta_bytes(fasta) if streamed is None else None
             if split is not None:
                 from dandd_b200 import dist as dd_dist
                 run_ks = sorted(need)                      # identical on every rank, whatever each one has cached
                 if b"\n+" in text or text[:1] == b"+":     # FASTQ: records as kseq reads them, then split
                     text = self.engine.fastq_to_fasta(text)
                 text = dd_dist.split_fasta(text, split[1], only=split[0])[split[0]]
-            seq = self._pack_text(text)
-            regs, cards = self.engine.sketch(seq, run_ks, p=p, canon=canon)
-            if split is not None:
-                dd_dist.union_over_ranks(regs)
-                cards = self.engine.cards(regs, p)
-            ent = {"regs": regs, "cards": cards.cpu().numpy(), "ks": {k: i for i, k in enumerate(run_ks)}}
+            if streamed is not None:
+                regs, cards = streamed
+            else:
+                seq = self._pack_text(text)
+                regs, cards = self.engine.sketch(seq, run_ks, p=p, canon=canon)
+                if split is not None:
+                    dd_dist.union_over_ranks(regs)
+                    cards = self.engine.cards(regs, p)
+                cards = cards.cpu().numpy()
+            ent = {"regs": regs, "cards": cards, "ks": {k: i for i, k in enumerate(run_ks)}}
             self._put(key, ent, regs.numel())
             self.stats["leaf_passes"] += 1
         out = {}
@@ -157,6 +168,25 @@ class GpuSketchStore:
                 self._write(out_paths[k], ent["regs"][i], p, card, leaf=True)
             out[k] = card
         return out
+
+    def _stream_leaf(self, fasta, run_ks, p, canon):
+        """Large FASTA: disk (or the prefetched bytes) -> pinned ring -> H2D -> K1 -> K2 in 64 MiB chunks,
+        the blake2b name computed from the same chunks (dandd_b200/streaming.py).  None if the text is
+        FASTQ (the whole-file path then rewrites it first)."""
+        from . import streaming
+        from .engine import FastqInput
+        text = ingest.fasta_bytes(fasta) if ingest.is_prefetched(fasta) else None
+        try:
+            regs, cards, digest, stats = streaming.sketch_file(self.engine, fasta, run_ks, p, canon, text=text)
+        except FastqInput:
+            return None
+        if digest:
+            ingest.set_digest(fasta, digest)
+        self.stream_stats.append(stats)
+        for key in ("read_s", "blake2b_s", "inflate_s", "gpu_span_s", "wall_s"):
+            if key in stats:
+                timing.add("stream_" + key, stats[key])
+        return regs, cards
 
     # ------------------------------------------------------------------ dashing union (+ card)
     def union_sketches(self, members_by_k: Dict[int, List[str]], p: int, out_paths: Dict[int, str]) -> Dict[int, float]:
@@ -176,9 +206,10 @@ class GpuSketchStore:
         for i, row in enumerate(tensors):
             for j, t in enumerate(row):
                 ptrs[i, j] = t.data_ptr()
-        cards, unions = self.engine.union_sets(ptrs, p, final_only=True, materialize=True)
-        self.stats["union_launches"] += 1
-        cards = cards.cpu().numpy().reshape(len(ks))
+        with timing.span("union_gpu"):
+            cards, unions = self.engine.union_sets(ptrs, p, final_only=True, materialize=True)
+            self.stats["union_launches"] += 1
+            cards = cards.cpu().numpy().reshape(len(ks))
         for i, k in enumerate(ks):
             regs = unions[i, 0]
             self._remember(out_paths[k], regs)
@@ -330,7 +361,9 @@ def get_store():
         from dandd_b200 import _startup
         if _startup.TRIM_REQUESTED:          # command-line start-up trim, see _startup.py
             _startup.trim_torch_cuda_init()
-        _store = GpuSketchStore()
+        with timing.span("engine_start"):    # CUDA context + library load (torch itself was imported with this module)
+            _store = GpuSketchStore()
+        timing.mark("engine_ready")
     return _store
 
 

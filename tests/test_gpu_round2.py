@@ -314,3 +314,63 @@ def test_config5_every_pair_every_k(eng):
         exp = np.array(list(ex.map(oracle_pair, pairs)))
     assert got.shape == exp.shape == (780, 23)
     assert np.allclose(got, exp, rtol=CARD_RTOL, atol=0)
+
+
+# ------------------------------------------------------------------------------------- streaming
+def test_streamed_file_sketch_matches_oracle(eng, tmp_path):
+    """dandd_b200/streaming.py: disk -> pinned ring -> H2D -> K1 -> K2 in small chunks == the oracle on
+    the whole file, and the blake2b it computes from the chunks == hashlib on the file; plain, gzip
+    and prefetched-bytes sources; FASTQ is reported, not mis-sketched."""
+    import gzip
+    import hashlib
+    from dandd_b200 import streaming
+    from dandd_b200.engine import FastqInput
+    rng = np.random.default_rng(77)
+    txt = b"preamble junk\n" + adversarial_fasta(rng, n=3_000_000) + kseq_fasta(rng, n=500_000)
+    path = tmp_path / "big.fa"
+    path.write_bytes(txt)
+    sym = orc.fasta_symbols(txt)
+    ks = [9, 14, 21, 32]
+    want = [orc.hll_sketch(sym, k, 16) for k in ks]
+    for chunk in (1 << 20, 64 << 20):
+        regs, cards, digest, stats = streaming.sketch_file(eng, str(path), ks, p=16, chunk_bytes=chunk)
+        assert digest == hashlib.blake2b(txt).hexdigest()
+        assert stats["chunks"] == (-(-len(txt) // (1 << 20)) if chunk == 1 << 20 else 1)
+        for i in range(len(ks)):
+            assert np.array_equal(regs[i].cpu().numpy(), want[i]), (chunk, ks[i])
+            assert cards[i] == pytest.approx(orc.card(want[i], 16), rel=CARD_RTOL)
+    gz = tmp_path / "big.fa.gz"
+    gz.write_bytes(gzip.compress(txt, 1))
+    regs, cards, digest, _ = streaming.sketch_file(eng, str(gz), ks, p=16, chunk_bytes=1 << 20)
+    assert digest == hashlib.blake2b(gz.read_bytes()).hexdigest()
+    assert all(np.array_equal(regs[i].cpu().numpy(), want[i]) for i in range(len(ks)))
+    regs, cards, digest, _ = streaming.sketch_file(eng, str(path), ks, p=16, chunk_bytes=1 << 20, text=txt)
+    assert digest is None and all(np.array_equal(regs[i].cpu().numpy(), want[i]) for i in range(len(ks)))
+    fq = tmp_path / "reads.fq"
+    fq.write_bytes(kseq_fasta(rng, n=2_000_000, fastq=True))
+    with pytest.raises(FastqInput):
+        streaming.sketch_file(eng, str(fq), ks, p=16, chunk_bytes=1 << 20)
+
+
+def test_store_streams_large_fastas(eng, tmp_path, monkeypatch):
+    """GpuSketchStore.leaf_sketches takes the streaming path above the size threshold, registers the
+    digest for the naming layer, and falls back to the whole-file FASTQ detour when needed."""
+    import hashlib
+    from dandd_b200 import hllfile, ingest, store as store_mod
+    monkeypatch.setattr(store_mod, "STREAM_MIN_BYTES", 1 << 20)
+    rng = np.random.default_rng(78)
+    texts = {"a.fa": to_fasta([(b"a", random_bases(rng, 2_500_000))], width=80),
+             "q.fq": kseq_fasta(rng, n=1_500_000, fastq=True)}
+    st = store_mod.GpuSketchStore(engine=eng, prefetch_all_k=False)
+    for name, txt in texts.items():
+        path = tmp_path / name
+        path.write_bytes(txt)
+        out = {k: str(tmp_path / "db" / f"k{k}" / (name + ".hll")) for k in (12, 31)}
+        cards = st.leaf_sketches(str(path), [12, 31], 14, True, out)
+        sym = orc.fasta_symbols(txt)
+        for k in (12, 31):
+            want = orc.hll_sketch(sym, k, 14)
+            assert np.array_equal(hllfile.read_hll(out[k])[0], want), (name, k)
+            assert cards[k] == pytest.approx(orc.card(want, 14), rel=CARD_RTOL)
+        assert ingest.digest(str(path)) == hashlib.blake2b(txt).hexdigest()
+    assert len(st.stream_stats) == 1          # the FASTA streamed; the FASTQ took the detour

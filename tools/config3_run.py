@@ -26,28 +26,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from tools.scale_check import synth_fasta  # noqa: E402
-
-
-def mutate_text(text: torch.Tensor, rate: float, seed: int) -> torch.Tensor:
-    """Substitute `rate` of the sequence letters (never touches headers, newlines or N)."""
-    g = torch.Generator(device=text.device)
-    g.manual_seed(seed)
-    out = text.clone()
-    n = out.numel()
-    nsub = int(n * rate)
-    # one position per stride-sized window: distinct by construction (duplicates would race in the
-    # scatter below) and no sort kernel needed
-    stride = max(1, n // max(1, nsub))
-    nsub = n // stride
-    pos = torch.arange(nsub, device=text.device) * stride + torch.randint(0, stride, (nsub,), device=text.device, generator=g)
-    cur = out[pos]
-    up = cur & 0xDF
-    is_base = (up == 65) | (up == 67) | (up == 71) | (up == 84)
-    new = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=text.device)[
-        torch.randint(0, 4, (nsub,), device=text.device, generator=g)]
-    out[pos[is_base]] = new[is_base] | (cur[is_base] & 0x20)
-    return out
+from tools.synth import mutate_text, synth_fasta  # noqa: E402
 
 
 def main():
@@ -94,7 +73,7 @@ def main():
         t_mut += dt
         seq, dt = gpu_wall(lambda: eng.pack(text, start=0))
         t_pack += dt
-        (_, cards), dt = gpu_wall(lambda: eng.sketch(seq, ks, p=p, out=local_regs[j], floor_every=int(args.chunk)))
+        (_, cards), dt = gpu_wall(lambda: eng.sketch(seq, ks, p=p, out=local_regs[j]))
         t_sketch += dt
         local_cards[j] = cards
         del text, seq

@@ -17,30 +17,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-
-
-def synth_fasta(n_bases: int, n_records: int, seed: int, device) -> torch.Tensor:
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    lens = torch.full((n_records,), n_bases // n_records, dtype=torch.int64)
-    lens[-1] += n_bases - int(lens.sum())
-    pieces = []
-    for r, ln in enumerate(lens.tolist()):
-        ln80 = (ln // 80) * 80
-        c = torch.randint(0, 4, (ln80,), dtype=torch.uint8, device=device, generator=g)
-        b = 65 + 2 * (c == 1).to(torch.uint8) + 6 * (c == 2).to(torch.uint8) + 19 * (c == 3).to(torch.uint8)
-        del c
-        low = torch.randint(0, 2, (ln80,), dtype=torch.uint8, device=device, generator=g)
-        b |= low * 32
-        del low
-        nruns = max(1, ln80 // 100000)               # ~1 % of the bases in N runs of 1000
-        starts = torch.randint(0, max(1, ln80 - 1000), (nruns,), device=device, generator=g)
-        idx = (starts[:, None] + torch.arange(1000, device=device)[None, :]).reshape(-1)
-        b[idx] = 78
-        body = torch.cat([b.view(-1, 80), torch.full((ln80 // 80, 1), 10, dtype=torch.uint8, device=device)], dim=1).reshape(-1)
-        head = torch.tensor(list(f">chr{r + 1} synthetic length={ln80}\n".encode()), dtype=torch.uint8, device=device)
-        pieces += [head, body]
-    return torch.cat(pieces)
+from tools.synth import synth_fasta  # noqa: E402
 
 
 def timed(fn):
