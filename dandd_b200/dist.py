@@ -29,6 +29,9 @@ def init(backend: str = None) -> (int, int):
         kwargs = {}
         if backend == "nccl":
             kwargs["device_id"] = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+            # object collectives pick torch's CURRENT device; a rank that never touched its GPU (everything
+            # cached) would otherwise run them on device 0
+            torch.cuda.set_device(kwargs["device_id"])
         dist.init_process_group(backend, **kwargs)
     return rank, world
 
