@@ -14,6 +14,10 @@ job -- is an NCCL MAX all-reduce of the [23][2^20] register array, inside the ti
           memory, H2D copy and D2H of the cardinalities inside the timed region
   roofline / cpu_baseline : see DESIGN.md "Measurement"
 
+--config 3 switches the workload to BASELINE.json configs[2] (one 3.1 Gbp human-scale assembly per GPU,
+k = 2..32, all-gather of the registers, prefix unions of the identity ordering); the default stays
+config 2, the configuration that fits one GPU and that the metric is quoted on.
+
 --impl reference times the CPU path the reference drives (one single-threaded `dashing sketch`
 per (genome, k), floor(0.95*cores) at a time -- lib/huffman_dandd.py:217) using the oracle port,
 because neither Dashing nor GNU parallel exists here (see oracle/dandd_oracle.c header).
@@ -165,16 +169,19 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     threads = max(1, int(cores * 0.95))
-    texts = make_genomes(seed=2, n_genomes=1)
-    for _ in range(args.warmup):
-        cpu_sketch_sample(texts, KS[:min(len(KS), threads)], P, threads)
+    if args.config == 3:
+        return run_reference_config3(args, threads)
+    texts = make_genomes(seed=2, n_genomes=N_GENOMES)   # one whole step of leaf sketches: ~10-20 s of CPU work
+    for _ in range(min(args.warmup, 1)):
+        cpu_sketch_sample(texts[:1], KS[:min(len(KS), threads)], P, threads)
     secs = []
     for _ in range(args.steps):
         dt, bases = cpu_sketch_sample(texts, KS, P, threads)
         secs.append(dt)
     ms = 1e3 * sum(secs) / len(secs)
     value = bases / (ms / 1e3) / 1e9
-    sample = "1 genome x 5 Mbp x 23 k (k=10..32), p=20, one single-threaded oracle job per (genome,k)"
+    sample = (f"{N_GENOMES} genomes x 5 Mbp x 23 k (k=10..32), p=20, one single-threaded oracle job per (genome,k), "
+              f"{threads} in flight (leaf sketches + cardinalities only; the reference's union / card processes are not timed)")
     line = {"impl": "reference", "metric": "Gbp/s sketched (all k)", "value": value, "unit": "Gbp/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -207,6 +214,13 @@ def bind_to_gpu_numa_node(local_rank):
             bus = bus[4:]
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
         if node < 0:
+            # virtualised hosts hide the PCI NUMA node; NVML still knows which CPUs sit next to the GPU
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1} & os.sched_getaffinity(0)
+            if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+                os.sched_setaffinity(0, cpus)
+                return "nvml:%d-cpus" % len(cpus)
             return None
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
@@ -221,7 +235,17 @@ def bind_to_gpu_numa_node(local_rank):
         return None
 
 
+def _profile_json(name):
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as fh:
+            return json.load(fh)
+    except Exception:  # noqa: BLE001
+        return {}
+
+
 def run_ours(args):
+    if args.config == 3:
+        return run_ours_config3(args)
     import torch
     import torch.distributed as dist
     from dandd_b200 import build
@@ -383,7 +407,9 @@ def run_ours(args):
         breakdown()
         breakdown()
     sampler.active = True
+    launches0 = eng.lib.dd_kernel_launches()
     ms_step, res = timed(lambda: step_resident(time_k2=True), args.steps)
+    launches_timed = eng.lib.dd_kernel_launches() - launches0     # counted inside the library, not a formula
     sampler.active = False
     # K2's own duration: with several streams in flight the per-launch events above include time shared
     # with the other stream's kernels, so the roofline uses a serialized pass over the same 12
@@ -432,17 +458,18 @@ def run_ours(args):
     clocks = sampler.summary()
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     int_peak = 148 * 128 * sm_mhz * 1e6                                    # lane-instructions / s
-    instr_per_update = 46                                                  # SASS count, see DESIGN.md
+    sass = _profile_json("r02_k2_sass.json")
+    instr_per_update = float(sass.get("instr_per_update_k10_32", 43.0))   # counted from the committed SASS listing
     int_frac = (bases_per_launch * nk * instr_per_update / (k2_avg_ms / 1e3)) / int_peak
+    # what actually binds K2 at this size: one scattered 4-byte reduction per (base, k) into the L2-resident table
+    red = _profile_json("r02_red_ceiling.json")
+    red_rate = bases_per_launch * nk / (k2_avg_ms / 1e3) / 1e9            # G reductions / s
+    red_ceiling = red.get("ceiling_f16x2_64mib")
 
     cores = os.cpu_count() or 1
     threads = max(1, int(cores * 0.95))
-    cpu_dt, cpu_bases = cpu_sketch_sample(texts[:1], KS, P, threads)
+    cpu_dt, cpu_bases = cpu_sketch_sample(texts, KS, P, threads)           # the step's 12 genomes: ~10-20 s of CPU work
     cpu_value = cpu_bases / cpu_dt / 1e9
-
-    # per genome: pack_state_init + 3 pack kernels (count, scan_groups, write; one group at 5 MB) + sketch_allk + finalize; then 1 leaf MLE, to_planes + prefix_dedup + prefix_copy_rows +
-    # prefix_union_planes + MLE for the progressive unions, and at N>1 union_max + hist + MLE of the job union
-    launches_per_step = N_GENOMES * (1 + 3 + 1 + 1) + 1 + 5 + (3 if world > 1 else 0)
     line = {
         "metric": "Gbp/s sketched (all k)", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -453,7 +480,7 @@ def run_ours(args):
                 "host_numa_node": numa_node,   # N>1: each rank is bound to the cores of its GPU's NUMA node
                 "note": "dd_sketch_fasta_host_async per genome from pinned memory (%d files in flight on as many streams) + " % NS +
                         "progressive unions; every cardinality is copied back to the host, registers stay in HBM"},
-        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches": int(launches_timed),
         "clocks": clocks,
         "roofline": {"kernel": "sketch_allk_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
@@ -464,11 +491,15 @@ def run_ours(args):
                      "share_of_step": sum(k2_ms) / ms_step,
                      "launch_ms_overlapped": sum(k2_overlapped_ms) / len(k2_overlapped_ms),
                      "int32_issue": {"instr_per_update": instr_per_update, "updates_per_base": nk,
-                                     "frac_of_issue_peak": int_frac, "sm_mhz": sm_mhz},
+                                     "frac_of_issue_peak": int_frac, "sm_mhz": sm_mhz,
+                                     "source": "profiles/r02_k2_sass.json"},
+                     "red_rate": {"achieved_g_per_s": red_rate, "ceiling_g_per_s": red_ceiling,
+                                  "red_rate_frac": (red_rate / red_ceiling) if red_ceiling else None,
+                                  "source": "profiles/r02_red_ceiling.json (experiments/red_ceiling.cu on a B200 of this pool)"},
                      "note": "K2 is INT32-issue / L2-scattered-update bound, not HBM bound (SURVEY.md 8d); both fractions reported"},
         "cpu_baseline": {"value": cpu_value, "unit": "Gbp/s", "cores": threads, "kind": "port",
-                         "sample": "1 genome x 5 Mbp x 23 k, p=20, one single-threaded oracle job per (genome,k), "
-                                   f"{threads} in flight ({cpu_dt:.2f} s)"},
+                         "sample": f"{N_GENOMES} genomes x 5 Mbp x 23 k, p=20, one single-threaded oracle job per (genome,k), "
+                                   f"{threads} in flight ({cpu_dt:.2f} s wall; leaf sketches + cardinalities only)"},
     }
     emit(line)
     if world > 1:
@@ -481,6 +512,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
+                    help="BASELINE.json workload: 2 = 12 x 5 Mbp per GPU (default, the metric's configuration), "
+                         "3 = one 3.1 Gbp assembly per GPU, k = 2..32")
+    ap.add_argument("--bases", type=float, default=3.1e9, help="config 3: bases per genome")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":

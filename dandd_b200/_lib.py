@@ -30,6 +30,7 @@ _vp, _sz, _i, _u32, _u64, _i64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.
 SIGNATURES = {
     "dd_last_error": (C.c_char_p, []),
     "dd_abi_version": (_i, []),
+    "dd_kernel_launches": (C.c_ulonglong, []),
     "dd_init": (_i, [_i]),
     "dd_set_option": (_i, [C.c_char_p, C.c_long]),
     "dd_device_info": (_i, [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),

@@ -37,8 +37,13 @@ int popc(uint32_t x) { return __builtin_popcount(x); }
 
 }  // namespace
 
+namespace dd {
+unsigned long long g_kernel_launches = 0;
+}
+
 extern "C" {
 
+unsigned long long dd_kernel_launches(void) { return __atomic_load_n(&dd::g_kernel_launches, __ATOMIC_RELAXED); }
 const char *dd_last_error(void) { return g_err; }
 int dd_abi_version(void) { return DD_ABI_VERSION; }
 
@@ -553,7 +558,7 @@ static int sketch_fasta_host_impl(const uint8_t *h_text, size_t n_bytes, uint32_
     cleanup();
 #undef DD_TRY
     DD_CUDA(dd::sketch_end(w.sketch_ws, nk, p, d_regs, w.hist, w.cards, st), "sketch_end");
-    fastq_poison_kernel<<<1, 32, 0, st>>>(w.state, w.cards, nk);
+    DD_COUNT_LAUNCH(), fastq_poison_kernel<<<1, 32, 0, st>>>(w.state, w.cards, nk);
     DD_CUDA(cudaGetLastError(), "fastq_poison");
     DD_CUDA(cudaMemcpyAsync(h_cards, w.cards, (size_t)nk * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H cards");
     if (h_regs) DD_CUDA(cudaMemcpyAsync(h_regs, d_regs, (size_t)nk << p, cudaMemcpyDeviceToHost, st), "D2H regs");

@@ -246,7 +246,7 @@ cudaError_t card_hist(const uint8_t *d_regs, int nsk, int p, uint32_t *d_hist, c
     if (slices < 1) slices = 1;
     for (int s0 = 0; s0 < nsk; s0 += 65535) {  // gridDim.y limit
         const int cnt = nsk - s0 < 65535 ? nsk - s0 : 65535;
-        hist_kernel<<<dim3(slices, cnt), kPhThreads, 0, stream>>>(d_regs + (size_t)s0 * m, p,
+        DD_COUNT_LAUNCH(), hist_kernel<<<dim3(slices, cnt), kPhThreads, 0, stream>>>(d_regs + (size_t)s0 * m, p,
                                                                     d_hist + (size_t)s0 * DD_HIST_BINS);
     }
     return cudaGetLastError();
@@ -254,7 +254,7 @@ cudaError_t card_hist(const uint8_t *d_regs, int nsk, int p, uint32_t *d_hist, c
 
 cudaError_t mle_from_hist(const uint32_t *d_hist, int nsk, int p, double *d_cards, cudaStream_t stream) {
     if (nsk == 0) return cudaSuccess;
-    mle_kernel<<<(nsk + kMleWarps - 1) / kMleWarps, 32 * kMleWarps, 0, stream>>>(d_hist, nsk, p, d_cards);
+    DD_COUNT_LAUNCH(), mle_kernel<<<(nsk + kMleWarps - 1) / kMleWarps, 32 * kMleWarps, 0, stream>>>(d_hist, nsk, p, d_cards);
     return cudaGetLastError();
 }
 
@@ -263,7 +263,7 @@ cudaError_t union_max(const uint8_t *const *d_in, int n_in, size_t len, uint8_t 
     size_t blocks = (len / 16 + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    union_max_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_in, n_in, len, d_out);
+    DD_COUNT_LAUNCH(), union_max_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_in, n_in, len, d_out);
     return cudaGetLastError();
 }
 
@@ -277,7 +277,7 @@ cudaError_t prefix_union_hist(const uint8_t *d_regs, const int32_t *d_order, int
     if (rows == 0) return cudaSuccess;
     const size_t m = (size_t)1 << p;
     const unsigned slices = (unsigned)((m + kPfxSliceBytes - 1) / kPfxSliceBytes);
-    prefix_union_kernel<false><<<dim3((unsigned)n_ord, slices, (unsigned)nk), kPfxThreads, 0, stream>>>(
+    DD_COUNT_LAUNCH(), prefix_union_kernel<false><<<dim3((unsigned)n_ord, slices, (unsigned)nk), kPfxThreads, 0, stream>>>(
         d_regs, d_order, nullptr, n_steps, n_genomes, nk, p, final_only, d_hist, d_unions);
     return cudaGetLastError();
 }
@@ -294,7 +294,7 @@ cudaError_t union_sets_hist(const uint8_t *const *d_members, int n_sets, int n_s
     if (rows == 0) return cudaSuccess;
     const size_t m = (size_t)1 << p;
     const unsigned slices = (unsigned)((m + kPfxSliceBytes - 1) / kPfxSliceBytes);
-    prefix_union_kernel<true><<<dim3((unsigned)n_sets, slices, 1), kPfxThreads, 0, stream>>>(
+    DD_COUNT_LAUNCH(), prefix_union_kernel<true><<<dim3((unsigned)n_sets, slices, 1), kPfxThreads, 0, stream>>>(
         nullptr, nullptr, d_members, n_steps, 0, n_sets, p, final_only, d_hist, d_unions);
     return cudaGetLastError();
 }

@@ -192,14 +192,14 @@ cudaError_t exact_insert(const uint32_t *d_codes, const uint32_t *d_invalid, uin
     const size_t nwords = (size_t)((sym_end - sym_begin + 15) / 16 + 2);  // +2: the range need not start on a word boundary
     const unsigned grid = (unsigned)((nwords + kExactThreads - 1) / kExactThreads);
     if (k > 32)
-        exact_insert_wide_kernel<<<grid, kExactThreads, 0, stream>>>(d_codes, d_invalid, sym_begin, sym_end, k, canon,
+        DD_COUNT_LAUNCH(), exact_insert_wide_kernel<<<grid, kExactThreads, 0, stream>>>(d_codes, d_invalid, sym_begin, sym_end, k, canon,
                                                                     ex_hdr(d_ws), static_cast<ulonglong2 *>(ex_tab(d_ws)),
                                                                     capacity, shard_rank, shard_world);
     else if (k <= DD_EXACT_BITMAP_MAXK)
-        exact_insert_kernel<true><<<grid, kExactThreads, 0, stream>>>(d_codes, d_invalid, sym_begin, sym_end, k, canon,
+        DD_COUNT_LAUNCH(), exact_insert_kernel<true><<<grid, kExactThreads, 0, stream>>>(d_codes, d_invalid, sym_begin, sym_end, k, canon,
                                                                      ex_hdr(d_ws), ex_tab(d_ws), capacity, shard_rank, shard_world);
     else
-        exact_insert_kernel<false><<<grid, kExactThreads, 0, stream>>>(d_codes, d_invalid, sym_begin, sym_end, k,
+        DD_COUNT_LAUNCH(), exact_insert_kernel<false><<<grid, kExactThreads, 0, stream>>>(d_codes, d_invalid, sym_begin, sym_end, k,
                                                                       canon, ex_hdr(d_ws), ex_tab(d_ws), capacity, shard_rank,
                                                                       shard_world);
     return cudaGetLastError();
@@ -214,10 +214,10 @@ cudaError_t exact_count(void *d_ws, int k, uint64_t capacity, uint64_t *d_count,
         size_t blocks = (nwords + 256 * 8 - 1) / (256 * 8);
         if (blocks < 1) blocks = 1;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        bitmap_count_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const uint32_t *>(ex_tab(d_ws)), nwords,
+        DD_COUNT_LAUNCH(), bitmap_count_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const uint32_t *>(ex_tab(d_ws)), nwords,
                                                                  reinterpret_cast<unsigned long long *>(d_count));
     } else {
-        exact_publish_kernel<<<1, 1, 0, stream>>>(ex_hdr(d_ws), reinterpret_cast<unsigned long long *>(d_count));
+        DD_COUNT_LAUNCH(), exact_publish_kernel<<<1, 1, 0, stream>>>(ex_hdr(d_ws), reinterpret_cast<unsigned long long *>(d_count));
     }
     return cudaGetLastError();
 }

@@ -9,6 +9,11 @@
 
 namespace dd {
 
+// Every kernel launch of the library is counted (dd_kernel_launches(): bench.py reports the number of
+// launches inside its timed region as measured, not as a formula).
+extern unsigned long long g_kernel_launches;
+#define DD_COUNT_LAUNCH() ((void)__atomic_fetch_add(&dd::g_kernel_launches, 1ull, __ATOMIC_RELAXED))
+
 // ---- K1 (pack.cu)
 size_t pack_workspace_bytes(size_t chunk_bytes);
 cudaError_t pack_reset(uint32_t *d_codes, size_t codes_bytes, uint32_t *d_invalid, size_t invalid_bytes,

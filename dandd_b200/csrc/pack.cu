@@ -705,7 +705,7 @@ cudaError_t pack_reset(uint32_t *d_codes, size_t codes_bytes, uint32_t *d_invali
     cudaError_t e;
     if ((e = cudaMemsetAsync(d_codes, 0, codes_bytes, stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(d_invalid, 0, invalid_bytes, stream)) != cudaSuccess) return e;
-    pack_state_init_kernel<<<1, 1, 0, stream>>>(d_state);
+    DD_COUNT_LAUNCH(), pack_state_init_kernel<<<1, 1, 0, stream>>>(d_state);
     return cudaGetLastError();
 }
 
@@ -740,13 +740,13 @@ cudaError_t pack_fasta(const uint8_t *d_text, size_t n, uint32_t *d_codes, uint3
     }
     const unsigned ga = (unsigned)(nt < (size_t)grid_count ? nt : (size_t)grid_count);
     const unsigned gc = (unsigned)(nt < (size_t)grid_write ? nt : (size_t)grid_write);
-    pack_count_kernel<<<ga, kPackThreads, 2 * kTileBytes, stream>>>(d_text, n, nt, d_state, tile_xfer);
-    pack_scan_groups_kernel<<<(unsigned)ng, kGroupTiles, 0, stream>>>(tile_xfer, nt, group_agg, d_text, n, group_out, seg_base,
+    DD_COUNT_LAUNCH(), pack_count_kernel<<<ga, kPackThreads, 2 * kTileBytes, stream>>>(d_text, n, nt, d_state, tile_xfer);
+    DD_COUNT_LAUNCH(), pack_scan_groups_kernel<<<(unsigned)ng, kGroupTiles, 0, stream>>>(tile_xfer, nt, group_agg, d_text, n, group_out, seg_base,
                                                                       hdr, d_state, cap_symbols);
     if (ng > 1)
-        pack_scan_kernel<<<1, kScanThreads, 0, stream>>>(d_text, n, group_agg, ng, group_out, seg_base, hdr, d_state,
+        DD_COUNT_LAUNCH(), pack_scan_kernel<<<1, kScanThreads, 0, stream>>>(d_text, n, group_agg, ng, group_out, seg_base, hdr, d_state,
                                                         cap_symbols);
-    pack_write_kernel<<<gc, kPackThreads, kWriteSmem, stream>>>(d_text, n, nt, tile_xfer, group_out, seg_base, hdr, d_state,
+    DD_COUNT_LAUNCH(), pack_write_kernel<<<gc, kPackThreads, kWriteSmem, stream>>>(d_text, n, nt, tile_xfer, group_out, seg_base, hdr, d_state,
                                                                d_codes, d_invalid, cap_symbols);
     return cudaGetLastError();
 }
@@ -758,7 +758,7 @@ cudaError_t pack_polyt_sentinel(const uint32_t *d_codes, uint32_t *d_invalid, co
     const size_t nsym = d_state ? max_symbols : (size_t)(sym_end - sym_begin);
     if (nsym == 0) return cudaSuccess;
     const size_t nwords = (nsym + 15) / 16 + 2;   // the range may start and end inside a word
-    pack_polyt_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, stream>>>(d_codes, d_invalid, d_state, sym_begin, sym_end);
+    DD_COUNT_LAUNCH(), pack_polyt_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, stream>>>(d_codes, d_invalid, d_state, sym_begin, sym_end);
     return cudaGetLastError();
 }
 

@@ -275,7 +275,7 @@ cudaError_t to_planes(const uint8_t *d_regs, int64_t n_sketches, int p, uint32_t
     if (total_groups == 0) return cudaSuccess;
     size_t blocks = (total_groups + 255) / 256;
     if (blocks > (size_t)148 * 64) blocks = (size_t)148 * 64;
-    to_planes_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_regs, d_planes, p, total_groups);
+    DD_COUNT_LAUNCH(), to_planes_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_regs, d_planes, p, total_groups);
     return cudaGetLastError();
 }
 
@@ -295,7 +295,7 @@ cudaError_t prefix_union_hist_from_planes(const uint32_t *d_planes, const int32_
     // (last steps, first steps) are always found there; pointless for a batch of distinct pairs
     const bool dedup = d_scratch && n_genomes <= 64 && n_ord > 1 && !(final_only && n_steps == 2) &&
                        (double)n_ord * (n_ord < kDedupWindow ? n_ord : kDedupWindow) * n_steps <= 5e7;
-    if (dedup) prefix_dedup_kernel<<<1, 1024, 0, stream>>>(d_order, n_ord, n_steps, n_genomes, masks, rep);
+    if (dedup) DD_COUNT_LAUNCH(), prefix_dedup_kernel<<<1, 1024, 0, stream>>>(d_order, n_ord, n_steps, n_genomes, masks, rep);
     else rep = nullptr;
     const size_t nvec = (m >> 5) >> 2;
     const unsigned slices = (unsigned)((nvec + kPlThreads - 1) / kPlThreads);
@@ -303,15 +303,15 @@ cudaError_t prefix_union_hist_from_planes(const uint32_t *d_planes, const int32_
     // gridDim.x has room for 2^31-1 of them
     const dim3 grid((unsigned)n_ord, slices, (unsigned)nk);
     if (final_only && n_steps == 2)
-        prefix_union_planes_kernel<true><<<grid, kPlThreads, 0, stream>>>(d_planes, d_order, n_steps, n_genomes, nk, p, final_only,
+        DD_COUNT_LAUNCH(), prefix_union_planes_kernel<true><<<grid, kPlThreads, 0, stream>>>(d_planes, d_order, n_steps, n_genomes, nk, p, final_only,
                                                                          rep, d_hist);
     else
-        prefix_union_planes_kernel<false><<<grid, kPlThreads, 0, stream>>>(d_planes, d_order, n_steps, n_genomes, nk, p, final_only,
+        DD_COUNT_LAUNCH(), prefix_union_planes_kernel<false><<<grid, kPlThreads, 0, stream>>>(d_planes, d_order, n_steps, n_genomes, nk, p, final_only,
                                                                           rep, d_hist);
     if (dedup) {
         const size_t cells = rows * DD_HIST_BINS;
         const unsigned cb = (unsigned)((cells + 255) / 256 < 1184 ? (cells + 255) / 256 : 1184);
-        prefix_copy_rows_kernel<<<cb, 256, 0, stream>>>(rep, n_ord, n_steps, nk, final_only, d_hist);
+        DD_COUNT_LAUNCH(), prefix_copy_rows_kernel<<<cb, 256, 0, stream>>>(rep, n_ord, n_steps, nk, final_only, d_hist);
     }
     return cudaGetLastError();
 }

@@ -481,7 +481,7 @@ cudaError_t sketch_update(const uint32_t *d_codes, const uint32_t *d_invalid, co
             const unsigned resident = persistent_grid(v, smem);
             if (grid > resident) grid = resident;
         }
-        v.fn<<<grid, v.threads, smem, stream>>>(a);
+        DD_COUNT_LAUNCH(), v.fn<<<grid, v.threads, smem, stream>>>(a);
     }
     return cudaGetLastError();
 }
@@ -522,8 +522,8 @@ cudaError_t sketch_refresh_floor(void *d_ws, uint32_t kmask, int p, cudaStream_t
     const int nk = __builtin_popcount(kmask);
     cudaError_t e = cudaMemsetAsync(ws_scratch(d_ws), 0xff, 32 * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-    floor_min_kernel<<<dim3(16, nk), 256, 0, stream>>>(ws_acc(d_ws), p, ws_hdr(d_ws), ws_scratch(d_ws));
-    floor_publish_kernel<<<1, 32, 0, stream>>>(ws_hdr(d_ws), ws_scratch(d_ws), kmask);
+    DD_COUNT_LAUNCH(), floor_min_kernel<<<dim3(16, nk), 256, 0, stream>>>(ws_acc(d_ws), p, ws_hdr(d_ws), ws_scratch(d_ws));
+    DD_COUNT_LAUNCH(), floor_publish_kernel<<<1, 32, 0, stream>>>(ws_hdr(d_ws), ws_scratch(d_ws), kmask);
     return cudaGetLastError();
 }
 
@@ -533,7 +533,7 @@ cudaError_t sketch_end(void *d_ws, int nk, int p, uint8_t *d_regs, uint32_t *d_h
     if (d_hist && (e = cudaMemsetAsync(d_hist, 0, (size_t)nk * DD_HIST_BINS * sizeof(uint32_t), stream)) != cudaSuccess)
         return e;
     const unsigned slices = (unsigned)((((size_t)1 << p) + kFinChunk - 1) / kFinChunk);
-    finalize_kernel<<<dim3(slices, nk), kPhThreads, 0, stream>>>(ws_acc(d_ws), p, d_regs, d_hist);
+    DD_COUNT_LAUNCH(), finalize_kernel<<<dim3(slices, nk), kPhThreads, 0, stream>>>(ws_acc(d_ws), p, d_regs, d_hist);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (d_hist && d_cards) return mle_from_hist(d_hist, nk, p, d_cards, stream);
     return cudaSuccess;

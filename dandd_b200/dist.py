@@ -21,11 +21,17 @@ import torch.distributed as dist
 
 
 def init(backend: str = None) -> (int, int):
-    """Initialise the default process group from the torchrun environment (no-op if world is 1)."""
+    """Initialise the default process group from the torchrun environment (no-op if world is 1).
+
+    backend=None (the command line): the default group is gloo -- it is up in a fraction of a second
+    and all the command line exchanges through it are small Python objects (cardinalities, names);
+    creating NCCL communicators for 8 ranks costs seconds, so the NCCL group that carries REGISTER
+    tensors (union_over_ranks / gather_registers) is created on first use only (tensor_group()).
+    backend="nccl" (bench.py, tools/): NCCL from the start, eagerly bound to LOCAL_RANK's GPU."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if world > 1 and not dist.is_initialized():
-        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        backend = backend or "gloo"
         kwargs = {}
         if backend == "nccl":
             kwargs["device_id"] = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
@@ -45,11 +51,29 @@ def world() -> (int, int):
 from .shard import shard_by_size  # noqa: E402,F401  (re-exported: the table every rank computes)
 
 
+_nccl_group = None
+
+
+def tensor_group(t: torch.Tensor):
+    """The process group for a collective on tensor `t`: the default group, or -- CUDA tensor while
+    the default group is gloo -- an NCCL group over all ranks, created the first time it is needed
+    (a collective call itself: every rank reaches it, because every rank enters the same tensor
+    collective)."""
+    global _nccl_group
+    if not t.is_cuda or dist.get_backend() == "nccl":
+        return None
+    if _nccl_group is None:
+        torch.cuda.set_device(t.device)
+        _nccl_group = dist.new_group(backend="nccl")
+    return _nccl_group
+
+
 def union_over_ranks(regs: torch.Tensor) -> torch.Tensor:
-    """In-place register-wise max over all ranks (uint8 tensor of any shape)."""
+    """In-place register-wise max over all ranks (uint8 tensor of any shape): NCCL MAX all-reduce
+    over NVLink for device tensors."""
     _, n = world()
     if n > 1:
-        dist.all_reduce(regs, op=dist.ReduceOp.MAX)
+        dist.all_reduce(regs, op=dist.ReduceOp.MAX, group=tensor_group(regs))
     return regs
 
 
@@ -65,7 +89,7 @@ def gather_registers(local: torch.Tensor, owners: List[List[int]]) -> torch.Tens
     padded = torch.zeros((width, nk, m), dtype=local.dtype, device=local.device)
     padded[:local.shape[0]] = local
     bucket = [torch.empty_like(padded) for _ in range(n)]
-    dist.all_gather(bucket, padded)
+    dist.all_gather(bucket, padded, group=tensor_group(padded))
     out = torch.empty((total, nk, m), dtype=local.dtype, device=local.device)
     for r, idxs in enumerate(owners):
         for j, g in enumerate(idxs):
@@ -81,7 +105,7 @@ def gather_cards(local: torch.Tensor, owners: List[List[int]]) -> torch.Tensor:
 def sum_counts(counts: torch.Tensor) -> torch.Tensor:
     _, n = world()
     if n > 1:
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=tensor_group(counts))
     return counts
 
 

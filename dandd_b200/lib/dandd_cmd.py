@@ -14,6 +14,7 @@ import huffman_dandd
 from huffman_dandd import write_listdict_to_csv
 
 VERSION = "%(prog)s 1.0.0 (dandd_b200)"
+COMMAND_LINE = False   # set by the `dandd` launcher: process-wide environment tweaks are only made for a real command-line run
 
 
 def insert_pre_ext(filename, string):
@@ -32,6 +33,9 @@ UNIVERSAL = [  # reference :23-30
                        help="Re-verify every sketch name hash against the sum of its component fasta hashes.")),
     (("--fast",), dict(action="store_true", default=False, dest="fast", help="Don't save so much stuff for second usage.")),
     (("--device",), dict(type=int, default=None, dest="device", metavar="GPU", help="CUDA device to use (default LOCAL_RANK or 0).")),
+    (("--gpus",), dict(type=int, default=None, dest="gpus", metavar="N",
+                       help="tree: use N GPUs of this node, one process each (what `torchrun --nproc-per-node N` sets up, "
+                            "without the launcher's start-up cost).")),
 ]
 KSWEEP = [  # reference :145-150
     (("--ksweep",), dict(dest="ksweep", default=None, action="store_true",
@@ -94,7 +98,53 @@ def add_universal_cmds(subparser: argparse.ArgumentParser):
 
 def _select_device(args):
     if getattr(args, "device", None) is not None:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            raise SystemExit("--device selects the GPU of a single-process run; under torchrun / --gpus each rank uses LOCAL_RANK")
         os.environ["LOCAL_RANK"] = str(args.device)
+    _narrow_visible_devices()
+
+
+def _narrow_visible_devices() -> None:
+    """A single-process run touches one GPU; on an 8-GPU node CUDA start-up is several seconds faster
+    when only that one is visible (the driver otherwise sets up all eight).  Must run before anything
+    initialises CUDA; does nothing under torchrun or when the user has set CUDA_VISIBLE_DEVICES."""
+    if not COMMAND_LINE or int(os.environ.get("WORLD_SIZE", "1")) > 1 or "CUDA_VISIBLE_DEVICES" in os.environ:
+        return
+    os.environ["CUDA_VISIBLE_DEVICES"] = os.environ.get("LOCAL_RANK", "0")
+    os.environ["LOCAL_RANK"] = "0"
+
+
+def _self_launch(args) -> list:
+    """--gpus N outside torchrun: this process becomes rank 0 and starts ranks 1..N-1 as copies of its
+    own command line, with the environment torchrun would have given them (RANK, LOCAL_RANK,
+    WORLD_SIZE, MASTER_ADDR, MASTER_PORT on the loopback interface).  Returns the child processes."""
+    import socket
+    import subprocess
+    n = int(args.gpus or 1)
+    if n < 2 or "WORLD_SIZE" in os.environ:
+        return []
+    with socket.socket() as sock:       # a free port for the rendezvous store
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    base = dict(os.environ, WORLD_SIZE=str(n), LOCAL_WORLD_SIZE=str(n), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    # each process sees only its own GPU (as device 0): CUDA start-up does not grow with the node's GPU count
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+    ids = visible.split(",") if visible else [str(i) for i in range(n)]
+    if len(ids) < n:
+        raise SystemExit(f"--gpus {n}: only {len(ids)} device(s) in CUDA_VISIBLE_DEVICES")
+    os.environ.update(base, RANK="0", LOCAL_RANK="0", CUDA_VISIBLE_DEVICES=ids[0])
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dandd")
+    children = []
+    for r in range(1, n):
+        env = dict(base, RANK=str(r), LOCAL_RANK="0", CUDA_VISIBLE_DEVICES=ids[r])
+        children.append(subprocess.Popen([sys.executable, script] + sys.argv[1:], env=env))
+    return children
+
+
+def _reap(children) -> None:
+    bad = [c.args for c in children if c.wait() != 0]
+    if bad:
+        raise SystemExit(f"dandd: {len(bad)} worker process(es) failed")
 
 
 def _single_rank_command(name) -> bool:
@@ -122,6 +172,7 @@ def tree_command(args):
     if not (args.genomedir or args.flist_loc):
         print("ERROR: You must provide either a datadirectory or a fasta file list!")
         sys.exit(1)
+    children = _self_launch(args)       # --gpus N: this process is rank 0, the others start now
     _select_device(args)
     if not args.sketchdir:
         args.sketchdir = os.path.join(args.outdir, "sketchdb")
@@ -150,12 +201,17 @@ def tree_command(args):
                 dtree.save(fileprefix=dtree.make_prefix(outdir=args.outdir, tag=args.tag, label=args.label), fast=args.fast)
     finally:
         if world > 1:           # release the ranks that serve exact-count requests, also when rank 0 fails
-            from dandd_b200.store import get_store
-            workers = getattr(get_store(), "exact_workers", None)
+            store_mod = sys.modules.get("dandd_b200.store")          # only an ALREADY created store: creating one
+            store = getattr(store_mod, "_store", None)               # here could mask the error being propagated
+            workers = getattr(store, "exact_workers", None)
             if workers is not None:
-                workers.stop()
+                try:
+                    workers.stop()
+                except Exception as err:  # noqa: BLE001
+                    print(f"dandd: could not release the exact-count workers: {err}", file=sys.stderr)
     with timing.span("finish_ranks"):
         _finish_ranks(world)
+        _reap(children)
 
 
 def _early_prefetch(args) -> None:

@@ -72,6 +72,8 @@ def _reader(path, ring: _Ring, out_q, hash_q, stats, raw_text: Optional[bytes]):
     try:
         if raw_text is None:
             fh = open(path, "rb", buffering=0)
+        else:
+            raw_view = memoryview(raw_text)      # slices of a view do not copy
         pos = 0
         while True:
             slot = ring.free.get()
@@ -85,7 +87,7 @@ def _reader(path, ring: _Ring, out_q, hash_q, stats, raw_text: Optional[bytes]):
                     n += more
             else:
                 n = min(ring.chunk, len(raw_text) - pos)
-                ring.views[slot][:n] = raw_text[pos:pos + n]
+                ring.views[slot][:n] = raw_view[pos:pos + n]
                 pos += n
             t_busy += time.perf_counter() - t0
             if not n:

@@ -54,6 +54,9 @@ typedef void *dd_stream;
 
 DD_API const char *dd_last_error(void);
 DD_API int dd_abi_version(void);
+/* Number of CUDA kernels this library has launched in this process so far (all threads, all streams;
+ * memsets and copies are not kernels).  Lets a benchmark report its launches as a measurement. */
+DD_API unsigned long long dd_kernel_launches(void);
 /* Select `device` for the calling thread and verify it is compute capability 10.x. */
 DD_API int dd_init(int device);
 /* Tuning knobs (never change results).  "sketch_k_per_pass" = n: K2 updates at most n k values per

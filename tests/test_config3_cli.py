@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 
 def _args(tmp_path, gpus, **kw):
     base = dict(gpus=gpus, genomes=8, bases=50e6, kmin=2, kmax=32, workdir=str(tmp_path / "cfg3"), union_files="full",
-                cpu_sample_bytes=0, oracle_ks="2,18,32", keep=True, out=None, _generate=False)
+                cpu_sample_bytes=0, oracle_ks="2,18,32", keep=True, out=None, _generate=False, launcher="self",
+                also_torchrun=False)
     base.update(kw)
     return argparse.Namespace(**base)
 
@@ -65,6 +66,6 @@ def test_config3_cli_two_ranks_same_results(tmp_path):
         pytest.skip("needs two GPUs")
     from tools import config3_cli
     one = config3_cli.run(_args(tmp_path / "a", gpus=1, oracle_ks=""))
-    two = config3_cli.run(_args(tmp_path / "b", gpus=2, oracle_ks=""))
-    assert one["leaf_cards"] == two["leaf_cards"]
+    two = config3_cli.run(_args(tmp_path / "b", gpus=2, oracle_ks="", also_torchrun=True))   # --gpus 2 and torchrun
+    assert one["leaf_cards"] == two["leaf_cards"] and two["torchrun_cards_identical"]
     assert one["prefix_delta"] == two["prefix_delta"] and one["prefix_argmax_k"] == two["prefix_argmax_k"]

@@ -153,12 +153,30 @@ def run(args):
     env = dict(os.environ, DANDD_B200_TIMING=timing_tree, DANDD_B200_UNION_FILES=args.union_files)
     tree_argv = [DANDD, "tree", "--datadir", data, "-o", out, "--tag", "cfg3", "--ksweep", "--mink", str(args.kmin),
                  "--maxk", str(args.kmax)]
-    dt, log = torchrun(args.gpus, tree_argv, env=env)
+    launcher = getattr(args, "launcher", "self")
+    rep["config"]["launcher"] = launcher if args.gpus > 1 else "single process"
+
+    def launch(argv, env_):
+        if launcher == "self" and args.gpus > 1:      # `dandd tree --gpus N`: rank 0 starts the other ranks itself
+            return torchrun(1, argv + ["--gpus", str(args.gpus)], env=env_)
+        return torchrun(args.gpus, argv, env=env_)
+    dt, log = launch(tree_argv, env)
     rep["tree_wall_s"] = round(dt, 3)
     rep["tree_stages"] = summarize_timing(read_timing(timing_tree))
     # a fully cached re-run (zero work)
-    dt, _ = torchrun(args.gpus, tree_argv, env=dict(env, DANDD_B200_TIMING=os.path.join(workdir, "timing_tree2.jsonl")))
+    dt, _ = launch(tree_argv, dict(env, DANDD_B200_TIMING=os.path.join(workdir, "timing_tree2.jsonl")))
     rep["tree_cached_rerun_wall_s"] = round(dt, 3)
+    if getattr(args, "also_torchrun", False) and args.gpus > 1:   # the same job under torchrun, into a fresh database
+        out2 = os.path.join(workdir, "out_torchrun")
+        argv2 = [DANDD, "tree", "--datadir", data, "-o", out2, "--tag", "cfg3", "--ksweep", "--mink", str(args.kmin),
+                 "--maxk", str(args.kmax)]
+        t2 = os.path.join(workdir, "timing_tree_torchrun.jsonl")
+        dt, _ = torchrun(args.gpus, argv2, env=dict(env, DANDD_B200_TIMING=t2))
+        rep["tree_wall_torchrun_s"] = round(dt, 3)
+        rep["tree_stages_torchrun"] = summarize_timing(read_timing(t2))
+        c2, _ = cards_by_genome(os.path.join(out2, "sketchdb"), "cfg3", args.genomes, ks)
+        rep["torchrun_cards_identical"] = True   # checked below once the first run's cards are read
+        rep["_cards_torchrun"] = c2
     # 3. dandd progressive -n 1 --ksweep (single process)
     pickle_path = os.path.join(out, f"cfg3_{args.genomes}_dashing_dtree.pickle")
     timing_prog = os.path.join(workdir, "timing_prog.jsonl")
@@ -168,6 +186,8 @@ def run(args):
     rep["progressive_stages"] = summarize_timing(read_timing(timing_prog))
     # 4. results
     cards, cardkey = cards_by_genome(sketchdir, "cfg3", args.genomes, ks)
+    if "_cards_torchrun" in rep:
+        rep["torchrun_cards_identical"] = rep.pop("_cards_torchrun") == cards
     karr = np.array(ks, dtype=np.float64)
     rep["leaf_argmax_k"] = [int(ks[int(np.argmax(np.array(cards[g]) / karr))]) for g in range(args.genomes)]
     rep["leaf_delta"] = [float((np.array(cards[g]) / karr).max()) for g in range(args.genomes)]
@@ -223,6 +243,9 @@ def main():
     ap.add_argument("--cpu-sample-bytes", type=float, default=64e6)
     ap.add_argument("--oracle-ks", default="")
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--launcher", default="self", choices=["self", "torchrun"],
+                    help="multi-GPU tree: `dandd tree --gpus N` (rank 0 starts the others) or torchrun")
+    ap.add_argument("--also-torchrun", action="store_true", help="additionally time the same tree job under torchrun")
     ap.add_argument("--out", default=None)
     ap.add_argument("--_generate", action="store_true")
     args = ap.parse_args()
