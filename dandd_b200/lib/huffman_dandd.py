@@ -706,6 +706,9 @@ def presketch_leaves_sharded(fastas, speciesinfo, experiment, kstart, halfwidth=
     found = {}
     scratch = dict(experiment, baseset=set())   # pre-sketching must not leak names into the tree's own bookkeeping
     for path in mine:
+        if os.path.basename(path) not in speciesinfo.fastahex and hasattr(get_store(), "warm_leaf"):
+            with timing.span("warm_leaves"):      # GPU work first: the name (blake2b) is still being computed
+                get_store().warm_leaf(path, int(experiment["registers"]), bool(experiment["canonicalize"]))
         leaf = DeltaTreeNode(node_title=path, children=[], speciesinfo=speciesinfo, experiment=scratch, progeny=[])
         with timing.span("presketch_leaves"):
             leaf.ksweep_update_node(mink=lo, maxk=hi)

@@ -169,6 +169,21 @@ class GpuSketchStore:
             out[k] = card
         return out
 
+    def warm_leaf(self, fasta: str, p: int, canon: bool) -> None:
+        """Sketch a large FASTA for all k NOW and keep the block in HBM, without naming or writing
+        anything: lets the caller start the GPU work before the file's blake2b name (which the sketch
+        database paths need, and which takes seconds for a multi-GB file) has been computed."""
+        key = ("leaf", fasta, int(p), bool(canon))
+        if not self.prefetch_all_k or self._get(key) is not None or not os.path.isfile(fasta) \
+                or os.path.getsize(fasta) < STREAM_MIN_BYTES:
+            return
+        run_ks = list(ALL_HLL_KS)
+        streamed = self._stream_leaf(fasta, run_ks, p, canon)
+        if streamed is not None:
+            regs, cards = streamed
+            self._put(key, {"regs": regs, "cards": cards, "ks": {k: i for i, k in enumerate(run_ks)}}, regs.numel())
+            self.stats["leaf_passes"] += 1
+
     def _stream_leaf(self, fasta, run_ks, p, canon):
         """Large FASTA: disk (or the prefetched bytes) -> pinned ring -> H2D -> K1 -> K2 in 64 MiB chunks,
         the blake2b name computed from the same chunks (dandd_b200/streaming.py).  None if the text is
