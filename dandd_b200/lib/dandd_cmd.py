@@ -127,6 +127,7 @@ def _self_launch(args) -> list:
         sock.bind(("127.0.0.1", 0))
         port = sock.getsockname()[1]
     base = dict(os.environ, WORLD_SIZE=str(n), LOCAL_WORLD_SIZE=str(n), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    base.setdefault("OMP_NUM_THREADS", "4")     # N processes share the host's cores (torchrun sets 1)
     # each process sees only its own GPU (as device 0): CUDA start-up does not grow with the node's GPU count
     visible = os.environ.get("CUDA_VISIBLE_DEVICES")
     ids = visible.split(",") if visible else [str(i) for i in range(n)]
@@ -179,6 +180,8 @@ def tree_command(args):
     from dandd_b200 import timing
     _early_prefetch(args)       # file reads + blake2b start now, under the ~4 s of torch import / CUDA start-up
     timing.mark("prefetch_started")
+    if COMMAND_LINE and not args.exact:
+        _start_engine_in_background()      # CUDA start-up (seconds) runs beside the process-group rendezvous
     with timing.span("init_ranks"):
         rank, world = _init_ranks()
     os.makedirs(args.sketchdir, exist_ok=True)
@@ -212,6 +215,17 @@ def tree_command(args):
     with timing.span("finish_ranks"):
         _finish_ranks(world)
         _reap(children)
+
+
+def _start_engine_in_background() -> None:
+    import threading
+
+    def start():
+        try:
+            huffman_dandd.get_store()
+        except Exception:  # noqa: BLE001 -- the main thread will hit the same error and report it
+            pass
+    threading.Thread(target=start, name="dd-engine-start", daemon=True).start()
 
 
 def _early_prefetch(args) -> None:

@@ -558,35 +558,135 @@ class DeltaTree:
                 print("WARNING: If BOTH minimum AND maximum k are not provided either by the input delta-tree or using "
                       "--mink and --maxk, the --jaccard flag will be ignored.")
                 jaccard = False
-        self._prefetch_pair_unions(leaves)
+        table = self._prefetch_pair_unions(leaves)
         kij_rows, j_rows = [], []
+        pair_index = 0
         for i, first in enumerate(leaves):
             for second in leaves[i + 1:]:
-                pair = SubSpider(leafnodes=[first, second], speciesinfo=self.speciesinfo, experiment=pair_experiment)
-                pair.root.find_delta(self.root_k())
-                kij_rows.append(pair.kij_summarize())
-                if jaccard:
-                    pair.ksweep(mink=mink, maxk=maxk)
-                    j_rows.extend(pair.jaccard_summarize(mink=mink, maxk=maxk))
+                rows = None
+                if table is not None:
+                    rows = self._pair_from_table(first, second, table, pair_index, pair_experiment, jaccard, mink, maxk)
+                pair_index += 1
+                if rows is None:         # exact mode, --safe, or a k outside the batched table: one SubSpider per pair
+                    pair = SubSpider(leafnodes=[first, second], speciesinfo=self.speciesinfo, experiment=pair_experiment)
+                    pair.root.find_delta(self.root_k())
+                    krow, jrows = pair.kij_summarize(), []
+                    if jaccard:
+                        pair.ksweep(mink=mink, maxk=maxk)
+                        jrows = pair.jaccard_summarize(mink=mink, maxk=maxk)
+                    rows = (krow, jrows)
+                kij_rows.append(rows[0])
+                j_rows.extend(rows[1])
         return kij_rows, j_rows
 
-    def _prefetch_pair_unions(self, leaves) -> None:
+    # ---------------------------------------------------------------- pairs from the batched K6 table
+    def _pair_from_table(self, first, second, table, row, pair_experiment, jaccard, mink, maxk):
+        """What `SubSpider([first, second])` + `root.find_delta(root_k)` + `kij_summarize()` (+ the Jaccard
+        sweep) would do (reference :666-695, :727-815), replayed on the cardinalities the batched pair job
+        already holds: the same hill-climb decisions (including the species-wide start k it mutates), the
+        same rows, and the same side effects on the sketch database -- a union sketch file, a cardinality
+        entry and a name registration for every k the reference would have touched -- without building
+        ~20 Python objects and issuing 3-8 store calls per pair.  Returns None when the replay needs a
+        k the table does not cover (the caller then takes the object path for this pair)."""
+        spec, exp = self.speciesinfo, pair_experiment
+        cards, col = table["cards"], table["col"]
+        registers, canon = exp["registers"], exp["canonicalize"]
+        files = sorted(os.path.basename(f) for f in (first.fastas[0], second.fastas[0]))
+        set_key = "".join(files)
+        stored = spec.fastahex.get(set_key)
+        if stored is None:
+            stored = hex(sum(int(spec.fastahex[name], 16) for name in files))
+        stem = f"{stored[:15]}_{registers}n2k"
+        nc = "" if canon else "nc"
+        state = {"delta": 0, "bestk": 0}
+        visited = []
+
+        def touch(lo, hi):
+            for k in range(max(1, lo), min(hi, HLL_MAX_K) + 1):
+                if k not in col:
+                    raise KeyError(k)
+                if k not in visited:
+                    visited.append(k)
+
+        def helper(k, direction):
+            if k > HLL_MAX_K:
+                raise ValueError("Exploratory k value is too high for dashing. Either something is amiss with your data "
+                                 "or you need to be using --exact mode")
+            touch(k - 1, k + 1)
+            candidate = float(cards[row, col[k]]) / k if k >= 1 else 0
+            if state["delta"] <= candidate:
+                spec.kstart = k
+                state["bestk"], state["delta"] = k, candidate
+                helper(k + direction, direction)
+
+        def find_delta(k):
+            helper(k, 1)
+            helper(k, -1)
+
+        kstart_before = spec.kstart
+        try:
+            find_delta(spec.kstart)                                   # SubSpider._build_tree
+            for k in sorted({first.bestk, second.bestk, state["bestk"]} - {0}):
+                touch(k, k)                                           # fill_tree
+            find_delta(self.root_k())                                 # pairwise_spiders
+            if jaccard:
+                touch(int(mink), int(maxk))                           # pair.ksweep + jaccard_summarize
+        except KeyError:
+            spec.kstart = kstart_before                               # the object path starts where this pair started
+            return None
+        # side effects on the database: names, files, cardinalities (SketchFilePath / DashSketchObj / store)
+        spec.fastahex.setdefault(set_key, stored)
+        store = get_store()
+        leaf_sketch = {n: n.ksketches for n in (first, second)}
+        for k in [0] + visited:
+            ktok = "{}" if k == 0 else str(k)
+            base = stem + ktok + nc
+            if base not in spec.sketchinfo:
+                spec.sketchinfo[base] = {"sketchbase": base, "files": files, "ngen": 2, "kval": k, "registers": registers}
+            exp["baseset"].add(base)
+            if k == 0:
+                continue
+            directory = os.path.join(spec.sketchdir, "ngen2", "k" + ktok)
+            path = os.path.join(directory, base) + ".hll"
+            card = float(cards[row, col[k]])
+            if not (os.path.exists(path) and os.path.getsize(path) > 0):
+                ensure_dir(directory)
+                store.materialize_union(path, int(registers), card, [leaf_sketch[first][k].sketch, leaf_sketch[second][k].sketch])
+            if not float(spec.cardkey.get(path) or 0):
+                spec.cardkey[path] = card
+        a, b = (first, second) if first.node_title <= second.node_title else (second, first)
+        kij = {"A": a.fastas[0], "B": b.fastas[0], "Adelta": a.delta, "Bdelta": b.delta, "Ak": a.bestk, "Bk": b.bestk,
+               "ABdelta": state["delta"], "ABk": state["bestk"], "Atitle": a.node_title, "Btitle": b.node_title}
+        kij["KIJ"] = (kij["Adelta"] + kij["Bdelta"] - kij["ABdelta"]) / kij["ABdelta"]
+        jrows = []
+        if jaccard:
+            for k in range(mink, maxk + 1):
+                jr = {"A": first.fastas[0], "B": second.fastas[0], "Atitle": first.node_title, "Btitle": second.node_title,
+                      "kval": k, "Acard": first.ksketches[k].card, "Bcard": second.ksketches[k].card,
+                      "ABcard": float(cards[row, col[k]])}
+                jr["jaccard"] = (jr["Acard"] + jr["Bcard"] - jr["ABcard"]) / jr["ABcard"]
+                jrows.append(jr)
+        return kij, jrows
+
+    def _prefetch_pair_unions(self, leaves):
         """K6: the union cardinality of every pair of leaves at every k the leaves hold is computed by
         ONE batched device job (sketches transposed once, pair matrix tiled) and kept by the store;
         the per-pair SubSpiders below then find every two-leaf union already evaluated and issue no
         device work of their own.  HLL mode only; exact mode goes pair by pair (k-mer sets are not
         mergeable sketches)."""
-        if self.experiment["tool"] != "dashing" or len(leaves) < 3 or not all(hasattr(leaf, "ksketches") for leaf in leaves):
-            return
+        if (self.experiment["tool"] != "dashing" or len(leaves) < 3 or self.experiment["safety"] or self.experiment["lowmem"]
+                or not all(hasattr(leaf, "ksketches") for leaf in leaves)):
+            return None
         store = get_store()
         if not hasattr(store, "pair_unions"):
-            return
+            return None
         ks = [k for k in range(1, HLL_MAX_K + 1)
               if all(k < len(leaf.ksketches) and leaf.ksketches[k] is not None for leaf in leaves)]
         if not ks:
-            return
+            return None
         leaf_paths = {k: [leaf.ksketches[k].sketch for leaf in leaves] for k in ks}
-        store.pair_unions(leaf_paths, int(self.experiment["registers"]))
+        cards = store.pair_unions(leaf_paths, int(self.experiment["registers"]))
+        return {"cards": cards, "col": {k: i for i, k in enumerate(ks)}}
 
     def prepare_AFproject(self, kijsummary, jsummary) -> List[Tuple]:
         """(tool, name1, name2, k, value, k1, k2, k12) tuples for helpers/AFproject.py: k = 0 rows carry

@@ -211,7 +211,7 @@ class GpuSketchStore:
         for k in sorted(members_by_k):   # cells a batched pair job (pair_unions) has already evaluated
             card = self._pair_lookup(members_by_k[k], p)
             if card is not None:
-                out[k] = self._materialize_precomputed(out_paths[k], p, card, members_by_k[k])
+                out[k] = self.materialize_union(out_paths[k], p, card, members_by_k[k])
         ks = sorted(k for k in members_by_k if k not in out)
         if not ks:
             return out
@@ -327,7 +327,7 @@ class GpuSketchStore:
         n = tab["n"]
         return float(tab["cards"][i * n - i * (i + 1) // 2 + (j - i - 1), tab["col"][a[1]]])
 
-    def _materialize_precomputed(self, path: str, p: int, card: float, members) -> float:
+    def materialize_union(self, path: str, p: int, card: float, members) -> float:
         """A union whose cardinality a batched job already produced is asked for as a FILE: write the
         marker (or, with union_files == 'full', build the registers from the members) -- no estimator run."""
         if self.union_files == "full":
@@ -368,17 +368,22 @@ class GpuSketchStore:
 
 
 _store = None
+_store_lock = __import__("threading").Lock()
 
 
 def get_store():
+    """The process-wide store.  Thread-safe: the command line starts it on a background thread (CUDA
+    start-up takes seconds) while the main thread joins the process group."""
     global _store
     if _store is None:
-        from dandd_b200 import _startup
-        if _startup.TRIM_REQUESTED:          # command-line start-up trim, see _startup.py
-            _startup.trim_torch_cuda_init()
-        with timing.span("engine_start"):    # CUDA context + library load (torch itself was imported with this module)
-            _store = GpuSketchStore()
-        timing.mark("engine_ready")
+        with _store_lock:
+            if _store is None:
+                from dandd_b200 import _startup
+                if _startup.TRIM_REQUESTED:          # command-line start-up trim, see _startup.py
+                    _startup.trim_torch_cuda_init()
+                with timing.span("engine_start"):    # CUDA context + library load (torch itself was imported with this module)
+                    _store = GpuSketchStore()
+                timing.mark("engine_ready")
     return _store
 
 

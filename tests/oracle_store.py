@@ -91,6 +91,22 @@ class OracleStore:
                         self._write(path, run.copy(), p, out[o, st, i])
         return out
 
+    def pair_unions(self, leaf_paths_by_k, p, tile_pairs=0, remember=True):
+        """[n(n-1)/2, nk] union cardinalities of every pair of leaves (the K6 job of the real store)."""
+        self.stats["union_launches"] += 1
+        ks = sorted(leaf_paths_by_k)
+        n = len(leaf_paths_by_k[ks[0]])
+        pairs = [(a, b) for a in range(n) for b in range(a + 1, n)]
+        out = np.zeros((len(pairs), len(ks)))
+        for j, (a, b) in enumerate(pairs):
+            for i, k in enumerate(ks):
+                out[j, i] = orc.card(np.maximum(self.registers(leaf_paths_by_k[k][a]), self.registers(leaf_paths_by_k[k][b])), p)
+        return out
+
+    def materialize_union(self, path, p, card, members):
+        self._write(path, orc.union_max([self.registers(m) for m in members]), p, card)
+        return float(card)
+
     def card_of_file(self, path, p=None):
         regs = self.registers(path)
         return orc.card(regs, int(regs.size).bit_length() - 1)
