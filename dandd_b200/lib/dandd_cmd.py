@@ -178,10 +178,11 @@ def tree_command(args):
     if not args.sketchdir:
         args.sketchdir = os.path.join(args.outdir, "sketchdb")
     from dandd_b200 import timing
-    _early_prefetch(args)       # file reads + blake2b start now, under the ~4 s of torch import / CUDA start-up
+    fresh = _early_prefetch(args)   # file reads + blake2b start now, under the ~4 s of torch import / CUDA start-up
     timing.mark("prefetch_started")
-    if COMMAND_LINE and not args.exact:
-        _start_engine_in_background()      # CUDA start-up (seconds) runs beside the process-group rendezvous
+    if COMMAND_LINE and fresh and not args.exact:
+        _start_engine_in_background()      # there is something to sketch: CUDA start-up (seconds) runs beside the
+                                           # process-group rendezvous (a fully cached run never imports torch)
     with timing.span("init_ranks"):
         rank, world = _init_ranks()
     os.makedirs(args.sketchdir, exist_ok=True)
@@ -228,16 +229,17 @@ def _start_engine_in_background() -> None:
     threading.Thread(target=start, name="dd-engine-start", daemon=True).start()
 
 
-def _early_prefetch(args) -> None:
+def _early_prefetch(args) -> list:
     """Start reading (and hashing) this process's share of the FASTAs in background threads before
     anything imports torch.  Only files the sketch database has never seen: a cached re-run reads
-    nothing, like the reference (its fastahex pickle short-circuits the hash)."""
+    nothing, like the reference (its fastahex pickle short-circuits the hash).
+    Returns the files it started on."""
     from dandd_b200 import ingest
     from dandd_b200.shard import shard_by_size
     try:
         fastas = huffman_dandd.list_fastas(args.genomedir, args.flist_loc)
     except (OSError, ValueError):
-        return                  # create_delta_tree reports the problem
+        return []               # create_delta_tree reports the problem
     known = set()
     try:
         with open(os.path.join(args.sketchdir, "dandd_fastahex.pickle"), "rb") as fh:
@@ -250,8 +252,10 @@ def _early_prefetch(args) -> None:
         owners = shard_by_size([os.path.getsize(f) for f in fastas], world)
         fastas = [fastas[i] for i in owners[rank]]
     elif world > 1 and rank > 0:
-        return                  # split-genome and exact modes: rank 0 hashes, every rank reads on demand
-    ingest.prefetch([f for f in fastas if os.path.basename(f) not in known])
+        return []               # split-genome and exact modes: rank 0 hashes, every rank reads on demand
+    fresh = [f for f in fastas if os.path.basename(f) not in known]
+    ingest.prefetch(fresh)
+    return fresh
 
 
 def _init_ranks():

@@ -675,6 +675,7 @@ class DeltaTree:
         device work of their own.  HLL mode only; exact mode goes pair by pair (k-mer sets are not
         mergeable sketches)."""
         if (self.experiment["tool"] != "dashing" or len(leaves) < 3 or self.experiment["safety"] or self.experiment["lowmem"]
+                or os.environ.get("DANDD_B200_PAIR_TABLE", "1") == "0"
                 or not all(hasattr(leaf, "ksketches") for leaf in leaves)):
             return None
         store = get_store()

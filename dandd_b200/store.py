@@ -43,6 +43,8 @@ class GpuSketchStore:
         # 'full': union sketches are written out like `dashing union -o` does; 'stub': a header-only
         # marker file (registers stay in HBM / are recomputed from the leaves on demand)
         self.union_files = union_files or os.environ.get("DANDD_B200_UNION_FILES", "full")
+        # all-pairs jobs leave N(N-1)/2 x (a few k) union sketches behind: markers unless full files were asked for
+        self.pair_union_files = union_files or os.environ.get("DANDD_B200_UNION_FILES", "stub")
         # One LRU over everything resident in HBM, keyed by kind: ("sketch", path) -> [2^p] u8,
         # ("leaf", fasta, p, canon) -> {"regs","cards","ks"}, ("packed", fasta) -> PackedSeq.  A sketch that
         # is a VIEW of a leaf block costs nothing by itself (the block is what occupies memory).
@@ -329,8 +331,10 @@ class GpuSketchStore:
 
     def materialize_union(self, path: str, p: int, card: float, members) -> float:
         """A union whose cardinality a batched job already produced is asked for as a FILE: write the
-        marker (or, with union_files == 'full', build the registers from the members) -- no estimator run."""
-        if self.union_files == "full":
+        marker (or, with DANDD_B200_UNION_FILES=full, build the registers from the members) -- no
+        estimator run.  The marker holds p, the cardinality and the member paths; registers() rebuilds
+        the union from them on demand."""
+        if self.pair_union_files == "full":
             regs = self.engine.union([self.registers(mb) for mb in members])
             self._remember(path, regs)
             self._write(path, regs, p, card, leaf=False, members=list(members))

@@ -99,3 +99,57 @@ def test_cached_rerun_as_a_process_imports_no_torch(tmp_path, oracle_store):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "TORCH_IMPORTED False" in r.stdout
+
+
+def _kij_run(tmp, table, jaccard):
+    """tree + kij on 7 genomes; returns everything the run leaves behind, paths made relative."""
+    import csv
+    import pickle
+    from tests.host_harness import run_dandd
+    from tests.util import make_dataset
+    data = make_dataset(os.path.join(tmp, "data"), 7, 6000, seed=31)
+    out = os.path.join(tmp, "out")
+    os.environ["DANDD_B200_PAIR_TABLE"] = "1" if table else "0"
+    try:
+        run_dandd(["tree", "-d", os.path.dirname(data[0]), "-s", "kj", "-k", "11", "-o", out, "-r", "10"])
+        argv = ["kij", "-d", os.path.join(out, "kj_7_dashing_dtree.pickle"), "-o", out, "--mink", "8", "--maxk", "13", "--afproject"]
+        run_dandd(argv + (["--jaccard"] if jaccard else []))
+    finally:
+        os.environ.pop("DANDD_B200_PAIR_TABLE", None)
+    db = os.path.join(out, "sketchdb")
+    rel = lambda p: os.path.relpath(p, tmp)     # noqa: E731
+    res = {"kij": [{k: (rel(v) if k in ("A", "B") else v) for k, v in r.items()} for r in csv.DictReader(open(os.path.join(out, "kj_7_dashing.kij.csv")))],
+           "files": sorted(rel(os.path.join(d, f)) for d, _, fs in os.walk(db) for f in fs if not f.endswith(".bkp"))}
+    if jaccard:
+        res["j"] = [{k: (rel(v) if k in ("A", "B") else v) for k, v in r.items()} for r in csv.DictReader(open(os.path.join(out, "kj_7_dashing.j.csv")))]
+    for name in ("kj_dashing_cardinalities", "dandd_fastahex", "dandd_sketchinfo"):
+        with open(os.path.join(db, name + ".pickle"), "rb") as fh:
+            obj = pickle.load(fh)
+        res[name] = {(rel(k) if os.path.isabs(k) else k): v for k, v in obj.items()}
+    with open(os.path.join(out, "kj_7_dashing_AFtuples.pickle"), "rb") as fh:
+        res["af"] = sorted((t[0], os.path.basename(str(t[1])), os.path.basename(str(t[2])), t[3], round(t[4], 9), t[5], t[6], t[7])
+                           for t in pickle.load(fh))
+    return res
+
+
+@pytest.mark.parametrize("jaccard", [False, True])
+def test_kij_from_the_batched_pair_table_equals_one_spider_per_pair(tmp_path, oracle_store, jaccard):
+    """DeltaTree._pair_from_table replays SubSpider + find_delta + kij_summarize on the K6 table; rows,
+    sketch files, cardinality cache, name registrations and AFproject tuples must equal what the
+    per-pair object path (the reference's shape, :666-695) leaves behind."""
+    a = _kij_run(str(tmp_path / "table"), True, jaccard)
+    ddstore.set_store(OracleStore())
+    b = _kij_run(str(tmp_path / "spiders"), False, jaccard)
+    ra = {k: {kk: (vv.replace("table/", "") if isinstance(vv, str) else vv) for kk, vv in r.items()} if isinstance(r, dict) else r
+          for k, r in enumerate(a["kij"])}
+    rb = {k: {kk: (vv.replace("spiders/", "") if isinstance(vv, str) else vv) for kk, vv in r.items()} if isinstance(r, dict) else r
+          for k, r in enumerate(b["kij"])}
+    assert ra == rb
+    strip = lambda x, tag: x.replace(tag + "/", "")     # noqa: E731
+    assert [strip(f, "table") for f in a["files"]] == [strip(f, "spiders") for f in b["files"]]
+    for name in ("kj_dashing_cardinalities", "dandd_fastahex", "dandd_sketchinfo"):
+        assert {strip(k, "table"): v for k, v in a[name].items()} == {strip(k, "spiders"): v for k, v in b[name].items()}, name
+    assert a["af"] == b["af"]
+    if jaccard:
+        assert [{k: (strip(v, "table") if isinstance(v, str) else v) for k, v in r.items()} for r in a["j"]] == \
+               [{k: (strip(v, "spiders") if isinstance(v, str) else v) for k, v in r.items()} for r in b["j"]]
