@@ -11,7 +11,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from tools.scale_check import synth_fasta  # noqa: E402
+from tools.synth import synth_fasta  # noqa: E402
 
 
 def best_ms(fn, reps=5, warm=3):
@@ -52,8 +52,17 @@ def main():
     ms = best_ms(lambda: eng.pack(text, start=0))
     add("K1 pack (count+scan+write), 1.01 GB text", text.numel() * 1.375, ms, "1 B read + 0.375 B written per base; incl. buffer zeroing")
     seq = eng.pack(text, start=0)
-    ms = best_ms(lambda: eng.sketch(seq, list(range(2, 33)), p=p, floor_every=64_000_000), reps=2, warm=1)
+    ms = best_ms(lambda: eng.sketch(seq, list(range(2, 33)), p=p), reps=2, warm=1)
     add("K2 sketch all-k (k=2..32), 1 Gbp", 1e9 * 1.0, ms, "1 B per base (SURVEY 8d); ALU-issue bound, not HBM")
+    # K5 exact distinct count (bitmap variant 0.375 B/base read + 4^k/8 B; hash-set variant
+    # 0.375 B/base read + one 8-byte key slot touched per k-mer, random access)
+    nsym = seq.nsym
+    for k, label in ((12, "bitmap 4^12 bits"), (16, "bitmap 4^16 bits = 512 MiB"), (24, "hash set, 64-bit keys"), (32, "hash set, 64-bit keys")):
+        cap = 1 << 31
+        ms = best_ms(lambda: eng.exact_counts([seq], k, capacity=cap), reps=2, warm=1)
+        algo = nsym * 0.375 + ((4 ** k) / 8 if k <= 16 else nsym * 8.0)
+        add(f"K5 exact count k={k} ({label}), 1 Gbp", algo, ms, "packed stream read + set traffic (bitmap: its size; hash set: 8 B per k-mer); "
+            "includes begin (zeroing the set), insert and count")
     del text, seq
     g = torch.Generator(device=eng.device)
     g.manual_seed(1)
