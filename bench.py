@@ -280,7 +280,7 @@ def run_ours(args):
     regs = torch.empty((N_GENOMES, nk, m), dtype=torch.uint8, device=dev)
     leaf_hist = torch.empty((N_GENOMES, nk, 64), dtype=torch.int32, device=dev)
     leaf_cards_host = torch.empty((N_GENOMES, nk), dtype=torch.float64).pin_memory()
-    NS = int(os.environ.get("DD_BENCH_STREAMS", "3"))   # genomes in flight
+    NS = int(os.environ.get("DD_BENCH_STREAMS", "2"))   # genomes in flight
     side = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     k2_events = []
 
