@@ -188,6 +188,74 @@ DD_HD int valid_run_long(const uint32_t (&I)[5], uint32_t sm) {
     return run;
 }
 
+// ---- k = 65..256 (exact mode only): k-mers of up to eight 64-bit words ---------------------------
+// out[0] is the LEAST significant word; the value is the k symbols as a base-4 number, first symbol
+// most significant, i.e. the same ordering as the 64- and 128-bit forms (and as comparing the symbol
+// strings lexicographically with A<C<G<T).  s_end = stream position of the k-mer's last symbol; the
+// caller guarantees s_end + 1 >= k.  Returns the number of words W = ceil(2k / 64).
+constexpr int kLongWords = 8;
+DD_HD int kmer_long_at(const uint32_t *codes, uint64_t s_end, int k, bool canon, uint64_t (&out)[kLongWords]) {
+    const int W = (2 * k + 63) / 64;
+    uint64_t fwd[kLongWords], rcw[kLongWords];
+    // window t = the 32 symbols ending at s_end - 32 t (symbols before the stream read as 0 and are masked / shifted out)
+    for (int t = 0; t < W; ++t) {
+        const int64_t s = (int64_t)s_end - 32 * (int64_t)t;
+        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        int j = 0;
+        if (s >= 0) {
+            const uint64_t w = (uint64_t)s >> 4;
+            j = (int)((uint64_t)s & 15);
+            w0 = codes[w];
+            w1 = w >= 1 ? codes[w - 1] : 0u;
+            w2 = w >= 2 ? codes[w - 2] : 0u;
+        }
+        const Window win = window_at(w0, w1, w2, revcomp_word(w0), revcomp_word(w1), revcomp_word(w2), j);
+        fwd[t] = s >= 0 ? win.fwd : 0ull;
+        rcw[t] = s >= 0 ? win.rc : 0ull;
+    }
+    const int top_bits = 2 * k - 64 * (W - 1);          // bits of the k-mer in the most significant word, 2..64
+    if (top_bits < 64) fwd[W - 1] &= (~0ull) >> (64 - top_bits);
+    if (!canon) {
+        for (int t = 0; t < W; ++t) out[t] = fwd[t];
+        return W;
+    }
+    // reverse complement: [rc(window 0) | rc(window 1) | ...] with window 0 most significant, shifted right
+    // by the 64 W - 2k bits that belong to symbols before the k-mer
+    const int drop = 64 - top_bits;                     // 0..62
+    uint64_t rc[kLongWords];
+    for (int t = 0; t < W; ++t) {                       // rc word t (little endian) before the shift = rcw[W - 1 - t]
+        const uint64_t lo = rcw[W - 1 - t];
+        const uint64_t hi = t + 1 < W ? rcw[W - 2 - t] : 0ull;
+        rc[t] = drop ? (lo >> drop) | (hi << (64 - drop)) : lo;
+    }
+    bool take_rc = false;
+    for (int t = W - 1; t >= 0; --t)
+        if (rc[t] != fwd[t]) {
+            take_rc = rc[t] < fwd[t];
+            break;
+        }
+    for (int t = 0; t < W; ++t) out[t] = take_rc ? rc[t] : fwd[t];
+    return W;
+}
+// Number of valid symbols ending at stream position s, saturating at `need` (any k): walks the
+// break-bit words backwards.  invalid word i covers symbols 32 i .. 32 i + 31, symbol s at bit 31 - s % 32.
+DD_HD int valid_run_upto(const uint32_t *invalid, uint64_t s, int need) {
+    int run = 0;
+    int64_t iw = (int64_t)(s >> 5);
+    uint32_t sm = (uint32_t)(s & 31);
+    // bits of word iw at and below symbol s, symbol s in bit 0
+    uint32_t win = invalid[iw] >> (31u - sm);
+    int have = (int)sm + 1;
+    for (;;) {
+        if (win) return run + ctz32(win);
+        run += have;
+        if (run >= need) return run;
+        if (--iw < 0) return run;                       // the stream starts here
+        win = invalid[iw];                              // next older word: its newest symbol (31) already sits in bit 0
+        have = 32;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // FASTA text classification for the packer.  16 text bytes -> bit masks
 // (bit i <-> byte i).  A pad byte ('\r') is inert: never a symbol, never changes line state.

@@ -8,7 +8,12 @@
 //   k  > 16 : an open-addressing table of 64-bit keys (linear probing, atomicCAS); the key is the
 //             k-mer value itself, so there are no false merges -- exact as long as the table is
 //             not full, which is reported, never ignored;
-//   k  > 32 : (to 64; KMC itself goes to 256) the same with 128-bit keys and `atom.cas.b128`.
+//   k  > 32 : (to 64) the same with 128-bit keys and `atom.cas.b128`;
+//   k  > 64 : (to 256, KMC's own limit) no atomic is wide enough for the key, so a 16-byte entry holds a
+//             64-bit fingerprint of the canonical k-mer plus a REFERENCE to one occurrence (stream,
+//             position); entries are still claimed with one `atom.cas.b128`, and a fingerprint match
+//             is settled by comparing the k-mer at the referenced position word for word -- exact,
+//             fingerprints only save comparisons.
 // Inserting several genomes into one set gives the union count; reading the count after each
 // insertion gives the progressive exact unions in one sweep (the reference re-merges databases
 // n(n+1)/2 times).
@@ -29,7 +34,9 @@ static size_t exact_table_bytes(int k, uint64_t capacity) {
     }
     return (size_t)capacity * (k > 32 ? 2 : 1) * sizeof(unsigned long long);
 }
-size_t exact_workspace_bytes(int k, uint64_t capacity) { return 256 + exact_table_bytes(k, capacity); }
+constexpr unsigned kMaxStreams = 512;   // k > 64: streams whose k-mers one set may reference
+static size_t exact_stream_table_bytes(int k) { return k > 64 ? kMaxStreams * sizeof(const uint32_t *) : 0; }
+size_t exact_workspace_bytes(int k, uint64_t capacity) { return 256 + exact_table_bytes(k, capacity) + exact_stream_table_bytes(k); }
 static ExactWsHeader *ex_hdr(void *ws) { return static_cast<ExactWsHeader *>(ws); }
 static void *ex_tab(void *ws) { return static_cast<uint8_t *>(ws) + 256; }
 
@@ -164,6 +171,80 @@ exact_insert_wide_kernel(const uint32_t *__restrict__ codes, const uint32_t *__r
     if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(&hdr->count, fresh);
 }
 
+// ---- k = 65..256: (fingerprint, reference) entries ------------------------------------------------
+constexpr int kRefPosBits = 48;
+
+// one thread: find or append `codes` in the set's stream table; publish its index for the insert kernel
+__global__ void exact_register_stream_kernel(ExactWsHeader *hdr, const uint32_t **streams, const uint32_t *codes) {
+    unsigned long long n = hdr->n_streams, i = 0;
+    while (i < n && streams[i] != codes) ++i;
+    if (i == n) {
+        if (n >= kMaxStreams) {
+            hdr->overflow = 1;
+            i = 0;
+        } else {
+            streams[n] = codes;
+            hdr->n_streams = n + 1;
+        }
+    }
+    hdr->cur_stream = i;
+}
+
+__global__ void __launch_bounds__(kExactThreads)
+exact_insert_long_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict__ invalid, uint64_t sym_begin,
+                         uint64_t sym_end, int k, int canon, ExactWsHeader *hdr, ulonglong2 *tab, uint64_t capacity,
+                         const uint32_t *const *streams, uint32_t shard_rank, uint32_t shard_world) {
+    const uint64_t w = (sym_begin >> 4) + (uint64_t)blockIdx.x * kExactThreads + threadIdx.x;
+    const uint64_t s0 = w << 4;
+    unsigned long long fresh = 0;
+    if (s0 < sym_end) {
+        const int j_lo = sym_begin > s0 ? (int)(sym_begin - s0) : 0;
+        const int j_hi = sym_end - s0 < 16 ? (int)(sym_end - s0) : 16;
+        const ulonglong2 empty = make_ulonglong2(kEmptyKey, kEmptyKey);
+        const uint64_t mask = capacity - 1;
+        const unsigned long long me = hdr->cur_stream << kRefPosBits;
+        int run = 0;
+        for (int j = j_lo; j < j_hi; ++j) {
+            const uint64_t s = s0 + j;
+            // valid symbols ending at s (saturating at k): the first position of the word walks the break
+            // bits backwards, the others extend its count
+            if (j == j_lo) {
+                run = valid_run_upto(invalid, s, k);
+            } else {
+                const bool bad = (invalid[s >> 5] >> (31u - (uint32_t)(s & 31))) & 1u;
+                run = bad ? 0 : (run < k ? run + 1 : k);
+            }
+            if (run < k) continue;
+            uint64_t key[kLongWords];
+            const int W = kmer_long_at(codes, s, k, canon != 0, key);
+            uint64_t h = 0;
+            for (int t = 0; t < W; ++t) h = slot_hash(h ^ key[t]);
+            if (!mine(h, shard_rank, shard_world)) continue;
+            const ulonglong2 entry = make_ulonglong2(h, me | s);
+            uint64_t slot = h & mask;
+            uint64_t probes = 0;
+            for (;;) {
+                ulonglong2 seen = __ldcg(tab + slot);
+                if (seen.x == kEmptyKey && seen.y == kEmptyKey) {
+                    seen = cas128(tab + slot, empty, entry);
+                    if (seen.x == kEmptyKey && seen.y == kEmptyKey) { ++fresh; break; }
+                }
+                if (seen.x == h) {   // same fingerprint: the k-mer at the referenced occurrence decides
+                    uint64_t other[kLongWords];
+                    kmer_long_at(streams[seen.y >> kRefPosBits], seen.y & ((1ull << kRefPosBits) - 1ull), k, canon != 0, other);
+                    bool same = true;
+                    for (int t = 0; t < W; ++t) same = same && other[t] == key[t];
+                    if (same) break;
+                }
+                slot = (slot + 1) & mask;
+                if (++probes > mask) { hdr->overflow = 1; break; }
+            }
+        }
+    }
+    fresh = __reduce_add_sync(0xffffffffu, (unsigned)fresh);
+    if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(&hdr->count, fresh);
+}
+
 __global__ void __launch_bounds__(256) bitmap_count_kernel(const uint32_t *__restrict__ bm, size_t nwords,
                                                            unsigned long long *out) {
     unsigned long long c = 0;
@@ -182,7 +263,10 @@ cudaError_t exact_begin(void *d_ws, int k, uint64_t capacity, cudaStream_t strea
     cudaError_t e = cudaMemsetAsync(d_ws, 0, 256, stream);
     if (e != cudaSuccess) return e;
     const int fill = k <= DD_EXACT_BITMAP_MAXK ? 0x00 : 0xff;
-    return cudaMemsetAsync(ex_tab(d_ws), fill, exact_table_bytes(k, capacity), stream);
+    if ((e = cudaMemsetAsync(ex_tab(d_ws), fill, exact_table_bytes(k, capacity), stream)) != cudaSuccess) return e;
+    if (k > 64)
+        return cudaMemsetAsync(static_cast<uint8_t *>(ex_tab(d_ws)) + exact_table_bytes(k, capacity), 0, exact_stream_table_bytes(k), stream);
+    return cudaSuccess;
 }
 
 cudaError_t exact_insert(const uint32_t *d_codes, const uint32_t *d_invalid, uint64_t sym_begin, uint64_t sym_end,
@@ -191,7 +275,14 @@ cudaError_t exact_insert(const uint32_t *d_codes, const uint32_t *d_invalid, uin
     if (sym_end <= sym_begin) return cudaSuccess;
     const size_t nwords = (size_t)((sym_end - sym_begin + 15) / 16 + 2);  // +2: the range need not start on a word boundary
     const unsigned grid = (unsigned)((nwords + kExactThreads - 1) / kExactThreads);
-    if (k > 32)
+    if (k > 64) {
+        if (sym_end >> kRefPosBits) return cudaErrorInvalidValue;
+        const uint32_t **streams = reinterpret_cast<const uint32_t **>(static_cast<uint8_t *>(ex_tab(d_ws)) + exact_table_bytes(k, capacity));
+        DD_COUNT_LAUNCH(), exact_register_stream_kernel<<<1, 1, 0, stream>>>(ex_hdr(d_ws), streams, d_codes);
+        DD_COUNT_LAUNCH(), exact_insert_long_kernel<<<grid, kExactThreads, 0, stream>>>(d_codes, d_invalid, sym_begin, sym_end, k, canon,
+                                                                    ex_hdr(d_ws), static_cast<ulonglong2 *>(ex_tab(d_ws)),
+                                                                    capacity, streams, shard_rank, shard_world);
+    } else if (k > 32)
         DD_COUNT_LAUNCH(), exact_insert_wide_kernel<<<grid, kExactThreads, 0, stream>>>(d_codes, d_invalid, sym_begin, sym_end, k, canon,
                                                                     ex_hdr(d_ws), static_cast<ulonglong2 *>(ex_tab(d_ws)),
                                                                     capacity, shard_rank, shard_world);

@@ -75,7 +75,8 @@ struct ExactWsHeader {
     unsigned long long count;     // distinct keys inserted (hash-set mode; bitmap mode counts on demand)
     unsigned long long overflow;  // table full
     unsigned long long saw_ones;  // the all-ones key (== the empty marker) was inserted
-    unsigned long long pad;
+    unsigned long long cur_stream;  // k > 64: index (in the stream table) of the stream being inserted
+    unsigned long long n_streams;   // k > 64: streams registered so far
 };
 size_t exact_workspace_bytes(int k, uint64_t capacity);
 cudaError_t exact_begin(void *d_ws, int k, uint64_t capacity, cudaStream_t stream);

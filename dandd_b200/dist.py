@@ -118,13 +118,13 @@ def split_work(n_items: int) -> range:
 
 
 # ---- one genome over several ranks -------------------------------------------------------------------
-def split_fasta(text, nparts: int, overlap_symbols: int = 63, only: int = None, min_grain: int = 4096) -> List[bytes]:
+def split_fasta(text, nparts: int, overlap_symbols: int = 255, only: int = None, min_grain: int = 4096) -> List[bytes]:
     """Cut ONE FASTA text into `nparts` FASTA texts whose sketches merge to the sketch of the whole
     ("genomes < GPUs"): register-wise max for HLL, set union for exact counts.
 
     k-mers never span records, so whole records can go anywhere; a record larger than its fair
     share is cut inside its sequence body and every later piece starts `overlap_symbols` symbols
-    early (>= k-1 for every k <= 64 by default) behind a synthetic header line, so each k-mer of the
+    early (>= k-1 for every k <= 256 by default) behind a synthetic header line, so each k-mer of the
     record lies wholly inside at least one piece.  Seeing a k-mer twice is harmless for a max / a
     set.  Pieces are assigned to parts largest-first; a part may be empty.  `only=r` materialises
     part r alone (the others come back as None) -- a rank needs just its own bytes.  Records are not

@@ -238,13 +238,17 @@ DD_API int dd_pairwise_union_card_planes(const uint32_t *d_planes, int n_genomes
  * Replaces `kmc -ci1 -cs2 -kK [-b] -fm ...` + `kmc_tools info` (lib/sketch_classes.py:389-399,
  * 434-449) and, by inserting several streams into one set, `kmc_tools complex` unions (:451-465).
  * The set lives in the workspace: a 4^k-bit presence bitmap when k <= DD_EXACT_BITMAP_MAXK, else
- * an open-addressing table of 64-bit keys (128-bit keys for 32 < k <= 64 -- the README's "to sweep
- * higher ks you must use KMC via --exact", README.md:82; KMC itself accepts k <= 256) with
- * `capacity` slots (power of two, must exceed the number of distinct k-mers; dd_exact_count reports
- * overflow as DD_ERR_WORKSPACE).  1 <= k <= DD_EXACT_MAXK.
+ * an open-addressing table with `capacity` slots (power of two, must exceed the number of distinct
+ * k-mers; dd_exact_count reports overflow as DD_ERR_WORKSPACE): 64-bit keys to k = 32, 128-bit keys to
+ * k = 64, and for 64 < k <= 256 -- KMC's own limit; the README's "to sweep higher ks you must use KMC
+ * via --exact" (README.md:82), helpers/allpairs.py:295 sweeps to 99 -- 16-byte (fingerprint, reference
+ * to one occurrence) entries whose matches are verified against the packed stream, so the count stays
+ * exact.  In that mode every stream inserted into a set must stay alive and unmodified until the last
+ * dd_exact_insert into that set has completed (at most 512 distinct streams per set).
+ * 1 <= k <= DD_EXACT_MAXK.
  * =========================================================================================== */
 #define DD_EXACT_BITMAP_MAXK 16
-#define DD_EXACT_MAXK 64
+#define DD_EXACT_MAXK 256
 DD_API size_t dd_exact_workspace_bytes(int k, uint64_t capacity);
 DD_API int dd_exact_begin(void *d_ws, size_t ws_bytes, int k, uint64_t capacity, dd_stream stream);
 DD_API int dd_exact_insert(const uint32_t *d_codes, const uint32_t *d_invalid, uint64_t sym_begin, uint64_t sym_end, int k,

@@ -340,8 +340,47 @@ static uint64_t orc_exact_count_wide(const uint8_t *const *sym, const size_t *n,
     return distinct;
 }
 
+/* k = 65..256 (KMC's own limit): k-mers as STRINGS of k symbol bytes -- a formulation that shares
+ * nothing with the packed multi-word arithmetic of the GPU path.  Canonical = the lexicographically
+ * smaller of the k-mer and its reverse complement in A<C<G<T order (identical to the numeric min of
+ * the 2-bit encodings, Appendix B).  Sorted with qsort + memcmp -- test sizes only. */
+static int orc_long_k = 0;
+static int orc_cmp_long(const void *a, const void *b) { return memcmp(a, b, (size_t)orc_long_k); }
+static uint64_t orc_exact_count_long(const uint8_t *const *sym, const size_t *n, int nseq, int k, int canon) {
+    size_t cap = 0, cnt = 0;
+    for (int s = 0; s < nseq; ++s) cap += n[s];
+    uint8_t *a = (uint8_t *)malloc((cap ? cap : 1) * (size_t)k);
+    uint8_t *rc = (uint8_t *)malloc((size_t)k);
+    for (int s = 0; s < nseq; ++s) {
+        size_t run = 0;
+        for (size_t i = 0; i < n[s]; ++i) {
+            if (sym[s][i] > 3) { run = 0; continue; }
+            if (++run < (size_t)k) continue;
+            const uint8_t *fwd = sym[s] + i + 1 - k;
+            const uint8_t *pick = fwd;
+            if (canon) {
+                for (int j = 0; j < k; ++j) rc[j] = (uint8_t)(3 - fwd[k - 1 - j]);
+                if (memcmp(rc, fwd, (size_t)k) < 0) pick = rc;
+            }
+            memcpy(a + cnt * (size_t)k, pick, (size_t)k);
+            ++cnt;
+        }
+    }
+    uint64_t distinct = 0;
+    if (cnt) {
+        orc_long_k = k;
+        qsort(a, cnt, (size_t)k, orc_cmp_long);
+        distinct = 1;
+        for (size_t i = 1; i < cnt; ++i) distinct += memcmp(a + i * (size_t)k, a + (i - 1) * (size_t)k, (size_t)k) != 0;
+    }
+    free(a);
+    free(rc);
+    return distinct;
+}
+
 /* Number of distinct (canonical) k-mers in the union of nseq symbol streams. */
 uint64_t orc_exact_count(const uint8_t *const *sym, const size_t *n, int nseq, int k, int canon) {
+    if (k > 64) return orc_exact_count_long(sym, n, nseq, k, canon);
     if (k > 32) return orc_exact_count_wide(sym, n, nseq, k, canon);
     struct orc_vec v = {0, 0, 0};
     for (int s = 0; s < nseq; ++s) orc_for_each_kmer(sym[s], n[s], k, canon, orc_vec_cb, &v);

@@ -52,6 +52,10 @@ def host_emul():
         getattr(L, name).argtypes = [C.c_uint64, C.c_int]
     L.emul_wang.restype = C.c_uint64
     L.emul_wang.argtypes = [C.c_uint64]
+    L.emul_kmer_long.restype = C.c_int
+    L.emul_kmer_long.argtypes = [u32p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    L.emul_valid_run.restype = C.c_int
+    L.emul_valid_run.argtypes = [u32p, C.c_uint64, C.c_int]
     L.emul_mle.restype = C.c_double
     L.emul_mle.argtypes = [u32p, C.c_int]
     return L

@@ -133,4 +133,14 @@ double emul_mle(const uint32_t *hist64, int p) {
     return ertl_mle(c, p);
 }
 
+// k = 65..256 (exact mode): the multi-word k-mer ending at symbol s_end -> out[0..W), returns W; and the
+// valid-run length used to decide whether such a k-mer exists there.
+int emul_kmer_long(const uint32_t *codes, uint64_t s_end, int k, int canon, uint64_t *out) {
+    uint64_t w[kLongWords];
+    const int W = kmer_long_at(codes, s_end, k, canon != 0, w);
+    for (int t = 0; t < W; ++t) out[t] = w[t];
+    return W;
+}
+int emul_valid_run(const uint32_t *invalid, uint64_t s, int need) { return valid_run_upto(invalid, s, need); }
+
 }  // extern "C"

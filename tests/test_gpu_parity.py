@@ -437,11 +437,40 @@ def test_exact_counts_wide_k(eng, k, canon):
 
 
 @pytest.mark.gpu
-def test_exact_k_above_64_is_refused(eng):
+@pytest.mark.parametrize("k", [65, 99, 128, 129, 200, 256])
+@pytest.mark.parametrize("canon", [True, False])
+def test_exact_counts_long_k(eng, k, canon):
+    """--exact for 64 < k <= 256 (KMC's own limit; helpers/allpairs.py:295 sweeps to 99): entries hold a
+    fingerprint + a reference to one occurrence, matches are verified against the packed stream.  The
+    oracle side is the string formulation (sort + unique of k-byte strings).  Progressive counts over
+    several streams exercise references into earlier streams; the reverse-complement text exercises
+    canonicalisation across word boundaries; a low-complexity text forces many verified duplicates."""
+    rng = np.random.default_rng(900 + k)
+    anc = random_bases(rng, 30000)
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+    rc = bytes(comp[b] for b in anc[5000:20000].tolist()[::-1])
+    repeat = np.tile(random_bases(rng, 700), 12)
+    txts = [to_fasta([(b"a", anc)]), adversarial_fasta(rng, n=15000),
+            to_fasta([(b"m", mutate(rng, anc, sub=0.01))], width=61), b">polyT\n" + b"T" * 600 + b"\n",
+            to_fasta([(b"rc", np.frombuffer(rc, dtype=np.uint8))]), to_fasta([(b"rep", repeat)], width=73)]
+    seqs = [eng.pack(t) for t in txts]
+    syms = [orc.fasta_symbols(t) for t in txts]
+    got = eng.exact_counts(seqs, k, canon)
+    want = [orc.exact_count(syms[:i + 1], k, canon) for i in range(len(syms))]
+    assert got == want
+    if canon:
+        assert got[4] == got[3]             # the reverse complement adds nothing to a canonical set
+    # key-range shards add up to the whole
+    parts = [eng.exact_counts(seqs, k, canon, shard=(r, 3)) for r in range(3)]
+    assert [sum(p[i] for p in parts) for i in range(len(seqs))] == want
+
+
+@pytest.mark.gpu
+def test_exact_k_above_256_is_refused(eng):
     from dandd_b200._lib import DandDError
     seq = eng.pack(b">x\n" + b"ACGT" * 100 + b"\n")
     with pytest.raises(DandDError):
-        eng.exact_counts([seq], 65)
+        eng.exact_counts([seq], 257)
 
 
 @pytest.mark.gpu

@@ -214,3 +214,38 @@ def test_sketch_fuzz_against_oracle(host_emul):
         assert np.array_equal(emul_sketch(host_emul, codes, invalid, nsym, k, p, canon, ranges=ranges), want)
 
     run()
+
+
+@pytest.mark.parametrize("k", [65, 96, 97, 128, 129, 200, 255, 256])
+@pytest.mark.parametrize("canon", [True, False])
+def test_long_kmers_match_string_formulation(host_emul, k, canon):
+    """kmer_long_at (common.cuh; exact mode for 64 < k <= 256): the multi-word value of every valid window
+    equals the base-4 number of the canonical symbol STRING, and valid_run_upto agrees with a walk."""
+    rng = np.random.default_rng(k)
+    txt = to_fasta([(b"a", random_bases(rng, 1500)), (b"b", random_bases(rng, 700))], width=61)
+    txt = txt.replace(b"\n", b"N\n", 3)          # a few breaks
+    sym = orc.fasta_symbols(txt)
+    codes, invalid, nsym = emul_pack(host_emul, txt)
+    out = (C.c_uint64 * 8)()
+    run = 0
+    checked = 0
+    for s in range(nsym):
+        run = 0 if sym[s] > 3 else run + 1
+        got_run = host_emul.emul_valid_run(invalid.ctypes.data_as(U32P), s, k)
+        assert min(run, k) == min(got_run, k), (s, run, got_run)
+        if run < k or (s % 7 and s % 64 > 3):          # every window near word boundaries, a sample elsewhere
+            continue
+        w = host_emul.emul_kmer_long(codes.ctypes.data_as(U32P), s, k, int(canon), out)
+        assert w == (2 * k + 63) // 64
+        value = sum(int(out[t]) << (64 * t) for t in range(w))
+        fwd = sym[s - k + 1:s + 1].tolist()
+        want_syms = fwd
+        if canon:
+            rc = [3 - c for c in reversed(fwd)]
+            want_syms = min(fwd, rc)
+        want = 0
+        for c in want_syms:
+            want = (want << 2) | int(c)
+        assert value == want, (s, k)
+        checked += 1
+    assert checked > 100
