@@ -322,9 +322,11 @@ int dd_prefix_union_card(const uint8_t *d_regs, const int32_t *d_order, int n_or
     if (!d_unions && d_ws && dd::g_prefix_planes && dd::planes_supported(p)) {
         void *base = reinterpret_cast<void *>(align_up(reinterpret_cast<uintptr_t>(d_ws), 256));
         const size_t lost = (size_t)(static_cast<uint8_t *>(base) - static_cast<uint8_t *>(d_ws));
-        if (ws_bytes < lost + dd::prefix_union_workspace_bytes(n_ord, n_steps, n_genomes, nk, p) - 256)
-            return fail(DD_ERR_WORKSPACE, "dd_prefix_union_card: workspace %zu < %zu", ws_bytes,
-                        dd::prefix_union_workspace_bytes(n_ord, n_steps, n_genomes, nk, p));
+        // pairs (two steps, final union only) never use the identical-prefix table: planes alone
+        const bool pairs_only = final_only && n_steps == 2;
+        const size_t need = dd::prefix_union_workspace_bytes(pairs_only ? 0 : n_ord, pairs_only ? 0 : n_steps, n_genomes, nk, p);
+        if (ws_bytes < lost + need - 256)
+            return fail(DD_ERR_WORKSPACE, "dd_prefix_union_card: workspace %zu < %zu", ws_bytes, need);
         DD_CUDA(dd::prefix_union_hist_planes(d_regs, d_order, n_ord, n_steps, n_genomes, nk, p, final_only, d_hist, base, S(stream)),
                 "dd_prefix_union_card(planes)");
     } else {

@@ -67,35 +67,48 @@ __device__ __forceinline__ void plane_max(uint32_t (&R)[kPlanes], const uint32_t
     for (int b = 0; b < kPlanes; ++b) R[b] = (X[b] & lt) | (R[b] & ~lt);
 }
 
-// registers of `members` whose low four bits equal J
+// Counting a dense bucket (16 values sharing the two top planes).  The four combinations of planes 0
+// and 1 inside the bucket are formed once per 32-register chunk (one LOP3 each); a value's registers are
+// then one more LOP3 away (that combination AND planes 2, 3 in the right polarity) -- 1.25 LOP3 per
+// (value, chunk) instead of 4.
+struct BucketLow2 {
+    uint32_t m[4][4];   // [chunk][value & 3]
+};
+__device__ __forceinline__ BucketLow2 bucket_low2(const uint32_t (&P)[4][kPlanes], const uint32_t (&mem)[4]) {
+    BucketLow2 b;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        b.m[c][0] = mem[c] & ~P[c][0] & ~P[c][1];
+        b.m[c][1] = mem[c] & P[c][0] & ~P[c][1];
+        b.m[c][2] = mem[c] & ~P[c][0] & P[c][1];
+        b.m[c][3] = mem[c] & P[c][0] & P[c][1];
+    }
+    return b;
+}
 template <int J>
-__device__ __forceinline__ uint32_t match_low4(const uint32_t (&P)[kPlanes], uint32_t members) {
-    uint32_t t = members;
-    t &= (J & 1) ? P[0] : ~P[0];
-    t &= (J & 2) ? P[1] : ~P[1];
-    t &= (J & 4) ? P[2] : ~P[2];
-    t &= (J & 8) ? P[3] : ~P[3];
-    return t;
+__device__ __forceinline__ uint32_t count_value(const uint32_t (&P)[4][kPlanes], const BucketLow2 &b) {
+    uint32_t n = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        n += __popc(b.m[c][J & 3] & ((J & 4) ? P[c][2] : ~P[c][2]) & ((J & 8) ? P[c][3] : ~P[c][3]));
+    return n;
 }
 
 // Two values per warp reduction (a lane holds at most 128 registers, so a warp sum fits 16 bits);
 // lane J keeps the warp's count of value J, and the sixteen lanes issue one shared-memory add
 // together at the end -- no branch, vote or atomic per value.
 template <int J>
-__device__ __forceinline__ uint32_t count_pair(const uint32_t (&P)[4][kPlanes], const uint32_t (&mem)[4]) {
-    const uint32_t a = __popc(match_low4<J>(P[0], mem[0])) + __popc(match_low4<J>(P[1], mem[1])) +
-                       __popc(match_low4<J>(P[2], mem[2])) + __popc(match_low4<J>(P[3], mem[3]));
-    const uint32_t b = __popc(match_low4<J + 1>(P[0], mem[0])) + __popc(match_low4<J + 1>(P[1], mem[1])) +
-                       __popc(match_low4<J + 1>(P[2], mem[2])) + __popc(match_low4<J + 1>(P[3], mem[3]));
-    return __reduce_add_sync(0xffffffffu, a | (b << 16));
+__device__ __forceinline__ uint32_t count_pair(const uint32_t (&P)[4][kPlanes], const BucketLow2 &b) {
+    return __reduce_add_sync(0xffffffffu, count_value<J>(P, b) | (count_value<J + 1>(P, b) << 16));
 }
 
 template <int... Js>
 __device__ __forceinline__ void count_bucket_dense(std::integer_sequence<int, Js...>, const uint32_t (&P)[4][kPlanes],
                                                    const uint32_t (&mem)[4], uint32_t *s_cnt, int lane) {
+    const BucketLow2 low = bucket_low2(P, mem);
     uint32_t mine = 0;
     (([&] {
-         const uint32_t both = count_pair<2 * Js>(P, mem);
+         const uint32_t both = count_pair<2 * Js>(P, low);
          if (lane == 2 * Js) mine = both & 0xFFFFu;
          if (lane == 2 * Js + 1) mine = both >> 16;
      }()),
@@ -257,6 +270,105 @@ prefix_union_planes_kernel(const uint32_t *__restrict__ planes, const int32_t *_
     }
 }
 
+// ---- pairs (K6) -----------------------------------------------------------------------------------
+// The prefix kernel above gives every 8192-register slice of every (set, k) its own CTA and flushes a
+// histogram per CTA.  For an all-pairs job -- half a million pairs x 23 k x 32 slices -- that is 4e8
+// tiny CTAs whose fixed cost (start-up, two loads' latency, three barriers, a dozen global atomics)
+// dwarfs the ~14k instructions of useful work.  Here ONE CTA owns a whole (pair, k): it walks all the
+// slices, keeps the per-value counts of dense buckets in registers (lane J of a warp holds value J's
+// running count), and writes the 64-bin row once.  grid = (pairs, Y, nk); Y > 1 only when there are too
+// few pairs to fill the chip, in which case the rows are accumulated with atomics.
+template <int... Js>
+__device__ __forceinline__ uint32_t count_bucket_dense_reg(std::integer_sequence<int, Js...>, const uint32_t (&P)[4][kPlanes],
+                                                           const uint32_t (&mem)[4], int lane) {
+    const BucketLow2 low = bucket_low2(P, mem);
+    uint32_t mine = 0;
+    (([&] {
+         const uint32_t both = count_pair<2 * Js>(P, low);
+         if (lane == 2 * Js) mine = both & 0xFFFFu;
+         if (lane == 2 * Js + 1) mine = both >> 16;
+     }()),
+     ...);
+    return mine;
+}
+
+__global__ void __launch_bounds__(kPlThreads, 1024 / kPlThreads)
+pair_union_planes_kernel(const uint32_t *__restrict__ planes, const int32_t *__restrict__ pairs, int n_genomes, int nk, int p,
+                         uint32_t *__restrict__ hist) {
+    __shared__ uint32_t s_cnt[DD_HIST_BINS];
+    const size_t ngroups = (size_t)1 << (p - 5);
+    const size_t nvec = ngroups >> 2;  // uint4 per plane
+    const int pr = blockIdx.x, k = blockIdx.z;
+    const int lane = threadIdx.x & 31;
+    const int ga = pairs[2 * (size_t)pr], gb = pairs[2 * (size_t)pr + 1];
+    const bool have_a = ga >= 0 && ga < n_genomes, have_b = gb >= 0 && gb < n_genomes;
+    const uint4 *pa = reinterpret_cast<const uint4 *>(planes + ((size_t)(have_a ? ga : 0) * nk + k) * kPlanes * ngroups);
+    const uint4 *pb = reinterpret_cast<const uint4 *>(planes + ((size_t)(have_b ? gb : 0) * nk + k) * kPlanes * ngroups);
+    if (threadIdx.x < DD_HIST_BINS) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    uint32_t acc[4] = {0u, 0u, 0u, 0u};   // lane J < 16: registers equal to 16 q + J seen by this warp so far
+    // every warp runs the same number of iterations (the warp-wide reductions need all lanes)
+    const size_t stride = (size_t)gridDim.y * kPlThreads;
+    for (size_t base = (size_t)blockIdx.y * kPlThreads; base < nvec; base += stride) {
+        const size_t vec = base + threadIdx.x;
+        const bool owner = vec < nvec;
+        uint32_t R[4][kPlanes];
+        uint4 xa[kPlanes], xb[kPlanes];
+#pragma unroll
+        for (int b = 0; b < kPlanes; ++b) {
+            xa[b] = owner && have_a ? __ldg(pa + (size_t)b * nvec + vec) : make_uint4(0, 0, 0, 0);
+            xb[b] = owner && have_b ? __ldg(pb + (size_t)b * nvec + vec) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int b = 0; b < kPlanes; ++b) {
+            R[0][b] = xa[b].x;
+            R[1][b] = xa[b].y;
+            R[2][b] = xa[b].z;
+            R[3][b] = xa[b].w;
+        }
+        {
+            uint32_t X[kPlanes];
+#pragma unroll
+            for (int b = 0; b < kPlanes; ++b) X[b] = xb[b].x;
+            plane_max(R[0], X);
+#pragma unroll
+            for (int b = 0; b < kPlanes; ++b) X[b] = xb[b].y;
+            plane_max(R[1], X);
+#pragma unroll
+            for (int b = 0; b < kPlanes; ++b) X[b] = xb[b].z;
+            plane_max(R[2], X);
+#pragma unroll
+            for (int b = 0; b < kPlanes; ++b) X[b] = xb[b].w;
+            plane_max(R[3], X);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // bucket q: values 16q .. 16q+15
+            uint32_t mem[4];
+            uint32_t any = 0u, n = 0u;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                mem[c] = owner ? (((q & 1) ? R[c][4] : ~R[c][4]) & ((q & 2) ? R[c][5] : ~R[c][5])) : 0u;
+                any |= mem[c];
+            }
+            if (!__any_sync(0xffffffffu, any != 0u)) continue;  // nobody in the warp has such values
+#pragma unroll
+            for (int c = 0; c < 4; ++c) n += __popc(mem[c]);
+            if (__any_sync(0xffffffffu, n > 12u)) acc[q] += count_bucket_dense_reg(std::make_integer_sequence<int, 8>{}, R, mem, lane);
+            else count_bucket_sparse(R, mem, s_cnt);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (lane < 16 && acc[q]) atomicAdd(&s_cnt[16 * q + lane], acc[q]);
+    __syncthreads();
+    if (threadIdx.x < DD_HIST_BINS) {
+        const uint32_t c = s_cnt[threadIdx.x];
+        uint32_t *cell = &hist[((size_t)pr * nk + k) * DD_HIST_BINS + threadIdx.x];
+        if (gridDim.y == 1) *cell = c;           // the row is this CTA's alone
+        else if (c) atomicAdd(cell, c);
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 bool planes_supported(int p) { return p >= 12; }   // whole uint4s of groups per plane, >= 1 CTA of work
 size_t planes_bytes(int64_t n_sketches, int p) { return (size_t)n_sketches * kPlanes * (((size_t)1 << p) / 8); }
@@ -285,9 +397,21 @@ cudaError_t prefix_union_hist_from_planes(const uint32_t *d_planes, const int32_
                                           cudaStream_t stream) {
     const int out_steps = final_only ? 1 : n_steps;
     const size_t rows = (size_t)n_ord * out_steps * nk;
-    cudaError_t e = cudaMemsetAsync(d_hist, 0, rows * DD_HIST_BINS * sizeof(uint32_t), stream);
-    if (e != cudaSuccess || rows == 0) return e;
+    if (rows == 0) return cudaSuccess;
     const size_t m = (size_t)1 << p;
+    if (final_only && n_steps == 2) {   // pairs: one CTA per (pair, k) -- or a few, when the job is too small to fill the chip
+        const size_t nvec_p = (m >> 5) >> 2;
+        const size_t max_y = (nvec_p + kPlThreads - 1) / kPlThreads;
+        size_t y = 1;
+        while (y < max_y && (size_t)n_ord * nk * y < (size_t)148 * 64) y <<= 1;
+        cudaError_t e0 = y > 1 ? cudaMemsetAsync(d_hist, 0, rows * DD_HIST_BINS * sizeof(uint32_t), stream) : cudaSuccess;
+        if (e0 != cudaSuccess) return e0;
+        DD_COUNT_LAUNCH(), pair_union_planes_kernel<<<dim3((unsigned)n_ord, (unsigned)y, (unsigned)nk), kPlThreads, 0, stream>>>(
+            d_planes, d_order, n_genomes, nk, p, d_hist);
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, rows * DD_HIST_BINS * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
     const size_t pairs = (size_t)n_ord * n_steps;
     unsigned long long *masks = reinterpret_cast<unsigned long long *>(d_scratch);
     int32_t *rep = d_scratch ? reinterpret_cast<int32_t *>(masks + pairs) : nullptr;
@@ -302,12 +426,8 @@ cudaError_t prefix_union_hist_from_planes(const uint32_t *d_planes, const int32_
     // the ordering / pair index is the fastest grid dimension (co-resident CTAs share slices in L2);
     // gridDim.x has room for 2^31-1 of them
     const dim3 grid((unsigned)n_ord, slices, (unsigned)nk);
-    if (final_only && n_steps == 2)
-        DD_COUNT_LAUNCH(), prefix_union_planes_kernel<true><<<grid, kPlThreads, 0, stream>>>(d_planes, d_order, n_steps, n_genomes, nk, p, final_only,
-                                                                         rep, d_hist);
-    else
-        DD_COUNT_LAUNCH(), prefix_union_planes_kernel<false><<<grid, kPlThreads, 0, stream>>>(d_planes, d_order, n_steps, n_genomes, nk, p, final_only,
-                                                                          rep, d_hist);
+    DD_COUNT_LAUNCH(), prefix_union_planes_kernel<false><<<grid, kPlThreads, 0, stream>>>(d_planes, d_order, n_steps, n_genomes, nk, p, final_only,
+                                                                      rep, d_hist);
     if (dedup) {
         const size_t cells = rows * DD_HIST_BINS;
         const unsigned cb = (unsigned)((cells + 255) / 256 < 1184 ? (cells + 255) / 256 : 1184);
