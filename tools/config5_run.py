@@ -3,7 +3,7 @@
 synthetic 5 Mbp genomes (clusters of 10 mutated copies), k = 10..32, p = 18 (allpairs default
 --nest 262144; reference helpers/allpairs.py:327,360-380 re-sketches BOTH FASTAs for every pair and k).
 
-    [torchrun --nproc-per-node G] python tools/config5_run.py --n 1000 --out profiles/r02_config5_nG.json
+    [torchrun --nproc-per-node G] python tools/config5_run.py --genomes 1000 --out profiles/r02_config5_nG.json
 
     sketch   genomes are sharded round-robin over the ranks; each rank packs + sketches only its own
     gather   NCCL all_gather of the register arrays: every rank then holds all N x 23 x 2^18 sketches
@@ -30,7 +30,7 @@ from tools.synth import mutate_text, synth_fasta  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=1000)
+    ap.add_argument("--genomes", dest="n", type=int, default=1000)
     ap.add_argument("--bases", type=float, default=5e6)
     ap.add_argument("--p", type=int, default=18)
     ap.add_argument("--tile", type=int, default=1 << 16)

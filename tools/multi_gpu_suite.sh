@@ -5,7 +5,7 @@ N=$1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
 $TR bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r02_bench_c2_n$N.json 2> gpurun_out/r02_bench_c2_n$N.err
 $TR bench.py --gpus $N --config 3 --steps 3 --warmup 3 > gpurun_out/r02_bench_c3_n$N.json 2> gpurun_out/r02_bench_c3_n$N.err
-$TR tools/config5_run.py --n 1000 --out gpurun_out/r02_config5_n$N.json > /dev/null 2> gpurun_out/r02_config5_n$N.err
+$TR tools/config5_run.py --genomes 1000 --out gpurun_out/r02_config5_n$N.json > /dev/null 2> gpurun_out/r02_config5_n$N.err
 if [ "$2" = "cli" ]; then
   python tools/config3_cli.py --gpus $N --genomes 8 --bases 3.1e9 --cpu-sample-bytes 256e6 --also-torchrun --out gpurun_out/r02_config3_cli_${N}gpu.json > /dev/null 2> gpurun_out/cfg3_${N}gpu.err
 fi
