@@ -81,6 +81,12 @@ class Engine:
         check(self.lib.dd_set_option(b"polyt_sentinel", int(self.polyt_sentinel)), "dd_set_option")
 
     # ---- plumbing ---------------------------------------------------------------------------
+    def bind_thread(self) -> None:
+        """Make this engine's GPU the calling thread's current device.  The CUDA runtime's current
+        device is per host thread: an engine created on one thread (the command line starts it in the
+        background) must be bound again on every other thread that launches through it."""
+        torch.cuda.set_device(self.device)
+
     @property
     def stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream

@@ -371,8 +371,11 @@ class GpuSketchStore:
         return self.exact_workers
 
 
+import threading as _threading  # noqa: E402
+
 _store = None
-_store_lock = __import__("threading").Lock()
+_store_lock = _threading.Lock()
+_bound_threads = set()
 
 
 def get_store():
@@ -388,6 +391,10 @@ def get_store():
                 with timing.span("engine_start"):    # CUDA context + library load (torch itself was imported with this module)
                     _store = GpuSketchStore()
                 timing.mark("engine_ready")
+    ident = _threading.get_ident()
+    if ident not in _bound_threads and hasattr(getattr(_store, "engine", None), "bind_thread"):
+        _store.engine.bind_thread()                  # the store may have been started on another thread
+        _bound_threads.add(ident)
     return _store
 
 
