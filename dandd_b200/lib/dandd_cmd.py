@@ -127,7 +127,7 @@ def _self_launch(args) -> list:
         sock.bind(("127.0.0.1", 0))
         port = sock.getsockname()[1]
     base = dict(os.environ, WORLD_SIZE=str(n), LOCAL_WORLD_SIZE=str(n), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    base.setdefault("OMP_NUM_THREADS", "4")     # N processes share the host's cores (torchrun sets 1)
+    base.setdefault("OMP_NUM_THREADS", "1")     # N processes share the host's cores (torchrun does the same)
     # each process sees only its own GPU (as device 0): CUDA start-up does not grow with the node's GPU count
     visible = os.environ.get("CUDA_VISIBLE_DEVICES")
     ids = visible.split(",") if visible else [str(i) for i in range(n)]

@@ -148,6 +148,9 @@ def run(args):
                                      "--bases", str(args.bases)], port=29621)
         rep["generate_s"] = round(dt, 2)
     rep["fasta_bytes"] = [os.path.getsize(os.path.join(data, f"genome{g}.fa")) for g in range(args.genomes)]
+    t0 = time.perf_counter()
+    subprocess.run(["sync"])      # the files were just written: let the write-back finish before anything is timed
+    rep["sync_after_generate_s"] = round(time.perf_counter() - t0, 2)
     # 2. dandd tree --ksweep under torchrun
     timing_tree = os.path.join(workdir, "timing_tree.jsonl")
     env = dict(os.environ, DANDD_B200_TIMING=timing_tree, DANDD_B200_UNION_FILES=args.union_files)
