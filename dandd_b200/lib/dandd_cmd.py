@@ -133,12 +133,15 @@ def _self_launch(args) -> list:
     ids = visible.split(",") if visible else [str(i) for i in range(n)]
     if len(ids) < n:
         raise SystemExit(f"--gpus {n}: only {len(ids)} device(s) in CUDA_VISIBLE_DEVICES")
-    os.environ.update(base, RANK="0", LOCAL_RANK="0", CUDA_VISIBLE_DEVICES=ids[0])
+    narrow = os.environ.get("DANDD_B200_NARROW_DEVICES", "1") != "0"
+
+    def rank_env(r):
+        return dict(RANK=str(r), LOCAL_RANK="0", CUDA_VISIBLE_DEVICES=ids[r]) if narrow else dict(RANK=str(r), LOCAL_RANK=str(r))
+    os.environ.update(base, **rank_env(0))
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dandd")
     children = []
     for r in range(1, n):
-        env = dict(base, RANK=str(r), LOCAL_RANK="0", CUDA_VISIBLE_DEVICES=ids[r])
-        children.append(subprocess.Popen([sys.executable, script] + sys.argv[1:], env=env))
+        children.append(subprocess.Popen([sys.executable, script] + sys.argv[1:], env=dict(base, **rank_env(r))))
     return children
 
 
