@@ -449,7 +449,7 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     try:   # DRAM bytes per K2 launch from the committed `ncu --set full` capture of this same command
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_k2_traffic.json")))["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_k2_traffic.json")))["dram_bytes_per_launch"]
     except Exception:
         traffic = None
     k2_avg_ms = sum(k2_ms) / len(k2_ms)
@@ -484,7 +484,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"kernel": "sketch_allk_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-                     "traffic_source": "profiles/r01_sketch_allk_final_ncu.md (dram__bytes_read+write per launch)",
+                     "traffic_source": "profiles/r02_sketch_allk_cfg2_ncu.md (dram__bytes_read+write per launch, ncu --set full of this command)",
                      "algorithmic_bytes_per_launch": bases_per_launch * 1.0,
                      "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650 GB/s",
                      "algorithmic_bytes_per_base": 1.0, "launch_ms": k2_avg_ms,
