@@ -26,6 +26,7 @@ extern int g_polyt_sentinel;  // dd_set_option("polyt_sentinel"): the *_host ent
 
 // ---- K2 (sketch.cu).  Workspace = [SketchWsHeader | u16 accumulators [nk][2^p]]
 extern int g_k_per_pass;
+extern int g_midk;
 struct SketchWsHeader {
     uint8_t floor[32];  // floor[k-1] <= min(register of k): updates with rank <= floor are no-ops
     uint32_t use_floor;

@@ -65,6 +65,7 @@ struct SketchArgs {
     uint32_t kmask_run;           // the k values this launch updates (subset of kmask)
     int p;
     uint32_t *acc;                // [nk][2^p / 2] words, two u16 registers per word
+    uint32_t *midk;               // presence bitmaps for k = 10..12 (kMidK variants only)
     const SketchWsHeader *hdr;
     uint32_t ntiles;              // upper bound on the (CTA size)-word tiles of the symbol range
 };
@@ -79,6 +80,22 @@ __host__ __device__ constexpr uint32_t bitmap_offset(int k) {  // words before t
 }
 constexpr uint32_t kBitmapWords = bitmap_offset(kBitmapMaxK + 1);  // 10924 words = 43.7 KB
 constexpr uint32_t kSmallKMask = (1u << kBitmapMaxK) - 1u;
+
+// Mid k (10..12) on LONG genomes.  4^k is still far below the number of k-mers of a multi-Gbp genome
+// (k = 12: 8.4 M canonical k-mers against 3.1 G windows), so almost every window repeats one already
+// hashed -- but the bitmaps (128 KiB + 512 KiB + 2 MiB) no longer fit in shared memory.  They live in
+// the workspace, shared by all CTAs through L2: one 4-byte load per (symbol, k) replaces the hash,
+// compare and branch of a repeat.  Sound by construction: a bit is only ever set by the thread that goes
+// on to issue that k-mer's update, and the same k-mer always yields the same (register, rank).  Only
+// launches deep inside a long stream use it (the host decides); short genomes keep the plain path,
+// where the extra L2 loads would compete with the reductions that bound it.
+constexpr int kMidKLo = 10, kMidKHi = 12;
+__host__ __device__ constexpr uint32_t midk_offset(int k) {   // words before the bitmap of k
+    uint32_t o = 0;
+    for (int j = kMidKLo; j < k; ++j) o += (1u << (2 * j)) / 32u;
+    return o;
+}
+constexpr uint32_t kMidKWords = midk_offset(kMidKHi + 1);     // 688 128 words = 2.6 MiB
 
 // 64-bit x times 32-bit constant: IMAD.WIDE.U32 + IMAD, both on the FMA pipe (PTX spelled out so
 // that ptxas does not split the high-word multiply-add).
@@ -176,10 +193,10 @@ struct KConsts {
 // Cost after the hash (SASS, profiles/r02_k2_sass.md): the common case -- rank <= floor on a long
 // genome -- is one funnel shift, one compare and one branch; rank, register index and address are
 // only computed by the lanes that actually update.
-template <int K, bool kCanon, uint32_t kStaticMask>
+template <int K, bool kCanon, uint32_t kStaticMask, bool kMidK>
 __device__ __forceinline__ void update_one_k(const Window &win, int run, uint32_t kmask, uint32_t kmask_run, int p,
                                              uint32_t *acc, uint32_t &off_k, const KConsts &kc, uint32_t *s_seen,
-                                             uint64_t minus_one) {
+                                             uint32_t *midk, uint64_t minus_one) {
     constexpr uint32_t bit = 1u << (K - 1);
     if (kStaticMask) {
         if (!(kStaticMask & bit)) return;    // compile time
@@ -197,6 +214,17 @@ __device__ __forceinline__ void update_one_k(const Window &win, int run, uint32_
         uint32_t *word = s_seen + bitmap_offset(K) + ((uint32_t)v >> 5);
         const uint32_t seen_bit = 1u << ((uint32_t)v & 31u);
         live = live && !(*word & seen_bit);
+        if (live) atomicOr(word, seen_bit);
+        if (!__any_sync(0xffffffffu, live)) {
+            if (!kStaticMask) off_k += 1u << (p - 1);
+            return;
+        }
+    }
+    if (kMidK && K >= kMidKLo && K <= kMidKHi) {
+        // already sent by ANY CTA of this sketch?  (L2-resident bitmap; a stale "not yet" only repeats an idempotent update)
+        uint32_t *word = midk + midk_offset(K) + ((uint32_t)v >> 5);
+        const uint32_t seen_bit = 1u << ((uint32_t)v & 31u);
+        live = live && !(__ldcg(word) & seen_bit);
         if (live) atomicOr(word, seen_bit);
         if (!__any_sync(0xffffffffu, live)) {
             if (!kStaticMask) off_k += 1u << (p - 1);
@@ -240,15 +268,15 @@ __device__ __forceinline__ void update_one_k(const Window &win, int run, uint32_
     if (!kStaticMask) off_k += 1u << (p - 1);
 }
 
-template <bool kCanon, uint32_t kStaticMask, int... Ks>
+template <bool kCanon, uint32_t kStaticMask, bool kMidK, int... Ks>
 __device__ __forceinline__ void update_all_k(std::integer_sequence<int, Ks...>, const Window &win, int run,
                                              uint32_t kmask, uint32_t kmask_run, int p, uint32_t *acc,
-                                             const KConsts &kc, uint32_t *s_seen, uint64_t minus_one) {
+                                             const KConsts &kc, uint32_t *s_seen, uint32_t *midk, uint64_t minus_one) {
     uint32_t off_k = 0;
-    (update_one_k<Ks + 1, kCanon, kStaticMask>(win, run, kmask, kmask_run, p, acc, off_k, kc, s_seen, minus_one), ...);
+    (update_one_k<Ks + 1, kCanon, kStaticMask, kMidK>(win, run, kmask, kmask_run, p, acc, off_k, kc, s_seen, midk, minus_one), ...);
 }
 
-template <bool kCanon, uint32_t kStaticMask, int kThreads>
+template <bool kCanon, uint32_t kStaticMask, int kThreads, bool kMidK = false>
 __global__ void __launch_bounds__(kThreads, min_ctas_for(kThreads)) sketch_allk_kernel(SketchArgs a) {
     extern __shared__ uint32_t s_seen[];  // presence bitmaps, only allocated when a k <= 9 is requested
     const bool small_k = ((kStaticMask ? kStaticMask : a.kmask_run) & kSmallKMask) != 0u;
@@ -298,8 +326,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas_for(kThreads)) sketch_allk_
             int run = all_valid ? 32 : valid_run(invalid_window(i0, i1, sm_base + (uint32_t)j));
             if (j < j_lo || j >= j_hi) run = 0;
             if (!__any_sync(0xffffffffu, run != 0)) continue;  // warp-uniform
-            update_all_k<kCanon, kStaticMask>(std::make_integer_sequence<int, 32>{}, win, run, a.kmask, a.kmask_run, a.p,
-                                              a.acc, kc, s_seen, minus_one);
+            update_all_k<kCanon, kStaticMask, kMidK>(std::make_integer_sequence<int, 32>{}, win, run, a.kmask, a.kmask_run, a.p,
+                                                     a.acc, kc, s_seen, a.midk, minus_one);
         }
     }
 }
@@ -380,7 +408,16 @@ struct SketchVariant {
     int threads;
     int id;   // index into the occupancy cache
 };
-static SketchVariant pick_kernel(bool canon, uint32_t kmask, uint32_t kmask_run) {
+static SketchVariant pick_kernel(bool canon, uint32_t kmask, uint32_t kmask_run, bool midk) {
+    if (midk && kmask == kmask_run && (kmask == kMask2to32 || kmask == kMask1to32)) {
+        const int id = 10 + (kmask == kMask1to32 ? 2 : 0) + (canon ? 1 : 0);
+        switch (id) {
+            case 10: return {sketch_allk_kernel<false, kMask2to32, kThreadsSmallK, true>, kThreadsSmallK, id};
+            case 11: return {sketch_allk_kernel<true, kMask2to32, kThreadsSmallK, true>, kThreadsSmallK, id};
+            case 12: return {sketch_allk_kernel<false, kMask1to32, kThreadsSmallK, true>, kThreadsSmallK, id};
+            default: return {sketch_allk_kernel<true, kMask1to32, kThreadsSmallK, true>, kThreadsSmallK, id};
+        }
+    }
     int v = 0;
     if (kmask == kmask_run) v = kmask == kMask10to32 ? 1 : kmask == kMask2to32 ? 2 : kmask == kMask1to32 ? 3 : 0;
     const bool small_k = (kmask_run & kSmallKMask) != 0u;
@@ -403,7 +440,7 @@ static SketchVariant pick_kernel(bool canon, uint32_t kmask, uint32_t kmask_run)
 // SM count x resident CTAs per SM for the persistent (small-k) launch, cached per (device, variant).
 static unsigned persistent_grid(const SketchVariant &v, size_t smem) {
     constexpr int kMaxDev = 64;
-    static unsigned cached[kMaxDev][10] = {};
+    static unsigned cached[kMaxDev][14] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     unsigned local = 0;
@@ -418,8 +455,12 @@ static unsigned persistent_grid(const SketchVariant &v, size_t smem) {
     return g;
 }
 
-size_t sketch_workspace_bytes(int nk, int p) {
-    return sizeof(SketchWsHeader) + 256 + (size_t)nk * sizeof(uint16_t) * ((size_t)1 << p);
+static size_t acc_bytes(int nk, int p) { return ((size_t)nk * sizeof(uint16_t) * ((size_t)1 << p) + 255) / 256 * 256; }
+size_t sketch_workspace_bytes(int nk, int p) {   // [header | scratch | accumulators | mid-k bitmaps]
+    return sizeof(SketchWsHeader) + 256 + acc_bytes(nk, p) + (size_t)kMidKWords * sizeof(uint32_t);
+}
+static uint32_t *ws_midk(void *ws, int nk, int p) {
+    return reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ws) + sizeof(SketchWsHeader) + 256 + acc_bytes(nk, p));
 }
 static SketchWsHeader *ws_hdr(void *ws) { return static_cast<SketchWsHeader *>(ws); }
 static uint32_t *ws_scratch(void *ws) { return reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ws) + sizeof(SketchWsHeader)); }
@@ -429,9 +470,21 @@ cudaError_t sketch_begin(void *d_ws, int nk, int p, cudaStream_t stream) {
     return cudaMemsetAsync(d_ws, 0, sketch_workspace_bytes(nk, p), stream);
 }
 
+int g_midk = 1;   // dd_set_option("sketch_midk", 0/1): tuning knob, never changes results
+
+static cudaError_t sketch_update_impl(const uint32_t *d_codes, const uint32_t *d_invalid, const dd_pack_state *d_state,
+                                      uint64_t sym_begin, uint64_t sym_end, size_t max_new_symbols, uint32_t kmask, int p,
+                                      int canon, void *d_ws, bool midk, cudaStream_t stream);
+
 cudaError_t sketch_update(const uint32_t *d_codes, const uint32_t *d_invalid, const dd_pack_state *d_state,
                           uint64_t sym_begin, uint64_t sym_end, size_t max_new_symbols, uint32_t kmask, int p,
                           int canon, void *d_ws, cudaStream_t stream) {
+    return sketch_update_impl(d_codes, d_invalid, d_state, sym_begin, sym_end, max_new_symbols, kmask, p, canon, d_ws, false, stream);
+}
+
+static cudaError_t sketch_update_impl(const uint32_t *d_codes, const uint32_t *d_invalid, const dd_pack_state *d_state,
+                                      uint64_t sym_begin, uint64_t sym_end, size_t max_new_symbols, uint32_t kmask, int p,
+                                      int canon, void *d_ws, bool midk, cudaStream_t stream) {
     SketchArgs a;
     a.codes = d_codes;
     a.invalid = d_invalid;
@@ -442,6 +495,7 @@ cudaError_t sketch_update(const uint32_t *d_codes, const uint32_t *d_invalid, co
     a.kmask_run = kmask;
     a.p = p;
     a.acc = ws_acc(d_ws);
+    a.midk = ws_midk(d_ws, __builtin_popcount(kmask), p);
     a.hdr = ws_hdr(d_ws);
     if (d_state && sym_end <= sym_begin) {   // state-relative range not given: the whole last pack call
         a.sym_begin = 0;
@@ -472,7 +526,7 @@ cudaError_t sketch_update(const uint32_t *d_codes, const uint32_t *d_invalid, co
         // the bitmaps in dynamic shared memory; otherwise one CTA per tile and no shared memory.
         const bool small_k = (run & kSmallKMask) != 0u;
         const size_t smem = small_k ? kBitmapWords * sizeof(uint32_t) : 0;
-        const SketchVariant v = pick_kernel(canon != 0, kmask, run);
+        const SketchVariant v = pick_kernel(canon != 0, kmask, run, midk);
         const size_t ntiles = (nwords + v.threads - 1) / v.threads;
         if (ntiles > 0xffffffffull) return cudaErrorInvalidValue;
         a.ntiles = (uint32_t)ntiles;
@@ -506,8 +560,10 @@ cudaError_t sketch_update_sched(const uint32_t *d_codes, const uint32_t *d_inval
         const uint64_t to_cut = cut - (seen_before + pos);
         const bool refresh = to_cut <= total - pos;
         const uint64_t upto = refresh ? pos + to_cut : total;
-        if ((e = sketch_update(d_codes, d_invalid, d_state, origin + pos, origin + upto, max_new_symbols, kmask, p, canon, d_ws,
-                               stream)) != cudaSuccess)
+        // pieces that start at least 4^12 symbols into the stream: the k = 10..12 presence bitmaps pay off
+        const bool midk = g_midk && seen_before + pos >= ((uint64_t)1 << 24);
+        if ((e = sketch_update_impl(d_codes, d_invalid, d_state, origin + pos, origin + upto, max_new_symbols, kmask, p, canon, d_ws,
+                                    midk, stream)) != cudaSuccess)
             return e;
         pos = upto;
         if (refresh) {

@@ -374,3 +374,39 @@ def test_store_streams_large_fastas(eng, tmp_path, monkeypatch):
             assert cards[k] == pytest.approx(orc.card(want, 14), rel=CARD_RTOL)
         assert ingest.digest(str(path)) == hashlib.blake2b(txt).hexdigest()
     assert len(st.stream_stats) == 1          # the FASTA streamed; the FASTQ took the detour
+
+
+# ------------------------------------------------------------------------------------- K2, long streams
+def test_midk_bitmaps_long_stream(eng):
+    """Pieces that start >= 2^24 symbols into a stream consult the L2-resident presence bitmaps for
+    k = 10..12 (sketch.cu, kMidK) and the floor schedule has refreshed several times by then: registers
+    for every k must still be bit-identical to the oracle, with the knob on and off, for the k = 2..32 and
+    k = 1..32 static variants, canonical and not."""
+    from dandd_b200._lib import check
+    rng = np.random.default_rng(2024)
+    n = 21_000_000
+    seq = random_bases(rng, n)
+    seq[rng.random(n) < 0.3] |= 0x20                      # soft-masked
+    for st in rng.integers(0, n - 2000, 40):
+        seq[st:st + 1500] = ord("N")
+    seq[18_000_000:18_000_600] = ord("T")                 # low complexity inside the mid-k region
+    txt = to_fasta([(b"chr%d" % i, seq[i * (n // 3):(i + 1) * (n // 3)]) for i in range(3)], width=80)
+    sym = orc.fasta_symbols(txt)
+    p = 14
+    packed = eng.pack(txt)
+    for ks, canon in ((list(range(2, 33)), True), (list(range(1, 33)), False)):
+        check_ks = [2, 9, 10, 11, 12, 13, 32] if canon else [1, 10, 12, 31]
+        with ThreadPoolExecutor(THREADS) as ex:
+            want = dict(zip(check_ks, ex.map(lambda k: orc.hll_sketch(sym, k, p, canon), check_ks)))
+        for knob in (1, 0):
+            check(eng.lib.dd_set_option(b"sketch_midk", knob))
+            try:
+                regs, cards = eng.sketch(packed, ks, p=p, canon=canon)
+            finally:
+                check(eng.lib.dd_set_option(b"sketch_midk", 1))
+            regs = regs.cpu().numpy()
+            for k in check_ks:
+                assert np.array_equal(regs[ks.index(k)], want[k]), (k, canon, knob)
+    hregs, _ = eng.sketch_fasta_host(txt, list(range(2, 33)), p=p)     # chunked host path: 32 MiB text chunks
+    for k in (10, 11, 12, 32):
+        assert np.array_equal(hregs[k - 2], orc.hll_sketch(sym, k, p)), k
