@@ -65,7 +65,8 @@ struct SketchArgs {
     uint32_t kmask_run;           // the k values this launch updates (subset of kmask)
     int p;
     uint32_t *acc;                // [nk][2^p / 2] words, two u16 registers per word
-    uint32_t *midk;               // presence bitmaps for k = 10..12 (kMidK variants only)
+    uint32_t *midk;               // presence bitmaps for k = 10..14 (kMidK variants only)
+    int midk_hi;                  // largest k whose bitmap this launch consults (12..14)
     const SketchWsHeader *hdr;
     uint32_t ntiles;              // upper bound on the (CTA size)-word tiles of the symbol range
 };
@@ -89,13 +90,13 @@ constexpr uint32_t kSmallKMask = (1u << kBitmapMaxK) - 1u;
 // on to issue that k-mer's update, and the same k-mer always yields the same (register, rank).  Only
 // launches deep inside a long stream use it (the host decides); short genomes keep the plain path,
 // where the extra L2 loads would compete with the reductions that bound it.
-constexpr int kMidKLo = 10, kMidKHi = 12;
+constexpr int kMidKLo = 10, kMidKHi = 14;   // k = 13 (8 MiB) and 14 (32 MiB) join once the stream is >= 4^k symbols long
 __host__ __device__ constexpr uint32_t midk_offset(int k) {   // words before the bitmap of k
     uint32_t o = 0;
     for (int j = kMidKLo; j < k; ++j) o += (1u << (2 * j)) / 32u;
     return o;
 }
-constexpr uint32_t kMidKWords = midk_offset(kMidKHi + 1);     // 688 128 words = 2.6 MiB
+constexpr uint32_t kMidKWords = midk_offset(kMidKHi + 1);     // 42.6 MiB in all; k <= 12 alone: 2.6 MiB
 
 // 64-bit x times 32-bit constant: IMAD.WIDE.U32 + IMAD, both on the FMA pipe (PTX spelled out so
 // that ptxas does not split the high-word multiply-add).
@@ -196,7 +197,7 @@ struct KConsts {
 template <int K, bool kCanon, uint32_t kStaticMask, bool kMidK>
 __device__ __forceinline__ void update_one_k(const Window &win, int run, uint32_t kmask, uint32_t kmask_run, int p,
                                              uint32_t *acc, uint32_t &off_k, const KConsts &kc, uint32_t *s_seen,
-                                             uint32_t *midk, uint64_t minus_one) {
+                                             uint32_t *midk, int midk_hi, uint64_t minus_one) {
     constexpr uint32_t bit = 1u << (K - 1);
     if (kStaticMask) {
         if (!(kStaticMask & bit)) return;    // compile time
@@ -220,7 +221,7 @@ __device__ __forceinline__ void update_one_k(const Window &win, int run, uint32_
             return;
         }
     }
-    if (kMidK && K >= kMidKLo && K <= kMidKHi) {
+    if (kMidK && K >= kMidKLo && K <= kMidKHi && (K <= 12 || K <= midk_hi)) {   // (warp-uniform)
         // already sent by ANY CTA of this sketch?  (L2-resident bitmap; a stale "not yet" only repeats an idempotent update)
         uint32_t *word = midk + midk_offset(K) + ((uint32_t)v >> 5);
         const uint32_t seen_bit = 1u << ((uint32_t)v & 31u);
@@ -271,9 +272,10 @@ __device__ __forceinline__ void update_one_k(const Window &win, int run, uint32_
 template <bool kCanon, uint32_t kStaticMask, bool kMidK, int... Ks>
 __device__ __forceinline__ void update_all_k(std::integer_sequence<int, Ks...>, const Window &win, int run,
                                              uint32_t kmask, uint32_t kmask_run, int p, uint32_t *acc,
-                                             const KConsts &kc, uint32_t *s_seen, uint32_t *midk, uint64_t minus_one) {
+                                             const KConsts &kc, uint32_t *s_seen, uint32_t *midk, int midk_hi,
+                                             uint64_t minus_one) {
     uint32_t off_k = 0;
-    (update_one_k<Ks + 1, kCanon, kStaticMask, kMidK>(win, run, kmask, kmask_run, p, acc, off_k, kc, s_seen, midk, minus_one), ...);
+    (update_one_k<Ks + 1, kCanon, kStaticMask, kMidK>(win, run, kmask, kmask_run, p, acc, off_k, kc, s_seen, midk, midk_hi, minus_one), ...);
 }
 
 template <bool kCanon, uint32_t kStaticMask, int kThreads, bool kMidK = false>
@@ -293,6 +295,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas_for(kThreads)) sketch_allk_
     }
     __syncthreads();
     const uint64_t minus_one = ~0ull;   // (ptxas splits the addend off the IMAD.WIDE whether or not it can see its value)
+    // k = 13 / 14 bitmaps: only those the header says were zeroed since dd_sketch_begin
+    const int midk_hi = kMidK ? min(a.midk_hi, max(12, (int)a.hdr->pad[0])) : 0;
     uint64_t sym_begin = a.sym_begin, sym_end = a.sym_end;
     if (a.state) {   // the range of the last pack call; a.sym_begin / a.sym_end select a sub-range of it, relative to its start
         const uint64_t first = a.state->prev_nsym, last = a.state->nsym;
@@ -327,9 +331,14 @@ __global__ void __launch_bounds__(kThreads, min_ctas_for(kThreads)) sketch_allk_
             if (j < j_lo || j >= j_hi) run = 0;
             if (!__any_sync(0xffffffffu, run != 0)) continue;  // warp-uniform
             update_all_k<kCanon, kStaticMask, kMidK>(std::make_integer_sequence<int, 32>{}, win, run, a.kmask, a.kmask_run, a.p,
-                                                     a.acc, kc, s_seen, a.midk, minus_one);
+                                                     a.acc, kc, s_seen, a.midk, midk_hi, minus_one);
         }
     }
+}
+
+// marks the presence bitmap of k (13 or 14) as zeroed since dd_sketch_begin (which clears the header)
+__global__ void midk_ready_kernel(SketchWsHeader *hdr, uint32_t k) {
+    if (hdr->pad[0] < k) hdr->pad[0] = k;
 }
 
 // ---- per-slot min(register): the "floor" filter ---------------------------------------------------
@@ -467,24 +476,27 @@ static uint32_t *ws_scratch(void *ws) { return reinterpret_cast<uint32_t *>(stat
 static uint32_t *ws_acc(void *ws) { return reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ws) + sizeof(SketchWsHeader) + 256); }
 
 cudaError_t sketch_begin(void *d_ws, int nk, int p, cudaStream_t stream) {
-    return cudaMemsetAsync(d_ws, 0, sketch_workspace_bytes(nk, p), stream);
+    // header, scratch, accumulators and the k <= 12 bitmaps; the 8 + 32 MiB of k = 13 / 14 are zeroed by the
+    // launch that first consults them (only streams longer than 4^13 symbols ever do)
+    return cudaMemsetAsync(d_ws, 0, sizeof(SketchWsHeader) + 256 + acc_bytes(nk, p) + (size_t)midk_offset(13) * sizeof(uint32_t), stream);
 }
 
 int g_midk = 1;   // dd_set_option("sketch_midk", 0/1): tuning knob, never changes results
 
 static cudaError_t sketch_update_impl(const uint32_t *d_codes, const uint32_t *d_invalid, const dd_pack_state *d_state,
                                       uint64_t sym_begin, uint64_t sym_end, size_t max_new_symbols, uint32_t kmask, int p,
-                                      int canon, void *d_ws, bool midk, cudaStream_t stream);
+                                      int canon, void *d_ws, int midk_hi, cudaStream_t stream);
 
 cudaError_t sketch_update(const uint32_t *d_codes, const uint32_t *d_invalid, const dd_pack_state *d_state,
                           uint64_t sym_begin, uint64_t sym_end, size_t max_new_symbols, uint32_t kmask, int p,
                           int canon, void *d_ws, cudaStream_t stream) {
-    return sketch_update_impl(d_codes, d_invalid, d_state, sym_begin, sym_end, max_new_symbols, kmask, p, canon, d_ws, false, stream);
+    return sketch_update_impl(d_codes, d_invalid, d_state, sym_begin, sym_end, max_new_symbols, kmask, p, canon, d_ws, 0, stream);
 }
 
 static cudaError_t sketch_update_impl(const uint32_t *d_codes, const uint32_t *d_invalid, const dd_pack_state *d_state,
                                       uint64_t sym_begin, uint64_t sym_end, size_t max_new_symbols, uint32_t kmask, int p,
-                                      int canon, void *d_ws, bool midk, cudaStream_t stream) {
+                                      int canon, void *d_ws, int midk_hi, cudaStream_t stream) {
+    const bool midk = midk_hi >= 12;
     SketchArgs a;
     a.codes = d_codes;
     a.invalid = d_invalid;
@@ -496,6 +508,7 @@ static cudaError_t sketch_update_impl(const uint32_t *d_codes, const uint32_t *d
     a.p = p;
     a.acc = ws_acc(d_ws);
     a.midk = ws_midk(d_ws, __builtin_popcount(kmask), p);
+    a.midk_hi = midk_hi;
     a.hdr = ws_hdr(d_ws);
     if (d_state && sym_end <= sym_begin) {   // state-relative range not given: the whole last pack call
         a.sym_begin = 0;
@@ -560,10 +573,26 @@ cudaError_t sketch_update_sched(const uint32_t *d_codes, const uint32_t *d_inval
         const uint64_t to_cut = cut - (seen_before + pos);
         const bool refresh = to_cut <= total - pos;
         const uint64_t upto = refresh ? pos + to_cut : total;
-        // pieces that start at least 4^12 symbols into the stream: the k = 10..12 presence bitmaps pay off
-        const bool midk = g_midk && seen_before + pos >= ((uint64_t)1 << 24);
+        // a k's presence bitmap pays off once the stream is >= 4^k symbols long: k <= 12 from 2^24 symbols on,
+        // k = 13 from 2^26, k = 14 from 2^28 (their bitmaps are zeroed when they are first consulted)
+        const uint64_t at = seen_before + pos, at_end = seen_before + upto;
+        const bool wide = kmask == kMask2to32 || kmask == kMask1to32;
+        const int midk_hi = !g_midk || !wide || at < ((uint64_t)1 << 24) ? 0 : at < ((uint64_t)1 << 26) ? 12 : at < ((uint64_t)1 << 28) ? 13 : 14;
+        // the piece during which the stream crosses 4^13 (4^14) symbols zeroes that bitmap for the pieces after it;
+        // the kernel only trusts a bitmap the header says has been zeroed since dd_sketch_begin
+        if (g_midk && wide)
+            for (int k = 13; k <= kMidKHi; ++k) {
+                const uint64_t T = (uint64_t)1 << (2 * k);
+                if (at < T && T <= at_end) {
+                    uint32_t *mk = ws_midk(d_ws, __builtin_popcount(kmask), p);
+                    if ((e = cudaMemsetAsync(mk + midk_offset(k), 0, (size_t)(midk_offset(k + 1) - midk_offset(k)) * sizeof(uint32_t),
+                                             stream)) != cudaSuccess)
+                        return e;
+                    DD_COUNT_LAUNCH(), midk_ready_kernel<<<1, 1, 0, stream>>>(ws_hdr(d_ws), (uint32_t)k);
+                }
+            }
         if ((e = sketch_update_impl(d_codes, d_invalid, d_state, origin + pos, origin + upto, max_new_symbols, kmask, p, canon, d_ws,
-                                    midk, stream)) != cudaSuccess)
+                                    midk_hi, stream)) != cudaSuccess)
             return e;
         pos = upto;
         if (refresh) {

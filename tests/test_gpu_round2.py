@@ -410,3 +410,26 @@ def test_midk_bitmaps_long_stream(eng):
     hregs, _ = eng.sketch_fasta_host(txt, list(range(2, 33)), p=p)     # chunked host path: 32 MiB text chunks
     for k in (10, 11, 12, 32):
         assert np.array_equal(hregs[k - 2], orc.hll_sketch(sym, k, p)), k
+
+
+def test_long_stream_schedule_equals_plain_pass(eng):
+    """300 Mbp (past 4^13 and 4^14 symbols, so the k = 13 and k = 14 presence bitmaps and several floor
+    refreshes are in play): the scheduled path must give exactly the registers of one plain pass with
+    no floor and no bitmaps (which the smaller tests pin to the oracle), for both wide static k sets;
+    and a second sketch in the SAME workspace must not see the first one's bitmaps."""
+    import torch
+    from tools.synth import synth_fasta
+    text = synth_fasta(300_000_000, 6, seed=11, device=eng.device)
+    seq = eng.pack(text, start=0)
+    n = seq.nsym
+    for ks in (list(range(2, 33)), list(range(1, 33))):
+        sched, _ = eng.sketch(seq, ks, p=12)
+        plain, _ = eng.sketch(seq, ks, p=12, ranges=[(0, n)])
+        assert bool((sched == plain).all()), ks[0]
+    other = synth_fasta(80_000_000, 3, seed=12, device=eng.device)
+    seq2 = eng.pack(other, start=0)
+    a, _ = eng.sketch(seq2, list(range(2, 33)), p=12)                      # same "sketch" workspace as above
+    b, _ = eng.sketch(seq2, list(range(2, 33)), p=12, ranges=[(0, seq2.nsym)])
+    assert bool((a == b).all())
+    del text, other
+    torch.cuda.empty_cache()
