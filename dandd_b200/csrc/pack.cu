@@ -725,11 +725,17 @@ cudaError_t pack_fasta(const uint8_t *d_text, size_t n, uint32_t *d_codes, uint3
     p += align_up((pack_ngroups(nt + 1) + 1) * sizeof(PackTileOut), 256);
     uint64_t *seg_base = reinterpret_cast<uint64_t *>(p);
 
-    // persistent grids: SM count x resident CTAs (shared memory decides), never more CTAs than tiles
-    static int grid_count = 0, grid_write = 0;
+    // persistent grids: SM count x resident CTAs (shared memory decides), never more CTAs than tiles;
+    // cached per device (the function attributes are per device as well)
+    constexpr int kMaxDev = 64;
+    static int grids[kMaxDev][2] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int local[2] = {0, 0};
+    int &grid_count = (dev >= 0 && dev < kMaxDev) ? grids[dev][0] : local[0];
+    int &grid_write = (dev >= 0 && dev < kMaxDev) ? grids[dev][1] : local[1];
     if (grid_count == 0) {
-        int dev = 0, sms = 148, a = 1, c = 1;
-        cudaGetDevice(&dev);
+        int sms = 148, a = 1, c = 1;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaFuncSetAttribute(pack_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kTileBytes));
         cudaFuncSetAttribute(pack_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWriteSmem);
