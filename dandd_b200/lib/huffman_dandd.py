@@ -358,6 +358,7 @@ class DeltaTree:
         nodes.sort()
         for leaf in nodes:
             self._evaluate(leaf)
+        self._prefetch_tree_unions(nodes, nchildren)
         self._dt = nodes
         cursor = 0       # first node not yet given a parent
         insert_at = 0    # where the previous parent went
@@ -374,6 +375,65 @@ class DeltaTree:
             cursor += nchildren
             if insert_at + stride > len(self._dt) - 1:
                 nchildren = len(self._dt) - cursor
+
+    @staticmethod
+    def plan_tree(ngens: List[int], nchildren: int) -> List[List[int]]:
+        """The shape _build_tree is going to produce, from the node sizes alone: for every parent, in
+        creation order, the indices (into the sorted leaf list) of its progeny leaves.  Same cursor /
+        insertion arithmetic as the loop below (reference :412-438) on (size, leaves) pairs."""
+        dt = [(n, [i]) for i, n in enumerate(ngens)]
+        parents, cursor, insert_at = [], 0, 0
+        while cursor != len(dt) - 1:
+            stride = nchildren - 1
+            group = dt[cursor:cursor + nchildren]
+            parent = (sum(g[0] for g in group), [leaf for g in group for leaf in g[1]])
+            parents.append(parent[1])
+            while insert_at < len(dt) - stride and dt[insert_at + stride][0] <= parent[0]:
+                insert_at += stride
+            dt.insert(insert_at + stride, parent)
+            cursor += nchildren
+            if insert_at + stride > len(dt) - 1:
+                nchildren = len(dt) - cursor
+        return parents
+
+    def _prefetch_tree_unions(self, leaves: List[DeltaTreeNode], nchildren: int) -> None:
+        """--ksweep: every (inner node, k) cell of the tree is known before any parent is evaluated -- the
+        shape depends on node sizes only, and a node's union is the max over its progeny LEAVES -- so all
+        of them go to the device as one batched job (GpuSketchStore.union_many) instead of one launch per
+        node; the parents built below then find their sketch files and cardinalities in place.  HLL mode
+        only; the hill-climb visits k adaptively and keeps the per-node batches."""
+        sweep = self.experiment["ksweep"]
+        if (sweep is None or self.experiment["tool"] != "dashing" or self.experiment["lowmem"] or len(leaves) < 3
+                or not all(leaf.ngen == 1 for leaf in leaves) or os.environ.get("DANDD_B200_TREE_BATCH", "1") == "0"):
+            return
+        store = get_store()
+        if not hasattr(store, "union_many"):
+            return
+        ks = list(range(max(1, int(sweep[0])), min(HLL_MAX_K, int(sweep[1])) + 1))
+        plan = self.plan_tree([1] * len(leaves), nchildren)
+        if len(plan) < 2 or not ks:
+            return                      # a spider has one inner node: the per-node batch is already one launch
+        probe = DashSketchObj(kval=0, sfp=SketchFilePath(filenames=[leaves[0].fastas[0]], kval=0, speciesinfo=self.speciesinfo,
+                                                         experiment=self.experiment),
+                              speciesinfo=self.speciesinfo, experiment=self.experiment)
+        jobs, targets = [], []
+        for progeny in plan:
+            fastas = [leaves[i].fastas[0] for i in progeny]
+            template = SketchFilePath(filenames=fastas, kval=0, speciesinfo=self.speciesinfo, experiment=self.experiment)
+            paths = {k: template.full.replace("{}", str(k)) for k in ks}
+            missing = [k for k in ks if not probe.sketch_check(path=paths[k])]
+            if not missing:
+                continue
+            for k in missing:
+                ensure_dir(os.path.dirname(paths[k]))
+            jobs.append(({k: [leaves[i].ksketches[k].sketch for i in progeny] for k in missing}, {k: paths[k] for k in missing}))
+            targets.append(paths)
+        if not jobs:
+            return
+        results = store.union_many(jobs, int(self.experiment["registers"]))
+        for (members, out_paths), cards in zip(jobs, results):
+            for k, card in cards.items():
+                self.speciesinfo.cardkey[out_paths[k]] = card
 
     def fill_tree(self, padding=False) -> None:
         """Give every node a sketch at every k that is some node's argmax (hill-climb mode), or sweep

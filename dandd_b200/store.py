@@ -234,6 +234,46 @@ class GpuSketchStore:
             out[k] = float(cards[i])
         return out
 
+    def union_many(self, jobs: Sequence[Tuple[Dict[int, List[str]], Dict[int, str]]], p: int,
+                   chunk_bytes: int = 4 << 30) -> List[Dict[int, float]]:
+        """union_sketches for MANY nodes at once (every inner node of a tree x every k): jobs[i] =
+        (members_by_k, out_paths).  The (node, k) cells are grouped by member count (powers of two, so the
+        pointer tables stay dense) and each group goes to the device as one launch -- or a few, when full
+        union files are wanted and the materialised unions of a group exceed chunk_bytes.  Returns one
+        {k: cardinality} per job; every out_path exists afterwards."""
+        cells = [(i, k, list(members[k])) for i, (members, _) in enumerate(jobs) for k in sorted(members)]
+        out: List[Dict[int, float]] = [dict() for _ in jobs]
+        groups: Dict[int, list] = {}
+        for cell in cells:
+            groups.setdefault(max(1, len(cell[2]) - 1).bit_length(), []).append(cell)
+        want_regs = self.union_files == "full"
+        m = 1 << p
+        for _, group in sorted(groups.items()):
+            step = max(1, chunk_bytes // m) if want_regs else len(group)
+            for g0 in range(0, len(group), step):
+                part = group[g0:g0 + step]
+                width = max(len(c[2]) for c in part)
+                held = [[self.registers(pth) for pth in c[2]] for c in part]
+                ptrs = np.zeros((len(part), width), dtype=np.int64)
+                for r, row in enumerate(held):
+                    ptrs[r, :len(row)] = [t.data_ptr() for t in row]
+                with timing.span("union_gpu"):
+                    res = self.engine.union_sets(ptrs, p, final_only=True, materialize=want_regs)
+                    cards, unions = (res if want_regs else (res, None))
+                    cards = cards.cpu().numpy().reshape(len(part))
+                self.stats["union_launches"] += 1
+                for r, (i, k, members) in enumerate(part):
+                    path = jobs[i][1][k]
+                    card = float(cards[r])
+                    if want_regs:
+                        self._remember(path, unions[r, 0])
+                        self._write(path, unions[r, 0], p, card, leaf=False, members=members)
+                    else:
+                        self._write(path, None, p, card, leaf=False, members=members)
+                    out[i][k] = card
+                del held
+        return out
+
     def prefix_unions(self, leaf_paths_by_k: Dict[int, List[str]], orderings: Sequence[Sequence[int]], p: int,
                       out_paths: Dict[tuple, str] = None, chunk_bytes: int = 4 << 30) -> np.ndarray:
         """Cardinalities of every prefix union: [n_orderings, n_steps, nk] for the k values (sorted)

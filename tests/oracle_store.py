@@ -74,6 +74,18 @@ class OracleStore:
             self._write(out_paths[k], regs, p, out[k])
         return out
 
+    def union_many(self, jobs, p, chunk_bytes=0):
+        self.stats["union_launches"] += 1
+        out = []
+        for members_by_k, out_paths in jobs:
+            row = {}
+            for k, members in members_by_k.items():
+                regs = orc.union_max([self.registers(m) for m in members])
+                row[k] = orc.card(regs, p)
+                self._write(out_paths[k], regs, p, row[k])
+            out.append(row)
+        return out
+
     def prefix_unions(self, leaf_paths_by_k, orderings, p, out_paths=None, chunk_bytes=0):
         self.stats["union_launches"] += 1
         ks = sorted(leaf_paths_by_k)

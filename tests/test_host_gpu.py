@@ -68,3 +68,26 @@ def test_stub_union_files(tmp_path, gpu_store):
     reported numbers do not change."""
     gpu_store.union_files = "stub"
     host_cases.scenario_tree_hillclimb(str(tmp_path))
+
+
+def test_tree_sweep_batched_unions_on_the_gpu_store(tmp_path, gpu_store):
+    """`tree --ksweep --nchildren 2` through GpuSketchStore.union_many (one batched job for every inner
+    node x k) == one union per node, full and stub union files alike."""
+    from tests.test_host_logic import _tree_run
+    from dandd_b200 import store as ddstore
+    from dandd_b200.store import GpuSketchStore
+    a = _tree_run(str(tmp_path / "batch"), True)
+    batched = gpu_store.stats["union_launches"]
+    st2 = GpuSketchStore(engine=gpu_store.engine, union_files="stub")
+    ddstore.set_store(st2)
+    try:
+        b = _tree_run(str(tmp_path / "nodes"), False)
+    finally:
+        ddstore.set_store(gpu_store)
+    strip = lambda x, tag: x.replace(tag + "/", "")     # noqa: E731
+    assert [strip(f, "batch") for f in a["files"]] == [strip(f, "nodes") for f in b["files"]]
+    assert a["deltas"] == b["deltas"]
+    ca = {strip(k, "batch"): v for k, v in a["tb_dashing_cardinalities"].items()}
+    cb = {strip(k, "nodes"): v for k, v in b["tb_dashing_cardinalities"].items()}
+    assert ca == cb
+    assert batched <= 3 and st2.stats["union_launches"] >= 6      # (batched: one launch per member-count group)

@@ -153,3 +153,71 @@ def test_kij_from_the_batched_pair_table_equals_one_spider_per_pair(tmp_path, or
     if jaccard:
         assert [{k: (strip(v, "table") if isinstance(v, str) else v) for k, v in r.items()} for r in a["j"]] == \
                [{k: (strip(v, "spiders") if isinstance(v, str) else v) for k, v in r.items()} for r in b["j"]]
+
+
+def test_plan_tree_matches_the_built_shape(tmp_path, oracle_store):
+    """DeltaTree.plan_tree (sizes only) must predict exactly the parents _build_tree creates, for the
+    odd n-ary shapes of the reference."""
+    import dandd_b200
+    dandd_b200.enable_compat()
+    import huffman_dandd
+    for n in (3, 4, 7, 10, 13):
+        for c in (2, 3, 4):
+            plan = huffman_dandd.DeltaTree.plan_tree([1] * n, c)
+            # replay with the real loop on stand-in nodes
+            class N:      # noqa: N801
+                def __init__(self, leaves):
+                    self.leaves, self.ngen = leaves, len(leaves)
+            dt, made, cursor, insert_at, nch = [N([i]) for i in range(n)], [], 0, 0, c
+            while cursor != len(dt) - 1:
+                stride = nch - 1
+                group = dt[cursor:cursor + nch]
+                parent = N([x for g in group for x in g.leaves])
+                made.append(parent.leaves)
+                while insert_at < len(dt) - stride and dt[insert_at + stride].ngen <= parent.ngen:
+                    insert_at += stride
+                dt.insert(insert_at + stride, parent)
+                cursor += nch
+                if insert_at + stride > len(dt) - 1:
+                    nch = len(dt) - cursor
+            assert plan == made, (n, c)
+
+
+def _tree_run(tmp, batch):
+    import csv
+    import pickle
+    from tests.host_harness import run_dandd
+    from tests.util import make_dataset
+    data = make_dataset(os.path.join(tmp, "data"), 7, 5000, seed=41)
+    out = os.path.join(tmp, "out")
+    os.environ["DANDD_B200_TREE_BATCH"] = "1" if batch else "0"
+    try:
+        run_dandd(["tree", "-d", os.path.dirname(data[0]), "-s", "tb", "-o", out, "-r", "10", "--nchildren", "2", "--ksweep",
+                   "--mink", "9", "--maxk", "13"])
+    finally:
+        os.environ.pop("DANDD_B200_TREE_BATCH", None)
+    db = os.path.join(out, "sketchdb")
+    rel = lambda p: os.path.relpath(p, tmp)     # noqa: E731
+    res = {"files": sorted(rel(os.path.join(d, f)) for d, _, fs in os.walk(db) for f in fs if not f.endswith(".bkp")),
+           "deltas": [{k: (v if k not in ("sketchloc", "fastas") else os.path.basename(v)) for k, v in r.items()}
+                      for r in csv.DictReader(open(os.path.join(out, "tb_7_dashing_deltas.csv")))]}
+    for name in ("tb_dashing_cardinalities", "dandd_fastahex", "dandd_sketchinfo"):
+        with open(os.path.join(db, name + ".pickle"), "rb") as fh:
+            res[name] = {(rel(k) if os.path.isabs(k) else k): v for k, v in pickle.load(fh).items()}
+    return res
+
+
+def test_tree_sweep_batched_unions_equal_per_node_unions(tmp_path, oracle_store):
+    """`tree --ksweep --nchildren 2`: all inner nodes x all k through ONE store.union_many call must leave
+    the same database, cardinalities and deltas as one union_sketches call per node."""
+    a = _tree_run(str(tmp_path / "batch"), True)
+    launches_batched = oracle_store.stats["union_launches"]
+    st2 = OracleStore()
+    ddstore.set_store(st2)
+    b = _tree_run(str(tmp_path / "nodes"), False)
+    strip = lambda x, tag: x.replace(tag + "/", "")     # noqa: E731
+    assert [strip(f, "batch") for f in a["files"]] == [strip(f, "nodes") for f in b["files"]]
+    assert a["deltas"] == b["deltas"]
+    for name in ("tb_dashing_cardinalities", "dandd_fastahex", "dandd_sketchinfo"):
+        assert {strip(k, "batch"): v for k, v in a[name].items()} == {strip(k, "nodes"): v for k, v in b[name].items()}, name
+    assert launches_batched == 1 and st2.stats["union_launches"] >= 3
