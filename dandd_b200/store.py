@@ -379,8 +379,12 @@ class GpuSketchStore:
             self._remember(path, regs)
             self._write(path, regs, p, card, leaf=False, members=list(members))
         else:
-            os.makedirs(os.path.dirname(path), exist_ok=True)
-            hllfile.write_stub(path, p, card, list(members))
+            with timing.span("write_union_markers"):
+                try:
+                    hllfile.write_stub(path, p, card, list(members))
+                except FileNotFoundError:
+                    os.makedirs(os.path.dirname(path), exist_ok=True)
+                    hllfile.write_stub(path, p, card, list(members))
             self.stats["files_written"] += 1
         return float(card)
 
