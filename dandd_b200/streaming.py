@@ -66,8 +66,9 @@ def _ring_for(device, chunk_bytes) -> _Ring:
     return _rings[key]
 
 
-def _reader(path, ring: _Ring, out_q, hash_q, stats, raw_text: Optional[bytes]):
-    """Fill slots with consecutive chunks of the file (or of already inflated text)."""
+def _reader(path, ring: _Ring, out_q, hash_q, stats, raw_text: Optional[bytes], stop: threading.Event):
+    """Fill slots with consecutive chunks of the file (or of already inflated text) until the end, or until
+    the feeder sets `stop` (it failed: the rest of the file is of no use to anyone)."""
     t_busy = 0.0
     try:
         if raw_text is None:
@@ -77,6 +78,9 @@ def _reader(path, ring: _Ring, out_q, hash_q, stats, raw_text: Optional[bytes]):
         pos = 0
         while True:
             slot = ring.free.get()
+            if stop.is_set():
+                ring.free.put(slot)
+                break
             t0 = time.perf_counter()
             if raw_text is None:
                 n = fh.readinto(ring.views[slot])
@@ -125,6 +129,18 @@ def _hasher(ring: _Ring, hash_q, result, stats):
     stats["blake2b_s"] = t_busy
 
 
+def _retire(ring: _Ring, slot: int, copied, quiet: bool = False):
+    """Give a pinned slot back once the copy engine has finished reading it.  With `quiet` (an error is
+    already being propagated) a failing synchronize must not mask the first error nor strand the slot."""
+    try:
+        copied.synchronize()
+    except Exception:  # noqa: BLE001
+        if not quiet:
+            ring.release(slot)
+            raise
+    ring.release(slot)
+
+
 def sketch_file(eng: Engine, path: str, ks: Sequence[int], p: int = 20, canon: bool = True,
                 chunk_bytes: int = CHUNK_BYTES, out: Optional[torch.Tensor] = None, text: Optional[bytes] = None):
     """All-k HLL sketch of the FASTA at `path`, streamed.  Returns (regs [nk, 2^p] u8 on the device,
@@ -162,8 +178,9 @@ def sketch_file(eng: Engine, path: str, ks: Sequence[int], p: int = 20, canon: b
     chunk_bytes = size
     ring = _ring_for(dev, chunk_bytes)
     out_q: "queue.Queue" = queue.Queue()
+    stop = threading.Event()
     hash_q = queue.Queue() if raw_text is None else None
-    threads = [threading.Thread(target=_reader, args=(path, ring, out_q, hash_q, stats, raw_text), daemon=True)]
+    threads = [threading.Thread(target=_reader, args=(path, ring, out_q, hash_q, stats, raw_text, stop), daemon=True)]
     if hash_q is not None:
         threads.append(threading.Thread(target=_hasher, args=(ring, hash_q, digest, stats), daemon=True))
     for t in threads:
@@ -195,51 +212,61 @@ def sketch_file(eng: Engine, path: str, ks: Sequence[int], p: int = 20, canon: b
     started = False           # first record marker found
     in_flight = []            # (slot, copied event) whose host slot is still being read by the copy engine
     err = None
-    while True:
-        item = out_q.get()
-        if item is None:
-            break
-        if isinstance(item, BaseException):
-            err = item
-            continue
-        slot, n = item
-        if err is not None:
-            ring.release(slot)
-            continue
+
+    def feed(slot, n):
+        """Enqueue the copy, pack and sketch of one chunk; returns True if the slot is now in flight."""
+        nonlocal seen, i, started
         off = 0
         if not started:       # kseq ignores everything before the first record marker
             off = int(lib.dd_fasta_first_record_host(ring.slots[slot].data_ptr(), n))
             started = off < n
         ln = n - off
-        if ln > 0:
-            b = i & 1
-            if i >= 2:
-                copy.wait_event(freed[b])
-            with torch.cuda.stream(copy):
-                d_text[b][:ln].copy_(ring.slots[slot][off:off + ln], non_blocking=True)
-                copied[b].record(copy)
-            compute.wait_event(copied[b])
-            check(lib.dd_pack_fasta(d_text[b].data_ptr(), ln, codes.data_ptr(), invalid.data_ptr(), max(total, 1),
-                                    state.data_ptr(), pack_ws.data_ptr(), pack_ws.numel(), st), "dd_pack_fasta")
-            freed[b].record(compute)
-            if eng.polyt_sentinel:
-                check(lib.dd_pack_polyt_sentinel(codes.data_ptr(), invalid.data_ptr(), state.data_ptr(), 0, 0, ln, st),
-                      "dd_pack_polyt_sentinel")
-            check(lib.dd_sketch_update_sched(codes.data_ptr(), invalid.data_ptr(), state.data_ptr(), 0, 0, ln, seen, kmask, p,
-                                             int(canon), sk_ws.data_ptr(), sk_ws.numel(), st), "dd_sketch_update_sched")
-            seen += ln
-            i += 1
-            in_flight.append((slot, copied[b]))
-            copied[b] = torch.cuda.Event()     # a fresh event per chunk: the old one is still referenced by in_flight
-        else:
+        if ln <= 0:
+            return False
+        b = i & 1
+        if i >= 2:
+            copy.wait_event(freed[b])
+        with torch.cuda.stream(copy):
+            d_text[b][:ln].copy_(ring.slots[slot][off:off + ln], non_blocking=True)
+            copied[b].record(copy)
+        in_flight.append((slot, copied[b]))
+        copied[b] = torch.cuda.Event()     # a fresh event per chunk: the old one is still referenced by in_flight
+        compute.wait_event(in_flight[-1][1])
+        check(lib.dd_pack_fasta(d_text[b].data_ptr(), ln, codes.data_ptr(), invalid.data_ptr(), max(total, 1),
+                                state.data_ptr(), pack_ws.data_ptr(), pack_ws.numel(), st), "dd_pack_fasta")
+        freed[b].record(compute)
+        if eng.polyt_sentinel:
+            check(lib.dd_pack_polyt_sentinel(codes.data_ptr(), invalid.data_ptr(), state.data_ptr(), 0, 0, ln, st),
+                  "dd_pack_polyt_sentinel")
+        check(lib.dd_sketch_update_sched(codes.data_ptr(), invalid.data_ptr(), state.data_ptr(), 0, 0, ln, seen, kmask, p,
+                                         int(canon), sk_ws.data_ptr(), sk_ws.numel(), st), "dd_sketch_update_sched")
+        seen += ln
+        i += 1
+        return True
+
+    while True:               # drains the reader's queue to the end whatever happens, so that every slot finds its
+        item = out_q.get()    # way back into the ring and the worker threads terminate
+        if item is None:
+            break
+        if isinstance(item, BaseException):
+            err = err or item
+            continue
+        slot, n = item
+        queued = False
+        if err is None:
+            before = len(in_flight)
+            try:
+                queued = feed(slot, n)
+            except BaseException as e:  # noqa: BLE001 -- re-raised below, after the pipeline has been drained
+                err = e
+                stop.set()
+                queued = len(in_flight) > before     # the copy was enqueued before the failure
+        if not queued:
             ring.release(slot)
-        while len(in_flight) > 1 or (in_flight and ln <= 0):   # keep one copy in flight, give the rest back to the reader
-            s0, ev = in_flight.pop(0)
-            ev.synchronize()
-            ring.release(s0)
+        while len(in_flight) > (1 if (err is None and queued) else 0):   # keep one copy in flight, give the rest back to the reader
+            _retire(ring, *in_flight.pop(0), quiet=err is not None)
     for s0, ev in in_flight:
-        ev.synchronize()
-        ring.release(s0)
+        _retire(ring, s0, ev, quiet=err is not None)
     for t in threads:
         t.join()
     if err is not None:

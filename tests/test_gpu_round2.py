@@ -352,6 +352,38 @@ def test_streamed_file_sketch_matches_oracle(eng, tmp_path):
         streaming.sketch_file(eng, str(fq), ks, p=16, chunk_bytes=1 << 20)
 
 
+def test_streaming_survives_a_failing_chunk(eng, tmp_path, monkeypatch):
+    """A C-ABI error in the middle of a stream (injected: the third dd_sketch_update_sched call reports
+    DD_ERR_ARG) is raised to the caller, every pinned slot returns to the ring, the reader and hasher
+    threads end, and the next file streams through the same ring bit-identically to the oracle."""
+    import threading
+    from dandd_b200 import streaming
+    rng = np.random.default_rng(79)
+    txt = to_fasta([(b"s", random_bases(rng, 6_000_000))], width=70)
+    path = tmp_path / "f.fa"
+    path.write_bytes(txt)
+    ks = [11, 31]
+    real = eng.lib.dd_sketch_update_sched
+    calls = {"n": 0}
+
+    def flaky(*a):
+        calls["n"] += 1
+        return -1 if calls["n"] == 3 else real(*a)
+
+    before = threading.active_count()
+    monkeypatch.setattr(eng.lib, "dd_sketch_update_sched", flaky, raising=False)
+    with pytest.raises(RuntimeError):
+        streaming.sketch_file(eng, str(path), ks, p=14, chunk_bytes=1 << 20)
+    monkeypatch.setattr(eng.lib, "dd_sketch_update_sched", real, raising=False)
+    assert threading.active_count() == before
+    ring = streaming._ring_for(eng.device, 1 << 20)
+    assert ring.free.qsize() == len(ring.slots)
+    regs, cards, digest, stats = streaming.sketch_file(eng, str(path), ks, p=14, chunk_bytes=1 << 20)
+    sym = orc.fasta_symbols(txt)
+    for i, k in enumerate(ks):
+        assert np.array_equal(regs[i].cpu().numpy(), orc.hll_sketch(sym, k, 14))
+
+
 def test_store_streams_large_fastas(eng, tmp_path, monkeypatch):
     """GpuSketchStore.leaf_sketches takes the streaming path above the size threshold, registers the
     digest for the naming layer, and falls back to the whole-file FASTQ detour when needed."""
