@@ -36,6 +36,15 @@ def test_library_exports_every_declared_symbol(lib):
     assert all(s.startswith("dd_") for s in exported), exported  # nothing else leaks out
 
 
+def test_integration_doc_maps_every_entry():
+    """INTEGRATION.md names, for every exported entry, the reference interface it stands in for."""
+    import re
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    named = set(re.findall(r"`(dd_[a-z0-9_]+)`", doc))
+    missing = sorted(set(header_symbols()) - named)
+    assert not missing, missing
+
+
 def test_abi_version_and_size_queries(lib):
     assert lib.dd_abi_version() == 2
     assert lib.dd_pack_codes_bytes(1 << 20) >= (1 << 20) // 4
