@@ -406,9 +406,6 @@ class DeltaTree:
         if (sweep is None or self.experiment["tool"] != "dashing" or self.experiment["lowmem"] or len(leaves) < 3
                 or not all(leaf.ngen == 1 for leaf in leaves) or os.environ.get("DANDD_B200_TREE_BATCH", "1") == "0"):
             return
-        store = get_store()
-        if not hasattr(store, "union_many"):
-            return
         ks = list(range(max(1, int(sweep[0])), min(HLL_MAX_K, int(sweep[1])) + 1))
         plan = self.plan_tree([1] * len(leaves), nchildren)
         if len(plan) < 2 or not ks:
@@ -429,6 +426,9 @@ class DeltaTree:
             jobs.append(({k: [leaves[i].ksketches[k].sketch for i in progeny] for k in missing}, {k: paths[k] for k in missing}))
             targets.append(paths)
         if not jobs:
+            return                      # a cached re-run: nothing to compute, and the store (CUDA start-up) is never created
+        store = get_store()
+        if not hasattr(store, "union_many"):
             return
         results = store.union_many(jobs, int(self.experiment["registers"]))
         for (members, out_paths), cards in zip(jobs, results):

@@ -110,6 +110,38 @@ def test_two_rank_tree_matches_reference(tmp_path):
     assert passes[0] > 0 and passes[1] > 0      # both ranks sketched leaves; k outside the pre-sketched window costs rank 0 extra passes
 
 
+def _cached_rerun_worker(rank, world, port, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from dandd_b200 import store as ddstore
+    from tests.oracle_store import OracleStore
+    from tests.host_harness import run_dandd
+    argv = ["tree", "-d", os.path.join(tmpdir, "data5"), "-s", "runC", "--ksweep", "--mink", "10", "--maxk", "14",
+            "-o", os.path.join(tmpdir, "outC")]
+    ddstore.set_store(OracleStore())
+    run_dandd(argv)
+    import torch.distributed as tdist
+    assert not tdist.is_initialized()          # the command leaves no process group behind
+
+    def trap(*a, **k):
+        raise AssertionError("a fully cached re-run created the sketch store (CUDA start-up)")
+    ddstore.set_store(None)
+    ddstore.GpuSketchStore = trap
+    run_dandd(argv)
+    with open(os.path.join(tmpdir, f"cached_ok{rank}"), "w") as fh:
+        fh.write("ok")
+
+
+def test_cached_rerun_never_creates_the_store(tmp_path):
+    """`dandd tree --ksweep` twice under two ranks: the second run finds every leaf and union sketch and
+    every cardinality in the database and must not create the store on any rank (that would cost
+    seconds of CUDA start-up per process for zero work; reference behaviour: SURVEY.md App. C.13)."""
+    from tests.util import make_dataset
+    make_dataset(str(tmp_path / "data5"), 5, 20000, seed=21)
+    mp.spawn(_cached_rerun_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / f"cached_ok{r}").exists() for r in (0, 1))
+
+
 # ---- one genome over several ranks -------------------------------------------------------------------
 def _split_cases():
     import numpy as np

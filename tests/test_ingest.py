@@ -60,3 +60,57 @@ def test_plain_gzip_and_near_bgzf_fall_back(tmp_path):
             ingest.gunzip(bytes(bad))                      # bad header, bad deflate data or bad CRC: never silent
     finally:
         ingest._BGZF_BATCH = ingest_batch
+
+
+def test_prefetch_keeps_every_worker_reading(tmp_path, monkeypatch):
+    """N files on an N-worker pool are all read at the same time: no pool task waits for a sibling's
+    future (the earlier read/text/hash triples left only a third of the workers doing anything), the
+    text of a file is available before its digest, errors reach both futures, and what comes out is
+    the file's bytes and hashlib's digest."""
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    n = 4
+    texts = {}
+    for i in range(n):
+        texts[str(tmp_path / f"g{i}.fa")] = b">g%d\n" % i + b"ACGT" * (1000 + i) + b"\n"
+        (tmp_path / f"g{i}.fa").write_bytes(texts[str(tmp_path / f"g{i}.fa")])
+    gz_path = str(tmp_path / "z.fa.gz")
+    with open(gz_path, "wb") as fh:
+        fh.write(gzip.compress(b">z\nACGTTGCA\n"))
+    monkeypatch.setattr(ingest, "_pool", ThreadPoolExecutor(max_workers=n))
+    monkeypatch.setattr(ingest, "_jobs", {})
+    together = threading.Barrier(n, timeout=20)
+    hash_gate = threading.Event()
+    real_read, real_hash = ingest._read, ingest._hash
+
+    def read_all_at_once(path):
+        if path in texts:
+            together.wait()          # breaks (and fails the futures) unless all n reads run concurrently
+        return real_read(path)
+
+    def gated_hash(raw):
+        hash_gate.wait(20)
+        return real_hash(raw)
+
+    monkeypatch.setattr(ingest, "_read", read_all_at_once)
+    monkeypatch.setattr(ingest, "_hash", gated_hash)
+    ingest.prefetch(list(texts))
+    for path, want in texts.items():
+        assert ingest.is_prefetched(path)
+        assert ingest.fasta_bytes(path) == want          # the text does not wait for the digest
+    hash_gate.set()
+    for path, want in texts.items():
+        assert ingest.digest(path) == hashlib.blake2b(want).hexdigest()
+    ingest.prefetch([gz_path])
+    assert ingest.fasta_bytes(gz_path) == b">z\nACGTTGCA\n"
+    assert ingest.digest(gz_path) == hashlib.blake2b(open(gz_path, "rb").read()).hexdigest()
+    # a file that disappears between prefetch() and the read: the error surfaces where the bytes are asked for
+    gone = tmp_path / "gone.fa"
+    gone.write_bytes(b">x\nAC\n")
+
+    def failing_read(path):
+        raise OSError("simulated read failure")
+    monkeypatch.setattr(ingest, "_read", failing_read)
+    ingest.prefetch([str(gone)])
+    with pytest.raises(OSError):
+        ingest.fasta_bytes(str(gone))
