@@ -18,6 +18,9 @@ from concurrent.futures import Future, ThreadPoolExecutor
 from typing import Dict, Iterable
 
 _MAX_CACHED_BYTES = int(os.environ.get("DANDD_B200_INGEST_BYTES", str(32 << 30)))
+# uncompressed files from this size on are streamed from disk by the sketch (store.STREAM_MIN_BYTES, the
+# same variable): prefetching prepares their NAME only
+HASH_ONLY_MIN_BYTES = int(os.environ.get("DANDD_B200_STREAM_MIN", str(32 << 20)))
 _pool = None
 _hash_pool = None
 _lock = threading.Lock()
@@ -114,6 +117,30 @@ def _hash(raw):
         return hashlib.blake2b(raw).hexdigest()
 
 
+def _hash_file(path, block=1 << 20):
+    """blake2b of a file in cache-sized reads (the buffer stays in L2; no large allocation)."""
+    from . import timing
+    with timing.span("prefetch_blake2b"):
+        h = hashlib.blake2b()
+        buf = bytearray(block)
+        view = memoryview(buf)
+        with open(path, "rb", buffering=0) as fh:
+            while True:
+                n = fh.readinto(buf)
+                if not n:
+                    break
+                h.update(view[:n])
+        return h.hexdigest()
+
+
+def _is_gzip(path) -> bool:
+    try:
+        with open(path, "rb") as fh:
+            return fh.read(2) == b"\x1f\x8b"
+    except OSError:
+        return False
+
+
 def _text(raw):
     return gunzip(raw) if raw[:2] == b"\x1f\x8b" else raw
 
@@ -134,9 +161,17 @@ class _Job:
     workers and 8 files queued as read/text/hash triples only 3 files made progress at a time, which
     tripled the naming time of the 8 x 3.1 GB run.)"""
 
-    def __init__(self, path, pool):
-        self.text: Future = Future()
+    def __init__(self, path, pool, hash_only=False):
         self.digest: Future = Future()
+        if hash_only:
+            # a large uncompressed file: nobody needs its bytes in one piece (streaming.py feeds the GPU from
+            # the file itself, through the page cache), so only the name is prepared -- hashed in 1 MiB
+            # reads, without materialising a multi-GB bytes object (whose page faults slowed everything
+            # else in the process down, CUDA start-up included)
+            self.text = None
+            _hash_pool_get().submit(self._run_hash_file, path)
+            return
+        self.text: Future = Future()
         pool.submit(self._run, path)
 
     def _run(self, path):
@@ -152,6 +187,12 @@ class _Job:
         except BaseException as err:  # noqa: BLE001
             self.text.set_exception(err)
 
+    def _run_hash_file(self, path):
+        try:
+            self.digest.set_result(_hash_file(path))
+        except BaseException as err:  # noqa: BLE001
+            self.digest.set_exception(err)
+
     def _run_hash(self, raw):
         try:
             self.digest.set_result(_hash(raw))
@@ -166,6 +207,9 @@ def prefetch(paths: Iterable[str]) -> None:
             if p in _jobs or not os.path.isfile(p):
                 continue
             size = os.path.getsize(p)
+            if size >= HASH_ONLY_MIN_BYTES and not _is_gzip(p):
+                _jobs[p] = _Job(p, None, hash_only=True)     # holds no bytes: not counted against the cache
+                continue
             if _cached + size > _MAX_CACHED_BYTES:
                 break                         # the rest is loaded on demand
             _cached += size
@@ -180,6 +224,10 @@ def _take(path):
         job = _jobs.pop(path, None)
     if job is None:
         return _load(path)
+    if job.text is None:                      # name-only job: read now, the digest keeps coming from the job
+        with _lock:
+            _digest_jobs[_key(path)] = job.digest
+        return _text(_read(path)), None
     text = job.text.result()
     with _lock:
         _cached = max(0, _cached - os.path.getsize(path))
@@ -191,8 +239,21 @@ _digest_jobs: Dict[tuple, Future] = {}
 
 
 def is_prefetched(path: str) -> bool:
+    """True if the file's BYTES are (being) held in memory for fasta_bytes()."""
     with _lock:
-        return path in _jobs
+        job = _jobs.get(path)
+        return job is not None and job.text is not None
+
+
+def has_digest(path: str) -> bool:
+    """True if the file's digest is known or being computed in the background (a streaming reader then
+    need not hash the chunks it reads)."""
+    try:
+        k = _key(path)
+    except OSError:
+        return False
+    with _lock:
+        return path in _jobs or k in _digest_jobs or k in _digests
 
 
 def fasta_bytes(path: str) -> bytes:
@@ -214,7 +275,8 @@ def drop(path: str) -> None:
     with _lock:
         job = _jobs.pop(path, None)
         if job is not None:
-            _cached = max(0, _cached - os.path.getsize(path))
+            if job.text is not None:
+                _cached = max(0, _cached - os.path.getsize(path))
             _digest_jobs[_key(path)] = job.digest
 
 

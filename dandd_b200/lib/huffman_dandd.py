@@ -934,6 +934,29 @@ def list_fastas(genomedir, flist_loc) -> List[str]:
     return fastas
 
 
+def _warm_fresh_leaves(fastas, speciesinfo, experiment) -> None:
+    """Single process: sketch the large FASTAs the database has never named BEFORE the tree is built.
+    Building a leaf node needs the file's blake2b name, seconds of hashing for a multi-GB genome (it
+    runs on background threads since prefetch); the GPU pass needs only the bytes.  Doing the passes
+    first puts the device work under the hashing instead of behind it; the leaf constructors then find
+    their all-k blocks in HBM and only name and write them.  (presketch_leaves_sharded does the same per
+    rank.)  Small files are not worth it, and a run without large fresh files never creates the store here."""
+    if experiment["tool"] != "dashing":
+        return
+    fresh = [f for f in fastas if os.path.basename(f) not in speciesinfo.fastahex and os.path.isfile(f)
+             and os.path.getsize(f) >= ingest.HASH_ONLY_MIN_BYTES]
+    if not fresh:
+        return
+    store = get_store()
+    if not hasattr(store, "warm_leaf"):
+        return
+    registers = int(experiment["registers"])
+    fit = int(getattr(store, "cache_bytes", 0) // 2 // (HLL_MAX_K << registers))    # all-k blocks that stay resident
+    for path in fresh[:fit]:
+        with timing.span("warm_leaves"):
+            store.warm_leaf(path, registers, bool(experiment["canonicalize"]))
+
+
 def create_delta_tree(tag: str, genomedir: str, sketchdir: str, kstart: int, nchildren=None, registers=0, flist_loc=None,
                       canonicalize=True, tool="dashing", debug=False, nthreads=0, safety=False, fast=False, verbose=False,
                       ksweep=None, lowmem=False):
@@ -958,6 +981,7 @@ def create_delta_tree(tag: str, genomedir: str, sketchdir: str, kstart: int, nch
     # read / gunzip / blake2b in the background while the GPU works -- only files the database has never
     # named (a cached re-run reads nothing; usually started already by dandd_cmd._early_prefetch)
     ingest.prefetch([f for f in fastas if os.path.basename(f) not in speciesinfo.fastahex])
+    _warm_fresh_leaves(fastas, speciesinfo, experiment)
     if nchildren:
         dtree = DeltaTree(fasta_files=fastas, speciesinfo=speciesinfo, nchildren=nchildren, experiment=experiment)
     else:

@@ -194,7 +194,8 @@ class GpuSketchStore:
         from .engine import FastqInput
         text = ingest.fasta_bytes(fasta) if ingest.is_prefetched(fasta) else None
         try:
-            regs, cards, digest, stats = streaming.sketch_file(self.engine, fasta, run_ks, p, canon, text=text)
+            regs, cards, digest, stats = streaming.sketch_file(self.engine, fasta, run_ks, p, canon, text=text,
+                                                               want_digest=not ingest.has_digest(fasta))
         except FastqInput:
             return None
         if digest:

@@ -142,11 +142,14 @@ def _retire(ring: _Ring, slot: int, copied, quiet: bool = False):
 
 
 def sketch_file(eng: Engine, path: str, ks: Sequence[int], p: int = 20, canon: bool = True,
-                chunk_bytes: int = CHUNK_BYTES, out: Optional[torch.Tensor] = None, text: Optional[bytes] = None):
+                chunk_bytes: int = CHUNK_BYTES, out: Optional[torch.Tensor] = None, text: Optional[bytes] = None,
+                want_digest: bool = True):
     """All-k HLL sketch of the FASTA at `path`, streamed.  Returns (regs [nk, 2^p] u8 on the device,
     cards numpy [nk], blake2b hex digest of the file bytes or None, stats dict of stage times).
     `text`: the (decompressed) bytes of the file if the caller already holds them (ingest.prefetch);
     they are then fed from memory and no digest is computed here.
+    `want_digest=False`: the caller gets the name elsewhere (ingest hashes the file on another thread);
+    the chunks are then not hashed here (a gzip file still is: its raw bytes are in hand anyway).
     Raises FastqInput if the text turns out to be FASTQ (the caller takes the whole-file detour)."""
     lib = eng.lib
     kmask = kmask_of(ks)
@@ -179,7 +182,7 @@ def sketch_file(eng: Engine, path: str, ks: Sequence[int], p: int = 20, canon: b
     ring = _ring_for(dev, chunk_bytes)
     out_q: "queue.Queue" = queue.Queue()
     stop = threading.Event()
-    hash_q = queue.Queue() if raw_text is None else None
+    hash_q = queue.Queue() if (raw_text is None and want_digest) else None
     threads = [threading.Thread(target=_reader, args=(path, ring, out_q, hash_q, stats, raw_text, stop), daemon=True)]
     if hash_q is not None:
         threads.append(threading.Thread(target=_hasher, args=(ring, hash_q, digest, stats), daemon=True))

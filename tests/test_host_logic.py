@@ -221,3 +221,52 @@ def test_tree_sweep_batched_unions_equal_per_node_unions(tmp_path, oracle_store)
     for name in ("tb_dashing_cardinalities", "dandd_fastahex", "dandd_sketchinfo"):
         assert {strip(k, "batch"): v for k, v in a[name].items()} == {strip(k, "nodes"): v for k, v in b[name].items()}, name
     assert launches_batched == 1 and st2.stats["union_launches"] >= 3
+
+
+def test_large_fresh_leaves_are_sketched_before_they_are_named(tmp_path, oracle_store, monkeypatch):
+    """Single-process `tree`: FASTAs above the streaming threshold that the database has never seen get
+    their all-k device pass BEFORE any blake2b name is asked for (the hashing runs in background
+    threads meanwhile); a cached re-run warms nothing and never creates the store; the outputs are
+    those of the plain path."""
+    from dandd_b200 import ingest, store as ddstore
+    from tests.host_harness import run_dandd
+    from tests.util import make_dataset
+    data = str(tmp_path / "data5")
+    make_dataset(data, 5, 20000, seed=21)
+    events = []
+    real_digest = ingest.digest
+
+    def spy_digest(path):
+        events.append(("digest", os.path.basename(path)))
+        return real_digest(path)
+
+    def warm_leaf(path, p, canon):
+        events.append(("warm", os.path.basename(path)))
+
+    monkeypatch.setattr(ingest, "digest", spy_digest)
+    oracle_store.warm_leaf = warm_leaf
+    oracle_store.cache_bytes = 64 << 30
+    argv = ["tree", "-d", data, "-s", "runW", "-k", "14", "-o"]
+    run_dandd(argv + [str(tmp_path / "out_plain")])                  # 20 kbp files: below the threshold
+    assert not [e for e in events if e[0] == "warm"]
+    plain = open(tmp_path / "out_plain" / "runW_5_dashing_deltas.csv").read()
+
+    events.clear()
+    monkeypatch.setattr(ingest, "HASH_ONLY_MIN_BYTES", 1000)
+    run_dandd(argv + [str(tmp_path / "out_warm")])
+    warms = [i for i, e in enumerate(events) if e[0] == "warm"]
+    digests = [i for i, e in enumerate(events) if e[0] == "digest"]
+    assert len(warms) == 5 and digests and max(warms) < min(digests)
+    assert sorted(e[1] for e in events if e[0] == "warm") == sorted(os.listdir(data))
+    assert open(tmp_path / "out_warm" / "runW_5_dashing_deltas.csv").read().replace("out_warm", "out_plain") == plain
+
+    events.clear()
+    ddstore.set_store(None)
+    try:
+        run_dandd(argv + [str(tmp_path / "out_warm")])               # cached: nothing to warm, no store
+        assert ddstore._store is None and not [e for e in events if e[0] == "warm"]
+    finally:
+        ddstore.set_store(oracle_store)
+    oracle_store.cache_bytes = 0                                     # no room to keep blocks: nothing is warmed
+    run_dandd(argv + [str(tmp_path / "out_nofit")])
+    assert not [e for e in events if e[0] == "warm"]

@@ -114,3 +114,34 @@ def test_prefetch_keeps_every_worker_reading(tmp_path, monkeypatch):
     ingest.prefetch([str(gone)])
     with pytest.raises(OSError):
         ingest.fasta_bytes(str(gone))
+
+
+def test_large_plain_files_get_name_only_jobs(tmp_path, monkeypatch):
+    """From HASH_ONLY_MIN_BYTES on, an uncompressed file is not held in memory by prefetch(): only its
+    digest is prepared (chunked reads); the bytes are still there for whoever asks, and a gzip file of
+    any size keeps the full job (its text only exists after inflation)."""
+    monkeypatch.setattr(ingest, "HASH_ONLY_MIN_BYTES", 1000)
+    monkeypatch.setattr(ingest, "_jobs", {})
+    monkeypatch.setattr(ingest, "_cached", 0)
+    rng = np.random.default_rng(9)
+    big = to_fasta([(b"big", random_bases(rng, 3_000_000))], width=60)       # several 1 MiB hash blocks
+    small = b">s\nACGT\n"
+    (tmp_path / "big.fa").write_bytes(big)
+    (tmp_path / "small.fa").write_bytes(small)
+    (tmp_path / "big.fa.gz").write_bytes(gzip.compress(big, 1))
+    paths = [str(tmp_path / n) for n in ("big.fa", "small.fa", "big.fa.gz")]
+    ingest.prefetch(paths)
+    assert not ingest.is_prefetched(paths[0]) and ingest.is_prefetched(paths[1]) and ingest.is_prefetched(paths[2])
+    assert all(ingest.has_digest(p) for p in paths) and not ingest.has_digest(str(tmp_path / "big.fa") + "x")
+    assert ingest._cached == len(small) + (tmp_path / "big.fa.gz").stat().st_size      # the name-only job holds no bytes
+    assert ingest.digest(paths[0]) == hashlib.blake2b(big).hexdigest()
+    assert ingest.fasta_bytes(paths[0]) == big and ingest.fasta_bytes(paths[2]) == big
+    assert ingest.digest(paths[2]) == hashlib.blake2b((tmp_path / "big.fa.gz").read_bytes()).hexdigest()
+    ingest.drop_all()
+    assert ingest.digest(paths[1]) == hashlib.blake2b(small).hexdigest()
+    # bytes asked for first, name later: the job's digest future survives the hand-over
+    (tmp_path / "big2.fa").write_bytes(big + b">t\nAC\n")
+    p2 = str(tmp_path / "big2.fa")
+    ingest.prefetch([p2])
+    assert ingest.fasta_bytes(p2) == big + b">t\nAC\n"
+    assert ingest.has_digest(p2) and ingest.digest(p2) == hashlib.blake2b(big + b">t\nAC\n").hexdigest()

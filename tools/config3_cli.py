@@ -181,12 +181,13 @@ def run(args):
         rep["torchrun_cards_identical"] = True   # checked below once the first run's cards are read
         rep["_cards_torchrun"] = c2
     # 3. dandd progressive -n 1 --ksweep (single process)
-    pickle_path = os.path.join(out, f"cfg3_{args.genomes}_dashing_dtree.pickle")
-    timing_prog = os.path.join(workdir, "timing_prog.jsonl")
-    dt, log = torchrun(1, [DANDD, "progressive", "-d", pickle_path, "-n", "1", "--ksweep", "--mink", str(args.kmin), "--maxk",
-                           str(args.kmax), "-o", out], env=dict(env, DANDD_B200_TIMING=timing_prog))
-    rep["progressive_wall_s"] = round(dt, 3)
-    rep["progressive_stages"] = summarize_timing(read_timing(timing_prog))
+    if not getattr(args, "skip_progressive", False):
+        pickle_path = os.path.join(out, f"cfg3_{args.genomes}_dashing_dtree.pickle")
+        timing_prog = os.path.join(workdir, "timing_prog.jsonl")
+        dt, log = torchrun(1, [DANDD, "progressive", "-d", pickle_path, "-n", "1", "--ksweep", "--mink", str(args.kmin), "--maxk",
+                               str(args.kmax), "-o", out], env=dict(env, DANDD_B200_TIMING=timing_prog))
+        rep["progressive_wall_s"] = round(dt, 3)
+        rep["progressive_stages"] = summarize_timing(read_timing(timing_prog))
     # 4. results
     cards, cardkey = cards_by_genome(sketchdir, "cfg3", args.genomes, ks)
     if "_cards_torchrun" in rep:
@@ -195,12 +196,13 @@ def run(args):
     rep["leaf_argmax_k"] = [int(ks[int(np.argmax(np.array(cards[g]) / karr))]) for g in range(args.genomes)]
     rep["leaf_delta"] = [float((np.array(cards[g]) / karr).max()) for g in range(args.genomes)]
     rep["leaf_cards"] = {str(g): cards[g] for g in range(args.genomes)}
-    summ = [r for r in csv.DictReader(open(glob.glob(os.path.join(out, "cfg3_progu1_*summary.csv"))[0]))]
-    by_n = {}
-    for r in summ:
-        by_n.setdefault(int(r["ngen"]), {})[int(r["kval"])] = float(r["delta_pos"])
-    rep["prefix_argmax_k"] = [max(by_n[n], key=by_n[n].get) for n in sorted(by_n)]
-    rep["prefix_delta"] = [max(by_n[n].values()) for n in sorted(by_n)]
+    if not getattr(args, "skip_progressive", False):
+        summ = [r for r in csv.DictReader(open(glob.glob(os.path.join(out, "cfg3_progu1_*summary.csv"))[0]))]
+        by_n = {}
+        for r in summ:
+            by_n.setdefault(int(r["ngen"]), {})[int(r["kval"])] = float(r["delta_pos"])
+        rep["prefix_argmax_k"] = [max(by_n[n], key=by_n[n].get) for n in sorted(by_n)]
+        rep["prefix_delta"] = [max(by_n[n].values()) for n in sorted(by_n)]
     rep["sketch_files"] = sum(len(fs) for _, _, fs in os.walk(sketchdir))
     total_bases = args.bases * args.genomes
     rep["tree_gbp_per_s_wall"] = total_bases / rep["tree_wall_s"] / 1e9
@@ -246,6 +248,7 @@ def main():
     ap.add_argument("--cpu-sample-bytes", type=float, default=64e6)
     ap.add_argument("--oracle-ks", default="")
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--skip-progressive", action="store_true", help="time the tree command only")
     ap.add_argument("--launcher", default="self", choices=["self", "torchrun"],
                     help="multi-GPU tree: `dandd tree --gpus N` (rank 0 starts the others) or torchrun")
     ap.add_argument("--also-torchrun", action="store_true", help="additionally time the same tree job under torchrun")
