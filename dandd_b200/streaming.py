@@ -32,15 +32,20 @@ from ._lib import DD_HIST_BINS, DD_PACK_FLAG_FASTQ, DD_PACK_FLAG_OVERFLOW, check
 from .engine import Engine, FastqInput, kmask_of
 
 CHUNK_BYTES = int(os.environ.get("DANDD_B200_STREAM_CHUNK", str(64 << 20)))
-RING_SLOTS = 4
+RING_SLOTS = 6
+# threads that copy a file from the page cache into ring slots at the same time: one kernel-to-user copy
+# runs at 6-7 GB/s, a B200 packs and sketches 20 GB/s of text
+READERS = max(1, int(os.environ.get("DANDD_B200_STREAM_READERS", "3")))
 
 
 class _Ring:
     """RING_SLOTS pinned host buffers; a slot is handed reader -> (hasher, feeder) -> reader."""
 
-    def __init__(self, chunk_bytes: int):
+    def __init__(self, chunk_bytes: int, pin: bool = True):
         self.chunk = chunk_bytes
-        self.slots = [torch.empty(chunk_bytes, dtype=torch.uint8).pin_memory() for _ in range(RING_SLOTS)]
+        self.slots = [torch.empty(chunk_bytes, dtype=torch.uint8) for _ in range(RING_SLOTS)]
+        if pin:
+            self.slots = [s.pin_memory() for s in self.slots]
         self.views = [memoryview(s.numpy()) for s in self.slots]
         self.free: "queue.Queue[int]" = queue.Queue()
         for i in range(RING_SLOTS):
@@ -75,7 +80,7 @@ def _reader(path, ring: _Ring, out_q, hash_q, stats, raw_text: Optional[bytes], 
             fh = open(path, "rb", buffering=0)
         else:
             raw_view = memoryview(raw_text)      # slices of a view do not copy
-        pos = 0
+        pos = seq = 0
         while True:
             slot = ring.free.get()
             if stop.is_set():
@@ -101,7 +106,8 @@ def _reader(path, ring: _Ring, out_q, hash_q, stats, raw_text: Optional[bytes], 
                 ring.pending[slot] = 2 if hash_q is not None else 1
             if hash_q is not None:
                 hash_q.put((slot, n))
-            out_q.put((slot, n))
+            out_q.put((seq, slot, n))
+            seq += 1
         if raw_text is None:
             fh.close()
     except BaseException as e:  # noqa: BLE001 -- handed to the feeder, which re-raises
@@ -111,6 +117,80 @@ def _reader(path, ring: _Ring, out_q, hash_q, stats, raw_text: Optional[bytes], 
         if hash_q is not None:
             hash_q.put(None)
         out_q.put(None)
+
+
+class _Cursor:
+    """Which chunk of the file the next free slot gets (shared by the positional readers)."""
+
+    def __init__(self, size: int, chunk: int):
+        self.size, self.chunk = size, chunk
+        self.off = self.seq = 0
+        self.busy = 0.0
+        self.lock = threading.Lock()
+
+    def claim(self):
+        with self.lock:
+            if self.off >= self.size:
+                return None
+            got = (self.seq, self.off, min(self.chunk, self.size - self.off))
+            self.off += got[2]
+            self.seq += 1
+            return got
+
+
+def _reader_at(fd: int, ring: _Ring, out_q, cursor: _Cursor, stop: threading.Event):
+    """One of READERS threads filling slots with pread(): a thread first owns a slot and only then claims
+    the next chunk, so the chunk the feeder is waiting for always has a buffer to land in."""
+    t_busy = 0.0
+    try:
+        while True:
+            slot = ring.free.get()
+            piece = None if stop.is_set() else cursor.claim()
+            if piece is None:
+                ring.free.put(slot)
+                break
+            seq, off, n = piece
+            t0 = time.perf_counter()
+            got = 0
+            try:
+                while got < n:
+                    more = os.preadv(fd, [ring.views[slot][got:n]], off + got)
+                    if not more:
+                        raise OSError("file shrank while it was being read")
+                    got += more
+            except BaseException:
+                ring.free.put(slot)
+                raise
+            t_busy += time.perf_counter() - t0
+            with ring.lock:
+                ring.pending[slot] = 1
+            out_q.put((seq, slot, n))
+    except BaseException as e:  # noqa: BLE001 -- handed to the feeder, which re-raises
+        stop.set()
+        out_q.put(e)
+    finally:
+        with cursor.lock:
+            cursor.busy += t_busy
+        out_q.put(None)
+
+
+def _in_order(out_q, producers: int):
+    """What the readers put on out_q, chunks in file order: ("chunk", slot, n) / ("error", exc, None), and once
+    every producer has finished ("orphan", slot, n) for chunks behind a gap a failed reader left."""
+    waiting, want = {}, 0
+    while producers:
+        item = out_q.get()
+        if item is None:
+            producers -= 1
+        elif isinstance(item, BaseException):
+            yield "error", item, None
+        else:
+            waiting[item[0]] = item[1:]
+            while want in waiting:
+                yield ("chunk",) + waiting.pop(want)
+                want += 1
+    for seq in sorted(waiting):
+        yield ("orphan",) + waiting[seq]
 
 
 def _hasher(ring: _Ring, hash_q, result, stats):
@@ -183,12 +263,6 @@ def sketch_file(eng: Engine, path: str, ks: Sequence[int], p: int = 20, canon: b
     out_q: "queue.Queue" = queue.Queue()
     stop = threading.Event()
     hash_q = queue.Queue() if (raw_text is None and want_digest) else None
-    threads = [threading.Thread(target=_reader, args=(path, ring, out_q, hash_q, stats, raw_text, stop), daemon=True)]
-    if hash_q is not None:
-        threads.append(threading.Thread(target=_hasher, args=(ring, hash_q, digest, stats), daemon=True))
-    for t in threads:
-        t.start()
-
     # device side
     cb, ib = lib.dd_pack_codes_bytes(max(total, 1)), lib.dd_pack_invalid_bytes(max(total, 1))
     codes = torch.empty(cb, dtype=torch.uint8, device=dev)
@@ -247,16 +321,29 @@ def sketch_file(eng: Engine, path: str, ks: Sequence[int], p: int = 20, canon: b
         i += 1
         return True
 
-    while True:               # drains the reader's queue to the end whatever happens, so that every slot finds its
-        item = out_q.get()    # way back into the ring and the worker threads terminate
-        if item is None:
-            break
-        if isinstance(item, BaseException):
-            err = err or item
+    # host side: the threads that fill the ring (started last: nothing above can fail and leave them waiting)
+    fd, cursor = None, None
+    if raw_text is None and hash_q is None and READERS > 1 and total > chunk_bytes:
+        # a plain file whose name comes from elsewhere: several threads pread() it into the ring
+        fd = os.open(path, os.O_RDONLY)
+        cursor = _Cursor(total, chunk_bytes)
+        producers = min(READERS, -(-total // chunk_bytes))
+        threads = [threading.Thread(target=_reader_at, args=(fd, ring, out_q, cursor, stop), daemon=True) for _ in range(producers)]
+    else:
+        producers = 1
+        threads = [threading.Thread(target=_reader, args=(path, ring, out_q, hash_q, stats, raw_text, stop), daemon=True)]
+        if hash_q is not None:
+            threads.append(threading.Thread(target=_hasher, args=(ring, hash_q, digest, stats), daemon=True))
+    for t in threads:
+        t.start()
+
+    for kind, slot, n in _in_order(out_q, producers):   # drains the readers' queue to the end whatever happens, so that
+        if kind == "error":                             # every slot finds its way back into the ring and the threads end
+            err = err or slot
+            stop.set()
             continue
-        slot, n = item
         queued = False
-        if err is None:
+        if err is None and kind == "chunk":
             before = len(in_flight)
             try:
                 queued = feed(slot, n)
@@ -272,6 +359,10 @@ def sketch_file(eng: Engine, path: str, ks: Sequence[int], p: int = 20, canon: b
         _retire(ring, s0, ev, quiet=err is not None)
     for t in threads:
         t.join()
+    if fd is not None:
+        os.close(fd)
+        stats["read_s"] = cursor.busy / max(1, producers)      # per reader, comparable with the single-reader figure
+        stats["readers"] = producers
     if err is not None:
         raise err
     check(lib.dd_sketch_end(sk_ws.data_ptr(), sk_ws.numel(), nk, p, regs.data_ptr(), hist.data_ptr(), cards.data_ptr(), st),

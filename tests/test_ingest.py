@@ -145,3 +145,14 @@ def test_large_plain_files_get_name_only_jobs(tmp_path, monkeypatch):
     ingest.prefetch([p2])
     assert ingest.fasta_bytes(p2) == big + b">t\nAC\n"
     assert ingest.has_digest(p2) and ingest.digest(p2) == hashlib.blake2b(big + b">t\nAC\n").hexdigest()
+
+
+def test_hash_file_pieces_and_empty_file(tmp_path):
+    data = np.random.default_rng(1).integers(0, 256, 1_234_567, dtype=np.uint8).tobytes()
+    path = tmp_path / "x.bin"
+    path.write_bytes(data)
+    want = hashlib.blake2b(data).hexdigest()
+    assert ingest._hash_file(str(path)) == want
+    assert ingest._hash_file(str(path), piece=4096) == want          # many mapped pieces
+    path.write_bytes(b"")
+    assert ingest._hash_file(str(path)) == hashlib.blake2b(b"").hexdigest()   # cannot be mapped: read path
