@@ -35,7 +35,8 @@ UNIVERSAL = [  # reference :23-30
     (("--device",), dict(type=int, default=None, dest="device", metavar="GPU", help="CUDA device to use (default LOCAL_RANK or 0).")),
     (("--gpus",), dict(type=int, default=None, dest="gpus", metavar="N",
                        help="tree: use N GPUs of this node, one process each (what `torchrun --nproc-per-node N` sets up, "
-                            "without the launcher's start-up cost).")),
+                            "without the launcher's start-up cost). The extra processes are only started when the run "
+                            "has FASTAs the sketch database has never seen (or with --exact).")),
 ]
 KSWEEP = [  # reference :145-150
     (("--ksweep",), dict(dest="ksweep", default=None, action="store_true",
@@ -122,6 +123,10 @@ def _self_launch(args) -> list:
     import subprocess
     n = int(args.gpus or 1)
     if n < 2 or "WORLD_SIZE" in os.environ:
+        return []
+    if not args.exact and not _fresh_fastas(args):
+        # every FASTA already has its name in the sketch database: what is left, if anything, is unions and
+        # the odd k outside the stored range -- less than the seconds N-1 more processes take to start
         return []
     with socket.socket() as sock:       # a free port for the rendezvous store
         sock.bind(("127.0.0.1", 0))
@@ -232,31 +237,42 @@ def _start_engine_in_background() -> None:
     threading.Thread(target=start, name="dd-engine-start", daemon=True).start()
 
 
-def _early_prefetch(args) -> list:
-    """Start reading (and hashing) this process's share of the FASTAs in background threads before
-    anything imports torch.  Only files the sketch database has never seen: a cached re-run reads
-    nothing, like the reference (its fastahex pickle short-circuits the hash).
-    Returns the files it started on."""
-    from dandd_b200 import ingest
-    from dandd_b200.shard import shard_by_size
+def _fresh_fastas(args) -> list:
+    """The FASTAs of this run that the sketch database has never named (the whole job's, not one rank's).
+    A fully cached re-run has none and reads nothing, like the reference (its fastahex pickle
+    short-circuits the hash)."""
     try:
         fastas = huffman_dandd.list_fastas(args.genomedir, args.flist_loc)
     except (OSError, ValueError):
         return []               # create_delta_tree reports the problem
+    sketchdir = args.sketchdir or os.path.join(args.outdir, "sketchdb")
     known = set()
     try:
-        with open(os.path.join(args.sketchdir, "dandd_fastahex.pickle"), "rb") as fh:
+        with open(os.path.join(sketchdir, "dandd_fastahex.pickle"), "rb") as fh:
             known = set(pickle.load(fh))
     except Exception:  # noqa: BLE001 -- no database yet (or unreadable): everything is new
         pass
-    fastas = [f for f in fastas if os.path.isfile(f)]
+    return [f for f in fastas if os.path.isfile(f) and os.path.basename(f) not in known]
+
+
+def _early_prefetch(args) -> list:
+    """Start reading (and hashing) this process's share of the FASTAs in background threads before
+    anything imports torch.  Only files the sketch database has never seen.  Returns the files it
+    started on."""
+    from dandd_b200 import ingest
+    from dandd_b200.shard import shard_by_size
+    try:
+        fastas = [f for f in huffman_dandd.list_fastas(args.genomedir, args.flist_loc) if os.path.isfile(f)]
+    except (OSError, ValueError):
+        return []
+    fresh_all = set(_fresh_fastas(args))
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if world > 1 and len(fastas) >= world and not args.exact:
         owners = shard_by_size([os.path.getsize(f) for f in fastas], world)
         fastas = [fastas[i] for i in owners[rank]]
     elif world > 1 and rank > 0:
         return []               # split-genome and exact modes: rank 0 hashes, every rank reads on demand
-    fresh = [f for f in fastas if os.path.basename(f) not in known]
+    fresh = [f for f in fastas if f in fresh_all]
     ingest.prefetch(fresh)
     return fresh
 

@@ -270,3 +270,67 @@ def test_large_fresh_leaves_are_sketched_before_they_are_named(tmp_path, oracle_
     oracle_store.cache_bytes = 0                                     # no room to keep blocks: nothing is warmed
     run_dandd(argv + [str(tmp_path / "out_nofit")])
     assert not [e for e in events if e[0] == "warm"]
+
+
+def test_gpus_flag_starts_workers_only_for_fresh_fastas(tmp_path, oracle_store, monkeypatch):
+    """`tree --gpus N`: ranks 1..N-1 are started (as copies of the command line, with the rendezvous
+    environment) when some FASTA has never been named by the sketch database -- and not at all on a
+    re-run over the same files, which then stays a single process that never imports torch."""
+    import argparse
+    import subprocess
+    import dandd_b200
+    from tests.host_harness import run_dandd
+    from tests.util import make_dataset
+    dandd_b200.enable_compat()
+    import dandd_cmd
+    data = str(tmp_path / "data5")
+    make_dataset(data, 5, 20000, seed=21)
+    out = str(tmp_path / "out")
+    started = []
+
+    class FakePopen:
+        def __init__(self, argv, env=None):
+            started.append((argv, env))
+            self.args = argv
+
+        def wait(self):
+            return 0
+
+    monkeypatch.setattr(subprocess, "Popen", FakePopen)
+    saved = dict(os.environ)
+    try:
+        for key in ("WORLD_SIZE", "RANK", "LOCAL_RANK", "CUDA_VISIBLE_DEVICES"):
+            os.environ.pop(key, None)
+        args = argparse.Namespace(gpus=3, exact=False, genomedir=data, flist_loc=None, sketchdir=None, outdir=out)
+        children = dandd_cmd._self_launch(args)
+        assert len(children) == 2 and len(started) == 2
+        envs = [env for _, env in started]
+        assert sorted(e["RANK"] for e in envs) == ["1", "2"] and all(e["WORLD_SIZE"] == "3" for e in envs)
+        assert all(e["MASTER_ADDR"] == "127.0.0.1" and e["MASTER_PORT"] == os.environ["MASTER_PORT"] for e in envs)
+        assert os.environ["RANK"] == "0" and os.environ["WORLD_SIZE"] == "3"
+    finally:
+        os.environ.clear()
+        os.environ.update(saved)
+    run_dandd(["tree", "-d", data, "-s", "runG", "-k", "14", "-o", out])          # names every FASTA
+    started.clear()
+    try:
+        for key in ("WORLD_SIZE", "RANK", "LOCAL_RANK", "CUDA_VISIBLE_DEVICES"):
+            os.environ.pop(key, None)
+        assert dandd_cmd._self_launch(args) == [] and not started and "WORLD_SIZE" not in os.environ
+        args.exact = True                      # exact counting shards over ranks whatever the names say
+        assert len(dandd_cmd._self_launch(args)) == 2
+    finally:
+        os.environ.clear()
+        os.environ.update(saved)
+    # one more FASTA: fresh again
+    with open(os.path.join(data, "zz_new.fa"), "wb") as fh:
+        fh.write(b">n\\nACGTACGTAC\\n")
+    started.clear()
+    try:
+        for key in ("WORLD_SIZE", "RANK", "LOCAL_RANK", "CUDA_VISIBLE_DEVICES"):
+            os.environ.pop(key, None)
+        args.exact = False
+        assert len(dandd_cmd._self_launch(args)) == 2
+    finally:
+        os.environ.clear()
+        os.environ.update(saved)
