@@ -649,7 +649,7 @@ class DeltaTree:
         ~20 Python objects and issuing 3-8 store calls per pair.  Returns None when the replay needs a
         k the table does not cover (the caller then takes the object path for this pair)."""
         spec, exp = self.speciesinfo, pair_experiment
-        cards, col = table["cards"], table["col"]
+        col = table.col
         registers, canon = exp["registers"], exp["canonicalize"]
         files = sorted(os.path.basename(f) for f in (first.fastas[0], second.fastas[0]))
         set_key = "".join(files)
@@ -660,6 +660,22 @@ class DeltaTree:
         nc = "" if canon else "nc"
         state = {"delta": 0, "bestk": 0}
         visited = []
+        cells = {}
+
+        def cell(k):
+            """(path, file is there, union cardinality) of this pair at k.  Like SketchObj (reference
+            lib/sketch_classes.py:244-262) a cardinality the database remembers is used when the sketch file
+            is also there; only a cell the database cannot answer asks for the batched device job (which
+            then evaluates every pair x every k at once)."""
+            hit = cells.get(k)
+            if hit is None:
+                path = os.path.join(spec.sketchdir, "ngen2", "k" + str(k), stem + str(k) + nc) + ".hll"
+                there = os.path.exists(path) and os.path.getsize(path) > 0
+                card = float(spec.cardkey.get(path) or 0) if there else 0.0
+                if not card > 0:
+                    card = float(table.cards()[row, col[k]])
+                hit = cells[k] = (path, there, card)
+            return hit
 
         def touch(lo, hi):
             for k in range(max(1, lo), min(hi, HLL_MAX_K) + 1):
@@ -673,7 +689,7 @@ class DeltaTree:
                 raise ValueError("Exploratory k value is too high for dashing. Either something is amiss with your data "
                                  "or you need to be using --exact mode")
             touch(k - 1, k + 1)
-            candidate = float(cards[row, col[k]]) / k if k >= 1 else 0
+            candidate = cell(k)[2] / k if k >= 1 else 0
             if state["delta"] <= candidate:
                 spec.kstart = k
                 state["bestk"], state["delta"] = k, candidate
@@ -691,12 +707,13 @@ class DeltaTree:
             find_delta(self.root_k())                                 # pairwise_spiders
             if jaccard:
                 touch(int(mink), int(maxk))                           # pair.ksweep + jaccard_summarize
+            for k in visited:
+                cell(k)                                               # may start the batched job: before any side effect
         except KeyError:
             spec.kstart = kstart_before                               # the object path starts where this pair started
             return None
         # side effects on the database: names, files, cardinalities (SketchFilePath / DashSketchObj / store)
         spec.fastahex.setdefault(set_key, stored)
-        store = get_store()
         leaf_sketch = {n: n.ksketches for n in (first, second)}
         for k in [0] + visited:
             ktok = "{}" if k == 0 else str(k)
@@ -706,12 +723,10 @@ class DeltaTree:
             exp["baseset"].add(base)
             if k == 0:
                 continue
-            directory = os.path.join(spec.sketchdir, "ngen2", "k" + ktok)
-            path = os.path.join(directory, base) + ".hll"
-            card = float(cards[row, col[k]])
-            if not (os.path.exists(path) and os.path.getsize(path) > 0):
-                ensure_dir(directory)
-                store.materialize_union(path, int(registers), card, [leaf_sketch[first][k].sketch, leaf_sketch[second][k].sketch])
+            path, there, card = cell(k)
+            if not there:
+                ensure_dir(os.path.dirname(path))
+                get_store().materialize_union(path, int(registers), card, [leaf_sketch[first][k].sketch, leaf_sketch[second][k].sketch])
             if not float(spec.cardkey.get(path) or 0):
                 spec.cardkey[path] = card
         a, b = (first, second) if first.node_title <= second.node_title else (second, first)
@@ -723,7 +738,7 @@ class DeltaTree:
             for k in range(mink, maxk + 1):
                 jr = {"A": first.fastas[0], "B": second.fastas[0], "Atitle": first.node_title, "Btitle": second.node_title,
                       "kval": k, "Acard": first.ksketches[k].card, "Bcard": second.ksketches[k].card,
-                      "ABcard": float(cards[row, col[k]])}
+                      "ABcard": cell(k)[2]}
                 jr["jaccard"] = (jr["Acard"] + jr["Bcard"] - jr["ABcard"]) / jr["ABcard"]
                 jrows.append(jr)
         return kij, jrows
@@ -738,16 +753,18 @@ class DeltaTree:
                 or os.environ.get("DANDD_B200_PAIR_TABLE", "1") == "0"
                 or not all(hasattr(leaf, "ksketches") for leaf in leaves)):
             return None
-        store = get_store()
-        if not hasattr(store, "pair_unions"):
-            return None
         ks = [k for k in range(1, HLL_MAX_K + 1)
               if all(k < len(leaf.ksketches) and leaf.ksketches[k] is not None for leaf in leaves)]
         if not ks:
             return None
-        leaf_paths = {k: [leaf.ksketches[k].sketch for leaf in leaves] for k in ks}
-        cards = store.pair_unions(leaf_paths, int(self.experiment["registers"]))
-        return {"cards": cards, "col": {k: i for i, k in enumerate(ks)}}
+        registers = int(self.experiment["registers"])
+
+        def compute():
+            store = get_store()
+            if not hasattr(store, "pair_unions"):
+                raise KeyError("this store has no batched pair job")       # -> the object path, pair by pair
+            return store.pair_unions({k: [leaf.ksketches[k].sketch for leaf in leaves] for k in ks}, registers)
+        return _PairTable(ks, compute)
 
     def prepare_AFproject(self, kijsummary, jsummary) -> List[Tuple]:
         """(tool, name1, name2, k, value, k1, k2, k12) tuples for helpers/AFproject.py: k = 0 rows carry
@@ -756,6 +773,22 @@ class DeltaTree:
         out = {(tool, r["Atitle"], r["Btitle"], 0, r["KIJ"], r["Ak"], r["Bk"], r["ABk"]) for r in kijsummary}
         out |= {(tool, r["Atitle"], r["Btitle"], r["kval"], r["jaccard"], None, None, None) for r in jsummary}
         return list(out)
+
+
+class _PairTable:
+    """Union cardinalities of every pair of leaves at every k: `cards()[pair, col[k]]`.  The batched device
+    job runs the first time a cell is asked for that the sketch database cannot answer -- a `kij` re-run
+    whose unions are all on record never creates the store (no torch import, no CUDA start-up)."""
+
+    def __init__(self, ks, compute):
+        self.col = {k: i for i, k in enumerate(ks)}
+        self._compute = compute
+        self._cards = None
+
+    def cards(self):
+        if self._cards is None:
+            self._cards = self._compute()
+        return self._cards
 
 
 class SubSpider(DeltaTree):

@@ -334,3 +334,47 @@ def test_gpus_flag_starts_workers_only_for_fresh_fastas(tmp_path, oracle_store, 
     finally:
         os.environ.clear()
         os.environ.update(saved)
+
+
+@pytest.mark.parametrize("jaccard", [False, True])
+def test_kij_rerun_is_answered_by_the_database(tmp_path, oracle_store, jaccard):
+    """A second `kij` over the same tree finds every pair union on record (file + cardinality) and must
+    not create the store -- no batched device job, no torch import -- while writing the same tables.
+    Deleting ONE union file brings the batched job back (for that cell the database has no answer)."""
+    import csv
+    from tests.host_harness import run_dandd
+    first = _kij_run(str(tmp_path), True, jaccard)
+    out = os.path.join(str(tmp_path), "out")
+    argv = ["kij", "-d", os.path.join(out, "kj_7_dashing_dtree.pickle"), "-o", out, "--mink", "8", "--maxk", "13", "--afproject"]
+    argv += ["--jaccard"] if jaccard else []
+
+    def rows():
+        return [{k: v for k, v in r.items() if k not in ("A", "B")} for r in csv.DictReader(open(os.path.join(out, "kj_7_dashing.kij.csv")))]
+    want = rows()
+
+    def trap(*a, **k):
+        raise AssertionError("a fully cached kij re-run created the sketch store")
+    real_cls = ddstore.GpuSketchStore
+    ddstore.set_store(None)
+    ddstore.GpuSketchStore = trap
+    try:
+        run_dandd(argv)
+        assert ddstore._store is None
+    finally:
+        ddstore.GpuSketchStore = real_cls
+        ddstore.set_store(oracle_store)
+    assert rows() == want and len(want) == 21
+    # one union sketch goes missing: the batched job runs again and restores it
+    db = os.path.join(out, "sketchdb", "ngen2")
+    victim = sorted(os.path.join(d, f) for d, _, fs in os.walk(db) for f in fs if f.endswith(".hll"))[3]
+    os.remove(victim)
+    calls = {"n": 0}
+    real_pairs = oracle_store.pair_unions
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return real_pairs(*a, **k)
+    oracle_store.pair_unions = counting
+    run_dandd(argv)
+    assert calls["n"] == 1 and os.path.getsize(victim) > 0 and rows() == want
+    assert len(first["kij"]) == 21
