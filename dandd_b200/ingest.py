@@ -41,7 +41,9 @@ def _hash_pool_get():
     global _hash_pool
     with _lock2:
         if _hash_pool is None:      # its own pool: a digest must not queue behind the reads of a thousand later files
-            _hash_pool = ThreadPoolExecutor(max_workers=max(2, min(16, (os.cpu_count() or 4) // 2)), thread_name_prefix="dd-blake2b")
+            # naming is the one stage of a fresh run that only host cores can do (one sequential blake2b per
+            # file, ~0.5 GB/s per busy core): it gets all of them but a few
+            _hash_pool = ThreadPoolExecutor(max_workers=max(2, min(32, (os.cpu_count() or 4) - 4)), thread_name_prefix="dd-blake2b")
     return _hash_pool
 
 

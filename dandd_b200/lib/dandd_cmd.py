@@ -35,8 +35,9 @@ UNIVERSAL = [  # reference :23-30
     (("--device",), dict(type=int, default=None, dest="device", metavar="GPU", help="CUDA device to use (default LOCAL_RANK or 0).")),
     (("--gpus",), dict(type=int, default=None, dest="gpus", metavar="N",
                        help="tree: use N GPUs of this node, one process each (what `torchrun --nproc-per-node N` sets up, "
-                            "without the launcher's start-up cost). The extra processes are only started when the run "
-                            "has FASTAs the sketch database has never seen (or with --exact).")),
+                            "without the launcher's start-up cost). N is an upper bound: one process per "
+                            "DANDD_B200_BYTES_PER_GPU (default 12 GiB; 0 = all N if any) of FASTA the sketch database has never "
+                            "seen, all N with --exact.")),
 ]
 KSWEEP = [  # reference :145-150
     (("--ksweep",), dict(dest="ksweep", default=None, action="store_true",
@@ -124,10 +125,23 @@ def _self_launch(args) -> list:
     n = int(args.gpus or 1)
     if n < 2 or "WORLD_SIZE" in os.environ:
         return []
-    if not args.exact and not _fresh_fastas(args):
-        # every FASTA already has its name in the sketch database: what is left, if anything, is unions and
-        # the odd k outside the stored range -- less than the seconds N-1 more processes take to start
-        return []
+    if not args.exact:
+        # N is an upper bound.  Every further process costs about a second of (serialised) CUDA context
+        # creation on top of its own interpreter start, which is what one GPU needs to pack and sketch
+        # ~13 GB of FASTA for all k; and the part of a fresh run that does not shrink with N -- naming the
+        # files, blake2b on the host's cores -- is the same however many processes share it.  So a worker
+        # is started per BYTES_PER_GPU of FASTA the sketch database has never seen (measured: 8 x 3.1 GB
+        # takes 8.8 s in one process on one GPU, 16-17 s in eight on eight), none for a re-run over named
+        # files (what is left then is unions and the odd k outside the stored range).
+        # DANDD_B200_BYTES_PER_GPU=0 starts all N whenever anything is fresh.
+        per_gpu = int(float(os.environ.get("DANDD_B200_BYTES_PER_GPU", str(12 << 30))))
+        fresh_bytes = sum(os.path.getsize(f) for f in _fresh_fastas(args))
+        if fresh_bytes == 0:
+            return []
+        if per_gpu > 0:
+            n = min(n, max(1, fresh_bytes // per_gpu))
+            if n < 2:
+                return []
     with socket.socket() as sock:       # a free port for the rendezvous store
         sock.bind(("127.0.0.1", 0))
         port = sock.getsockname()[1]

@@ -298,10 +298,26 @@ def test_gpus_flag_starts_workers_only_for_fresh_fastas(tmp_path, oracle_store, 
 
     monkeypatch.setattr(subprocess, "Popen", FakePopen)
     saved = dict(os.environ)
+    fresh_bytes = sum(os.path.getsize(os.path.join(data, f)) for f in os.listdir(data))
     try:
         for key in ("WORLD_SIZE", "RANK", "LOCAL_RANK", "CUDA_VISIBLE_DEVICES"):
             os.environ.pop(key, None)
         args = argparse.Namespace(gpus=3, exact=False, genomedir=data, flist_loc=None, sketchdir=None, outdir=out)
+        # N is an upper bound: one process per DANDD_B200_BYTES_PER_GPU of fresh FASTA
+        os.environ.pop("DANDD_B200_BYTES_PER_GPU", None)
+        assert dandd_cmd._self_launch(args) == [] and not started          # 100 kB is far below 12 GiB
+        os.environ["DANDD_B200_BYTES_PER_GPU"] = str(fresh_bytes // 2)
+        assert len(dandd_cmd._self_launch(args)) == 1                      # two processes' worth
+        assert started[0][1]["WORLD_SIZE"] == "2"
+    finally:
+        os.environ.clear()
+        os.environ.update(saved)
+    started.clear()
+    saved["DANDD_B200_BYTES_PER_GPU"] = "0"                                # from here on: all N whenever anything is fresh
+    os.environ["DANDD_B200_BYTES_PER_GPU"] = "0"
+    try:
+        for key in ("WORLD_SIZE", "RANK", "LOCAL_RANK", "CUDA_VISIBLE_DEVICES"):
+            os.environ.pop(key, None)
         children = dandd_cmd._self_launch(args)
         assert len(children) == 2 and len(started) == 2
         envs = [env for _, env in started]
@@ -334,6 +350,7 @@ def test_gpus_flag_starts_workers_only_for_fresh_fastas(tmp_path, oracle_store, 
     finally:
         os.environ.clear()
         os.environ.update(saved)
+        os.environ.pop("DANDD_B200_BYTES_PER_GPU", None)
 
 
 @pytest.mark.parametrize("jaccard", [False, True])

@@ -154,6 +154,11 @@ def run(args):
     # 2. dandd tree --ksweep under torchrun
     timing_tree = os.path.join(workdir, "timing_tree.jsonl")
     env = dict(os.environ, DANDD_B200_TIMING=timing_tree, DANDD_B200_UNION_FILES=args.union_files)
+    if args.gpus > 1:
+        # this tool measures the N-process path: `--gpus N` is an upper bound otherwise (one worker per 12 GiB of
+        # fresh FASTA, dandd_cmd._self_launch) and would run config 3 (25 GB) in a single process
+        env.setdefault("DANDD_B200_BYTES_PER_GPU", "0")
+        rep["config"]["bytes_per_gpu_policy"] = env["DANDD_B200_BYTES_PER_GPU"]
     tree_argv = [DANDD, "tree", "--datadir", data, "-o", out, "--tag", "cfg3", "--ksweep", "--mink", str(args.kmin),
                  "--maxk", str(args.kmax)]
     launcher = getattr(args, "launcher", "self")
