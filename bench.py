@@ -260,7 +260,7 @@ def run_ours(args):
     if world > 1:
         dd_dist.init("nccl")
         dist.barrier()
-    from dandd_b200.engine import Engine, kmask_of
+    from dandd_b200.engine import Engine
     from dandd_b200._lib import check
     eng = Engine(local)
     if os.environ.get("DD_K_PER_PASS"):

@@ -13,7 +13,7 @@ Backend: NCCL over NVLink on GPUs, gloo in the CPU tests (tests/test_dist.py, wo
 The payloads are tiny next to NVLink bandwidth (<= 31 MiB per genome), so plain collectives on the
 compute stream are the right tool; there is no compute kernel to fuse them into."""
 import os
-from typing import List, Sequence
+from typing import List
 
 import numpy as np
 import torch

@@ -4,7 +4,6 @@ import csv
 import json
 import os
 import pickle
-import sys
 
 import pytest
 

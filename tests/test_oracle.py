@@ -13,7 +13,7 @@ import pytest
 
 from oracle import pyoracle as orc
 from oracle import ref_numpy as ref
-from tests.util import adversarial_fasta, mutate, random_bases, to_fasta
+from tests.util import adversarial_fasta, random_bases, to_fasta
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
