@@ -410,6 +410,10 @@ class DeltaTree:
         plan = self.plan_tree([1] * len(leaves), nchildren)
         if len(plan) < 2 or not ks:
             return                      # a spider has one inner node: the per-node batch is already one launch
+        if any(not progeny for progeny in plan):
+            return                      # the reference's cursor arithmetic runs off the list for some (n, nchildren),
+                                        # e.g. (4, 3) or (6, 4), and then fails naming a parent without members
+                                        # (lib/huffman_dandd.py:412-438): leave that to _build_tree, same error
         probe = DashSketchObj(kval=0, sfp=SketchFilePath(filenames=[leaves[0].fastas[0]], kval=0, speciesinfo=self.speciesinfo,
                                                          experiment=self.experiment),
                               speciesinfo=self.speciesinfo, experiment=self.experiment)

@@ -395,3 +395,20 @@ def test_kij_rerun_is_answered_by_the_database(tmp_path, oracle_store, jaccard):
     run_dandd(argv)
     assert calls["n"] == 1 and os.path.getsize(victim) > 0 and rows() == want
     assert len(first["kij"]) == 21
+
+
+@pytest.mark.parametrize("sweep", [False, True])
+@pytest.mark.parametrize("n,nchildren", [(3, 4), (4, 3), (6, 4)])
+def test_nary_shapes_the_reference_cannot_build_fail_the_same_way(tmp_path, oracle_store, n, nchildren, sweep):
+    """For some (genomes, --nchildren) the reference's parent-insertion cursor runs off the node list and it
+    dies naming a parent without members: FileNotFoundError on '' (lib/huffman_dandd.py:412-438,
+    lib/sketch_classes.py:12-18; found by tests/test_reference_live.py).  The drop-in must fail the
+    same way -- also with --ksweep, where the batched tree-union job would otherwise be handed an empty set."""
+    from tests.host_harness import run_dandd
+    from tests.util import make_dataset
+    data = str(tmp_path / "d")
+    make_dataset(data, n, 1500, seed=7 + n, sub=0.05)
+    argv = ["tree", "-d", data, "-s", "x", "-k", "10", "-r", "10", "-n", str(nchildren), "-o", str(tmp_path / "out")]
+    with pytest.raises(FileNotFoundError) as err:
+        run_dandd(argv + (["--ksweep", "--mink", "9", "--maxk", "11"] if sweep else []))
+    assert "''" in str(err.value)
