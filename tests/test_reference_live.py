@@ -152,3 +152,103 @@ def test_random_tree_progressive_kij_match_the_reference(tmp_path, golden, oracl
     assert all(close(ours_db["cardkey"][k], v) for k, v in want_db["cardkey"].items())
     assert ours_db["fastahex"] == want_db["fastahex"] and ours_db["sketchinfo"] == want_db["sketchinfo"]
     print(f"LIVE seed {seed}: tree + progressive + kij compared {case}")
+
+
+def _draw_options(seed):
+    rng = random.Random(1000 + seed)
+    n = rng.randint(3, 6)
+    case = {"n": n, "length": rng.choice([2000, 5000]), "seed": 300 + seed, "kstart": rng.randint(10, 14),
+            "exact": rng.random() < 0.5, "sweep": None, "step": rng.choice([1, 1, 2]),
+            "orderings": {tuple(range(n))} | {tuple(rng.sample(range(n), n)) for _ in range(rng.randint(1, 3))},
+            "subset": sorted(rng.sample(range(n), rng.randint(2, n - 1))), "safe": rng.random() < 0.5, "fast": rng.random() < 0.3}
+    if rng.random() < 0.6:
+        lo = rng.randint(9, 12)
+        case["sweep"] = (lo, lo + rng.randint(2, 4))
+    return case
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("DANDD_LIVE_SEEDS", "6"))))
+def test_random_exact_orderings_subsets_match_the_reference(tmp_path, golden, oracle_store, seed):
+    """More of the option space, same method: --exact (with the one-method run-time patch of the reference that
+    tests/golden/make_reference_golden.py documents), progressive over an orderings file with --step,
+    and a tree over a file-list subset with --safe / --fast."""
+    import pickle
+    from oracle import pyoracle
+    case = _draw_options(seed)
+    bindir = pyoracle.install_shims(str(tmp_path / "bin"))
+    data = str(tmp_path / "data")
+    files = make_dataset(data, case["n"], case["length"], seed=case["seed"], sub=0.05)
+    tool = "kmc" if case["exact"] else "dashing"
+    tag = f"x{seed}"
+    prefix = f"{tag}_{case['n']}_{tool}"
+    ref_out, our_out = str(tmp_path / "ref"), str(tmp_path / "ours")
+    sweep = ["--ksweep", "--mink", str(case["sweep"][0]), "--maxk", str(case["sweep"][1])] if case["sweep"] else []
+    extra = ["--exact"] if case["exact"] else ["-r", "12"]
+
+    def both(ref_argv, our_argv):
+        import subprocess
+        try:
+            golden.run_ref(bindir, ref_argv, exact=case["exact"])
+        except subprocess.CalledProcessError as failed:
+            last = failed.stderr.decode(errors="replace").strip().split("\n")[-1]
+            with pytest.raises(Exception) as ours_err:
+                run_dandd(our_argv)
+            assert type(ours_err.value).__name__ in last, (last, repr(ours_err.value))
+            return False
+        run_dandd(our_argv)
+        return True
+
+    tree = lambda out: ["tree", "-d", data, "-s", tag, "-k", str(case["kstart"]), "-o", out] + extra + sweep   # noqa: E731
+    if not both(tree(ref_out), tree(our_out)):
+        print(f"LIVE options seed {seed}: both fail at tree {case}")
+        return
+    assert_tree_matches(collect_tree(our_out, prefix, os.path.join(our_out, "sketchdb"), tool),
+                        golden.collect_tree(ref_out, prefix, os.path.join(ref_out, "sketchdb"), tool), exact=case["exact"])
+    # ---- progressive over an orderings file (+ --step): cells keyed by member set, the ordering numbers follow
+    #      list(set) order, which is process-specific
+    ofile = str(tmp_path / "orderings.pickle")
+    with open(ofile, "wb") as fh:
+        pickle.dump(case["orderings"], fh)
+    prog = lambda out: (["progressive", "-d", os.path.join(out, prefix + "_dtree.pickle"), "-r", ofile, "-s", tag + "o", "-o", out,   # noqa: E731
+                         "--step", str(case["step"])] + sweep)
+    if both(prog(ref_out), prog(our_out)):
+        name = f"{tag}o_progu0_{case['n']}_{tool}"
+        cells = {}
+        for side, out in (("ref", ref_out), ("ours", our_out)):
+            rows = read_csv(os.path.join(out, name + "summary.csv"))
+            cells[side] = sorted({(r["title"], int(r["kval"]), float(r["card"])) for r in rows})
+        assert [c[:2] for c in cells["ours"]] == [c[:2] for c in cells["ref"]]
+        assert all((a[2] == b[2]) if case["exact"] else close(a[2], b[2]) for a, b in zip(cells["ours"], cells["ref"]))
+        main = {}
+        for side, out in (("ref", ref_out), ("ours", our_out)):
+            main[side] = sorted((int(r["ngen"]), r["kval"], r["delta"][:12], r["fastas"].count(",")) for r in read_csv(os.path.join(out, name + ".csv")))
+        assert [(m[0], m[1], m[3]) for m in main["ours"]] == [(m[0], m[1], m[3]) for m in main["ref"]]
+    else:
+        print(f"LIVE options seed {seed}: both fail at progressive {case}")
+    # ---- a tree over a subset given as a file list, into the SAME sketch database (cached leaves are reused)
+    flist = str(tmp_path / "flist.txt")
+    with open(flist, "w") as fh:
+        fh.write("\n".join(files[i] for i in case["subset"]) + "\n")
+    opts = (["--safe"] if case["safe"] else []) + (["--fast"] if case["fast"] else [])
+    sub = lambda out: (["tree", "-f", flist, "-s", tag + "s", "-k", str(case["kstart"]), "-o", out, "--sketchdir",   # noqa: E731
+                        os.path.join(out, "sketchdb")] + extra + sweep + opts)
+    if not both(sub(ref_out), sub(our_out)):
+        print(f"LIVE options seed {seed}: both fail at subset tree {case}")
+        return
+    sub_prefix = f"{tag}s_{len(case['subset'])}_{tool}"
+    rows = {}
+    for side, out in (("ref", ref_out), ("ours", our_out)):
+        rows[side] = [(r["title"], int(r["ngen"]), int(r["k"]), float(r["card"]), float(r["delta"]))
+                      for r in read_csv(os.path.join(out, sub_prefix + "_deltas.csv"))]
+        outputs = sorted(f for f in os.listdir(out) if f.startswith(tag + "s_"))
+        rows[side + "_outputs"] = outputs
+    assert [r[:3] for r in rows["ours"]] == [r[:3] for r in rows["ref"]]
+    assert all(close(a[3], b[3]) and close(a[4], b[4]) for a, b in zip(rows["ours"], rows["ref"]))
+    assert rows["ours_outputs"] == rows["ref_outputs"]                  # --fast writes the deltas table only
+    want_db = golden.collect_tree(ref_out, prefix, os.path.join(ref_out, "sketchdb"), tool)
+    ours_db = collect_tree(our_out, prefix, os.path.join(our_out, "sketchdb"), tool)
+    assert ours_db["files"] == want_db["files"]
+    if not case["fast"]:          # (--fast skips saving the caches)
+        assert sorted(ours_db["cardkey"]) == sorted(want_db["cardkey"])
+        assert ours_db["fastahex"] == want_db["fastahex"] and ours_db["sketchinfo"] == want_db["sketchinfo"]
+    print(f"LIVE options seed {seed}: tree + orderings + subset tree compared {case}")
