@@ -183,8 +183,9 @@ class _Job:
     workers and 8 files queued as read/text/hash triples only 3 files made progress at a time, which
     tripled the naming time of the 8 x 3.1 GB run.)"""
 
-    def __init__(self, path, pool, hash_only=False):
-        self.digest: Future = Future()
+    def __init__(self, path, pool, hash_only=False, want_digest=True):
+        # want_digest=False: bytes only (callers that never name the file: helpers/allpairs.py)
+        self.digest: Future = Future() if want_digest else None
         if hash_only:
             # a large uncompressed file: nobody needs its bytes in one piece (streaming.py feeds the GPU from
             # the file itself, through the page cache), so only the name is prepared -- hashed in 1 MiB
@@ -201,9 +202,11 @@ class _Job:
             raw = _read(path)
         except BaseException as err:  # noqa: BLE001 -- delivered to whoever asks for the text or the digest
             self.text.set_exception(err)
-            self.digest.set_exception(err)
+            if self.digest is not None:
+                self.digest.set_exception(err)
             return
-        _hash_pool_get().submit(self._run_hash, raw)
+        if self.digest is not None:
+            _hash_pool_get().submit(self._run_hash, raw)
         try:
             self.text.set_result(_text(raw))
         except BaseException as err:  # noqa: BLE001
@@ -222,7 +225,9 @@ class _Job:
             self.digest.set_exception(err)
 
 
-def prefetch(paths: Iterable[str]) -> None:
+def prefetch(paths: Iterable[str], want_digest: bool = True) -> None:
+    """Start reading (and inflating) these files in the background; with want_digest also their blake2b
+    names.  Idempotent per path."""
     global _cached
     with _lock:
         for p in paths:
@@ -230,12 +235,13 @@ def prefetch(paths: Iterable[str]) -> None:
                 continue
             size = os.path.getsize(p)
             if size >= HASH_ONLY_MIN_BYTES and not _is_gzip(p):
-                _jobs[p] = _Job(p, None, hash_only=True)     # holds no bytes: not counted against the cache
+                if want_digest:
+                    _jobs[p] = _Job(p, None, hash_only=True)     # holds no bytes: not counted against the cache
                 continue
             if _cached + size > _MAX_CACHED_BYTES:
                 break                         # the rest is loaded on demand
             _cached += size
-            _jobs[p] = _Job(p, _pool_get())
+            _jobs[p] = _Job(p, _pool_get(), want_digest=want_digest)
 
 
 def _take(path):
@@ -253,7 +259,8 @@ def _take(path):
     text = job.text.result()
     with _lock:
         _cached = max(0, _cached - os.path.getsize(path))
-        _digest_jobs[_key(path)] = job.digest
+        if job.digest is not None:
+            _digest_jobs[_key(path)] = job.digest
     return text, None
 
 
@@ -275,7 +282,8 @@ def has_digest(path: str) -> bool:
     except OSError:
         return False
     with _lock:
-        return path in _jobs or k in _digest_jobs or k in _digests
+        job = _jobs.get(path)
+        return (job is not None and job.digest is not None) or k in _digest_jobs or k in _digests
 
 
 def fasta_bytes(path: str) -> bytes:
@@ -299,7 +307,8 @@ def drop(path: str) -> None:
         if job is not None:
             if job.text is not None:
                 _cached = max(0, _cached - os.path.getsize(path))
-            _digest_jobs[_key(path)] = job.digest
+            if job.digest is not None:
+                _digest_jobs[_key(path)] = job.digest
 
 
 def drop_all() -> None:

@@ -134,11 +134,37 @@ class GpuSketchStore:
         (dist.split_fasta), the registers are max-reduced over the ranks, every rank gets the
         cardinalities of the whole file and rank 0 writes the sketch files (fewer
         genomes than GPUs)."""
+        need = [int(k) for k in ks]
+        ent = self._leaf_entry(fasta, need, p, canon, split)
+        out = {}
+        for k in need:
+            i = ent["ks"][k]
+            card = float(ent["cards"][i])
+            self._remember(out_paths[k], ent["regs"][i], view_of_block=True)
+            if split is None or split[0] == 0:
+                self._write(out_paths[k], ent["regs"][i], p, card, leaf=True)
+            out[k] = card
+        return out
+
+    def leaf_block(self, fasta: str, ks: Sequence[int], p: int, canon: bool) -> Tuple[torch.Tensor, np.ndarray]:
+        """(registers [len(ks), 2^p] uint8 on the device, cardinalities [len(ks)]) of one FASTA, rows in the
+        order of `ks`; nothing is named or written (`dashing hll` leaves no sketch behind:
+        reference helpers/allpairs.py:32-35).  Same fused all-k pass and HBM cache as leaf_sketches."""
+        need = [int(k) for k in ks]
+        ent = self._leaf_entry(fasta, need, p, canon, None, all_k=False)    # no later request for other k will come
+        rows = [ent["ks"][k] for k in need]
+        return ent["regs"][rows], np.asarray([float(ent["cards"][i]) for i in rows], dtype=np.float64)
+
+    def _leaf_entry(self, fasta: str, need: List[int], p: int, canon: bool, split: Optional[Tuple[int, int]],
+                    all_k: Optional[bool] = None) -> dict:
+        """The all-k block of one FASTA: {"regs": [nk, 2^p] device tensor, "cards": [nk], "ks": {k: row}},
+        from the HBM cache or one fused pass (streamed above STREAM_MIN_BYTES).  all_k: sketch k = 1..32
+        whatever is asked for (default: the store's prefetch_all_k)."""
         key = ("leaf", fasta, int(p), bool(canon))
         ent = self._get(key)
-        need = [int(k) for k in ks]
         if split is not None or ent is None or any(k not in ent["ks"] for k in need):
-            run_ks = list(ALL_HLL_KS) if self.prefetch_all_k else sorted(set(need) | set(ent["ks"] if ent else ()))
+            all_k = self.prefetch_all_k if all_k is None else all_k
+            run_ks = list(ALL_HLL_KS) if all_k else sorted(set(need) | set(ent["ks"] if ent else ()))
             streamed = None
             if split is None and os.path.getsize(fasta) >= STREAM_MIN_BYTES:
                 streamed = self._stream_leaf(fasta, run_ks, p, canon)
@@ -161,15 +187,7 @@ class GpuSketchStore:
             ent = {"regs": regs, "cards": cards, "ks": {k: i for i, k in enumerate(run_ks)}}
             self._put(key, ent, regs.numel())
             self.stats["leaf_passes"] += 1
-        out = {}
-        for k in need:
-            i = ent["ks"][k]
-            card = float(ent["cards"][i])
-            self._remember(out_paths[k], ent["regs"][i], view_of_block=True)
-            if split is None or split[0] == 0:
-                self._write(out_paths[k], ent["regs"][i], p, card, leaf=True)
-            out[k] = card
-        return out
+        return ent
 
     def warm_leaf(self, fasta: str, p: int, canon: bool) -> None:
         """Sketch a large FASTA for all k NOW and keep the block in HBM, without naming or writing
@@ -343,19 +361,32 @@ class GpuSketchStore:
                 regs[g, i].copy_(self.registers(pth))
         iu = np.triu_indices(n, 1)
         pairs = np.stack(iu, axis=1).astype(np.int32)
-        out = np.empty((pairs.shape[0], len(ks)), dtype=np.float64)
+        out = self.pair_cards(regs, pairs, p, tile_pairs)
+        if remember:
+            self.pair_table = {"p": int(p), "n": n, "col": {k: i for i, k in enumerate(ks)}, "cards": out,
+                               "leaf": {pth: (g, k) for k in ks for g, pth in enumerate(leaf_paths_by_k[k])}}
+        return out
+
+    def pair_cards(self, regs: torch.Tensor, pairs, p: int, tile_pairs: int = 1 << 16) -> np.ndarray:
+        """card(A u B) for the listed pairs (int [t, 2] genome indices into regs [n, nk, 2^p], on the device)
+        at every k: float64 [t, nk] on the host.  The sketches are transposed into bit planes once, the
+        pair list goes through K6 in tiles (reference helpers/allpairs.py:360-370 runs one
+        `dashing hll A B` -- two FASTA passes -- per pair and k)."""
+        eng = self.engine
+        n, nk = int(regs.shape[0]), int(regs.shape[1])
+        pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        out = np.empty((pairs.shape[0], nk), dtype=np.float64)
+        if not pairs.shape[0]:
+            return out
         planes = eng.to_planes(regs, p) if p >= 12 else None
         for t0 in range(0, pairs.shape[0], tile_pairs):
             tile = pairs[t0:t0 + tile_pairs]
             if planes is not None:
-                cards = eng.pairwise_cards(None, tile, p, planes=planes, n_genomes=n, nk=len(ks))
+                cards = eng.pairwise_cards(None, tile, p, planes=planes, n_genomes=n, nk=nk)
             else:
                 cards = eng.pairwise_cards(regs, tile, p)
             out[t0:t0 + tile.shape[0]] = cards.cpu().numpy()
             self.stats["union_launches"] += 1
-        if remember:
-            self.pair_table = {"p": int(p), "n": n, "col": {k: i for i, k in enumerate(ks)}, "cards": out,
-                               "leaf": {pth: (g, k) for k in ks for g, pth in enumerate(leaf_paths_by_k[k])}}
         return out
 
     def _pair_lookup(self, members: Sequence[str], p: int):

@@ -115,6 +115,25 @@ class OracleStore:
                 out[j, i] = orc.card(np.maximum(self.registers(leaf_paths_by_k[k][a]), self.registers(leaf_paths_by_k[k][b])), p)
         return out
 
+    def leaf_block(self, fasta, ks, p, canon):
+        """(registers [len(ks), 2^p] torch uint8, cardinalities [len(ks)]): GpuSketchStore.leaf_block on the CPU."""
+        import torch
+        self.stats["leaf_passes"] += 1
+        sym = self.symbols(fasta)
+        regs = np.stack([orc.hll_sketch(sym, int(k), p, canon) for k in ks])
+        return torch.from_numpy(regs), np.asarray([orc.card(r, p) for r in regs], dtype=np.float64)
+
+    def pair_cards(self, regs, pairs, p, tile_pairs=0):
+        """[t, nk] union cardinalities of the listed pairs of regs [n, nk, 2^p] (GpuSketchStore.pair_cards)."""
+        self.stats["union_launches"] += 1
+        regs = regs.numpy()
+        pairs = np.asarray(pairs).reshape(-1, 2)
+        out = np.zeros((len(pairs), regs.shape[1]))
+        for j, (a, b) in enumerate(pairs):
+            for i in range(regs.shape[1]):
+                out[j, i] = orc.card(np.maximum(regs[a, i], regs[b, i]), p)
+        return out
+
     def materialize_union(self, path, p, card, members):
         self._write(path, orc.union_max([self.registers(m) for m in members]), p, card)
         return float(card)

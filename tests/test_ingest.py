@@ -156,3 +156,29 @@ def test_hash_file_pieces_and_empty_file(tmp_path):
     assert ingest._hash_file(str(path), piece=4096) == want          # many mapped pieces
     path.write_bytes(b"")
     assert ingest._hash_file(str(path)) == hashlib.blake2b(b"").hexdigest()   # cannot be mapped: read path
+
+
+def test_bytes_only_prefetch_never_hashes(tmp_path, monkeypatch):
+    """prefetch(want_digest=False) (helpers/allpairs.py: files that are never named): bytes are read in the
+    background, no hashing task is queued, large plain files get no job at all, and a digest asked for
+    later is still right."""
+    monkeypatch.setattr(ingest, "HASH_ONLY_MIN_BYTES", 1000)
+    monkeypatch.setattr(ingest, "_jobs", {})
+    monkeypatch.setattr(ingest, "_cached", 0)
+    hashed = []
+    real = ingest._hash
+    monkeypatch.setattr(ingest, "_hash", lambda raw: hashed.append(len(raw)) or real(raw))
+    small, big = b">s\nACGTTGCA\n", b">b\n" + b"ACGT" * 1000 + b"\n"
+    (tmp_path / "s.fa").write_bytes(small)
+    (tmp_path / "b.fa").write_bytes(big)
+    (tmp_path / "b.fa.gz").write_bytes(gzip.compress(big))
+    paths = [str(tmp_path / n) for n in ("s.fa", "b.fa", "b.fa.gz")]
+    ingest.prefetch(paths, want_digest=False)
+    assert ingest.is_prefetched(paths[0]) and not ingest.is_prefetched(paths[1]) and ingest.is_prefetched(paths[2])
+    assert paths[1] not in ingest._jobs and not any(ingest.has_digest(p) for p in paths)
+    assert ingest.fasta_bytes(paths[0]) == small and ingest.fasta_bytes(paths[1]) == big and ingest.fasta_bytes(paths[2]) == big
+    assert hashed == [] and ingest._cached == 0
+    assert ingest.digest(paths[0]) == hashlib.blake2b(small).hexdigest()
+    ingest.prefetch([paths[0]], want_digest=False)
+    ingest.drop(paths[0])                                  # a dropped bytes-only job leaves no digest future behind
+    assert ingest._cached == 0 and ingest.digest(paths[2]) == hashlib.blake2b((tmp_path / "b.fa.gz").read_bytes()).hexdigest()
