@@ -65,8 +65,11 @@ class GpuSketchStore:
         self._cost[key] = int(cost)
         self._bytes += int(cost)
         while self._bytes > self.cache_bytes and len(self._lru) > 1:
-            old, _ = self._lru.popitem(last=False)
+            old, gone = self._lru.popitem(last=False)
             self._bytes -= self._cost.pop(old)
+            if old[0] == "leaf":       # the per-k sketches that are views of this block would keep it in HBM, uncounted
+                for path in gone.get("views", ()):
+                    self.forget(path)
 
     def _get(self, key: tuple):
         value = self._lru.get(key)
@@ -140,6 +143,7 @@ class GpuSketchStore:
         for k in need:
             i = ent["ks"][k]
             card = float(ent["cards"][i])
+            ent.setdefault("views", set()).add(out_paths[k])     # (first: the next line may evict the block itself)
             self._remember(out_paths[k], ent["regs"][i], view_of_block=True)
             if split is None or split[0] == 0:
                 self._write(out_paths[k], ent["regs"][i], p, card, leaf=True)

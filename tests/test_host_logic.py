@@ -412,3 +412,31 @@ def test_nary_shapes_the_reference_cannot_build_fail_the_same_way(tmp_path, orac
     with pytest.raises(FileNotFoundError) as err:
         run_dandd(argv + (["--ksweep", "--mink", "9", "--maxk", "11"] if sweep else []))
     assert "''" in str(err.value)
+
+
+def test_store_cache_evicts_a_leaf_block_together_with_its_views():
+    """GpuSketchStore's byte budget: per-k sketches that are views of an all-k leaf block cost nothing
+    by themselves, so when the block is evicted they must go too (they would keep its memory alive,
+    uncounted); tensors a caller still holds stay valid.  Cache plumbing only: no device is touched."""
+    import torch
+    st = ddstore.GpuSketchStore(engine=object(), cache_bytes=100)
+    blocks = {}
+    for name in ("a", "b", "c"):
+        regs = torch.full((4, 10), ord(name), dtype=torch.uint8)          # 40 "bytes" per block
+        ent = {"regs": regs, "cards": [0.0] * 4, "ks": {k: k for k in range(4)}, "views": set()}
+        blocks[name] = ent
+        st._put(("leaf", name, 10, True), ent, regs.numel())
+        for k in range(4):
+            ent["views"].add(f"/db/{name}.{k}")
+            st._remember(f"/db/{name}.{k}", regs[k], view_of_block=True)
+    # 3 x 40 > 100: block a went, and with it its four views; b and c are whole
+    assert st._get(("leaf", "a", 10, True)) is None and all(st._get(("sketch", f"/db/a.{k}")) is None for k in range(4))
+    assert all(st._get(("sketch", f"/db/{n}.{k}")) is not None for n in "bc" for k in range(4))
+    assert st._bytes == 80 and sum(st._cost.values()) == 80 and set(st._cost) == set(st._lru)
+    assert int(blocks["a"]["regs"][2, 0]) == ord("a")                      # a held tensor is untouched
+    # a standalone sketch (read from a file, or a union) is charged its own size and evicts the oldest block
+    st._remember("/db/u", torch.zeros(30, dtype=torch.uint8))
+    assert st._get(("leaf", "b", 10, True)) is None and st._get(("sketch", "/db/b.0")) is None
+    assert st._get(("sketch", "/db/c.3")) is not None and st._bytes == 70
+    st.forget("/db/u")
+    assert st._bytes == 40
