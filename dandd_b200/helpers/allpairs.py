@@ -205,15 +205,12 @@ def card_table(tool: str, inputs: Sequence[str], names: Sequence[str], klist: Se
     if tool == "dashing":
         p = int(math.log2(nest))
         uniq = sorted(set(ks))
-        blocks = [store.leaf_block(inputs[g], uniq, p, canon) for g in owners[rank]]
-        like = blocks[0][0] if blocks else None
-        if like is None:                      # more ranks than FASTAs: this one only takes part in the exchange
-            dev = getattr(getattr(store, "engine", None), "device", "cpu")
-            local = torch.zeros((0, len(uniq), 1 << p), dtype=torch.uint8, device=dev)
-        else:
-            local = torch.stack([b[0] for b in blocks])
-        local_cards = torch.as_tensor(np.stack([b[1] for b in blocks]) if blocks else np.zeros((0, len(uniq))),
-                                      dtype=torch.float64, device=local.device)
+        dev = getattr(getattr(store, "engine", None), "device", "cpu")
+        local = torch.empty((len(owners[rank]), len(uniq), 1 << p), dtype=torch.uint8, device=dev)
+        local_cards = np.zeros((len(owners[rank]), len(uniq)))
+        for j, g in enumerate(owners[rank]):          # the registers land in their slice of the job's array
+            local_cards[j] = store.leaf_block(inputs[g], uniq, p, canon, out=local[j])[1]
+        local_cards = torch.as_tensor(local_cards, dtype=torch.float64, device=dev)
         regs = dd_dist.gather_registers(local, owners)                         # [n, nk, 2^p] on every rank
         single = dd_dist.gather_cards(local_cards, owners).cpu().numpy()
         part = store.pair_cards(regs, mine, p, tile_pairs)

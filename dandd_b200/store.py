@@ -150,20 +150,29 @@ class GpuSketchStore:
             out[k] = card
         return out
 
-    def leaf_block(self, fasta: str, ks: Sequence[int], p: int, canon: bool) -> Tuple[torch.Tensor, np.ndarray]:
+    def leaf_block(self, fasta: str, ks: Sequence[int], p: int, canon: bool,
+                   out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, np.ndarray]:
         """(registers [len(ks), 2^p] uint8 on the device, cardinalities [len(ks)]) of one FASTA, rows in the
         order of `ks`; nothing is named or written (`dashing hll` leaves no sketch behind:
-        reference helpers/allpairs.py:32-35).  Same fused all-k pass and HBM cache as leaf_sketches."""
+        reference helpers/allpairs.py:32-35).  Same fused pass as leaf_sketches, for exactly these k; a
+        block already in the HBM cache is used, a new one is not added to it (the caller keeps the
+        registers: with `out` they are written straight into its [len(ks), 2^p] slice)."""
         need = [int(k) for k in ks]
-        ent = self._leaf_entry(fasta, need, p, canon, None, all_k=False)    # no later request for other k will come
+        ent = self._leaf_entry(fasta, need, p, canon, None, all_k=False, keep=False)
         rows = [ent["ks"][k] for k in need]
-        return ent["regs"][rows], np.asarray([float(ent["cards"][i]) for i in rows], dtype=np.float64)
+        cards = np.asarray([float(ent["cards"][i]) for i in rows], dtype=np.float64)
+        if rows == list(range(ent["regs"].shape[0])):
+            regs = ent["regs"] if out is None else out.copy_(ent["regs"])
+        else:
+            index = torch.as_tensor(rows, dtype=torch.int64, device=ent["regs"].device)
+            regs = torch.index_select(ent["regs"], 0, index) if out is None else torch.index_select(ent["regs"], 0, index, out=out)
+        return regs, cards
 
     def _leaf_entry(self, fasta: str, need: List[int], p: int, canon: bool, split: Optional[Tuple[int, int]],
-                    all_k: Optional[bool] = None) -> dict:
+                    all_k: Optional[bool] = None, keep: bool = True) -> dict:
         """The all-k block of one FASTA: {"regs": [nk, 2^p] device tensor, "cards": [nk], "ks": {k: row}},
         from the HBM cache or one fused pass (streamed above STREAM_MIN_BYTES).  all_k: sketch k = 1..32
-        whatever is asked for (default: the store's prefetch_all_k)."""
+        whatever is asked for (default: the store's prefetch_all_k); keep: remember a new block in the cache."""
         key = ("leaf", fasta, int(p), bool(canon))
         ent = self._get(key)
         if split is not None or ent is None or any(k not in ent["ks"] for k in need):
@@ -189,7 +198,8 @@ class GpuSketchStore:
                     cards = self.engine.cards(regs, p)
                 cards = cards.cpu().numpy()
             ent = {"regs": regs, "cards": cards, "ks": {k: i for i, k in enumerate(run_ks)}}
-            self._put(key, ent, regs.numel())
+            if keep:
+                self._put(key, ent, regs.numel())
             self.stats["leaf_passes"] += 1
         return ent
 

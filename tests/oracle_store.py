@@ -115,13 +115,14 @@ class OracleStore:
                 out[j, i] = orc.card(np.maximum(self.registers(leaf_paths_by_k[k][a]), self.registers(leaf_paths_by_k[k][b])), p)
         return out
 
-    def leaf_block(self, fasta, ks, p, canon):
+    def leaf_block(self, fasta, ks, p, canon, out=None):
         """(registers [len(ks), 2^p] torch uint8, cardinalities [len(ks)]): GpuSketchStore.leaf_block on the CPU."""
         import torch
         self.stats["leaf_passes"] += 1
         sym = self.symbols(fasta)
         regs = np.stack([orc.hll_sketch(sym, int(k), p, canon) for k in ks])
-        return torch.from_numpy(regs), np.asarray([orc.card(r, p) for r in regs], dtype=np.float64)
+        t = torch.from_numpy(regs)
+        return (t if out is None else out.copy_(t)), np.asarray([orc.card(r, p) for r in regs], dtype=np.float64)
 
     def pair_cards(self, regs, pairs, p, tile_pairs=0):
         """[t, nk] union cardinalities of the listed pairs of regs [n, nk, 2^p] (GpuSketchStore.pair_cards)."""
