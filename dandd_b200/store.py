@@ -161,6 +161,8 @@ class GpuSketchStore:
         ent = self._leaf_entry(fasta, need, p, canon, None, all_k=False, keep=False)
         rows = [ent["ks"][k] for k in need]
         cards = np.asarray([float(ent["cards"][i]) for i in rows], dtype=np.float64)
+        if out is not None and (tuple(out.shape) != (len(rows), 1 << p) or out.dtype != torch.uint8 or not out.is_contiguous()):
+            raise ValueError(f"leaf_block: out must be a contiguous uint8 [{len(rows)}, {1 << p}] tensor, got {tuple(out.shape)}")
         if rows == list(range(ent["regs"].shape[0])):
             regs = ent["regs"] if out is None else out.copy_(ent["regs"])
         else:
