@@ -200,7 +200,7 @@ def card_table(tool: str, inputs: Sequence[str], names: Sequence[str], klist: Se
     mine = pairs[span.start:span.stop]
     if tool == "dashing" and (nest < 1 or nest & (nest - 1)):
         raise RuntimeError("--nest must be a power of 2 for dashing (got %d)" % nest)
-    from dandd_b200 import ingest
+    from dandd_b200 import ingest, timing
     ingest.prefetch([inputs[g] for g in owners[rank]], want_digest=False)    # file i+1.. are read while the GPU works on file i
     if tool == "dashing":
         p = int(math.log2(nest))
@@ -208,19 +208,23 @@ def card_table(tool: str, inputs: Sequence[str], names: Sequence[str], klist: Se
         dev = getattr(getattr(store, "engine", None), "device", "cpu")
         local = torch.empty((len(owners[rank]), len(uniq), 1 << p), dtype=torch.uint8, device=dev)
         local_cards = np.zeros((len(owners[rank]), len(uniq)))
-        for j, g in enumerate(owners[rank]):          # the registers land in their slice of the job's array
-            local_cards[j] = store.leaf_block(inputs[g], uniq, p, canon, out=local[j])[1]
+        with timing.span("allpairs_sketch"):
+            for j, g in enumerate(owners[rank]):      # the registers land in their slice of the job's array
+                local_cards[j] = store.leaf_block(inputs[g], uniq, p, canon, out=local[j])[1]
         local_cards = torch.as_tensor(local_cards, dtype=torch.float64, device=dev)
-        regs = dd_dist.gather_registers(local, owners)                         # [n, nk, 2^p] on every rank
-        single = dd_dist.gather_cards(local_cards, owners).cpu().numpy()
-        part = store.pair_cards(regs, mine, p, tile_pairs)
+        with timing.span("allpairs_gather"):
+            regs = dd_dist.gather_registers(local, owners)                     # [n, nk, 2^p] on every rank
+            single = dd_dist.gather_cards(local_cards, owners).cpu().numpy()
+        with timing.span("allpairs_pairs"):
+            part = store.pair_cards(regs, mine, p, tile_pairs)
         col = [uniq.index(k) for k in ks]
         single, part = single[:, col], part[:, col]
     else:
-        single_mine = np.array([[store.exact_count([inputs[g]], k, canon) for k in ks] for g in owners[rank]],
-                               dtype=np.float64).reshape(len(owners[rank]), len(ks))
-        part = np.array([[store.exact_count([inputs[a], inputs[b]], k, canon) for k in ks] for a, b in mine],
-                        dtype=np.float64).reshape(len(mine), len(ks))
+        with timing.span("allpairs_exact"):
+            single_mine = np.array([[store.exact_count([inputs[g]], k, canon) for k in ks] for g in owners[rank]],
+                                   dtype=np.float64).reshape(len(owners[rank]), len(ks))
+            part = np.array([[store.exact_count([inputs[a], inputs[b]], k, canon) for k in ks] for a, b in mine],
+                            dtype=np.float64).reshape(len(mine), len(ks))
         single = np.zeros((n, len(ks)))
         for r, rows in enumerate(_gather_objects(single_mine, world)):
             single[owners[r]] = rows
@@ -495,9 +499,14 @@ def go(argv=None):
         os.makedirs(args.name)
     inputs, names, seqid_to_treid = load_dataset(args.dataset)
     klist = [int(k) for k in args.klist.split(",")]
-    table = card_table(args.tool, inputs, names, klist, nest=args.nest, extra=args.extra)
-    if rank == 0:
-        write_outputs(table, args, seqid_to_treid, inputs)
+    from dandd_b200 import timing
+    try:
+        table = card_table(args.tool, inputs, names, klist, nest=args.nest, extra=args.extra)
+        if rank == 0:
+            with timing.span("allpairs_outputs"):
+                write_outputs(table, args, seqid_to_treid, inputs)
+    finally:
+        timing.dump()          # DANDD_B200_TIMING=<file>: one JSON line of stage times per process
     return table
 
 

@@ -185,3 +185,18 @@ def test_two_ranks(tmp_path, tool):
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), tool), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_config5_cli_tool_smoke(tmp_path):
+    """tools/config5_cli.py (config 5 from FASTA files through the driver) on the oracle-backed store."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "rep.json"
+    subprocess.run([sys.executable, os.path.join(root, "tools", "config5_cli.py"), "--genomes", "12", "--bases", "8000", "--p", "10",
+                    "--kmin", "9", "--kmax", "12", "--oracle-store", "--workdir", str(tmp_path / "w"), "--out", str(out)],
+                   check=True, stdout=subprocess.DEVNULL, timeout=300)
+    rep = json.loads(out.read_text())
+    assert rep["pairs"] == 66 and rep["oracle_max_rel_err"] == 0.0 and rep["output_files"] == 2 + 2 * 5
+    assert rep["kij_within_clusters"] > 3 * rep["kij_between_clusters"]
+    assert {"allpairs_sketch", "allpairs_pairs", "allpairs_outputs"} <= set(rep["stages_rank0"])
