@@ -1,9 +1,12 @@
 """Command-line front end: `dandd tree | progressive | kij` (reference lib/dandd_cmd.py).
 
 Same sub-commands, flags, defaults and output file names as the reference, so existing scripts
-and pickles keep working; the `info` sub-parser exists without a handler there (reference
-:235-246) and is omitted here.  One addition: `--device N` selects the GPU (default: LOCAL_RANK
-or 0).  Flag tables below cite the reference lines they mirror.
+and pickles keep working.  The reference registers an `info` sub-parser whose handler is commented
+out (reference :234-246), so `dandd info` dies there with an AttributeError; here the same flags are
+accepted and the command does what its help text says: it loads a tree pickle, adds the sketches a
+--ksweep asks for, prints the tree's delta table and (with --ksweep) writes the per-k table of every
+node.  Additions: `--device N` selects the GPU (default: LOCAL_RANK or 0), `--gpus N`.  Flag tables below
+cite the reference lines they mirror.
 """
 import argparse
 import os
@@ -85,6 +88,15 @@ KIJ = [  # reference :260-272
     (("-l", "--label"), dict(dest="label", metavar="SUFFIX TAG", default="", required=False, help="extra label in output names")),
     (("--afproject",), dict(dest="afproject", default=False, action="store_true", help="also write the AFproject tuple pickle")),
     (("--jaccard",), dict(dest="jaccard", default=False, action="store_true", help="also report per-k Jaccard")),
+]
+
+
+INFO = [  # reference :234-244
+    (("-d", "--dtree"), dict(dest="delta_tree", metavar="DELTA TREE", required=True,
+                             help="pickle produced by the tree command; nodes are updated to hold the sketches a --ksweep needs")),
+    (("-s", "--tag"), dict(dest="tag", metavar="PREFIX TAG", type=str, required=False, help="output tag")),
+    (("-o", "--outdir"), dict(dest="outdir", default=os.getcwd(), type=str, metavar="OUTPUT DIR", help="output directory")),
+    (("-l", "--label"), dict(dest="label", metavar="SUFFIX TAG", default="", required=False, help="extra label in output names")),
 ]
 
 
@@ -348,6 +360,33 @@ def kij_command(args):
             pickle.dump(obj=dtree.prepare_AFproject(kij_results, j_results), file=fh)
 
 
+def info_command(args):
+    """`dandd info` (the reference's parser :234-246 has no handler): the delta table of a saved tree on
+    stdout; with --ksweep every node is brought up to the k range first (sketching what is missing) and
+    <prefix>_info.csv holds one row per (node, k) -- ngen, kval, card, delta_pos, title -- like the
+    summary table of `progressive`."""
+    if _single_rank_command("info"):
+        return
+    _select_device(args)
+    dtree = _load_tree(args.delta_tree)
+    dtree.speciesinfo.update(tool=dtree.experiment["tool"])
+    args.tag = args.tag or dtree.speciesinfo.tag
+    write_listdict_to_csv(outfile=None, listdict=dtree.report_deltas())
+    if args.ksweep:
+        lo, hi = int(args.mink), int(args.maxk)
+        if dtree.experiment["tool"] == "dashing":
+            hi = min(hi, huffman_dandd.HLL_MAX_K)
+        dtree.experiment["ksweep"] = (lo, hi)
+        dtree.ksweep(mink=lo, maxk=hi)
+        rows = []
+        for node in dtree._dt:
+            rows.extend(node.summarize(mink=max(1, lo), maxk=hi))
+        prefix = dtree.make_prefix(tag=args.tag, label=args.label, outdir=args.outdir)
+        write_listdict_to_csv(outfile=prefix + "_info.csv", listdict=rows)
+        dtree.speciesinfo.save_cardkey(dtree.experiment["tool"])
+        dtree.speciesinfo.save_references(fast=False)
+
+
 def parse_arguments():
     """Top-level parser + the list of sub-command names (reference :138-288)."""
     universal = add_universal_cmds(argparse.ArgumentParser(add_help=False))
@@ -362,10 +401,12 @@ def parse_arguments():
         ("progressive", PROGRESSIVE, progressive_command,
          "Measure delta as each fasta is added to the set, over one given or several random orderings."),
         ("kij", KIJ, kij_command, "K Independent Jaccard (and optionally per-k Jaccard) for every pair of inputs."),
+        ("info", INFO, info_command, "Print the delta table of a saved tree; with --ksweep also write every node's per-k table."),
     ]
     commands = []
     for name, table, handler, text in specs:
         sub = _add(subparsers.add_parser(name, help=text, parents=[universal, ksweep]), table)
         sub.set_defaults(func=handler)
-        commands.append(name)
+        if name != "info":         # (the reference's list of command names leaves it out as well, :234)
+            commands.append(name)
     return parser, commands

@@ -440,3 +440,39 @@ def test_store_cache_evicts_a_leaf_block_together_with_its_views():
     assert st._get(("sketch", "/db/c.3")) is not None and st._bytes == 70
     st.forget("/db/u")
     assert st._bytes == 40
+
+
+def test_info_command(tmp_path, oracle_store, capsys):
+    """`dandd info`: same flags as the reference's handler-less sub-parser; prints the delta table of a saved
+    tree and, with --ksweep, writes one row per (node, k) after sketching whatever the range still lacks."""
+    import csv
+    import dandd_b200
+    from oracle import pyoracle as orc
+    from tests.host_harness import run_dandd
+    from tests.util import make_dataset
+    files = make_dataset(str(tmp_path / "data"), 3, 4000, seed=31)
+    out = str(tmp_path / "out")
+    run_dandd(["tree", "-d", str(tmp_path / "data"), "-s", "inf", "-k", "11", "-o", out, "-r", "10"])
+    pickle_path = os.path.join(out, "inf_3_dashing_dtree.pickle")
+    capsys.readouterr()
+    run_dandd(["info", "-d", pickle_path, "-o", out])
+    shown = capsys.readouterr().out.splitlines()
+    with open(os.path.join(out, "inf_3_dashing_deltas.csv")) as fh:
+        assert shown == fh.read().splitlines()                      # the table `tree` saved, nothing else
+    assert not os.path.exists(os.path.join(out, "inf_3_dashing_info.csv"))
+    passes = oracle_store.stats["leaf_passes"]
+    run_dandd(["info", "-d", pickle_path, "-o", out, "-l", "wide", "--ksweep", "--mink", "8", "--maxk", "40"])
+    with open(os.path.join(out, "inf_wide_3_dashing_info.csv"), newline="") as fh:
+        rows = list(csv.DictReader(fh))
+    assert len(rows) == 4 * (32 - 8 + 1)                            # 3 leaves + the root, k = 8..32 (Dashing's limit)
+    assert oracle_store.stats["leaf_passes"] > passes               # the range was wider than what the hill-climb had visited
+    sym = orc.fasta_symbols(open(files[1], "rb").read())
+    for r in rows:
+        assert float(r["delta_pos"]) == pytest.approx(float(r["card"]) / int(r["kval"]), rel=1e-12)
+        if r["title"] == "g1" and r["kval"] in ("8", "21", "32"):
+            assert float(r["card"]) == pytest.approx(orc.card(orc.hll_sketch(sym, int(r["kval"]), 10), 10), rel=1e-9)
+    parser, commands = __import__("dandd_cmd").parse_arguments()
+    assert commands == ["tree", "progressive", "kij"]
+    with pytest.raises(SystemExit):
+        parser.parse_args(["info"])                                  # -d is required, as in the reference
+    assert dandd_b200.LIB_DIR
