@@ -74,27 +74,39 @@ def test_single_process_is_identity():
     assert list(dd_dist.split_work(5)) == [0, 1, 2, 3, 4]
 
 
-def _tree_worker(rank, world, port, tmpdir):
+def _install_store(kind):
+    """'oracle': the oracle-backed double of the whole store; 'real': the shipped GpuSketchStore on the CPU
+    engine double (tests/fake_engine.py) -- its sharded and split-genome paths under gloo."""
+    from dandd_b200 import store as ddstore
+    if kind == "real":
+        from tests.fake_engine import FakeEngine
+        st = ddstore.GpuSketchStore(engine=FakeEngine())
+    else:
+        from tests.oracle_store import OracleStore
+        st = OracleStore()
+    ddstore.set_store(st)
+    return st
+
+
+def _tree_worker(rank, world, port, tmpdir, kind="oracle"):
     """`dandd tree` under two ranks (gloo): leaves are sketched by different ranks into the shared
     sketchdb, rank 0 builds the tree; the outputs must equal the reference golden."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
-    from dandd_b200 import store as ddstore
-    from tests.oracle_store import OracleStore
     from tests.host_harness import run_dandd
-    st = OracleStore()
-    ddstore.set_store(st)
+    st = _install_store(kind)
     data = os.path.join(tmpdir, "data5")
     run_dandd(["tree", "-d", data, "-s", "runA", "-k", "14", "-o", os.path.join(tmpdir, "outA")])
     with open(os.path.join(tmpdir, f"leafpasses{rank}"), "w") as fh:
         fh.write(str(st.stats["leaf_passes"]))
 
 
-def test_two_rank_tree_matches_reference(tmp_path):
+@pytest.mark.parametrize("kind", ["oracle", "real"])
+def test_two_rank_tree_matches_reference(tmp_path, kind):
     from tests.host_harness import assert_tree_matches, collect_tree, gold_runs
     from tests.util import make_dataset
     make_dataset(str(tmp_path / "data5"), 5, 20000, seed=21)
-    mp.spawn(_tree_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_tree_worker, args=(2, _free_port(), str(tmp_path), kind), nprocs=2, join=True)
     out = str(tmp_path / "outA")
     ours = collect_tree(out, "runA_5_dashing", os.path.join(out, "sketchdb"), "dashing")
     gold = gold_runs()["A_tree_hillclimb"]
@@ -177,28 +189,26 @@ def test_split_fasta_parts_merge_to_the_whole(nparts):
     assert max(sizes) <= 1.35 * (sum(sizes) / nparts)      # balanced by size
 
 
-def _split_tree_worker(rank, world, port, tmpdir, outname):
+def _split_tree_worker(rank, world, port, tmpdir, outname, kind="oracle"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
-    from dandd_b200 import store as ddstore
-    from tests.oracle_store import OracleStore
     from tests.host_harness import run_dandd
-    st = OracleStore()
-    ddstore.set_store(st)
+    st = _install_store(kind)
     run_dandd(["tree", "-d", os.path.join(tmpdir, "data2"), "-s", "runS", "-k", "14", "-o", os.path.join(tmpdir, outname),
                "--ksweep", "--mink", "12", "--maxk", "16"])
     with open(os.path.join(tmpdir, f"{outname}_passes{rank}"), "w") as fh:
         fh.write(str(st.stats["leaf_passes"]))
 
 
-def test_fewer_genomes_than_ranks_split_each_genome(tmp_path):
+@pytest.mark.parametrize("kind", ["oracle", "real"])
+def test_fewer_genomes_than_ranks_split_each_genome(tmp_path, kind):
     """`dandd tree` on 2 genomes under 3 ranks (gloo): every rank sketches a part of each genome,
     registers are max-reduced, rank 0 builds the tree -- same outputs as one process."""
     from tests.host_harness import collect_tree
     from tests.util import make_dataset
     make_dataset(str(tmp_path / "data2"), 2, 30000, seed=5)
-    _split_tree_worker(0, 1, _free_port(), str(tmp_path), "out1")
-    mp.spawn(_split_tree_worker, args=(3, _free_port(), str(tmp_path), "out3"), nprocs=3, join=True)
+    _split_tree_worker(0, 1, _free_port(), str(tmp_path), "out1", kind)
+    mp.spawn(_split_tree_worker, args=(3, _free_port(), str(tmp_path), "out3", kind), nprocs=3, join=True)
     one = collect_tree(str(tmp_path / "out1"), "runS_2_dashing", str(tmp_path / "out1" / "sketchdb"), "dashing")
     three = collect_tree(str(tmp_path / "out3"), "runS_2_dashing", str(tmp_path / "out3" / "sketchdb"), "dashing")
     assert one["deltas"] == three["deltas"]
@@ -208,27 +218,25 @@ def test_fewer_genomes_than_ranks_split_each_genome(tmp_path):
     assert all(p >= 2 for p in passes)          # every rank took part in both genomes
 
 
-def _exact_tree_worker(rank, world, port, tmpdir):
+def _exact_tree_worker(rank, world, port, tmpdir, kind="oracle"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
-    from dandd_b200 import store as ddstore
-    from tests.oracle_store import OracleStore
     from tests.host_harness import run_dandd
-    st = OracleStore()
-    ddstore.set_store(st)
+    st = _install_store(kind)
     run_dandd(["tree", "-d", os.path.join(tmpdir, "data5"), "-s", "runE", "-k", "14", "-o", os.path.join(tmpdir, "outE"),
                "--exact"])
     with open(os.path.join(tmpdir, f"shardcalls{rank}"), "w") as fh:
-        fh.write(str(st.stats.get("shard_calls", 0)))
+        fh.write(str(st.engine.calls["exact_counts"] if kind == "real" else st.stats.get("shard_calls", 0)))
 
 
-def test_two_rank_exact_tree_matches_reference(tmp_path):
+@pytest.mark.parametrize("kind", ["oracle", "real"])
+def test_two_rank_exact_tree_matches_reference(tmp_path, kind):
     """`dandd tree --exact` under two ranks: rank 0 walks the tree, rank 1 serves every exact-count
     request on its key-range shard until rank 0 says stop; outputs equal the reference golden."""
     from tests.host_harness import assert_tree_matches, collect_tree, gold_runs
     from tests.util import make_dataset
     make_dataset(str(tmp_path / "data5"), 5, 20000, seed=21)
-    mp.spawn(_exact_tree_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_exact_tree_worker, args=(2, _free_port(), str(tmp_path), kind), nprocs=2, join=True)
     out = str(tmp_path / "outE")
     assert_tree_matches(collect_tree(out, "runE_5_kmc", os.path.join(out, "sketchdb"), "kmc"), gold_runs()["E_tree_exact"],
                         exact=True)
