@@ -26,11 +26,23 @@ if HEADER_FLAG_WORDS not in (4, 5):
 HEADERS = {4: struct.Struct("<4I I d"), 5: struct.Struct("<5I I d")}
 HEADER = HEADERS[HEADER_FLAG_WORDS]
 JESTIM_ERTL_MLE = 2          # value recalled for hll::EstimationMethod::ERTL_MLE (unconfirmed)
+JESTIM_ERTL_JOINT_MLE = 3    # value recalled for hll::JointEstimationMethod::ERTL_JOINT_MLE (unconfirmed)
 ERTL_MLE = ERTL_JOINT_MLE = JESTIM_ERTL_MLE   # older names, kept for callers
 
 
 def _pack_header(known: int, p: int, card: float) -> bytes:
-    flags = [known, 0, JESTIM_ERTL_MLE, JESTIM_ERTL_MLE] + ([1] if HEADER_FLAG_WORDS == 5 else [])
+    """Two readings of the four-word header are in circulation (both recollections):
+        (is_calculated, clamp, estimation method, joint estimation method)      the survey's
+        (is_calculated, estimation method, joint estimation method, <unused>)   later dnbaker/sketch
+    The words written here, (known, 2, 2, 3), name the Ertl MLE under BOTH: clamp = 2 is just "true" (it
+    only matters to the original estimator), a joint method of 2 (ERTL_MLE) or 3 (ERTL_JOINT_MLE) is a
+    valid choice either way -- so a real Dashing that re-estimates one of these files (after a `union`,
+    say) does not silently fall back to estimator 0, the original HyperLogLog formula.  The five-word
+    form is unambiguous: (is_calculated, clamp, method, joint method, threads)."""
+    if HEADER_FLAG_WORDS == 5:
+        flags = [known, 0, JESTIM_ERTL_MLE, JESTIM_ERTL_JOINT_MLE, 1]
+    else:
+        flags = [known, JESTIM_ERTL_MLE, JESTIM_ERTL_MLE, JESTIM_ERTL_JOINT_MLE]
     return HEADER.pack(*flags, p, card)
 
 

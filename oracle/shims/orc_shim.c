@@ -66,7 +66,7 @@ static uint8_t *fasta_symbols(const char *path, size_t *nsym) {
 static void hll_write(const char *path, const uint8_t *regs, int p, int compress) {
     gzFile f = gzopen(path, compress ? "wb1" : "wbT");
     if (!f) die("cannot write", path);
-    uint32_t flags[4] = {0, 0, 2 /*ERTL_MLE*/, 2 /*ERTL_JOINT_MLE*/};
+    uint32_t flags[4] = {0, 2, 2, 3}; /* the Ertl MLE under both recalled readings of the header: dandd_b200/hllfile.py */
     uint32_t np = (uint32_t)p;
     double value = 0.0;
     gzwrite(f, flags, sizeof flags);

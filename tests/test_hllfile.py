@@ -59,3 +59,14 @@ def test_reader_accepts_both_header_widths(tmp_path):
             got, gp, card = hllfile.read_hll(str(path))
             assert np.array_equal(got, regs) and gp == p and card == 4242.5
     assert hllfile.HEADER.size == 12 + 4 * hllfile.HEADER_FLAG_WORDS
+
+
+def test_flag_words_name_the_ertl_mle_under_both_recalled_layouts(tmp_path):
+    """(is_calculated, clamp, method, joint) or (is_calculated, method, joint, unused): either way the
+    method word is 2 (ERTL_MLE) and the joint word is a valid joint method (2 or 3), never 0 (original)."""
+    path = str(tmp_path / "f.hll")
+    hllfile.write_hll(path, np.zeros(1 << 6, dtype=np.uint8), 6, 5.0)
+    w = struct.unpack_from("<4I", open(path, "rb").read())
+    assert w[0] == 1
+    assert w[2] == hllfile.JESTIM_ERTL_MLE and w[3] == hllfile.JESTIM_ERTL_JOINT_MLE       # survey's order
+    assert w[1] == hllfile.JESTIM_ERTL_MLE and w[2] in (hllfile.JESTIM_ERTL_MLE, hllfile.JESTIM_ERTL_JOINT_MLE)   # later order
