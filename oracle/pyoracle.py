@@ -15,8 +15,10 @@ SHIM = os.path.join(_HERE, "_build", "orc_shim")
 def build(force=False):
     """Compile liboracle.so and the CLI shims with gcc (idempotent)."""
     src = os.path.join(_HERE, "dandd_oracle.c")
+    shim_src = os.path.join(_HERE, "shims", "orc_shim.c")
     stale = (not os.path.exists(_SO) or not os.path.exists(SHIM)
-             or os.path.getmtime(_SO) < os.path.getmtime(src))
+             or os.path.getmtime(_SO) < os.path.getmtime(src)
+             or os.path.getmtime(SHIM) < max(os.path.getmtime(src), os.path.getmtime(shim_src)))
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
