@@ -138,3 +138,122 @@ def test_allpairs_tables(tmp_path, real_store, name):
 def test_allpairs_exact(tmp_path, real_store):
     allpairs_cases.scenario_exact(
         str(tmp_path), lambda fastas, k: orc.exact_count([orc.fasta_symbols(open(f, "rb").read()) for f in fastas], k, True))
+
+
+# ---- the streaming branch of the store (files above STREAM_MIN_BYTES) on CPU doubles -----------------------
+class _OracleLib:
+    """The slice of the C ABI that dandd_b200/streaming.py drives, answered by the oracle: the text given to
+    dd_pack_fasta is accumulated, dd_sketch_end writes the oracle's registers, histogram-free cardinalities
+    and the FASTQ flag where the real library would."""
+
+    def __init__(self, real):
+        self.real, self.fed, self.kmask, self.canon = real, [], 0, True
+
+    def dd_pack_codes_bytes(self, n):
+        return 64
+
+    dd_pack_invalid_bytes = dd_pack_codes_bytes
+
+    def dd_pack_workspace_bytes(self, n):
+        return 64
+
+    def dd_sketch_workspace_bytes(self, nk, p):
+        return 64
+
+    def dd_pack_reset(self, codes, cb, invalid, ib, state, st):
+        import ctypes
+        self.fed, self.state = [], state
+        ctypes.memset(state, 0, 32)
+        return 0
+
+    def dd_sketch_begin(self, *a):
+        return 0
+
+    def dd_fasta_first_record_host(self, ptr, n):
+        return self.real.dd_fasta_first_record_host(ptr, n)
+
+    def dd_pack_fasta(self, d_text, ln, *rest):
+        import ctypes
+        self.fed.append(ctypes.string_at(d_text, ln))
+        return 0
+
+    def dd_sketch_update_sched(self, codes, invalid, state, a, b, ln, seen, kmask, p, canon, *rest):
+        self.kmask, self.canon = kmask, bool(canon)
+        return 0
+
+    def dd_sketch_end(self, ws, wsb, nk, p, regs, hist, cards, st):
+        import ctypes
+        text = b"".join(self.fed)
+        if text[:1] == b"+" or b"\n+" in text:                      # DD_PACK_FLAG_FASTQ in dd_pack_state.reserved
+            (ctypes.c_uint64 * 4).from_address(self.state)[3] = 2
+            return 0
+        sym = orc.fasta_symbols(text)
+        ks = [k for k in range(1, 33) if (self.kmask >> (k - 1)) & 1]
+        assert len(ks) == nk
+        for i, k in enumerate(ks):
+            r = orc.hll_sketch(sym, k, p, self.canon)
+            ctypes.memmove(regs + (i << p), r.ctypes.data, 1 << p)
+            (ctypes.c_double * nk).from_address(cards)[i] = orc.card(r, p)
+        return 0
+
+    def dd_last_error(self):
+        return b"oracle lib"
+
+
+def test_store_streams_large_fastas_on_cpu(tmp_path, monkeypatch):
+    """tests/test_gpu_round2.py::test_store_streams_large_fastas on CPU doubles: above the size threshold
+    leaf_sketches / warm_leaf take dandd_b200/streaming.py (ring, readers, in-order feed), the digest
+    reaches the naming layer, FASTQ falls back to the whole-file detour."""
+    import hashlib
+    import types
+    import torch
+    from dandd_b200 import _lib, ingest, streaming
+    from dandd_b200._lib import DD_PACK_FLAG_FASTQ
+    from tests.test_streaming_host import _FakeCuda
+    from tests.util import kseq_fasta, random_bases, to_fasta
+    assert DD_PACK_FLAG_FASTQ == 2
+    fake_torch = types.SimpleNamespace(cuda=_FakeCuda, empty=torch.empty, Tensor=torch.Tensor, uint8=torch.uint8,
+                                       int32=torch.int32, float64=torch.float64)
+    monkeypatch.setattr(streaming, "torch", fake_torch)
+    monkeypatch.setattr(streaming, "_Ring", lambda chunk, pin=True, _R=streaming._Ring: _R(chunk, pin=False))
+    monkeypatch.setattr(streaming, "_rings", {})
+    monkeypatch.setattr(ddstore, "STREAM_MIN_BYTES", 1 << 20)
+    monkeypatch.setattr(ingest, "_jobs", {})
+    eng = FakeEngine()
+    eng.lib = _OracleLib(_lib.load())
+    scratch = {}
+
+    def grow_only_buffer(nbytes, tag):                      # Engine._buf
+        if tag not in scratch or scratch[tag].numel() < nbytes:
+            scratch[tag] = torch.empty(max(int(nbytes), 256), dtype=torch.uint8)
+        return scratch[tag]
+    eng._buf = grow_only_buffer
+    rng = np.random.default_rng(78)
+    texts = {"a.fa": to_fasta([(b"a", random_bases(rng, 2_500_000))], width=80),
+             "q.fq": kseq_fasta(rng, n=1_500_000, fastq=True)}
+    st = ddstore.GpuSketchStore(engine=eng, prefetch_all_k=False)
+    for name, txt in texts.items():
+        path = tmp_path / name
+        path.write_bytes(txt)
+        out = {k: str(tmp_path / "db" / f"k{k}" / (name + ".hll")) for k in (12, 31)}
+        cards = st.leaf_sketches(str(path), [12, 31], 14, True, out)
+        sym = orc.fasta_symbols(txt)
+        for k in (12, 31):
+            want = orc.hll_sketch(sym, k, 14)
+            assert np.array_equal(hllfile.read_hll(out[k])[0], want), (name, k)
+            assert cards[k] == orc.card(want, 14)
+        assert ingest.digest(str(path)) == hashlib.blake2b(txt).hexdigest()
+    assert len(st.stream_stats) == 1 and st.stream_stats[0]["chunks"] >= 1      # the FASTA streamed; the FASTQ took the detour
+    assert eng.calls["pack"] == 2                                               # (FASTQ: flagged, rewritten, packed again)
+    # warm_leaf: the all-k pass of a large fresh FASTA before anything is named or written
+    big = tmp_path / "w.fa"
+    big.write_bytes(to_fasta([(b"w", random_bases(rng, 1_400_000))], width=60))
+    st2 = ddstore.GpuSketchStore(engine=eng)
+    st2.warm_leaf(str(big), 12, True)
+    assert st2.stats["leaf_passes"] == 1 and st2.stats["files_written"] == 0
+    out = {k: str(tmp_path / "db2" / f"k{k}.hll") for k in (9, 32)}
+    got = st2.leaf_sketches(str(big), [9, 32], 12, True, out)
+    assert st2.stats["leaf_passes"] == 1                                        # served from the warmed block
+    wsym = orc.fasta_symbols(big.read_bytes())
+    assert got[32] == orc.card(orc.hll_sketch(wsym, 32, 12), 12)
+    assert np.array_equal(hllfile.read_hll(out[9])[0], orc.hll_sketch(wsym, 9, 12))
