@@ -492,11 +492,17 @@ def go(argv=None):
     args = parse_arguments(argv)
     from dandd_b200 import dist as dd_dist
     rank, world = dd_dist.init()
+    refusal = None
     if rank == 0:
         print('Performing run with name "%s"' % args.name)
         if os.path.exists(args.name):
-            raise RuntimeError('Output directory with name "%s" already exists' % args.name)
-        os.makedirs(args.name)
+            refusal = 'Output directory with name "%s" already exists' % args.name
+        else:
+            os.makedirs(args.name)
+    if world > 1:                      # every rank leaves together, none is left waiting in a collective
+        refusal = dd_dist.broadcast_object(refusal)
+    if refusal:
+        raise RuntimeError(refusal)
     inputs, names, seqid_to_treid = load_dataset(args.dataset)
     klist = [int(k) for k in args.klist.split(",")]
     from dandd_b200 import timing

@@ -170,6 +170,8 @@ def _worker(rank, world, port, tmp, tool):
         assert st.stats["leaf_passes"] == 3                    # each rank sketched only its own three FASTAs
         if rank == 0:
             cases.check_against_gold(tmp, case, table)
+        with pytest.raises(RuntimeError, match="already exists"):      # rank 0 sees the directory; every rank leaves
+            allpairs.go(cases.argv_for(tmp, case, dataset, tool=tool))
     else:
         inputs = [os.path.join(tmp, "in%d" % rank, "data", "g%d.fasta" % g) for g in range(3)]
         for c, k in enumerate(case["klist"]):
