@@ -25,7 +25,7 @@ from math import factorial
 from random import sample, shuffle
 from typing import Dict, List, Set, Tuple
 
-from sketch_classes import DashSketchObj, KMCSketchObj, SketchFilePath, SketchObj, ensure_dir  # noqa: F401
+from sketch_classes import DashSketchObj, KMCSketchObj, SketchFilePath, SketchObj, ensure_dir, nonempty_file  # noqa: F401
 from species_specifics import SpeciesSpecifics
 
 from dandd_b200 import ingest, timing
@@ -231,13 +231,32 @@ class DeltaTreeNode:
             if self.ngen < 2:
                 cards = store.leaf_sketches(self.fastas[0], ks, registers, canon, out_paths)
             else:
-                members = {k: [tpl.replace("{}", str(k)) for tpl in child_templates] for k in ks}
+                if self.experiment["lowmem"]:
+                    members = {k: self._union_members(k) for k in ks}
+                else:
+                    members = {k: [tpl.replace("{}", str(k)) for tpl in child_templates] for k in ks}
                 cards = store.union_sketches(members, registers, out_paths)
             for k, card in cards.items():
                 self.speciesinfo.cardkey[out_paths[k]] = card
         else:
             for k in ks:   # exact mode: one GPU k-mer set per k (sets of different k share nothing)
                 KMCSketchObj.build_db(out_paths[k], k, canon, self.fastas, self.speciesinfo.cardkey)
+
+    def _union_members(self, k: int) -> List[str]:
+        """The sketches whose register-wise max is this node's sketch at k: its children's -- except that under
+        --lowmem a child union may be a cardinality on record without a file (it is trusted and not rebuilt,
+        reference lib/sketch_classes.py:223-225), in which case the child's own members stand in for it.  (The
+        reference hands `dashing union` the missing path; the union comes out empty, its cardinality 0.)"""
+        out = []
+        for child in self.children:
+            template = child.ksketches[0].sfp if child.ksketches[0] is not None else SketchFilePath(
+                filenames=child.fastas, kval=0, speciesinfo=self.speciesinfo, experiment=self.experiment)
+            path = template.full.replace("{}", str(k))
+            if child.ngen > 1 and not nonempty_file(path):
+                out.extend(child._union_members(k))
+            else:
+                out.append(path)
+        return out
 
     # ---------------------------------------------------------------- per-k objects (reference :243-287)
     def update_node(self, kval):

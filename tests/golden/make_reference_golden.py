@@ -46,8 +46,12 @@ args.func(args)
 
 
 def run_ref(bindir, argv, exact=False, cwd=None):
+    # (TMPDIR: the reference's ksweep_update_node makes a temporary directory per call and never removes it,
+    # lib/huffman_dandd.py:161,187 -- keep those next to the stand-ins, where the caller's clean-up finds them)
+    scratch = os.path.join(bindir, "tmp")
+    os.makedirs(scratch, exist_ok=True)
     env = dict(os.environ, PATH=bindir + os.pathsep + os.environ["PATH"], PYTHONPATH=REF, PYTHONHASHSEED="0",
-               ORC_PARALLEL_JOBS="4")
+               ORC_PARALLEL_JOBS="4", TMPDIR=scratch)
     if exact:
         wrapper = os.path.join(bindir, "exact_wrapper.py")
         with open(wrapper, "w") as fh:

@@ -476,3 +476,56 @@ def test_info_command(tmp_path, oracle_store, capsys):
     with pytest.raises(SystemExit):
         parser.parse_args(["info"])                                  # -d is required, as in the reference
     assert dandd_b200.LIB_DIR
+
+
+def test_lowmem_union_over_a_trusted_child_whose_file_is_gone(tmp_path, oracle_store):
+    """--lowmem trusts the cardinality on record of a multi-FASTA sketch whose file was deleted and does not
+    rebuild it; a parent union at a k the parent has never seen must then be built from that child's own
+    members (the leaves), not from the missing file.  (Found by tests/test_reference_live.py: the store
+    raised FileNotFoundError.)  A hill-climbed binary tree gives such cells: every node visits its own ks."""
+    import pickle
+    import numpy as np
+    from dandd_b200 import hllfile
+    from oracle import pyoracle as orc
+    from tests.host_harness import run_dandd
+    from tests.util import make_dataset
+    files = make_dataset(str(tmp_path / "data"), 5, 4000, seed=77, sub=0.2)
+    out = str(tmp_path / "out")
+    base = ["tree", "-d", str(tmp_path / "data"), "-s", "lm", "-k", "9", "-o", out, "-r", "10", "-n", "2"]
+    run_dandd(base)
+    db = os.path.join(out, "sketchdb")
+    with open(os.path.join(db, "lm_dashing_cardinalities.pickle"), "rb") as fh:
+        before = pickle.load(fh)
+    # one inner node of that tree, swept on its own over ks the whole tree never visited: its unions are now on
+    # record (and on disk) at k = 4..6, the root's are not
+    from tests.host_harness import read_csv
+    inner = [r for r in read_csv(os.path.join(out, "lm_5_dashing_deltas.csv")) if int(r["ngen"]) == 2][0]
+    flist = str(tmp_path / "inner.txt")
+    with open(flist, "w") as fh:
+        fh.write("\n".join(inner["fastas"].split("|")) + "\n")
+    run_dandd(["tree", "-f", flist, "-s", "lm", "-k", "5", "-o", str(tmp_path / "out2"), "-r", "10", "-c", os.path.join(out, "sketchdb"),
+               "--ksweep", "--mink", "4", "--maxk", "6"])
+    with open(os.path.join(db, "lm_dashing_cardinalities.pickle"), "rb") as fh:
+        before = pickle.load(fh)
+    unions = [p for p in before if os.sep + "ngen1" + os.sep not in p]
+    assert any(os.sep + "ngen2" + os.sep + "k4" + os.sep in p for p in unions) and not any(os.sep + "ngen5" + os.sep + "k4" + os.sep in p for p in unions)
+    for p in unions:
+        os.remove(p)
+    oracle_store._regs.clear()
+    run_dandd(base + ["--ksweep", "--mink", "4", "--maxk", "14", "--lowmem"])
+    syms = [orc.fasta_symbols(open(f, "rb").read()) for f in files]
+    with open(os.path.join(db, "lm_dashing_cardinalities.pickle"), "rb") as fh:
+        cardkey = pickle.load(fh)
+    checked = 0
+    for k in range(4, 15):                                      # the root at every k: rebuilt from whatever was at hand, or trusted
+        directory = os.path.join(db, "ngen5", f"k{k}")
+        paths = [os.path.join(directory, f) for f in (os.listdir(directory) if os.path.isdir(directory) else [])]
+        want = orc.union_max([orc.hll_sketch(s, k, 10) for s in syms])
+        if paths:
+            assert np.array_equal(hllfile.read_hll(paths[0])[0], want), k
+            assert cardkey[paths[0]] == pytest.approx(orc.card(want, 10), rel=1e-9)
+            checked += 1
+        else:
+            trusted = [p for p in before if os.sep + "ngen5" + os.sep + f"k{k}" + os.sep in p]
+            assert trusted and cardkey[trusted[0]] == before[trusted[0]] > 0
+    assert checked >= 5

@@ -252,3 +252,153 @@ def test_random_exact_orderings_subsets_match_the_reference(tmp_path, golden, or
         assert sorted(ours_db["cardkey"]) == sorted(want_db["cardkey"])
         assert ours_db["fastahex"] == want_db["fastahex"] and ours_db["sketchinfo"] == want_db["sketchinfo"]
     print(f"LIVE options seed {seed}: tree + orderings + subset tree compared {case}")
+
+
+def _draw_lowmem(seed):
+    rng = random.Random(5000 + seed)
+    n = rng.randint(4, 6)
+    case = {"n": n, "length": rng.choice([3000, 6000]), "seed": 700 + seed, "kstart": rng.randint(10, 14),
+            "registers": rng.choice([10, 12]), "nchildren": rng.choice([None, 2, 3]), "sweep": None,
+            "label": rng.choice(["", "lab"]), "subset": sorted(rng.sample(range(n), rng.randint(3, n - 1))),
+            "jaccard": rng.random() < 0.5, "drop": rng.choice(["unions", "all-unions-and-a-leaf-k"])}
+    if rng.random() < 0.6:
+        lo = rng.randint(9, 12)
+        case["sweep"] = (lo, lo + rng.randint(2, 4))
+    return case
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("DANDD_LIVE_SEEDS", "4"))))
+def test_random_lowmem_labels_and_subsets_match_the_reference(tmp_path, golden, oracle_store, seed):
+    """`--lowmem` re-runs over a sketch database whose multi-FASTA sketches were deleted (cardinalities on
+    record are trusted, anything else is rebuilt), output labels (-l), and `kij` / `progressive` over a
+    file-list subset with --afproject -- same method as above: both sides, same inputs, same outputs
+    (or the same failure)."""
+    import pickle
+    import shutil
+    from oracle import pyoracle
+    case = _draw_lowmem(seed)
+    bindir = pyoracle.install_shims(str(tmp_path / "bin"))
+    data = str(tmp_path / "data")
+    files = make_dataset(data, case["n"], case["length"], seed=case["seed"], sub=0.05)
+    tag = f"m{seed}"
+    label = ("_" + case["label"]) if case["label"] else ""
+    prefix = f"{tag}{label}_{case['n']}_dashing"
+    ref_out, our_out = str(tmp_path / "ref"), str(tmp_path / "ours")
+    sweep = ["--ksweep", "--mink", str(case["sweep"][0]), "--maxk", str(case["sweep"][1])] if case["sweep"] else []
+
+    def tree(out, more=()):
+        argv = ["tree", "-d", data, "-s", tag, "-k", str(case["kstart"]), "-o", out, "-r", str(case["registers"])] + sweep
+        if case["label"]:
+            argv += ["-l", case["label"]]
+        if case["nchildren"]:
+            argv += ["-n", str(case["nchildren"])]
+        return argv + list(more)
+
+    def compare(stage):
+        want = golden.collect_tree(ref_out, prefix, os.path.join(ref_out, "sketchdb"), "dashing")
+        ours = collect_tree(our_out, prefix, os.path.join(our_out, "sketchdb"), "dashing")
+        assert_tree_matches(ours, want)
+        return want
+
+    if not _both(golden, bindir, tree(ref_out), tree(our_out)):
+        print(f"LIVE lowmem seed {seed}: both fail at tree {case}")
+        return
+    first = compare("tree")
+    # ---- drop sketches from BOTH databases (the same relative files), then re-run with --lowmem
+    doomed = [f for f in first["files"] if not f.startswith("ngen1" + os.sep)]
+    if case["drop"] != "unions":
+        doomed += [f for f in first["files"] if f.startswith("ngen1" + os.sep)][:1]
+    for out in (ref_out, our_out):
+        for rel_path in doomed:
+            os.remove(os.path.join(out, "sketchdb", rel_path))
+    oracle_store._regs.clear()                                   # (a new process would not hold them either)
+    if not _both(golden, bindir, tree(ref_out, ["--lowmem"]), tree(our_out, ["--lowmem"])):
+        print(f"LIVE lowmem seed {seed}: both fail at the --lowmem re-run {case}")
+        return
+    again = compare("lowmem re-run")                             # same tables; the same files (not) rebuilt on both sides
+    assert len(again["files"]) <= len(first["files"])
+    # ---- the ONE deliberate difference in this area.  Under --lowmem the reference answers 0 for the cardinality of
+    #      any sketch that is not yet in its table -- also one it has just built (lib/sketch_classes.py:280-284) -- so a
+    #      search over NEW sketches sees delta = 0 everywhere, climbs to k = 33 and raises; the flag is carried into
+    #      `kij` by the tree pickle.  The drop-in records a cardinality when it creates the sketch.  Pinned here: where
+    #      the reference gives up with that error, the drop-in's table equals what BOTH produce from a tree saved
+    #      without the flag (next step).
+    import subprocess
+    kij_plain = lambda out: ["kij", "-d", os.path.join(out, prefix + "_dtree.pickle"), "-o", out, "-s", tag + "low"]   # noqa: E731
+    kij_under_lowmem = None
+    for out in (ref_out, our_out):                                  # (both databases are put back afterwards)
+        shutil.copytree(os.path.join(out, "sketchdb"), os.path.join(out, "sketchdb.before"))
+    try:
+        golden.run_ref(bindir, kij_plain(ref_out))
+    except subprocess.CalledProcessError as failed:
+        last = failed.stderr.decode(errors="replace").strip().split("\n")[-1]
+        try:
+            run_dandd(kij_plain(our_out))
+        except Exception as ours_err:  # noqa: BLE001 -- another of the reference's failures (e.g. a sweep-built tree): the same one
+            assert type(ours_err).__name__ in last, (last, repr(ours_err))
+        else:
+            assert "Exploratory k value is too high" in last, last         # the only failure the drop-in does not share
+            kij_under_lowmem = read_csv(os.path.join(our_out, f"{tag}low_{case['n']}_dashing.kij.csv"))
+    else:
+        run_dandd(kij_plain(our_out))
+    for out in (ref_out, our_out):
+        shutil.rmtree(os.path.join(out, "sketchdb"))
+        os.rename(os.path.join(out, "sketchdb.before"), os.path.join(out, "sketchdb"))
+    oracle_store._regs.clear()
+    if not _both(golden, bindir, tree(ref_out), tree(our_out)):           # no flag: what lowmem skipped is rebuilt, on both sides
+        print(f"LIVE lowmem seed {seed}: both fail at the plain re-run {case}")
+        return
+    compare("plain re-run")
+    # ---- kij with --afproject and its own label; then over a subset given as a file list, which the reference
+    #      cannot do as shipped (it hands file NAMES to SubSpider, lib/huffman_dandd.py:672-685): same failure
+    rng = random.Random(seed)
+    order = [files[i] for i in rng.sample(case["subset"], len(case["subset"]))]
+    flist = str(tmp_path / "subset.txt")
+    with open(flist, "w") as fh:
+        fh.write("\n".join(order) + "\n")
+    jac = ["--jaccard", "--mink", str(case["sweep"][0]), "--maxk", str(case["sweep"][1])] if (case["sweep"] and case["jaccard"]) else []
+    kij = lambda out, more=(): (["kij", "-d", os.path.join(out, prefix + "_dtree.pickle"), "-o", out, "--afproject"] + jac   # noqa: E731
+                                + (["-l", "sub"] if case["label"] else []) + list(more))
+    assert not _both(golden, bindir, kij(ref_out, ["-f", flist]), kij(our_out, ["-f", flist]))
+    if _both(golden, bindir, kij(ref_out), kij(our_out)):
+        # (the kij output prefix is the tag with kij's OWN label, not the tree's: reference dandd_cmd.py:113-116)
+        kij_prefix = f"{tag}{'_sub' if case['label'] else ''}_{case['n']}_dashing"
+        pair = lambda r: (r["Atitle"], r["Btitle"])              # noqa: E731
+        kij_ref = {pair(r): r for r in read_csv(os.path.join(ref_out, kij_prefix + ".kij.csv"))}
+        kij_our = read_csv(os.path.join(our_out, kij_prefix + ".kij.csv"))
+        k = case["n"]
+        assert sorted(map(pair, kij_our)) == sorted(kij_ref) and len(kij_our) == k * (k - 1) // 2
+        for r in kij_our:
+            g = kij_ref[pair(r)]
+            assert (int(r["Ak"]), int(r["Bk"]), int(r["ABk"])) == (int(g["Ak"]), int(g["Bk"]), int(g["ABk"]))
+            assert float(r["KIJ"]) == pytest.approx(float(g["KIJ"]), rel=1e-6, abs=1e-6)
+        tuples = {}
+        for side, out in (("ref", ref_out), ("ours", our_out)):
+            with open(os.path.join(out, kij_prefix + "_AFtuples.pickle"), "rb") as fh:
+                tuples[side] = sorted((t[0], t[1], t[2], t[3], t[5], t[6], t[7]) for t in pickle.load(fh))
+        assert tuples["ours"] == tuples["ref"]
+        if kij_under_lowmem is not None:
+            cols = ("Atitle", "Btitle", "Ak", "Bk", "ABk", "Adelta", "Bdelta", "ABdelta", "KIJ")
+            assert [[r[c] for c in cols] for r in kij_under_lowmem] == [[r[c] for c in cols] for r in kij_our]
+    else:
+        print(f"LIVE lowmem seed {seed}: both fail at kij {case}")
+    # ---- progressive over the file list: without -n / -r there is nothing to order by (same ValueError), with
+    #      -n 1 the order of the FILE is the ordering (reference lib/huffman_dandd.py:581-589)
+    prog = lambda out, more=(): (["progressive", "-d", os.path.join(out, prefix + "_dtree.pickle"), "-f", flist, "-s", tag + "p",   # noqa: E731
+                                  "-o", out] + sweep + list(more))
+    assert not _both(golden, bindir, prog(ref_out), prog(our_out))
+    if _both(golden, bindir, prog(ref_out, ["-n", "1"]), prog(our_out, ["-n", "1"])):
+        name = f"{tag}p_progu1_{case['n']}_dashing"
+        from tests.host_harness import norm_fastas
+        rows = {side: [(int(r["ngen"]), r["kval"], norm_fastas(r["fastas"], ",")) for r in read_csv(os.path.join(out, name + ".csv"))]
+                for side, out in (("ref", ref_out), ("ours", our_out))}
+        assert rows["ours"] == rows["ref"] and len(rows["ours"]) >= len(order)
+        assert rows["ours"][-1][2] == ",".join(os.path.basename(f) for f in order)        # the file's order, not the sorted one
+        cells = {side: sorted((r["title"], int(r["kval"]), float(r["card"])) for r in read_csv(os.path.join(out, name + "summary.csv")))
+                 for side, out in (("ref", ref_out), ("ours", our_out))}
+        assert [c[:2] for c in cells["ours"]] == [c[:2] for c in cells["ref"]]
+        assert all(close(a[2], b[2]) for a, b in zip(cells["ours"], cells["ref"]))
+    else:
+        print(f"LIVE lowmem seed {seed}: both fail at progressive -n 1 {case}")
+    shutil.rmtree(str(tmp_path / "bin"), ignore_errors=True)
+    print(f"LIVE lowmem seed {seed}: tree, --lowmem re-run, kij -f --afproject, progressive -f compared {case}")
