@@ -402,3 +402,144 @@ def test_random_lowmem_labels_and_subsets_match_the_reference(tmp_path, golden, 
         print(f"LIVE lowmem seed {seed}: both fail at progressive -n 1 {case}")
     shutil.rmtree(str(tmp_path / "bin"), ignore_errors=True)
     print(f"LIVE lowmem seed {seed}: tree, --lowmem re-run, kij -f --afproject, progressive -f compared {case}")
+
+
+def _draw_inputs(seed):
+    rng = random.Random(9000 + seed)
+    n = rng.randint(3, 5)
+    case = {"n": n, "length": rng.choice([2500, 5000]), "seed": 900 + seed, "kstart": rng.randint(10, 13),
+            "exact": rng.random() < 0.4, "canon": rng.random() < 0.6, "threads": rng.choice([0, 2]),
+            "ext": [rng.choice([".fasta", ".fa", ".fa.gz", ".fna.gz", ".fasta.gz"]) for _ in range(n)],
+            "crlf": rng.random() < 0.3, "headless": rng.random() < 0.25, "sweep": None, "custom_db": rng.random() < 0.5,
+            "nchildren": rng.choice([None, None, 2])}
+    if rng.random() < 0.5:
+        lo = rng.randint(9, 11)
+        case["sweep"] = (lo, lo + rng.randint(2, 3))
+    return case
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("DANDD_LIVE_SEEDS", "4"))))
+def test_random_input_formats_exact_kij_and_shared_databases_match_the_reference(tmp_path, golden, oracle_store, seed):
+    """Input side of the path: gzip-compressed and plain FASTAs under every extension the reference names, CRLF line
+    ends, a file whose records hold no sequence at all; --exact with -C / --nthreads; `kij` in exact mode; a second
+    tree (other tag, fewer genomes) into the same --sketchdir.  Same outputs, or the same failure."""
+    import gzip
+    from oracle import pyoracle
+    case = _draw_inputs(seed)
+    bindir = pyoracle.install_shims(str(tmp_path / "bin"))
+    data = str(tmp_path / "data")
+    files = make_dataset(data, case["n"], case["length"], seed=case["seed"], sub=0.08)
+    final = []
+    for i, (path, ext) in enumerate(zip(files, case["ext"])):
+        with open(path, "rb") as fh:
+            text = fh.read()
+        if case["crlf"] and i % 2 == 0:
+            text = text.replace(b"\n", b"\r\n")
+        if case["headless"] and i == case["n"] - 1:        # records without sequence between real ones
+            text = b">nothing here\n>nor here\n\n" + text + b">empty at the end\n"
+        os.remove(path)
+        new = path[:-len(".fasta")] + ext
+        with open(new, "wb") as fh:
+            fh.write(gzip.compress(text, mtime=0) if ext.endswith(".gz") else text)
+        final.append(new)
+    tool = "kmc" if case["exact"] else "dashing"
+    tag = f"i{seed}"
+    prefix = f"{tag}_{case['n']}_{tool}"
+    ref_out, our_out = str(tmp_path / "ref"), str(tmp_path / "ours")
+    sweep = ["--ksweep", "--mink", str(case["sweep"][0]), "--maxk", str(case["sweep"][1])] if case["sweep"] else []
+    mode = (["--exact"] + (["-e", str(case["threads"])] if case["threads"] else [])) if case["exact"] else ["-r", "10"]
+    mode += [] if case["canon"] else ["-C"]
+    if case["nchildren"]:
+        mode += ["-n", str(case["nchildren"])]
+    db = lambda out: os.path.join(out, "shared_db" if case["custom_db"] else "sketchdb")       # noqa: E731
+    extra_db = lambda out: ["-c", db(out)] if case["custom_db"] else []                         # noqa: E731
+
+    def both(ref_argv, our_argv):
+        import subprocess
+        try:
+            golden.run_ref(bindir, ref_argv, exact=case["exact"])
+        except subprocess.CalledProcessError as failed:
+            last = failed.stderr.decode(errors="replace").strip().split("\n")[-1]
+            with pytest.raises(Exception) as ours_err:
+                run_dandd(our_argv)
+            assert type(ours_err.value).__name__ in last, (last, repr(ours_err.value))
+            return False
+        run_dandd(our_argv)
+        return True
+
+    tree = lambda out: ["tree", "-d", data, "-s", tag, "-k", str(case["kstart"]), "-o", out] + mode + sweep + extra_db(out)   # noqa: E731
+    if not both(tree(ref_out), tree(our_out)):
+        print(f"LIVE inputs seed {seed}: both fail at tree {case}")
+        return
+    assert_tree_matches(collect_tree(our_out, prefix, db(our_out), tool), golden.collect_tree(ref_out, prefix, db(ref_out), tool),
+                        exact=case["exact"])
+    # ---- kij (exact mode goes pair by pair on both sides; HLL mode through the batched table on ours)
+    kij = lambda out: ["kij", "-d", os.path.join(out, prefix + "_dtree.pickle"), "-o", out] + (   # noqa: E731
+        ["--jaccard", "--mink", str(case["sweep"][0]), "--maxk", str(case["sweep"][1])] if case["sweep"] else [])
+    if both(kij(ref_out), kij(our_out)):
+        pair = lambda r: (r["Atitle"], r["Btitle"])     # noqa: E731
+        kij_ref = {pair(r): r for r in read_csv(os.path.join(ref_out, prefix + ".kij.csv"))}
+        kij_our = read_csv(os.path.join(our_out, prefix + ".kij.csv"))
+        assert sorted(map(pair, kij_our)) == sorted(kij_ref)
+        for r in kij_our:
+            g = kij_ref[pair(r)]
+            assert (int(r["Ak"]), int(r["Bk"]), int(r["ABk"])) == (int(g["Ak"]), int(g["Bk"]), int(g["ABk"])), pair(r)
+            assert float(r["KIJ"]) == pytest.approx(float(g["KIJ"]), rel=1e-6, abs=1e-6)
+        if case["sweep"]:
+            j_ref = {(r["Atitle"], r["Btitle"], int(r["kval"])): r for r in read_csv(os.path.join(ref_out, prefix + ".j.csv"))}
+            j_our = read_csv(os.path.join(our_out, prefix + ".j.csv"))
+            assert sorted((r["Atitle"], r["Btitle"], int(r["kval"])) for r in j_our) == sorted(j_ref)
+            for r in j_our:
+                g = j_ref[(r["Atitle"], r["Btitle"], int(r["kval"]))]
+                assert float(r["jaccard"]) == pytest.approx(float(g["jaccard"]), rel=1e-6, abs=1e-6)
+    else:
+        print(f"LIVE inputs seed {seed}: both fail at kij {case}")
+    # ---- a second tree, other tag, over the first n-1 files, into the SAME database: leaves are found, not redone
+    flist = str(tmp_path / "fewer.txt")
+    with open(flist, "w") as fh:
+        fh.write("\n".join(final[:-1]) + "\n")
+    tag2 = tag + "b"
+    second = lambda out: (["tree", "-f", flist, "-s", tag2, "-k", str(case["kstart"]), "-o", out, "-c", db(out)] + mode + sweep)   # noqa: E731
+    passes = oracle_store.stats["leaf_passes"]
+    if both(second(ref_out), second(our_out)):
+        prefix2 = f"{tag2}_{case['n'] - 1}_{tool}"
+        rows = {side: [(r["title"], int(r["ngen"]), int(r["k"]), float(r["card"]), float(r["delta"]))
+                       for r in read_csv(os.path.join(out, prefix2 + "_deltas.csv"))] for side, out in (("ref", ref_out), ("ours", our_out))}
+        assert [r[:3] for r in rows["ours"]] == [r[:3] for r in rows["ref"]]
+        assert all((a[3] == b[3]) if case["exact"] else (close(a[3], b[3]) and close(a[4], b[4])) for a, b in zip(rows["ours"], rows["ref"]))
+        want_db = golden.collect_tree(ref_out, prefix, db(ref_out), tool)
+        ours_db = collect_tree(our_out, prefix, db(our_out), tool)
+        assert ours_db["files"] == want_db["files"] and ours_db["fastahex"] == want_db["fastahex"]
+        assert ours_db["sketchinfo"] == want_db["sketchinfo"]
+    else:
+        print(f"LIVE inputs seed {seed}: both fail at the second tree {case}")
+    print(f"LIVE inputs seed {seed}: tree, kij, second tree into the same database compared {case}")
+
+
+def test_a_genome_without_any_kmer(tmp_path, golden, oracle_store):
+    """The second deliberate difference in error behaviour.  A FASTA whose records hold no sequence has
+    cardinality 0 at every k; the reference reads a stored 0 as "not computed yet", recomputes, stores 0 again and
+    ends in its retry path with an UnboundLocalError (lib/sketch_classes.py:254-291).  The drop-in keeps the 0:
+    a sweep completes, and a hill-climb ends with the reference's own message for data that is amiss."""
+    import subprocess
+    from oracle import pyoracle
+    bindir = pyoracle.install_shims(str(tmp_path / "bin"))
+    data = str(tmp_path / "data")
+    files = make_dataset(data, 3, 2500, seed=9, sub=0.05)
+    with open(files[-1], "wb") as fh:
+        fh.write(b">nothing here\n>nor here\n\n")
+    sweep = ["--ksweep", "--mink", "11", "--maxk", "13"]
+    for mode in (sweep, []):
+        argv = lambda out: ["tree", "-d", data, "-s", "e", "-k", "10", "-o", out, "-r", "10"] + mode     # noqa: E731
+        with pytest.raises(subprocess.CalledProcessError) as ref_err:
+            golden.run_ref(bindir, argv(str(tmp_path / ("ref%d" % len(mode)))))
+        assert "UnboundLocalError" in ref_err.value.stderr.decode(errors="replace")
+        if mode:
+            run_dandd(argv(str(tmp_path / "ours")))
+            db = collect_tree(str(tmp_path / "ours"), "e_3_dashing", str(tmp_path / "ours" / "sketchdb"), "dashing")
+            empty = [v for k, v in db["cardkey"].items() if os.sep + "ngen1" + os.sep in os.sep + k and "g2" in k]
+            assert len(empty) == 3 and all(v == 0 for v in empty)
+            assert all(v > 0 for k, v in db["cardkey"].items() if "g2." not in os.path.basename(k))
+        else:
+            with pytest.raises(ValueError, match="Exploratory k value is too high"):
+                run_dandd(argv(str(tmp_path / "ours_climb")))
