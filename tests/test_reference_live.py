@@ -543,3 +543,60 @@ def test_a_genome_without_any_kmer(tmp_path, golden, oracle_store):
         else:
             with pytest.raises(ValueError, match="Exploratory k value is too high"):
                 run_dandd(argv(str(tmp_path / "ours_climb")))
+
+
+def test_changed_inputs_and_damaged_databases(tmp_path, golden, oracle_store):
+    """What both sides do when the world changes between runs: a FASTA is replaced (the stale name is reused
+    without --safe, --safe refuses with the same message), a database pickle is damaged (both recover from the
+    .bkp copy).  With the .bkp gone as well the reference stops (it catches FileExistsError where it means
+    FileNotFoundError, lib/species_specifics.py:23-38) and the drop-in starts from an empty table, as the
+    reference's own comment there intends -- the third and last deliberate difference."""
+    import shutil
+    import subprocess
+    from oracle import pyoracle
+    bindir = pyoracle.install_shims(str(tmp_path / "bin"))
+    data = str(tmp_path / "data")
+    files = make_dataset(data, 4, 3000, seed=19, sub=0.05)
+    ref_out, our_out = str(tmp_path / "ref"), str(tmp_path / "ours")
+    argv = lambda out, more=(): ["tree", "-d", data, "-s", "t", "-k", "11", "-o", out, "-r", "10"] + list(more)   # noqa: E731
+
+    def same():
+        assert_tree_matches(collect_tree(our_out, "t_4_dashing", os.path.join(our_out, "sketchdb"), "dashing"),
+                            golden.collect_tree(ref_out, "t_4_dashing", os.path.join(ref_out, "sketchdb"), "dashing"))
+    assert _both(golden, bindir, argv(ref_out), argv(our_out))
+    same()
+    for side in (ref_out, our_out):
+        shutil.copytree(side, side + ".pristine")
+    # ---- a FASTA is replaced by another genome
+    other = make_dataset(str(tmp_path / "other"), 4, 3000, seed=99, sub=0.05)
+    shutil.copy(other[2], files[2])
+    oracle_store._syms.clear()
+    oracle_store._regs.clear()
+    assert _both(golden, bindir, argv(ref_out), argv(our_out))                        # stale name, stale sketches: on both sides
+    same()
+    with pytest.raises(subprocess.CalledProcessError) as ref_err:
+        golden.run_ref(bindir, argv(ref_out, ["--safe"]))
+    with pytest.raises(RuntimeError) as our_err:
+        run_dandd(argv(our_out, ["--safe"]))
+    assert str(our_err.value) in ref_err.value.stderr.decode(errors="replace")        # "Checksum does not match stored value for g2.fasta: ..."
+    make_dataset(data, 4, 3000, seed=19, sub=0.05)                                    # the original genome is back
+    oracle_store._syms.clear()
+    # ---- damaged pickles
+    for name in ("dandd_fastahex.pickle", "dandd_sketchinfo.pickle", "t_dashing_cardinalities.pickle"):
+        for keep_backup in (True, False):
+            for side in (ref_out, our_out):
+                shutil.rmtree(side)
+                shutil.copytree(side + ".pristine", side)
+                with open(os.path.join(side, "sketchdb", name), "wb") as fh:
+                    fh.write(b"\\x80\\x04garbage")
+                if not keep_backup:
+                    os.remove(os.path.join(side, "sketchdb", name + ".bkp"))
+            oracle_store._regs.clear()
+            if keep_backup:
+                assert _both(golden, bindir, argv(ref_out), argv(our_out))
+            else:
+                with pytest.raises(subprocess.CalledProcessError) as ref_err:
+                    golden.run_ref(bindir, argv(ref_out))
+                assert "FileNotFoundError" in ref_err.value.stderr.decode(errors="replace")
+                run_dandd(argv(our_out))                                              # starts from an empty table, rebuilds, saves
+                assert os.path.getsize(os.path.join(our_out, "sketchdb", name)) > 20
