@@ -282,12 +282,22 @@ class DeltaTreeNode:
         self.ksweep_update_node(mink=mink, maxk=maxk)
         lo, hi = max(1, int(mink)), int(maxk)
         if self.experiment["tool"] == "dashing":
+            for kval in range(max(lo, HLL_MAX_K + 1), hi + 1):
+                self._name_only(kval)
             hi = min(hi, HLL_MAX_K)
         for kval in range(lo, hi + 1):
             if self.ksketches[kval] is None:
                 self.update_node(kval)
         self.mink = mink
         self.maxk = maxk
+
+    def _name_only(self, kval: int) -> None:
+        """A k beyond Dashing's limit: the reference still NAMES the sketch (and its children's) in the sketch
+        database's registry before `dashing` refuses to build it (reference :243-269); nothing else happens."""
+        SketchFilePath(filenames=self.fastas, kval=kval, speciesinfo=self.speciesinfo, experiment=self.experiment)
+        if self.ngen > 1:
+            for child in self.children:
+                child._name_only(kval)
 
     def summarize(self, mink: int = 0, maxk: int = 0, ordering_number=0):
         """One row per k with the candidate delta card/k (reference :289-301)."""

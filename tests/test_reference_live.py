@@ -600,3 +600,52 @@ def test_changed_inputs_and_damaged_databases(tmp_path, golden, oracle_store):
                 assert "FileNotFoundError" in ref_err.value.stderr.decode(errors="replace")
                 run_dandd(argv(our_out))                                              # starts from an empty table, rebuilds, saves
                 assert os.path.getsize(os.path.join(our_out, "sketchdb", name)) > 20
+
+
+EXTREMES = [
+    # (name, extra argv, exact, what to expect: "same" = same outputs or the same failure; otherwise the exception the
+    #  REFERENCE dies with where the drop-in completes -- the deliberate differences (4) and (5) of DESIGN.md section 2)
+    ("k2", ["-k", "2"], False, "same"), ("k3", ["-k", "3"], False, "same"), ("k30", ["-k", "30"], False, "same"),
+    ("k31", ["-k", "31"], False, "same"), ("k32", ["-k", "32"], False, "same"), ("k33", ["-k", "33"], False, "same"),
+    ("k1", ["-k", "1"], False, "KeyError"),                       # exploring k - 1 = 0 collides with the k = 0 template slot
+    ("sweep_1_3", ["-k", "10", "--ksweep", "--mink", "1", "--maxk", "3"], False, "same"),
+    ("sweep_0_2", ["-k", "10", "--ksweep", "--mink", "0", "--maxk", "2"], False, "KeyError"),
+    ("sweep_30_34", ["-k", "10", "--ksweep", "--mink", "30", "--maxk", "34"], False, "same"),   # names of k = 33, 34 are registered, no more
+    ("sweep_32_32", ["-k", "10", "--ksweep", "--mink", "32", "--maxk", "32"], False, "same"),
+    ("sweep_5_4", ["-k", "10", "--ksweep", "--mink", "5", "--maxk", "4"], False, "same"),
+    ("registers_4", ["-k", "10", "-r", "4"], False, "same"), ("registers_24", ["-k", "10", "-r", "24"], False, "same"),
+    ("exact_k2", ["-k", "2", "--exact"], True, "same"),
+    ("exact_k1", ["-k", "1", "--exact"], True, "KeyError"),
+    ("exact_k33", ["-k", "33", "--exact"], True, "IndexError"),   # "higher ks need --exact" (README.md:82), but a climb from there overruns a list
+]
+
+
+@pytest.mark.parametrize("name,extra,exact,expect", EXTREMES, ids=[e[0] for e in EXTREMES])
+def test_extreme_k_sweeps_and_register_counts(tmp_path, golden, oracle_store, name, extra, exact, expect):
+    import subprocess
+    from oracle import pyoracle
+    bindir = pyoracle.install_shims(str(tmp_path / "bin"))
+    data = str(tmp_path / "data")
+    make_dataset(data, 3, 3000, seed=5, sub=0.05)
+    tool = "kmc" if exact else "dashing"
+    ref_out, our_out = str(tmp_path / "ref"), str(tmp_path / "ours")
+    argv = lambda out: ["tree", "-d", data, "-s", "t", "-o", out] + ([] if exact or "-r" in extra else ["-r", "10"]) + extra   # noqa: E731
+    if expect == "same":
+        try:
+            golden.run_ref(bindir, argv(ref_out), exact=exact)
+        except subprocess.CalledProcessError as failed:
+            last = failed.stderr.decode(errors="replace").strip().split("\n")[-1]
+            with pytest.raises(Exception) as ours_err:
+                run_dandd(argv(our_out))
+            assert type(ours_err.value).__name__ in last, (last, repr(ours_err.value))
+            return
+        run_dandd(argv(our_out))
+        assert_tree_matches(collect_tree(our_out, f"t_3_{tool}", os.path.join(our_out, "sketchdb"), tool),
+                            golden.collect_tree(ref_out, f"t_3_{tool}", os.path.join(ref_out, "sketchdb"), tool), exact=exact)
+    else:
+        with pytest.raises(subprocess.CalledProcessError) as ref_err:
+            golden.run_ref(bindir, argv(ref_out), exact=exact)
+        assert expect in ref_err.value.stderr.decode(errors="replace").strip().split("\n")[-1]
+        run_dandd(argv(our_out))
+        rows = read_csv(os.path.join(our_out, f"t_3_{tool}_deltas.csv"))
+        assert len(rows) == 4 and ("--ksweep" in extra or all(float(r["delta"]) > 0 and int(r["k"]) >= 1 for r in rows))
