@@ -770,8 +770,8 @@ class DeltaTree:
         if jaccard:
             for k in range(mink, maxk + 1):
                 jr = {"A": first.fastas[0], "B": second.fastas[0], "Atitle": first.node_title, "Btitle": second.node_title,
-                      "kval": k, "Acard": first.ksketches[k].card, "Bcard": second.ksketches[k].card,
-                      "ABcard": cell(k)[2]}
+                      "kval": k, "Acard": _card_at(first, k), "Bcard": _card_at(second, k),
+                      "ABcard": cell(k)[2] if k <= HLL_MAX_K else 0.0}
                 jr["jaccard"] = (jr["Acard"] + jr["Bcard"] - jr["ABcard"]) / jr["ABcard"]
                 jrows.append(jr)
         return kij, jrows
@@ -884,10 +884,19 @@ class SubSpider(DeltaTree):
         rows = []
         for k in range(mink, maxk + 1):
             row = {"A": a.fastas[0], "B": b.fastas[0], "Atitle": a.node_title, "Btitle": b.node_title, "kval": k,
-                   "Acard": a.ksketches[k].card, "Bcard": b.ksketches[k].card, "ABcard": self.root.ksketches[k].card}
+                   "Acard": _card_at(a, k), "Bcard": _card_at(b, k), "ABcard": _card_at(self.root, k)}
             row["jaccard"] = (row["Acard"] + row["Bcard"] - row["ABcard"]) / row["ABcard"]
             rows.append(row)
         return rows
+
+
+def _card_at(node, k: int) -> float:
+    """Cardinality of a node's sketch at k for the Jaccard tables.  Beyond Dashing's k limit no sketch exists and
+    the reference works with the 0 it gets for a sketch that could not be made -- so that a Jaccard range reaching
+    past k = 32 ends in the same ZeroDivisionError there and here."""
+    if k > HLL_MAX_K and node.experiment["tool"] == "dashing" and (k >= len(node.ksketches) or node.ksketches[k] is None):
+        return 0.0
+    return node.ksketches[k].card
 
 
 class DeltaSpider(DeltaTree):
