@@ -1058,6 +1058,10 @@ def create_delta_tree(tag: str, genomedir: str, sketchdir: str, kstart: int, nch
     ingest.prefetch([f for f in fastas if os.path.basename(f) not in speciesinfo.fastahex])
     _warm_fresh_leaves(fastas, speciesinfo, experiment)
     if nchildren:
+        if int(nchildren) == 1 and len(fastas) > 1:
+            # (the reference never returns here: every new node takes ONE node off its list and puts one back,
+            # lib/huffman_dandd.py:377-438)
+            raise ValueError("--nchildren 1 cannot build a tree over more than one fasta: every node would have a single child")
         dtree = DeltaTree(fasta_files=fastas, speciesinfo=speciesinfo, nchildren=nchildren, experiment=experiment)
     else:
         dtree = DeltaSpider(fasta_files=fastas, speciesinfo=speciesinfo, experiment=experiment)

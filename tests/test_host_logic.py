@@ -529,3 +529,13 @@ def test_lowmem_union_over_a_trusted_child_whose_file_is_gone(tmp_path, oracle_s
             trusted = [p for p in before if os.sep + "ngen5" + os.sep + f"k{k}" + os.sep in p]
             assert trusted and cardkey[trusted[0]] == before[trusted[0]] > 0
     assert checked >= 5
+
+
+def test_nchildren_one_is_refused(tmp_path, oracle_store):
+    """`--nchildren 1` over several FASTAs: the reference loops forever (each new node has one child, the node
+    list never shrinks; verified with a 25 s timeout in the build container); the drop-in refuses."""
+    from tests.host_harness import run_dandd
+    from tests.util import make_dataset
+    make_dataset(str(tmp_path / "data"), 3, 2000, seed=5)
+    with pytest.raises(ValueError, match="--nchildren 1"):
+        run_dandd(["tree", "-d", str(tmp_path / "data"), "-s", "t", "-k", "11", "-o", str(tmp_path / "out"), "-r", "10", "-n", "1"])

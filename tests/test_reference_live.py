@@ -725,3 +725,57 @@ def test_progressive_and_kij_corner_options(tmp_path, golden, oracle_store):
         else:
             assert not outputs, name + ": both failed (the same way) where outputs were expected"
         print("LIVE corner", name, "compared")
+
+
+def test_input_listing_corners(tmp_path, golden, oracle_store):
+    """How the inputs of `tree` are found: --nchildren beyond what can be built, file lists with blank lines,
+    duplicates, missing files, one file, no file; directories with one FASTA, none, a trailing slash, a relative
+    path; tags with underscores -- same outputs or the same failure.  The sixth and last deliberate difference:
+    for a --datadir that does not exist the reference CONSTRUCTS a ValueError but never raises it
+    (lib/huffman_dandd.py:866-867) and fails later on an empty file name; the drop-in raises that ValueError."""
+    import shutil
+    import subprocess
+    from oracle import pyoracle
+    bindir = pyoracle.install_shims(str(tmp_path / "bin"))
+    data = str(tmp_path / "data")
+    files = make_dataset(data, 4, 3000, seed=5, sub=0.05)
+    base = lambda out, more: ["tree", "-s", "t", "-k", "11", "-o", out, "-r", "10"] + more     # noqa: E731
+    flist = str(tmp_path / "list.txt")
+    one, none = str(tmp_path / "one"), str(tmp_path / "none")
+    os.makedirs(one)
+    os.makedirs(none)
+    shutil.copy(files[0], one)
+    cases = [("nchildren_2", ["-d", data, "-n", "2"], None, 4), ("nchildren_4", ["-d", data, "-n", "4"], None, 4),
+             ("nchildren_5", ["-d", data, "-n", "5"], None, 4), ("nchildren_9", ["-d", data, "-n", "9"], None, 4),
+             ("list_blank_line", ["-f", flist], "\n".join(files[:3]) + "\n\n", 3),
+             ("list_duplicate", ["-f", flist], "\n".join([files[0], files[1], files[0]]) + "\n", 3),
+             ("list_missing_file", ["-f", flist], "\n".join([files[0], files[1], str(tmp_path / "nope.fasta")]) + "\n", 3),
+             ("list_single", ["-f", flist], files[0] + "\n", 1), ("list_empty", ["-f", flist], "", 0),
+             ("dir_single", ["-d", one], None, 1), ("dir_empty", ["-d", none], None, 0),
+             ("dir_trailing_slash", ["-d", data + "/"], None, 4), ("tag_with_underscores", ["-d", data, "-s", "my_tag_1"], None, 4)]
+    for name, more, list_text, n in cases:
+        if list_text is not None:
+            with open(flist, "w") as fh:
+                fh.write(list_text)
+        ref_out, our_out = str(tmp_path / ("ref_" + name)), str(tmp_path / ("ours_" + name))
+        oracle_store._regs.clear()
+        if _both(golden, bindir, base(ref_out, more), base(our_out, more)):
+            tag = "my_tag_1" if "my_tag_1" in more else "t"
+            assert_tree_matches(collect_tree(our_out, f"{tag}_{n}_dashing", os.path.join(our_out, "sketchdb"), "dashing"),
+                                golden.collect_tree(ref_out, f"{tag}_{n}_dashing", os.path.join(ref_out, "sketchdb"), "dashing"))
+        print("LIVE inputs", name, "compared")
+    missing = ["-d", str(tmp_path / "no_such_directory")]
+    with pytest.raises(subprocess.CalledProcessError) as ref_err:
+        golden.run_ref(bindir, base(str(tmp_path / "ref_missing"), missing))
+    assert "FileNotFoundError" in ref_err.value.stderr.decode(errors="replace")
+    with pytest.raises(ValueError, match="You must provide either an existing directory of fastas"):
+        run_dandd(base(str(tmp_path / "ours_missing"), missing))
+    for side in ("ref", "ours"):                                   # neither input option: both print the same line and exit 1
+        try:
+            (golden.run_ref(bindir, base(str(tmp_path / "ref_nothing"), [])) if side == "ref"
+             else run_dandd(base(str(tmp_path / "ours_nothing"), [])))
+            raise AssertionError(side + " accepted a run without inputs")
+        except subprocess.CalledProcessError as failed:
+            assert failed.returncode == 1
+        except SystemExit as stop:
+            assert stop.code == 1
