@@ -173,17 +173,23 @@ static int dashing_main(int argc, char **argv) {
 }
 
 /* ---- KMC stand-in: database = sorted distinct u64 k-mers ---- */
-static int cmp_u64(const void *a, const void *b) {
-    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
-    return x < y ? -1 : x > y;
+/* A shim database is the sorted list of distinct k-mers as fixed-width records: 8 bytes (the 2-bit value as a
+ * uint64) for k <= 32, k bytes (one symbol per byte, what KMC's k <= 256 needs) above.  Private to this shim. */
+static size_t g_width = 8;
+static int cmp_rec(const void *a, const void *b) {
+    if (g_width == 8) {
+        uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+        return x < y ? -1 : x > y;
+    }
+    return memcmp(a, b, g_width);
 }
 
-static void kmcdb_write(const char *base, const uint64_t *a, uint64_t n, int k, int canon) {
+static void kmcdb_write(const char *base, const uint8_t *recs, uint64_t n, size_t width, int k, int canon) {
     char path[4096];
     snprintf(path, sizeof path, "%s.kmc_pre", base);
     FILE *f = fopen(path, "wb");
     if (!f) die("cannot write", path);
-    uint64_t hdr[4] = {0x434d4b43524fULL /* "ORCKMC" */, (uint64_t)k, (uint64_t)canon, n};
+    uint64_t hdr[5] = {0x434d4b43524fULL /* "ORCKMC" */, (uint64_t)k, (uint64_t)canon, n, (uint64_t)width};
     fwrite(hdr, sizeof hdr, 1, f);
     fclose(f);
     snprintf(path, sizeof path, "%s.kmc_suf", base);
@@ -191,13 +197,13 @@ static void kmcdb_write(const char *base, const uint64_t *a, uint64_t n, int k, 
     if (!f) die("cannot write", path);
     uint64_t magic = 0x46555343524fULL;
     fwrite(&magic, sizeof magic, 1, f); /* never empty, even for 0 k-mers */
-    fwrite(a, sizeof(uint64_t), n, f);
+    fwrite(recs, width, n, f);
     fclose(f);
 }
 
-static uint64_t *kmcdb_read(const char *base, uint64_t *n_out) {
+static uint8_t *kmcdb_read(const char *base, uint64_t *n_out, size_t *width_out) {
     char path[4096];
-    uint64_t hdr[4];
+    uint64_t hdr[5];
     snprintf(path, sizeof path, "%s.kmc_pre", base);
     FILE *f = fopen(path, "rb");
     if (!f || fread(hdr, sizeof hdr, 1, f) != 1) die("cannot read db", path);
@@ -206,19 +212,49 @@ static uint64_t *kmcdb_read(const char *base, uint64_t *n_out) {
     f = fopen(path, "rb");
     if (!f) die("cannot read db", path);
     uint64_t magic, n = hdr[3];
-    uint64_t *a = (uint64_t *)malloc((n ? n : 1) * sizeof(uint64_t));
-    if (fread(&magic, sizeof magic, 1, f) != 1 || fread(a, sizeof(uint64_t), n, f) != n) die("short db", path);
+    size_t width = (size_t)hdr[4];
+    uint8_t *a = (uint8_t *)malloc((n ? n : 1) * width);
+    if (fread(&magic, sizeof magic, 1, f) != 1 || fread(a, width, n, f) != n) die("short db", path);
     fclose(f);
     *n_out = n;
+    *width_out = width;
     return a;
 }
 
-static uint64_t uniq(uint64_t *a, uint64_t n) {
+static uint64_t uniq(uint8_t *a, uint64_t n, size_t width) {
     if (!n) return 0;
-    qsort(a, n, sizeof(uint64_t), cmp_u64);
+    g_width = width;
+    qsort(a, n, width, cmp_rec);
     uint64_t o = 1;
-    for (uint64_t i = 1; i < n; ++i) if (a[i] != a[o - 1]) a[o++] = a[i];
+    for (uint64_t i = 1; i < n; ++i)
+        if (memcmp(a + i * width, a + (o - 1) * width, width)) memmove(a + (o++) * width, a + i * width, width);
     return o;
+}
+
+/* k > 32: every valid window of the symbol stream as a k-byte record (canonical = the smaller of the window and
+ * its reverse complement, compared as strings -- the same order as comparing the 2-bit integers). */
+static uint8_t *long_kmers(const uint8_t *sym, size_t ns, int k, int canon, uint64_t *cnt_out) {
+    uint64_t cnt = 0;
+    size_t run = 0;
+    for (size_t i = 0; i < ns; ++i) { run = sym[i] > 3 ? 0 : run + 1; if (run >= (size_t)k) ++cnt; }
+    uint8_t *out = (uint8_t *)malloc((cnt ? cnt : 1) * (size_t)k), *rc = (uint8_t *)malloc((size_t)k);
+    uint64_t o = 0;
+    run = 0;
+    for (size_t i = 0; i < ns; ++i) {
+        run = sym[i] > 3 ? 0 : run + 1;
+        if (run < (size_t)k) continue;
+        const uint8_t *w = sym + i + 1 - k;
+        const uint8_t *pick = w;
+        if (canon) {
+            for (int j = 0; j < k; ++j) rc[j] = (uint8_t)(3 - w[k - 1 - j]);
+            if (memcmp(rc, w, (size_t)k) < 0) pick = rc;
+        }
+        memcpy(out + o * (size_t)k, pick, (size_t)k);
+        ++o;
+    }
+    free(rc);
+    *cnt_out = cnt;
+    return out;
 }
 
 static int kmc_main(int argc, char **argv) {
@@ -232,13 +268,19 @@ static int kmc_main(int argc, char **argv) {
         else if (npos < 3) pos[npos++] = a;
     }
     if (npos < 2) die("kmc: need <input> <output> <tmp>", NULL);
-    if (k < 1 || k > 32) die("kmc shim: only k<=32", NULL);
+    if (k < 1 || k > 256) die("kmc: k-mer length must be in [1, 256]", NULL);
     size_t ns; uint8_t *sym = fasta_symbols(pos[0], &ns);
-    size_t cnt = orc_kmers(sym, ns, k, canon, NULL, 0);
-    uint64_t *a = (uint64_t *)malloc((cnt ? cnt : 1) * sizeof(uint64_t));
-    orc_kmers(sym, ns, k, canon, a, cnt);
-    uint64_t n = uniq(a, cnt);
-    kmcdb_write(pos[1], a, n, k, canon);
+    if (k <= 32) {
+        size_t cnt = orc_kmers(sym, ns, k, canon, NULL, 0);
+        uint64_t *a = (uint64_t *)malloc((cnt ? cnt : 1) * sizeof(uint64_t));
+        orc_kmers(sym, ns, k, canon, a, cnt);
+        uint64_t n = uniq((uint8_t *)a, cnt, 8);
+        kmcdb_write(pos[1], (uint8_t *)a, n, 8, k, canon);
+    } else {
+        uint64_t cnt; uint8_t *a = long_kmers(sym, ns, k, canon, &cnt);
+        uint64_t n = uniq(a, cnt, (size_t)k);
+        kmcdb_write(pos[1], a, n, (size_t)k, k, canon);
+    }
     return 0;
 }
 
@@ -247,7 +289,7 @@ static int kmc_tools_main(int argc, char **argv) {
     while (i < argc && argv[i][0] == '-') ++i;
     if (i >= argc) die("kmc_tools: missing operation", NULL);
     if (!strcmp(argv[i], "info")) {
-        uint64_t n; uint64_t *a = kmcdb_read(argv[i + 1], &n);
+        uint64_t n; size_t width; uint8_t *a = kmcdb_read(argv[i + 1], &n, &width);
         free(a);
         printf("k                 :  0\ntotal k-mers      :  %llu\n", (unsigned long long)n);
         return 0;
@@ -257,16 +299,20 @@ static int kmc_tools_main(int argc, char **argv) {
         FILE *f = fopen(argv[i + 1], "r");
         if (!f) die("kmc_tools: cannot open", argv[i + 1]);
         char line[65536], out[4096] = "";
-        uint64_t *acc = NULL, nacc = 0;
+        uint8_t *acc = NULL;
+        uint64_t nacc = 0;
+        size_t width = 8;
         int in_output = 0;
         while (fgets(line, sizeof line, f)) {
             char name[4096], path[4096];
             if (strstr(line, "INPUT:")) { in_output = 0; continue; }
             if (strstr(line, "OUTPUT:")) { in_output = 1; continue; }
             if (!in_output && sscanf(line, " %4095s = %4095s", name, path) == 2) {
-                uint64_t n; uint64_t *a = kmcdb_read(path, &n);
-                acc = (uint64_t *)realloc(acc, (nacc + n + 1) * sizeof(uint64_t));
-                memcpy(acc + nacc, a, n * sizeof(uint64_t));
+                uint64_t n; size_t w; uint8_t *a = kmcdb_read(path, &n, &w);
+                if (nacc && w != width) die("kmc_tools complex: inputs of different k", path);
+                width = w;
+                acc = (uint8_t *)realloc(acc, (nacc + n + 1) * width);
+                memcpy(acc + nacc * width, a, n * width);
                 nacc += n; free(a);
             } else if (in_output && sscanf(line, " %4095s =", out) == 1) {
                 break;
@@ -274,8 +320,8 @@ static int kmc_tools_main(int argc, char **argv) {
         }
         fclose(f);
         if (!out[0]) die("kmc_tools complex: no OUTPUT", NULL);
-        uint64_t n = uniq(acc, nacc);
-        kmcdb_write(out, acc, n, 0, 1);
+        uint64_t n = uniq(acc, nacc, width);
+        kmcdb_write(out, acc, n, width, 0, 1);
         return 0;
     }
     die("kmc_tools: unsupported operation", argv[i]);

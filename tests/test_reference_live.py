@@ -64,14 +64,14 @@ def _tree_argv(case, data, out, tag):
     return argv
 
 
-def _both(golden, bindir, ref_argv, our_argv):
+def _both(golden, bindir, ref_argv, our_argv, exact=False):
     """Run one command on both sides.  True if both succeeded; False if the reference failed and the
     drop-in failed with the same exception (error behaviour is part of the interface: several option
     combinations crash the reference as shipped, e.g. n-ary shapes whose cursor runs off the node
     list, or `kij` hill-climbing out of the k range a sweep-built tree holds)."""
     import subprocess
     try:
-        golden.run_ref(bindir, ref_argv)
+        golden.run_ref(bindir, ref_argv, exact=exact)
     except subprocess.CalledProcessError as failed:
         last = failed.stderr.decode(errors="replace").strip().split("\n")[-1]
         with pytest.raises(Exception) as ours_err:
@@ -604,7 +604,7 @@ def test_changed_inputs_and_damaged_databases(tmp_path, golden, oracle_store):
 
 EXTREMES = [
     # (name, extra argv, exact, what to expect: "same" = same outputs or the same failure; otherwise the exception the
-    #  REFERENCE dies with where the drop-in completes -- the deliberate differences (4) and (5) of DESIGN.md section 2)
+    #  REFERENCE dies with where the drop-in completes -- deliberate difference (4) of DESIGN.md section 2)
     ("k2", ["-k", "2"], False, "same"), ("k3", ["-k", "3"], False, "same"), ("k30", ["-k", "30"], False, "same"),
     ("k31", ["-k", "31"], False, "same"), ("k32", ["-k", "32"], False, "same"), ("k33", ["-k", "33"], False, "same"),
     ("k1", ["-k", "1"], False, "KeyError"),                       # exploring k - 1 = 0 collides with the k = 0 template slot
@@ -616,7 +616,20 @@ EXTREMES = [
     ("registers_4", ["-k", "10", "-r", "4"], False, "same"), ("registers_24", ["-k", "10", "-r", "24"], False, "same"),
     ("exact_k2", ["-k", "2", "--exact"], True, "same"),
     ("exact_k1", ["-k", "1", "--exact"], True, "KeyError"),
-    ("exact_k33", ["-k", "33", "--exact"], True, "IndexError"),   # "higher ks need --exact" (README.md:82), but a climb from there overruns a list
+    ("exact_k33", ["-k", "33", "--exact"], True, "same"), ("exact_k64", ["-k", "64", "--exact"], True, "same"),
+    ("exact_k65", ["-k", "65", "--exact"], True, "same"),
+    ("exact_sweep_30_36", ["-k", "31", "--exact", "--ksweep", "--mink", "30", "--maxk", "36"], True, "same"),    # across the 64-bit k-mer
+    ("exact_sweep_62_67", ["-k", "31", "--exact", "--ksweep", "--mink", "62", "--maxk", "67"], True, "same"),    # across the 128-bit k-mer
+    ("exact_sweep_99_100_nocanon", ["-k", "31", "--exact", "-C", "--ksweep", "--mink", "99", "--maxk", "100"], True, "same"),
+]
+
+
+CORNERS_EXACT = [   # on an --exact tree: k-mer sets instead of sketches, ranges that cross k = 32 (real for KMC, the stand-in follows)
+    ("exact_progressive_identity", ["progressive", "-n", "1"], ["x_progu1_4_kmc.csv", "x_progu1_4_kmcsummary.csv"]),
+    ("exact_progressive_sweep_31_35", ["progressive", "-n", "1", "-s", "xh", "--ksweep", "--mink", "31", "--maxk", "35"],
+     ["xh_progu1_4_kmc.csv", "xh_progu1_4_kmcsummary.csv"]),
+    ("exact_kij", ["kij"], ["x_4_kmc.kij.csv"]),
+    ("exact_kij_jaccard_31_35", ["kij", "-s", "xk", "--jaccard", "--mink", "31", "--maxk", "35"], ["xk_4_kmc.kij.csv", "xk_4_kmc.j.csv"]),
 ]
 
 
@@ -711,9 +724,13 @@ def test_progressive_and_kij_corner_options(tmp_path, golden, oracle_store):
     ref_out, our_out = str(tmp_path / "ref"), str(tmp_path / "ours")
     tree = lambda out: ["tree", "-d", data, "-s", "t", "-k", "11", "-o", out, "-r", "10"]     # noqa: E731
     assert _both(golden, bindir, tree(ref_out), tree(our_out))
-    for name, command, outputs in CORNERS:
-        argv = lambda out: [command[0], "-d", os.path.join(out, "t_4_dashing_dtree.pickle"), "-o", out] + command[1:]   # noqa: E731
-        if _both(golden, bindir, argv(ref_out), argv(our_out)):
+    xtree = lambda out: ["tree", "-d", data, "-s", "x", "-k", "11", "-o", out, "--exact"]     # noqa: E731
+    golden.run_ref(bindir, xtree(ref_out), exact=True)
+    run_dandd(xtree(our_out))
+    for name, command, outputs in CORNERS + CORNERS_EXACT:
+        pickle_name = "x_4_kmc_dtree.pickle" if name.startswith("exact_") else "t_4_dashing_dtree.pickle"
+        argv = lambda out: [command[0], "-d", os.path.join(out, pickle_name), "-o", out] + command[1:]   # noqa: E731
+        if _both(golden, bindir, argv(ref_out), argv(our_out), exact=name.startswith("exact_")):
             assert outputs, name + ": both succeeded where a shared failure was expected"
             for filename in outputs:
                 if "progu24" in filename or "progu100" in filename:       # random orderings: every permutation, whatever the order
@@ -730,7 +747,7 @@ def test_progressive_and_kij_corner_options(tmp_path, golden, oracle_store):
 def test_input_listing_corners(tmp_path, golden, oracle_store):
     """How the inputs of `tree` are found: --nchildren beyond what can be built, file lists with blank lines,
     duplicates, missing files, one file, no file; directories with one FASTA, none, a trailing slash, a relative
-    path; tags with underscores -- same outputs or the same failure.  The sixth and last deliberate difference:
+    path; tags with underscores -- same outputs or the same failure.  Deliberate difference (5):
     for a --datadir that does not exist the reference CONSTRUCTS a ValueError but never raises it
     (lib/huffman_dandd.py:866-867) and fails later on an empty file name; the drop-in raises that ValueError."""
     import shutil
