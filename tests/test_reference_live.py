@@ -82,7 +82,7 @@ def _both(golden, bindir, ref_argv, our_argv, exact=False):
     return True
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("DANDD_LIVE_SEEDS", "5"))))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("DANDD_LIVE_SEEDS", "2"))))
 def test_random_tree_progressive_kij_match_the_reference(tmp_path, golden, oracle_store, seed):
     from oracle import pyoracle
     case = _draw(seed)
@@ -167,7 +167,7 @@ def _draw_options(seed):
     return case
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("DANDD_LIVE_SEEDS", "3"))))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("DANDD_LIVE_SEEDS", "2"))))
 def test_random_exact_orderings_subsets_match_the_reference(tmp_path, golden, oracle_store, seed):
     """More of the option space, same method: --exact (with the one-method run-time patch of the reference that
     tests/golden/make_reference_golden.py documents), progressive over an orderings file with --step,
@@ -267,7 +267,7 @@ def _draw_lowmem(seed):
     return case
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("DANDD_LIVE_SEEDS", "3"))))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("DANDD_LIVE_SEEDS", "2"))))
 def test_random_lowmem_labels_and_subsets_match_the_reference(tmp_path, golden, oracle_store, seed):
     """`--lowmem` re-runs over a sketch database whose multi-FASTA sketches were deleted (cardinalities on
     record are trusted, anything else is rebuilt), output labels (-l), and `kij` / `progressive` over a
@@ -418,7 +418,7 @@ def _draw_inputs(seed):
     return case
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("DANDD_LIVE_SEEDS", "3"))))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("DANDD_LIVE_SEEDS", "2"))))
 def test_random_input_formats_exact_kij_and_shared_databases_match_the_reference(tmp_path, golden, oracle_store, seed):
     """Input side of the path: gzip-compressed and plain FASTAs under every extension the reference names, CRLF line
     ends, a file whose records hold no sequence at all; --exact with -C / --nthreads; `kij` in exact mode; a second
