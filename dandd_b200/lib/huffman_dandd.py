@@ -1051,6 +1051,10 @@ def create_delta_tree(tag: str, genomedir: str, sketchdir: str, kstart: int, nch
         raise ValueError("You must provide either an existing directory of fastas or a file listing the paths of the "
                          f"desired fastas. The directory you provided was {speciesinfo.inputdir}.")
     fastas.sort()
+    if nchildren and int(nchildren) == 1 and len(fastas) > 1:
+        # (the reference never returns from such a run: every new node takes ONE node off its list and puts one
+        # back, lib/huffman_dandd.py:377-438.  Refused before any rank reads or sketches anything.)
+        raise ValueError("--nchildren 1 cannot build a tree over more than one fasta: every node would have a single child")
     if presketch_leaves_sharded(fastas, speciesinfo, experiment, kstart) > 0:
         return None           # ranks > 0 only contribute leaf sketches; rank 0 builds and saves the tree
     # read / gunzip / blake2b in the background while the GPU works -- only files the database has never
@@ -1058,10 +1062,6 @@ def create_delta_tree(tag: str, genomedir: str, sketchdir: str, kstart: int, nch
     ingest.prefetch([f for f in fastas if os.path.basename(f) not in speciesinfo.fastahex])
     _warm_fresh_leaves(fastas, speciesinfo, experiment)
     if nchildren:
-        if int(nchildren) == 1 and len(fastas) > 1:
-            # (the reference never returns here: every new node takes ONE node off its list and puts one back,
-            # lib/huffman_dandd.py:377-438)
-            raise ValueError("--nchildren 1 cannot build a tree over more than one fasta: every node would have a single child")
         dtree = DeltaTree(fasta_files=fastas, speciesinfo=speciesinfo, nchildren=nchildren, experiment=experiment)
     else:
         dtree = DeltaSpider(fasta_files=fastas, speciesinfo=speciesinfo, experiment=experiment)
