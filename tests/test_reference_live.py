@@ -796,3 +796,47 @@ def test_input_listing_corners(tmp_path, golden, oracle_store):
             assert failed.returncode == 1
         except SystemExit as stop:
             assert stop.code == 1
+
+
+def test_command_line_surface_equals_the_reference():
+    """Every sub-command, option string, destination, default, type, nargs and choice of the reference's argparse
+    tree exists unchanged in the drop-in's; the drop-in adds --device and --gpus, and a handler for `info`."""
+    import argparse
+    import subprocess
+    import sys
+    import textwrap
+    probe = textwrap.dedent("""
+        import argparse, json, sys
+        sys.path.insert(0, sys.argv[1])
+        if len(sys.argv) > 2:
+            sys.path.insert(1, sys.argv[2])
+        import dandd_cmd
+        parser = dandd_cmd.parse_arguments()[0]
+        subs = [a for a in parser._actions if isinstance(a, argparse._SubParsersAction)][0]
+        out = {}
+        for name, sp in subs.choices.items():
+            out[name] = {"|".join(a.option_strings): [a.dest, repr(a.default), repr(a.nargs), getattr(a.type, "__name__", repr(a.type)),
+                                                       a.required, repr(a.choices), type(a).__name__]
+                         for a in sp._actions if not isinstance(a, argparse._HelpAction)}
+            out[name]["<handler>"] = sp.get_default("func") is not None
+        print(json.dumps(out))
+    """)
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    surfaces = {}
+    for side, args in (("ref", [REF]), ("ours", [os.path.join(root, "dandd_b200", "lib"), root])):
+        done = subprocess.run([sys.executable, "-W", "ignore", "-c", probe] + args, capture_output=True, text=True, check=True)
+        surfaces[side] = json.loads(done.stdout)
+    assert sorted(surfaces["ours"]) == sorted(surfaces["ref"]) == ["info", "kij", "progressive", "tree"]
+    for command, options in surfaces["ref"].items():
+        for option, spec in options.items():
+            if option == "<handler>":
+                continue
+            ours = surfaces["ours"][command][option]
+            if option == "-o|--out" or option == "-o|--outdir":
+                spec, ours = spec[:1] + spec[2:], ours[:1] + ours[2:]          # default = the current directory of each probe
+            assert ours == spec, (command, option, spec, ours)
+        extra = set(surfaces["ours"][command]) - set(options)
+        assert extra == {"--device", "--gpus"}, (command, extra)
+    assert surfaces["ref"]["info"]["<handler>"] is False and surfaces["ours"]["info"]["<handler>"] is True
+    assert all(surfaces[s][c]["<handler>"] for s in surfaces for c in ("tree", "progressive", "kij"))
